@@ -1,0 +1,218 @@
+"""ctypes binding of the CPU oracle (oracle/vfind_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package (vfind_b200) never imports it.
+
+Parity status: see oracle/vfind_oracle.h — exact search, translate, thresholds and the
+reference's own fixtures are pinned; the DP's gapped / tie behaviour is "parity unpinned"
+(parasail cannot be built or imported in this image).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libvfind_oracle.so")
+
+NONE = -1
+INT32_MIN = -(2 ** 31)
+
+
+class DpRules(C.Structure):
+    _fields_ = [("gap_tie_open", C.c_int), ("h_priority", C.c_int),
+                ("end_rule", C.c_int), ("wildcard_zero", C.c_int)]
+
+    def __init__(self, gap_tie_open=0, h_priority=0, end_rule=0, wildcard_zero=1):
+        super().__init__(gap_tie_open, h_priority, end_rule, wildcard_zero)
+
+
+class Params(C.Structure):
+    _fields_ = [("prefix", C.c_char_p), ("prefix_len", C.c_size_t),
+                ("suffix", C.c_char_p), ("suffix_len", C.c_size_t),
+                ("match_score", C.c_int32), ("mismatch_score", C.c_int32),
+                ("gap_open_penalty", C.c_int32), ("gap_extend_penalty", C.c_int32),
+                ("accept_prefix_alignment", C.c_double), ("accept_suffix_alignment", C.c_double),
+                ("skip_translation", C.c_int32), ("rules", DpRules)]
+
+
+DIAG_DTYPE = np.dtype([("exact_prefix", "<i4"), ("exact_suffix", "<i4"),
+                       ("score_prefix", "<i4"), ("len_prefix", "<i4"),
+                       ("score_suffix", "<i4"), ("len_suffix", "<i4"),
+                       ("start", "<i4"), ("end", "<i4")])
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with oracle/Makefile (gcc).  Building the checker is not using it."""
+    src = os.path.join(_HERE, "vfind_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "libvfind_oracle.so"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        L.vfo_memmem.restype = C.c_int64
+        L.vfo_memmem.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+        L.vfo_threshold_preflight.argtypes = [C.c_double, C.POINTER(C.c_int)]
+        L.vfo_min_score.restype = C.c_double
+        L.vfo_min_score.argtypes = [C.c_double, C.c_int32, C.c_size_t]
+        L.vfo_sg_stats.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.POINTER(DpRules)] + [C.POINTER(C.c_int)] * 4
+        L.vfo_translate.restype = C.c_int64
+        L.vfo_translate.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p]
+        L.vfo_is_utf8.argtypes = [C.c_char_p, C.c_size_t]
+        L.vfo_aa_table.restype = C.c_char_p
+        L.vfo_ascii_to_index.restype = C.POINTER(C.c_uint8)
+        L.vfo_table_new.restype = C.c_void_p
+        L.vfo_table_free.argtypes = [C.c_void_p]
+        L.vfo_table_rows.restype = C.c_uint64
+        L.vfo_table_rows.argtypes = [C.c_void_p]
+        L.vfo_table_key_bytes.restype = C.c_uint64
+        L.vfo_table_key_bytes.argtypes = [C.c_void_p]
+        L.vfo_table_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.vfo_process_reads.argtypes = [C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_uint64, C.c_int, C.c_void_p, C.c_void_p,
+                                        C.POINTER(C.c_uint64)]
+        L.vfo_find_variants_file.argtypes = [C.c_char_p, C.POINTER(Params), C.c_int, C.c_void_p,
+                                             C.POINTER(C.c_uint64), C.c_char_p, C.c_size_t]
+        _lib = L
+    return _lib
+
+
+def memmem(hay: bytes, needle: bytes) -> int:
+    return int(lib().vfo_memmem(hay, len(hay), needle, len(needle)))
+
+
+def threshold_preflight(thr: float):
+    """Returns skip_alignment (bool); raises ValueError like src/lib.rs:107-109."""
+    skip = C.c_int(0)
+    if lib().vfo_threshold_preflight(thr, C.byref(skip)) != 0:
+        raise ValueError("Accept alignment threshold must be between 0 and 1.")
+    return bool(skip.value)
+
+
+def min_score(thr: float, match_score: int, adapter_len: int) -> float:
+    return float(lib().vfo_min_score(thr, match_score, adapter_len))
+
+
+def sg_stats(adapter: bytes, read: bytes, match=3, mismatch=-2, gap_open=5, gap_extend=2,
+             rules: DpRules | None = None):
+    """(score, length, end_i, end_j) of the semi-global alignment with statistics."""
+    r = rules or DpRules()
+    out = [C.c_int(0) for _ in range(4)]
+    rc = lib().vfo_sg_stats(adapter, len(adapter), read, len(read), match, mismatch, gap_open,
+                            gap_extend, C.byref(r), *[C.byref(o) for o in out])
+    if rc != 0:
+        raise ValueError("empty adapter or read")
+    return tuple(o.value for o in out)
+
+
+def translate(seq: bytes):
+    buf = C.create_string_buffer(len(seq) // 3 + 1)
+    k = lib().vfo_translate(seq, len(seq), buf)
+    return None if k < 0 else buf.raw[:k]
+
+
+def is_utf8(b: bytes) -> bool:
+    return bool(lib().vfo_is_utf8(b, len(b)))
+
+
+def aa_table() -> str:
+    return lib().vfo_aa_table().decode()
+
+
+def ascii_to_index():
+    p = lib().vfo_ascii_to_index()
+    return [p[i] for i in range(128)]
+
+
+def make_params(adapters, match_score=3, mismatch_score=-2, gap_open_penalty=5,
+                gap_extend_penalty=2, accept_prefix_alignment=0.75, accept_suffix_alignment=0.75,
+                skip_translation=False, rules: DpRules | None = None) -> Params:
+    pre = adapters[0] if isinstance(adapters[0], bytes) else adapters[0].encode()
+    suf = adapters[1] if isinstance(adapters[1], bytes) else adapters[1].encode()
+    p = Params(pre, len(pre), suf, len(suf), match_score, mismatch_score, gap_open_penalty,
+               gap_extend_penalty, accept_prefix_alignment, accept_suffix_alignment,
+               1 if skip_translation else 0, rules or DpRules())
+    p._keep = (pre, suf)
+    return p
+
+
+def _export(t) -> dict:
+    L = lib()
+    rows = int(L.vfo_table_rows(t))
+    kb = int(L.vfo_table_key_bytes(t))
+    offs = np.zeros(rows + 1, dtype=np.uint64)
+    data = np.zeros(max(kb, 1), dtype=np.uint8)
+    counts = np.zeros(max(rows, 1), dtype=np.uint64)
+    L.vfo_table_export(t, offs.ctypes.data, data.ctypes.data, counts.ctypes.data)
+    raw = data.tobytes()
+    return {raw[int(offs[i]):int(offs[i + 1])]: int(counts[i]) for i in range(rows)}
+
+
+def process_reads(params: Params, text, off, length, n_threads=1, want_diag=False):
+    """Run the worker+reducer closures over packed reads.
+
+    text: bytes / uint8 array; off, length: uint32 arrays.  Returns (table dict, diag|None, cells).
+    """
+    L = lib()
+    text = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else \
+        np.ascontiguousarray(text, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.uint32)
+    length = np.ascontiguousarray(length, dtype=np.uint32)
+    n = len(off)
+    diag = np.zeros(n, dtype=DIAG_DTYPE) if want_diag else None
+    cells = C.c_uint64(0)
+    t = L.vfo_table_new()
+    try:
+        rc = L.vfo_process_reads(C.byref(params), text.ctypes.data if len(text) else None,
+                                 off.ctypes.data if n else None,
+                                 length.ctypes.data if n else None, n, n_threads, t,
+                                 diag.ctypes.data if want_diag and n else None, C.byref(cells))
+        if rc == -1:
+            raise ValueError("Accept alignment threshold must be between 0 and 1.")
+        return _export(t), diag, int(cells.value)
+    finally:
+        L.vfo_table_free(t)
+
+
+def pack_reads(seqs):
+    """Pack a list of byte strings back to back -> (text uint8, off uint32, len uint32)."""
+    seqs = [s if isinstance(s, bytes) else s.encode() for s in seqs]
+    length = np.array([len(s) for s in seqs], dtype=np.uint32)
+    off = np.zeros(len(seqs), dtype=np.uint32)
+    if len(seqs):
+        off[1:] = np.cumsum(length[:-1], dtype=np.uint64).astype(np.uint32)
+    text = np.frombuffer(b"".join(seqs), dtype=np.uint8)
+    return text, off, length
+
+
+def find_variants_file(path: str, adapters, n_threads=1, **kw) -> dict:
+    """Oracle end-to-end over a gzipped FASTQ: {sequence bytes: count}."""
+    L = lib()
+    p = make_params(adapters, **kw)
+    t = L.vfo_table_new()
+    err = C.create_string_buffer(256)
+    n = C.c_uint64(0)
+    try:
+        rc = L.vfo_find_variants_file(os.fsencode(path), C.byref(p), n_threads, t, C.byref(n),
+                                      err, 256)
+        if rc == -1:
+            raise ValueError(err.value.decode())
+        if rc == -2:
+            raise FileNotFoundError(err.value.decode())
+        if rc != 0:
+            raise RuntimeError(err.value.decode())
+        return _export(t)
+    finally:
+        L.vfo_table_free(t)
