@@ -1,0 +1,221 @@
+/*
+ * vfind_b200.h — C ABI of the B200-native variant-recovery path.
+ *
+ * This is the drop-in boundary for vFind's `find_variants` hot path.  The reference
+ * (nsbuitrago/vfind, /root/reference) has no FFI of its own for this path: the whole
+ * path is Rust behind one PyO3 function (src/lib.rs:168-320).  The entry points below
+ * are what a `vfind-b200-sys` FFI crate would bind from that function's body — one
+ * entry point per stage of `find_variants` — and what vfind_b200/api.py binds with ctypes.
+ * INTEGRATION.md shows both bindings.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function returns a
+ * vfb_status (0 = ok); on failure vfb_last_error() (thread-local) describes it.  Device
+ * pointers are CUDA device addresses in the calling process's primary context.  There is
+ * no CPU fallback anywhere behind this interface: without a CUDA device every compute
+ * entry point fails with VFB_ERR_CUDA.
+ */
+#ifndef VFIND_B200_H
+#define VFIND_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VFB_ABI_VERSION 1
+
+typedef enum vfb_status {
+    VFB_OK = 0,
+    VFB_ERR_VALUE = 1,   /* -> Python ValueError   (src/lib.rs:107-109)                     */
+    VFB_ERR_IO = 2,      /* -> Python OSError      (File::open `?`, src/lib.rs:233)          */
+    VFB_ERR_FORMAT = 3,  /* malformed gzip/FASTQ: the reference panics (src/lib.rs:308)      */
+    VFB_ERR_CUDA = 4,    /* CUDA runtime failure / no device                                 */
+    VFB_ERR_ARG = 5,     /* bad argument to this ABI (null pointer, unsupported size)        */
+    VFB_ERR_NOMEM = 6
+} vfb_status;
+
+#define VFB_NONE 0xFFFFFFFFu
+
+/* Arguments of find_variants (src/lib.rs:219-231), in the reference's order, followed by
+ * GPU-side knobs that the reference does not have (all optional, 0 = default). */
+typedef struct vfb_params {
+    uint32_t struct_size;             /* sizeof(vfb_params), for ABI evolution              */
+    const uint8_t *prefix;            /* adapters.0                      src/lib.rs:221     */
+    uint64_t prefix_len;
+    const uint8_t *suffix;            /* adapters.1                                          */
+    uint64_t suffix_len;
+    int32_t match_score;              /* :222 */
+    int32_t mismatch_score;           /* :223 */
+    int32_t gap_open_penalty;         /* :224 (positive = penalty, README.md:137-138)       */
+    int32_t gap_extend_penalty;       /* :225 */
+    double accept_prefix_alignment;   /* :226 */
+    double accept_suffix_alignment;   /* :227 */
+    uint32_t n_threads;               /* :228 host ingest threads (inflate/parse)           */
+    uint64_t queue_len;               /* :229 batches in flight                             */
+    int32_t skip_translation;         /* :230 */
+    int32_t show_progress;            /* :231 accepted, ignored (the reference's spinner is never ticked) */
+    /* ---- additions ---- */
+    int32_t device;                   /* CUDA ordinal; -1 = current device                  */
+    int32_t diagnostics;              /* keep per-read diagnostics of the last batch        */
+    uint64_t batch_reads;             /* max reads per device batch (0 = 8 Mi)              */
+    uint64_t batch_bytes;             /* max text bytes per device batch (0 = 2 GiB)        */
+    uint64_t table_capacity_hint;     /* expected distinct variants (0 = grow on demand)    */
+    int32_t debug_hash_bits;          /* tests only: keep this many hash bits (0 = all 64)  */
+    int32_t force_generic_dp;         /* tests only: use the unpacked fallback DP kernel    */
+    int32_t dp_compute_all;           /* 1 = run the suffix DP even when the prefix failed
+                                         (what the reference does, src/lib.rs:278-286; the
+                                         result table is identical either way)              */
+    int32_t reserved;
+} vfb_params;
+
+/* One read inside a text buffer: text[off .. off+len). */
+typedef struct vfb_span {
+    uint32_t off;
+    uint32_t len;
+} vfb_span;
+
+/* Per-read diagnostics, field-compatible with the oracle's vfo_read_diag. */
+typedef struct vfb_read_diag {
+    int32_t exact_prefix;   /* leftmost exact position or -1         src/lib.rs:148   */
+    int32_t exact_suffix;
+    int32_t score_prefix;   /* DP score; INT32_MIN when no DP ran    src/lib.rs:156   */
+    int32_t len_prefix;     /* DP length statistic; -1 when no DP    src/lib.rs:159   */
+    int32_t score_suffix;
+    int32_t len_suffix;
+    int32_t start;          /* region boundaries or -1               src/lib.rs:278-286 */
+    int32_t end;
+} vfb_read_diag;
+
+/* The result: HashMap<String,u64> unzipped to columns (src/lib.rs:312-317), Arrow-style.
+ * Row i is data[offsets[i] .. offsets[i+1]) with counts[i].  Row order is unspecified. */
+typedef struct vfb_table {
+    uint64_t rows;
+    uint64_t key_bytes;
+    uint64_t *offsets;      /* rows + 1 */
+    uint8_t *data;          /* key_bytes */
+    uint64_t *counts;       /* rows */
+} vfb_table;
+
+typedef struct vfb_stats {
+    uint64_t reads;             /* reads submitted since create/reset                  */
+    uint64_t dp_prefix;         /* prefix alignments performed                         */
+    uint64_t dp_suffix;
+    uint64_t dp_cells;          /* sum of adapter_len * read_len over alignments       */
+    uint64_t counted;           /* reads that contributed to the table                 */
+    uint64_t unique;            /* distinct keys                                       */
+    uint64_t text_bytes;        /* sum of read lengths                                 */
+    uint64_t kernel_launches;   /* kernels launched by this library since create/reset */
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+    /* device time per stage in ms (CUDA events on the compute stream), summed over
+     * batches; only filled when vfb_set_profiling(ctx, 1). */
+    double ms_scan, ms_worklist, ms_dp, ms_translate, ms_count, ms_total;
+    uint64_t dp_kernel_launches;
+    int32_t dp_kernel_kind;     /* 1 = packed DPX kernel, 2 = generic fallback          */
+    int32_t reserved;
+} vfb_stats;
+
+typedef struct vfb_ctx vfb_ctx;
+
+const char *vfb_last_error(void);
+int vfb_abi_version(void);
+
+/* Fill *p with the reference's defaults (src/lib.rs:169-182). */
+void vfb_default_params(vfb_params *p);
+
+/* Setup half of find_variants (src/lib.rs:236-261): validates both thresholds
+ * (VFB_ERR_VALUE with the reference's message), builds the adapter profiles, converts
+ * `thr * match * len` (evaluated in f64 exactly as :260-261) to integer accept bounds. */
+int vfb_create(const vfb_params *p, vfb_ctx **out);
+int vfb_destroy(vfb_ctx *ctx);
+
+/* Clear the count table and the statistics (keeps allocations). */
+int vfb_reset(vfb_ctx *ctx);
+int vfb_set_profiling(vfb_ctx *ctx, int enabled);
+
+/* The per-read hot loop (worker + reducer closures, src/lib.rs:275-306) over a batch of
+ * reads held in HOST memory: host->device copies happen inside.  `text`/`spans` may be
+ * pageable or pinned (pinned is copied directly).  Asynchronous: returns once the batch
+ * is staged; vfb_sync / vfb_finish wait. */
+int vfb_submit_host(vfb_ctx *ctx, const uint8_t *text, uint64_t text_bytes,
+                    const vfb_span *spans, uint64_t n_reads);
+
+/* Same, reads already resident in device memory (any size: split internally). */
+int vfb_submit_device(vfb_ctx *ctx, const uint8_t *d_text, uint64_t text_bytes,
+                      const vfb_span *d_spans, uint64_t n_reads);
+
+/* Whole find_variants ingest (src/lib.rs:233-234, :271-308): gzip (multi-member) FASTQ
+ * file -> inflate -> parse -> batches -> the hot loop.  VFB_ERR_IO if it cannot be
+ * opened, VFB_ERR_FORMAT on malformed gzip/FASTQ. */
+int vfb_run_file(vfb_ctx *ctx, const char *path, uint64_t *n_reads);
+
+int vfb_sync(vfb_ctx *ctx);
+
+/* Queue all kernels on the caller's CUDA stream (a cudaStream_t) instead of the context's
+ * own, so that the caller's events and collectives order with them.  The caller keeps
+ * ownership of the stream. */
+int vfb_set_compute_stream(vfb_ctx *ctx, void *stream);
+
+/* `variants.into_iter().unzip()` (src/lib.rs:312): waits for all batches, copies the
+ * table to the host.  Free with vfb_table_free.  The context stays usable. */
+int vfb_finish(vfb_ctx *ctx, vfb_table *out);
+void vfb_table_free(vfb_table *t);
+
+int vfb_get_stats(vfb_ctx *ctx, vfb_stats *out);
+
+/* Diagnostics of the most recent batch (requires params.diagnostics = 1 and that the
+ * last submit was a single batch).  Parity tests compare these with the oracle. */
+int vfb_get_diag(vfb_ctx *ctx, vfb_read_diag *out, uint64_t n_reads);
+
+/* ---- multi-GPU merge (no reference equivalent) ----
+ * Keys are owned by rank = owner(hash(key)) in [0, n_parts).  Export the local table as
+ * n_parts self-describing chunks in device memory, exchange them with any transport
+ * (NCCL all-to-all in vfind_b200/distributed.py), then absorb the received chunks. */
+int vfb_table_partition_sizes(vfb_ctx *ctx, uint32_t n_parts, uint64_t *chunk_bytes /* n_parts */);
+int vfb_table_partition_fill(vfb_ctx *ctx, uint32_t n_parts, uint8_t *d_buf,
+                             const uint64_t *chunk_offsets /* n_parts */);
+int vfb_table_clear(vfb_ctx *ctx);
+int vfb_table_absorb(vfb_ctx *ctx, const uint8_t *d_chunk, uint64_t chunk_bytes);
+/* Host-side view of a chunk (for CPU tests of the exchange plumbing). */
+int vfb_chunk_rows(const uint8_t *h_chunk, uint64_t chunk_bytes, uint64_t *rows);
+
+/* ---- synthetic reads (bench + tests; BASELINE.json configs) ---- */
+typedef struct vfb_synth_cfg {
+    uint64_t seed;
+    uint32_t read_len;        /* L */
+    uint32_t adapter_len;     /* A (both adapters) */
+    uint32_t region_len;      /* V, multiple of 3 */
+    uint32_t n_variants;      /* U library size */
+    uint32_t zipf;            /* 1 = octave-Zipf(s~1) over the library, 0 = uniform */
+    uint32_t p_err_ppm;       /* per-adapter probability of being mutated, in 1e-6 */
+    uint32_t indel_ppm;       /* probability that one edit is an indel, in 1e-6 (rest substitutions) */
+    uint32_t force_indel;     /* 1 = first edit of a mutated adapter is always an indel (config #3) */
+    uint32_t frameshift_ppm;  /* fraction of library entries with V±1 */
+    uint32_t noise_ppm;       /* per-base substitution noise inside the region */
+    uint32_t n_ppm;           /* per-base probability of an 'N' inside the region */
+    uint32_t reserved;
+} vfb_synth_cfg;
+
+/* The two adapters the generator embeds (deterministic in cfg->seed). */
+int vfb_synth_adapters(const vfb_synth_cfg *cfg, uint8_t *prefix, uint8_t *suffix);
+/* Reads [first, first+n) as fixed-stride records: text[i*read_len ..), spans[i] = {i*read_len, read_len}.
+ * Host and device produce identical bytes. */
+int vfb_synth_host(const vfb_synth_cfg *cfg, uint64_t first, uint64_t n, uint8_t *text, vfb_span *spans);
+int vfb_synth_device(const vfb_synth_cfg *cfg, uint64_t first, uint64_t n, uint8_t *d_text,
+                     vfb_span *d_spans, int device);
+
+/* ---- measurement helpers ---- */
+/* Dependent-free integer microbenchmark on `device`: peak lane-ops/s of the INT32 ALU
+ * pipe (IADD3/VIADDMNMX mix) and of ALU+FMA-pipe dual issue (IADD3 + IMAD).  Giga-ops/s. */
+int vfb_measure_int_peak(int device, double *alu_gops, double *dual_gops);
+
+/* Pinned host memory for callers without their own allocator. */
+int vfb_host_alloc(void **p, uint64_t bytes);
+int vfb_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,8 @@
+"""vfind_b200 — B200-native implementation of vFind's per-read variant-recovery path.
+
+`find_variants` is a drop-in for `vfind.find_variants` of nsbuitrago/vfind; everything
+behind it runs as hand-written sm_100a CUDA kernels in libvfind_b200.so.
+"""
+from .api import Context, PanicException, find_variants  # noqa: F401
+
+__all__ = ["find_variants", "Context", "PanicException"]

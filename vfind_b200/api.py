@@ -1,0 +1,414 @@
+"""ctypes binding of include/vfind_b200.h and the Python mirror of `vfind.find_variants`.
+
+The reference's boundary is the PyO3 function `find_variants`
+(/root/reference/src/lib.rs:168-232): same names, positional order, defaults, coercions and
+exception types here.  All compute happens in libvfind_b200.so (hand-written sm_100a CUDA);
+there is no CPU path — importing works anywhere, calling needs a CUDA device and the
+built library, and fails loudly otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvfind_b200.so")
+
+VFB_OK, VFB_ERR_VALUE, VFB_ERR_IO, VFB_ERR_FORMAT, VFB_ERR_CUDA, VFB_ERR_ARG, VFB_ERR_NOMEM = range(7)
+NONE = 0xFFFFFFFF
+INT32_MIN = -(2 ** 31)
+
+SPAN_DTYPE = np.dtype([("off", "<u4"), ("len", "<u4")])
+DIAG_DTYPE = np.dtype([("exact_prefix", "<i4"), ("exact_suffix", "<i4"),
+                       ("score_prefix", "<i4"), ("len_prefix", "<i4"),
+                       ("score_suffix", "<i4"), ("len_suffix", "<i4"),
+                       ("start", "<i4"), ("end", "<i4")])
+
+
+class Params(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32),
+                ("prefix", C.c_char_p), ("prefix_len", C.c_uint64),
+                ("suffix", C.c_char_p), ("suffix_len", C.c_uint64),
+                ("match_score", C.c_int32), ("mismatch_score", C.c_int32),
+                ("gap_open_penalty", C.c_int32), ("gap_extend_penalty", C.c_int32),
+                ("accept_prefix_alignment", C.c_double), ("accept_suffix_alignment", C.c_double),
+                ("n_threads", C.c_uint32), ("queue_len", C.c_uint64),
+                ("skip_translation", C.c_int32), ("show_progress", C.c_int32),
+                ("device", C.c_int32), ("diagnostics", C.c_int32),
+                ("batch_reads", C.c_uint64), ("batch_bytes", C.c_uint64),
+                ("table_capacity_hint", C.c_uint64),
+                ("debug_hash_bits", C.c_int32), ("force_generic_dp", C.c_int32),
+                ("dp_compute_all", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Table(C.Structure):
+    _fields_ = [("rows", C.c_uint64), ("key_bytes", C.c_uint64),
+                ("offsets", C.POINTER(C.c_uint64)), ("data", C.POINTER(C.c_uint8)),
+                ("counts", C.POINTER(C.c_uint64))]
+
+
+class Stats(C.Structure):
+    _fields_ = [("reads", C.c_uint64), ("dp_prefix", C.c_uint64), ("dp_suffix", C.c_uint64),
+                ("dp_cells", C.c_uint64), ("counted", C.c_uint64), ("unique", C.c_uint64),
+                ("text_bytes", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("ms_scan", C.c_double), ("ms_worklist", C.c_double), ("ms_dp", C.c_double),
+                ("ms_translate", C.c_double), ("ms_count", C.c_double), ("ms_total", C.c_double),
+                ("dp_kernel_launches", C.c_uint64), ("dp_kernel_kind", C.c_int32),
+                ("reserved", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+class SynthCfg(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("read_len", C.c_uint32), ("adapter_len", C.c_uint32),
+                ("region_len", C.c_uint32), ("n_variants", C.c_uint32), ("zipf", C.c_uint32),
+                ("p_err_ppm", C.c_uint32), ("indel_ppm", C.c_uint32), ("force_indel", C.c_uint32),
+                ("frameshift_ppm", C.c_uint32), ("noise_ppm", C.c_uint32), ("n_ppm", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+_lib = None
+
+
+def load_library():
+    """Load the CUDA library.  Raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "vfind_b200: %s is missing — build it with `python -m vfind_b200.build` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+    L.vfb_last_error.restype = C.c_char_p
+    L.vfb_abi_version.restype = i32
+    L.vfb_default_params.argtypes = [C.POINTER(Params)]
+    L.vfb_default_params.restype = None
+    L.vfb_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+    L.vfb_destroy.argtypes = [vp]
+    L.vfb_reset.argtypes = [vp]
+    L.vfb_set_profiling.argtypes = [vp, i32]
+    L.vfb_submit_host.argtypes = [vp, vp, u64, vp, u64]
+    L.vfb_submit_device.argtypes = [vp, vp, u64, vp, u64]
+    L.vfb_run_file.argtypes = [vp, C.c_char_p, C.POINTER(u64)]
+    L.vfb_sync.argtypes = [vp]
+    L.vfb_set_compute_stream.argtypes = [vp, vp]
+    L.vfb_finish.argtypes = [vp, C.POINTER(Table)]
+    L.vfb_table_free.argtypes = [C.POINTER(Table)]
+    L.vfb_table_free.restype = None
+    L.vfb_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.vfb_get_diag.argtypes = [vp, vp, u64]
+    L.vfb_table_partition_sizes.argtypes = [vp, u32, C.POINTER(u64)]
+    L.vfb_table_partition_fill.argtypes = [vp, u32, vp, C.POINTER(u64)]
+    L.vfb_table_clear.argtypes = [vp]
+    L.vfb_table_absorb.argtypes = [vp, vp, u64]
+    L.vfb_chunk_rows.argtypes = [vp, u64, C.POINTER(u64)]
+    L.vfb_synth_adapters.argtypes = [C.POINTER(SynthCfg), vp, vp]
+    L.vfb_synth_host.argtypes = [C.POINTER(SynthCfg), u64, u64, vp, vp]
+    L.vfb_synth_device.argtypes = [C.POINTER(SynthCfg), u64, u64, vp, vp, i32]
+    L.vfb_measure_int_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.vfb_host_alloc.argtypes = [C.POINTER(vp), u64]
+    L.vfb_host_free.argtypes = [vp]
+    _lib = L
+    return L
+
+
+class PanicException(RuntimeError):
+    """Where the reference panics (malformed gzip/FASTQ, src/lib.rs:308) this build raises
+    a RuntimeError subclass named after pyo3_runtime.PanicException."""
+
+
+def _check(rc: int):
+    if rc == VFB_OK:
+        return
+    msg = load_library().vfb_last_error().decode("utf-8", "replace")
+    if rc == VFB_ERR_VALUE:
+        raise ValueError(msg)
+    if rc == VFB_ERR_IO:
+        if "No such file" in msg:
+            raise FileNotFoundError(msg)
+        raise OSError(msg)
+    if rc == VFB_ERR_FORMAT:
+        raise PanicException(msg)
+    if rc == VFB_ERR_NOMEM:
+        raise MemoryError(msg)
+    raise RuntimeError(msg)
+
+
+def _as_bytes(s, what):
+    if isinstance(s, str):
+        return s.encode("utf-8")
+    if isinstance(s, (bytes, bytearray)):
+        return bytes(s)
+    raise TypeError("%s must be str" % what)
+
+
+class Context:
+    """One configured variant-recovery pipeline on one GPU (vfb_ctx)."""
+
+    def __init__(self, adapters, match_score=3, mismatch_score=-2, gap_open_penalty=5,
+                 gap_extend_penalty=2, accept_prefix_alignment=0.75, accept_suffix_alignment=0.75,
+                 n_threads=3, queue_len=2, skip_translation=False, show_progress=True, *,
+                 device=None, diagnostics=False, batch_reads=0, batch_bytes=0,
+                 table_capacity_hint=0, debug_hash_bits=0, force_generic_dp=False,
+                 dp_compute_all=False):
+        L = load_library()
+        self._lib = L
+        self._h = C.c_void_p()
+        p = Params()
+        L.vfb_default_params(C.byref(p))
+        self._pre = _as_bytes(adapters[0], "adapters[0]")
+        self._suf = _as_bytes(adapters[1], "adapters[1]")
+        p.prefix, p.prefix_len = self._pre, len(self._pre)
+        p.suffix, p.suffix_len = self._suf, len(self._suf)
+        p.match_score, p.mismatch_score = match_score, mismatch_score
+        p.gap_open_penalty, p.gap_extend_penalty = gap_open_penalty, gap_extend_penalty
+        p.accept_prefix_alignment = accept_prefix_alignment
+        p.accept_suffix_alignment = accept_suffix_alignment
+        p.n_threads, p.queue_len = n_threads, queue_len
+        p.skip_translation = 1 if skip_translation else 0
+        p.show_progress = 1 if show_progress else 0
+        p.device = -1 if device is None else int(device)
+        p.diagnostics = 1 if diagnostics else 0
+        p.batch_reads, p.batch_bytes = int(batch_reads), int(batch_bytes)
+        p.table_capacity_hint = int(table_capacity_hint)
+        p.debug_hash_bits = int(debug_hash_bits)
+        p.force_generic_dp = 1 if force_generic_dp else 0
+        p.dp_compute_all = 1 if dp_compute_all else 0
+        _check(L.vfb_create(C.byref(p), C.byref(self._h)))
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.vfb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- the hot loop
+    def submit_host(self, text, spans):
+        """text: uint8 array / bytes; spans: SPAN_DTYPE array or (n,2) uint32."""
+        text = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else text
+        assert text.dtype == np.uint8 and text.flags.c_contiguous
+        spans = np.ascontiguousarray(spans)
+        n = spans.shape[0]
+        assert spans.nbytes == n * 8
+        _check(self._lib.vfb_submit_host(self._h, text.ctypes.data if text.size else None, text.size,
+                                         spans.ctypes.data if n else None, n))
+
+    def submit_host_ptr(self, text_ptr, text_bytes, spans_ptr, n):
+        _check(self._lib.vfb_submit_host(self._h, text_ptr, text_bytes, spans_ptr, n))
+
+    def submit_device(self, text_ptr, text_bytes, spans_ptr, n):
+        _check(self._lib.vfb_submit_device(self._h, text_ptr, text_bytes, spans_ptr, n))
+
+    def run_file(self, path) -> int:
+        n = C.c_uint64(0)
+        _check(self._lib.vfb_run_file(self._h, os.fsencode(path), C.byref(n)))
+        return int(n.value)
+
+    def sync(self):
+        _check(self._lib.vfb_sync(self._h))
+
+    def reset(self):
+        _check(self._lib.vfb_reset(self._h))
+
+    def set_compute_stream(self, stream_ptr: int):
+        _check(self._lib.vfb_set_compute_stream(self._h, stream_ptr))
+
+    def set_profiling(self, on: bool):
+        _check(self._lib.vfb_set_profiling(self._h, 1 if on else 0))
+
+    def stats(self) -> dict:
+        s = Stats()
+        _check(self._lib.vfb_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def diag(self, n):
+        out = np.zeros(n, dtype=DIAG_DTYPE)
+        _check(self._lib.vfb_get_diag(self._h, out.ctypes.data, n))
+        return out
+
+    # -- results
+    def finish_arrays(self):
+        """(offsets uint64[rows+1], data uint8[key_bytes], counts uint64[rows]) — host copies."""
+        t = Table()
+        _check(self._lib.vfb_finish(self._h, C.byref(t)))
+        try:
+            rows, kb = int(t.rows), int(t.key_bytes)
+            offsets = np.ctypeslib.as_array(t.offsets, shape=(rows + 1,)).copy()
+            data = np.ctypeslib.as_array(t.data, shape=(kb,)).copy() if kb else np.zeros(0, np.uint8)
+            counts = np.ctypeslib.as_array(t.counts, shape=(rows,)).copy() if rows else np.zeros(0, np.uint64)
+        finally:
+            self._lib.vfb_table_free(C.byref(t))
+        return offsets, data, counts
+
+    def finish_dict(self) -> dict:
+        offsets, data, counts = self.finish_arrays()
+        raw = data.tobytes()
+        return {raw[int(offsets[i]):int(offsets[i + 1])]: int(counts[i]) for i in range(len(counts))}
+
+    # -- multi-GPU merge plumbing (see vfind_b200/distributed.py)
+    def partition_sizes(self, n_parts: int):
+        out = (C.c_uint64 * n_parts)()
+        _check(self._lib.vfb_table_partition_sizes(self._h, n_parts, out))
+        return [int(x) for x in out]
+
+    def partition_fill(self, n_parts: int, buf_ptr: int, offsets):
+        arr = (C.c_uint64 * n_parts)(*[int(o) for o in offsets])
+        _check(self._lib.vfb_table_partition_fill(self._h, n_parts, buf_ptr, arr))
+
+    def table_clear(self):
+        _check(self._lib.vfb_table_clear(self._h))
+
+    def absorb(self, chunk_ptr: int, chunk_bytes: int):
+        _check(self._lib.vfb_table_absorb(self._h, chunk_ptr, chunk_bytes))
+
+
+def table_to_frame(offsets, data, counts):
+    """Columns `sequence` (String) and `count` (UInt64) (src/lib.rs:312-317) as a
+    polars.DataFrame when polars is importable, else a pyarrow.Table with the same schema."""
+    import pyarrow as pa
+    rows = len(counts)
+    if rows and int(offsets[-1]) >= 2 ** 31:
+        seq = pa.Array.from_buffers(pa.large_string(), rows,
+                                    [None, pa.py_buffer(offsets.astype(np.int64)), pa.py_buffer(data)])
+    else:
+        seq = pa.Array.from_buffers(pa.string(), rows,
+                                    [None, pa.py_buffer(offsets.astype(np.int32)), pa.py_buffer(data)])
+    cnt = pa.array(counts, type=pa.uint64())
+    tbl = pa.table({"sequence": seq, "count": cnt})
+    try:
+        import polars as pl
+    except ImportError:
+        return tbl
+    return pl.from_arrow(tbl)
+
+
+def _int_arg(v, name, lo, hi):
+    if isinstance(v, bool) or not hasattr(v, "__index__"):
+        if isinstance(v, bool):
+            v = int(v)
+        else:
+            raise TypeError("argument '%s': '%s' object cannot be interpreted as an integer"
+                            % (name, type(v).__name__))
+    v = v.__index__()
+    if v < lo or v > hi:
+        raise OverflowError("argument '%s': out of range integral type conversion attempted" % name)
+    return v
+
+
+def _float_arg(v, name):
+    if isinstance(v, (int, float, np.floating, np.integer)) and not isinstance(v, bool):
+        return float(v)
+    if isinstance(v, bool):
+        return float(v)
+    raise TypeError("argument '%s': must be real number, not %s" % (name, type(v).__name__))
+
+
+def _bool_arg(v, name):
+    if isinstance(v, (bool, np.bool_)):
+        return bool(v)
+    raise TypeError("argument '%s': '%s' object cannot be converted to 'PyBool'" % (name, type(v).__name__))
+
+
+def find_variants(fq_path, adapters, match_score=3, mismatch_score=-2, gap_open_penalty=5,
+                  gap_extend_penalty=2, accept_prefix_alignment=0.75, accept_suffix_alignment=0.75,
+                  n_threads=3, queue_len=2, skip_translation=False, show_progress=True, *,
+                  device=None, batch_reads=0, table_capacity_hint=0):
+    """Find variable regions flanked by adapters in a gzipped FASTQ dataset.
+
+    Drop-in for `vfind.find_variants` (/root/reference/src/lib.rs:168-232): same positional
+    order, defaults and error behaviour; the work runs on a B200.
+
+    Returns a table with columns `sequence` (string) and `count` (uint64): a
+    polars.DataFrame when polars is installed, else a pyarrow.Table.  Row order is
+    unspecified (as in the reference, src/lib.rs:312).
+
+    Extra keyword-only arguments: device (CUDA ordinal), batch_reads, table_capacity_hint.
+    """
+    if isinstance(fq_path, os.PathLike):
+        fq_path = os.fspath(fq_path)
+    if not isinstance(fq_path, str):
+        raise TypeError("argument 'fq_path': '%s' object cannot be converted to 'PyString'"
+                        % type(fq_path).__name__)
+    if not isinstance(adapters, (tuple, list)):
+        raise TypeError("argument 'adapters': '%s' object cannot be converted to 'PyTuple'"
+                        % type(adapters).__name__)
+    if len(adapters) != 2:
+        raise ValueError("argument 'adapters': expected tuple of length 2, but got tuple of length %d"
+                         % len(adapters))
+    for a in adapters:
+        if not isinstance(a, str):
+            raise TypeError("argument 'adapters': '%s' object cannot be converted to 'PyString'"
+                            % type(a).__name__)
+    i32 = (-(2 ** 31), 2 ** 31 - 1)
+    match_score = _int_arg(match_score, "match_score", *i32)
+    mismatch_score = _int_arg(mismatch_score, "mismatch_score", *i32)
+    gap_open_penalty = _int_arg(gap_open_penalty, "gap_open_penalty", *i32)
+    gap_extend_penalty = _int_arg(gap_extend_penalty, "gap_extend_penalty", *i32)
+    accept_prefix_alignment = _float_arg(accept_prefix_alignment, "accept_prefix_alignment")
+    accept_suffix_alignment = _float_arg(accept_suffix_alignment, "accept_suffix_alignment")
+    n_threads = _int_arg(n_threads, "n_threads", 0, 2 ** 32 - 1)
+    queue_len = _int_arg(queue_len, "queue_len", 0, 2 ** 64 - 1)
+    skip_translation = _bool_arg(skip_translation, "skip_translation")
+    show_progress = _bool_arg(show_progress, "show_progress")
+
+    # The reference opens the file before validating thresholds (src/lib.rs:233 vs :239).
+    with open(fq_path, "rb"):
+        pass
+    with Context(adapters, match_score, mismatch_score, gap_open_penalty, gap_extend_penalty,
+                 accept_prefix_alignment, accept_suffix_alignment, n_threads, queue_len,
+                 skip_translation, show_progress, device=device, batch_reads=batch_reads,
+                 table_capacity_hint=table_capacity_hint) as ctx:
+        ctx.run_file(fq_path)
+        return table_to_frame(*ctx.finish_arrays())
+
+
+# ---- synthetic reads (bench + tests) ----------------------------------------------------
+def synth_cfg(seed=1003, read_len=250, adapter_len=20, region_len=198, n_variants=1000000, zipf=1,
+              p_err=0.30, indel=0.5, force_indel=1, frameshift=0.05, noise=0.001, n_rate=1e-4) -> SynthCfg:
+    ppm = lambda x: int(round(x * 1e6))
+    return SynthCfg(seed, read_len, adapter_len, region_len, n_variants, zipf, ppm(p_err), ppm(indel),
+                    force_indel, ppm(frameshift), ppm(noise), ppm(n_rate), 0)
+
+
+def synth_adapters(cfg: SynthCfg):
+    L = load_library()
+    a = C.create_string_buffer(64)
+    b = C.create_string_buffer(64)
+    _check(L.vfb_synth_adapters(C.byref(cfg), a, b))
+    return a.raw[:cfg.adapter_len], b.raw[:cfg.adapter_len]
+
+
+def synth_host(cfg: SynthCfg, first: int, n: int):
+    L = load_library()
+    text = np.zeros(n * cfg.read_len, dtype=np.uint8)
+    spans = np.zeros(n, dtype=SPAN_DTYPE)
+    _check(L.vfb_synth_host(C.byref(cfg), first, n, text.ctypes.data, spans.ctypes.data))
+    return text, spans
+
+
+def synth_device(cfg: SynthCfg, first: int, n: int, text_ptr: int, spans_ptr: int, device: int = -1):
+    _check(load_library().vfb_synth_device(C.byref(cfg), first, n, text_ptr, spans_ptr, device))
+
+
+def measure_int_peak(device: int = -1):
+    a, d = C.c_double(0), C.c_double(0)
+    _check(load_library().vfb_measure_int_peak(device, C.byref(a), C.byref(d)))
+    return a.value, d.value

@@ -1,0 +1,1004 @@
+// Host side of the C ABI (include/vfind_b200.h): context, batching, streams, table growth.
+//
+// Mirrors the setup + hot loop of find_variants (/root/reference/src/lib.rs:233-320): the
+// reference's `parallel_fastq(reader, n_threads, queue_len, WORK, REDUCE)` becomes batches of
+// reads moving through  H2D copy -> K1 scan -> worklists -> K2 DP -> K3 keys -> K4 count  on a
+// compute stream, with the next batch's copy overlapping on a second stream.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "hash.h"
+#include "synth.h"
+#include "vfb_internal.cuh"
+
+namespace vfb {
+
+thread_local std::string g_error;
+thread_local uint64_t g_launches = 0;
+
+void set_error(const std::string &msg) { g_error = msg; }
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    g_error = buf;
+    return VFB_ERR_CUDA;
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes, bool keep = false, cudaStream_t st = 0)
+    {
+        if (bytes <= cap) return VFB_OK;
+        size_t ncap = bytes + bytes / 4 + 256;
+        void *np = nullptr;
+        cudaError_t e = cudaMalloc(&np, ncap);
+        if (e != cudaSuccess) {
+            set_error("out of device memory allocating " + std::to_string(ncap) + " bytes");
+            cudaGetLastError();
+            return VFB_ERR_NOMEM;
+        }
+        if (p) {
+            if (keep && cap) {
+                VFB_CUDA(cudaMemcpyAsync(np, p, cap, cudaMemcpyDeviceToDevice, st));
+                VFB_CUDA(cudaStreamSynchronize(st));
+            }
+            VFB_CUDA(cudaFree(p));
+        }
+        p = np;
+        cap = ncap;
+        return VFB_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return VFB_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t ncap = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaMallocHost(&p, ncap);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            cudaGetLastError();
+            set_error("cannot allocate pinned host memory");
+            return VFB_ERR_NOMEM;
+        }
+        cap = ncap;
+        return VFB_OK;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Slot {
+    DevBuf d_text, d_spans;
+    PinBuf h_text, h_spans;
+    cudaEvent_t copied = nullptr, computed = nullptr;
+    bool busy = false;
+};
+
+// device counters of one batch
+enum { C_NPRE = 0, C_NSUF, C_FBPRE, C_FBSUF, C_COUNT32 };
+// 64-bit device counters
+enum { T_CELLS = 0, T_DPPRE, T_DPSUF, T_KEYBYTES, T_COUNT64 };
+
+}  // namespace vfb
+
+using namespace vfb;
+
+struct vfb_ctx {
+    vfb_params prm;
+    std::string prefix, suffix;
+    AdapterBytes ad_pre, ad_suf;
+    DpScoring sc;
+    bool align_pre = false, align_suf = false;
+    int min_accept_pre = 0, min_accept_suf = 0;
+    bool packed_pre = false, packed_suf = false;
+    DpLayout lay_pre, lay_suf;
+    uint32_t lcap_pre = 0, lcap_suf = 0;
+    DevBuf d_code_pre, d_code_suf;   // adapter codes for the fallback kernel
+    DevBuf d_generic_scratch;
+    uint32_t generic_threads = 0;
+
+    int device = 0, sm_count = 148;
+    cudaStream_t st_compute = nullptr, st_copy = nullptr;
+    Slot slots[2];
+    uint64_t batch_seq = 0;
+    uint64_t batch_reads = 0, batch_bytes = 0;
+
+    // per-batch scratch
+    DevBuf d_start, d_end, d_list_a, d_list_b, d_fb_a, d_fb_b, d_c32, d_t64;
+    DevBuf d_keys, d_koff, d_klen, d_khash, d_owner;
+    DevBuf d_diag_exact_pre, d_diag_exact_suf, d_diag_score_pre, d_diag_len_pre, d_diag_score_suf, d_diag_len_suf;
+    uint64_t diag_n = 0;
+    bool diag_valid = false;
+
+    // table
+    DevTable tab{};
+    DevBuf t_slots, t_counts, t_row_hash, t_row_off, t_row_len, t_arena, t_counters, t_row_count;
+    uint64_t ub_rows = 0, ub_arena = 0;   // host-side upper bounds of rows / arena bytes
+
+    // merge scratch
+    DevBuf m_part_rows, m_part_keys, m_cursors, m_chunk_off;
+    std::vector<uint64_t> h_part_rows, h_part_keys;
+
+    bool profiling = false;
+    bool own_compute_stream = true;
+    std::vector<cudaEvent_t> evpool;   // 8 events per profiled batch, resolved at sync time
+    size_t ev_used = 0;
+    vfb_stats stats{};
+};
+
+// Profiling: events are recorded on the compute stream without blocking; the per-stage
+// times are accumulated when the stream is next synchronised.
+static int prof_events(vfb_ctx *c, cudaEvent_t **out)
+{
+    if (c->ev_used + 8 > c->evpool.size()) {
+        size_t old = c->evpool.size();
+        c->evpool.resize(old + 64, nullptr);
+        for (size_t i = old; i < c->evpool.size(); ++i) VFB_CUDA(cudaEventCreate(&c->evpool[i]));
+    }
+    *out = &c->evpool[c->ev_used];
+    c->ev_used += 8;
+    return VFB_OK;
+}
+
+static int prof_resolve(vfb_ctx *c)
+{
+    for (size_t b = 0; b + 8 <= c->ev_used; b += 8) {
+        cudaEvent_t *ev = &c->evpool[b];
+        float ms;
+        VFB_CUDA(cudaEventElapsedTime(&ms, ev[0], ev[1])); c->stats.ms_scan += ms;
+        VFB_CUDA(cudaEventElapsedTime(&ms, ev[1], ev[2])); c->stats.ms_worklist += ms;
+        VFB_CUDA(cudaEventElapsedTime(&ms, ev[2], ev[3])); c->stats.ms_dp += ms;
+        VFB_CUDA(cudaEventElapsedTime(&ms, ev[3], ev[4])); c->stats.ms_worklist += ms;
+        VFB_CUDA(cudaEventElapsedTime(&ms, ev[4], ev[5])); c->stats.ms_dp += ms;
+        VFB_CUDA(cudaEventElapsedTime(&ms, ev[5], ev[6])); c->stats.ms_translate += ms;
+        VFB_CUDA(cudaEventElapsedTime(&ms, ev[6], ev[7])); c->stats.ms_count += ms;
+        VFB_CUDA(cudaEventElapsedTime(&ms, ev[0], ev[7])); c->stats.ms_total += ms;
+    }
+    c->ev_used = 0;
+    return VFB_OK;
+}
+
+static int bump_launches(vfb_ctx *c, uint64_t before)
+{
+    c->stats.kernel_launches += g_launches - before;
+    return VFB_OK;
+}
+
+// ------------------------------------------------------------------------------------ helpers
+static int table_alloc(vfb_ctx *c, uint64_t capacity, uint64_t rows_cap, uint64_t arena_cap)
+{
+    int rc;
+    if ((rc = c->t_slots.ensure(capacity * 8))) return rc;
+    if ((rc = c->t_counts.ensure(capacity * 8))) return rc;
+    if ((rc = c->t_row_hash.ensure(rows_cap * 8, true, c->st_compute))) return rc;
+    if ((rc = c->t_row_off.ensure(rows_cap * 8, true, c->st_compute))) return rc;
+    if ((rc = c->t_row_len.ensure(rows_cap * 4, true, c->st_compute))) return rc;
+    if ((rc = c->t_arena.ensure(arena_cap, true, c->st_compute))) return rc;
+    c->tab.slots = c->t_slots.as<unsigned long long>();
+    c->tab.counts = c->t_counts.as<unsigned long long>();
+    c->tab.capacity = capacity;
+    c->tab.row_hash = c->t_row_hash.as<uint64_t>();
+    c->tab.row_off = c->t_row_off.as<uint64_t>();
+    c->tab.row_len = c->t_row_len.as<uint32_t>();
+    c->tab.row_capacity = rows_cap;
+    c->tab.arena = c->t_arena.as<uint8_t>();
+    c->tab.arena_capacity = arena_cap;
+    c->tab.counters = c->t_counters.as<unsigned long long>();
+    return VFB_OK;
+}
+
+static uint64_t pow2_at_least(uint64_t v)
+{
+    uint64_t p = 1024;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+static int table_init(vfb_ctx *c)
+{
+    int rc;
+    if ((rc = c->t_counters.ensure(8 * 8))) return rc;
+    uint64_t hint = c->prm.table_capacity_hint;
+    uint64_t cap = pow2_at_least(hint ? hint * 2 : (1u << 16));
+    uint64_t rows = hint ? hint : (1u << 15);
+    if ((rc = table_alloc(c, cap, rows, rows * 32))) return rc;
+    VFB_CUDA(cudaMemsetAsync(c->tab.slots, 0, cap * 8, c->st_compute));
+    VFB_CUDA(cudaMemsetAsync(c->tab.counts, 0, cap * 8, c->st_compute));
+    VFB_CUDA(cudaMemsetAsync(c->tab.counters, 0, 8 * 8, c->st_compute));
+    c->ub_rows = 0;
+    c->ub_arena = 0;
+    return VFB_OK;
+}
+
+// Make room for `new_keys` more keys of `new_bytes` padded key bytes (upper bounds).
+static int table_reserve(vfb_ctx *c, uint64_t new_keys, uint64_t new_bytes)
+{
+    uint64_t want_rows = c->ub_rows + new_keys, want_arena = c->ub_arena + new_bytes;
+    const bool fits = want_rows * 2 <= c->tab.capacity && want_rows <= c->tab.row_capacity &&
+                      want_arena <= c->tab.arena_capacity && want_rows < 0x7FFFFFF0ull;
+    if (fits) {
+        c->ub_rows = want_rows;
+        c->ub_arena = want_arena;
+        return VFB_OK;
+    }
+    // tighten the bounds with the true counters, then grow if still needed
+    unsigned long long ctr[2];
+    VFB_CUDA(cudaMemcpyAsync(ctr, c->tab.counters, sizeof ctr, cudaMemcpyDeviceToHost, c->st_compute));
+    VFB_CUDA(cudaStreamSynchronize(c->st_compute));
+    c->stats.d2h_bytes += sizeof ctr;
+    c->ub_rows = ctr[0];
+    c->ub_arena = ctr[1];
+    want_rows = c->ub_rows + new_keys;
+    want_arena = c->ub_arena + new_bytes;
+    if (want_rows >= 0x7FFFFFF0ull) {
+        set_error("more than 2^31 distinct variants are not supported");
+        return VFB_ERR_ARG;
+    }
+    int rc;
+    uint64_t rows_cap = c->tab.row_capacity, arena_cap = c->tab.arena_capacity;
+    if (want_rows > rows_cap) rows_cap = want_rows + want_rows / 2;
+    if (want_arena > arena_cap) arena_cap = want_arena + want_arena / 2;
+    if (want_rows * 2 > c->tab.capacity) {
+        // rehash into a larger slot array
+        uint64_t ncap = pow2_at_least(want_rows * 3);
+        DevBuf nslots, ncounts;
+        if ((rc = nslots.ensure(ncap * 8))) return rc;
+        if ((rc = ncounts.ensure(ncap * 8))) { nslots.release(); return rc; }
+        VFB_CUDA(cudaMemsetAsync(nslots.p, 0, ncap * 8, c->st_compute));
+        VFB_CUDA(cudaMemsetAsync(ncounts.p, 0, ncap * 8, c->st_compute));
+        DevTable nt = c->tab;
+        nt.slots = nslots.as<unsigned long long>();
+        nt.counts = ncounts.as<unsigned long long>();
+        nt.capacity = ncap;
+        if ((rc = launch_rehash(c->tab, nt, c->st_compute))) return rc;
+        VFB_CUDA(cudaStreamSynchronize(c->st_compute));
+        c->t_slots.release();
+        c->t_counts.release();
+        c->t_slots = nslots;
+        c->t_counts = ncounts;
+        c->tab.capacity = ncap;
+    }
+    if ((rc = table_alloc(c, c->tab.capacity, rows_cap, arena_cap))) return rc;
+    c->ub_rows = want_rows;
+    c->ub_arena = want_arena;
+    return VFB_OK;
+}
+
+static void fill_adapter(AdapterBytes *a, const std::string &s)
+{
+    memset(a, 0, sizeof *a);
+    a->len = (uint32_t)s.size();
+    memcpy(a->b, s.data(), s.size());
+}
+
+// score as f64 > min  <=>  score >= floor(min) + 1   (any finite min)   src/lib.rs:157,260-261
+static int accept_bound(double thr, int32_t match, size_t len)
+{
+    volatile double a = thr * (double)match;
+    volatile double m = a * (double)len;
+    double f = std::floor((double)m);
+    if (f > 2.0e9) return INT32_MAX;
+    if (f < -2.0e9) return INT32_MIN + 1;
+    return (int)f + 1;
+}
+
+// ------------------------------------------------------------------------------------ ABI
+extern "C" {
+
+const char *vfb_last_error(void) { return g_error.c_str(); }
+int vfb_abi_version(void) { return VFB_ABI_VERSION; }
+
+void vfb_default_params(vfb_params *p)
+{
+    memset(p, 0, sizeof *p);
+    p->struct_size = sizeof *p;
+    p->match_score = 3;            // src/lib.rs:172-181
+    p->mismatch_score = -2;
+    p->gap_open_penalty = 5;
+    p->gap_extend_penalty = 2;
+    p->accept_prefix_alignment = 0.75;
+    p->accept_suffix_alignment = 0.75;
+    p->n_threads = 3;
+    p->queue_len = 2;
+    p->skip_translation = 0;
+    p->show_progress = 1;
+    p->device = -1;
+}
+
+static int preflight(double thr, bool *skip)
+{
+    // src/lib.rs:100-110 (NaN fails both tests and reaches the error)
+    if (thr > 0. && thr < 1.) { *skip = false; return VFB_OK; }
+    if (thr == 1.) { *skip = true; return VFB_OK; }
+    set_error("Accept alignment threshold must be between 0 and 1.");
+    return VFB_ERR_VALUE;
+}
+
+int vfb_create(const vfb_params *p, vfb_ctx **out)
+{
+    if (!p || !out) { set_error("null argument"); return VFB_ERR_ARG; }
+    if (p->struct_size != sizeof(vfb_params)) { set_error("vfb_params size mismatch"); return VFB_ERR_ARG; }
+    if ((p->prefix_len && !p->prefix) || (p->suffix_len && !p->suffix)) { set_error("null adapter"); return VFB_ERR_ARG; }
+    bool skip_pre, skip_suf;
+    int rc;
+    if ((rc = preflight(p->accept_prefix_alignment, &skip_pre))) return rc;   // :239
+    if ((rc = preflight(p->accept_suffix_alignment, &skip_suf))) return rc;   // :249
+    if (p->prefix_len > VFB_MAX_SCAN_ADAPTER || p->suffix_len > VFB_MAX_SCAN_ADAPTER) {
+        set_error("adapters longer than 256 bases are not supported");
+        return VFB_ERR_ARG;
+    }
+    if ((!skip_pre && p->prefix_len == 0) || (!skip_suf && p->suffix_len == 0)) {
+        // Profile::new on an empty adapter fails and the reference unwraps it (src/lib.rs:124-126)
+        set_error("Error creating profile for adapter: empty adapter");
+        return VFB_ERR_VALUE;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (this library has no CPU fallback)");
+        return VFB_ERR_CUDA;
+    }
+    vfb_ctx *c = new vfb_ctx();
+    c->prm = *p;
+    c->prefix.assign((const char *)p->prefix, p->prefix_len);
+    c->suffix.assign((const char *)p->suffix, p->suffix_len);
+    c->prm.prefix = (const uint8_t *)c->prefix.data();
+    c->prm.suffix = (const uint8_t *)c->suffix.data();
+    fill_adapter(&c->ad_pre, c->prefix);
+    fill_adapter(&c->ad_suf, c->suffix);
+    c->sc = DpScoring{p->match_score, p->mismatch_score, p->gap_open_penalty, p->gap_extend_penalty};
+    c->align_pre = !skip_pre;
+    c->align_suf = !skip_suf;
+    c->min_accept_pre = accept_bound(p->accept_prefix_alignment, p->match_score, p->prefix_len);
+    c->min_accept_suf = accept_bound(p->accept_suffix_alignment, p->match_score, p->suffix_len);
+    c->batch_reads = p->batch_reads ? p->batch_reads : (8ull << 20);
+    c->batch_bytes = p->batch_bytes ? p->batch_bytes : (2ull << 30);
+    if (c->batch_reads > 0x7FFFFFFFull) c->batch_reads = 0x7FFFFFFFull;
+    if (c->batch_bytes > 0xFFFFFFFFull) c->batch_bytes = 0xFFFFFFFFull;
+
+    auto fail = [&](int code) { vfb_destroy(c); return code; };
+    if (p->device >= 0) {
+        if ((e = cudaSetDevice(p->device)) != cudaSuccess) return fail(cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__));
+        c->device = p->device;
+    } else if ((e = cudaGetDevice(&c->device)) != cudaSuccess) {
+        return fail(cuda_fail(e, "cudaGetDevice", __FILE__, __LINE__));
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, c->device)) != cudaSuccess)
+        return fail(cuda_fail(e, "cudaGetDeviceProperties", __FILE__, __LINE__));
+    c->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&c->st_compute, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking)) != cudaSuccess)
+        return fail(cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__));
+    for (auto &s : c->slots) {
+        if ((e = cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&s.computed, cudaEventDisableTiming)) != cudaSuccess)
+            return fail(cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__));
+    }
+
+    // DP setup: packed layout when the scores fit, else the fallback kernel
+    const bool force_generic = p->force_generic_dp != 0;
+    auto setup_dp = [&](const std::string &ad, bool enabled, bool *packed, DpLayout *lay, uint32_t *lcap,
+                        DevBuf *codes) -> int {
+        *packed = false;
+        if (!enabled) return VFB_OK;
+        if (ad.size() > VFB_MAX_ADAPTER) { set_error("adapter too long for alignment"); return VFB_ERR_ARG; }
+        long long worst = (long long)(std::abs((long long)c->sc.match) + std::abs((long long)c->sc.mismatch) +
+                                      std::abs((long long)c->sc.open) + std::abs((long long)c->sc.extend));
+        if (worst > (1 << 20)) { set_error("alignment scores beyond +-2^20 are not supported"); return VFB_ERR_ARG; }
+        if (!force_generic && make_dp_layout(c->sc, (uint32_t)ad.size(), 0, lay)) {
+            *packed = true;
+            *lcap = dp_lcap(*lay, (uint32_t)ad.size(), c->sc.extend);
+        }
+        std::vector<uint8_t> code(ad.size());
+        for (size_t i = 0; i < ad.size(); ++i) code[i] = (uint8_t)dp_code((uint8_t)ad[i]);
+        int r = codes->ensure(code.size());
+        if (r) return r;
+        VFB_CUDA(cudaMemcpy(codes->p, code.data(), code.size(), cudaMemcpyHostToDevice));
+        return VFB_OK;
+    };
+    if ((rc = setup_dp(c->prefix, c->align_pre, &c->packed_pre, &c->lay_pre, &c->lcap_pre, &c->d_code_pre))) return fail(rc);
+    if ((rc = setup_dp(c->suffix, c->align_suf, &c->packed_suf, &c->lay_suf, &c->lcap_suf, &c->d_code_suf))) return fail(rc);
+    if (c->align_pre || c->align_suf) {
+        c->generic_threads = dp_generic_threads(c->sm_count);
+        size_t amax = c->prefix.size() > c->suffix.size() ? c->prefix.size() : c->suffix.size();
+        if ((rc = c->d_generic_scratch.ensure(4 * amax * (size_t)c->generic_threads * sizeof(int32_t)))) return fail(rc);
+    }
+    if ((rc = c->d_c32.ensure(C_COUNT32 * 4))) return fail(rc);
+    if ((rc = c->d_t64.ensure(T_COUNT64 * 8))) return fail(rc);
+    if ((e = cudaMemsetAsync(c->d_t64.p, 0, T_COUNT64 * 8, c->st_compute)) != cudaSuccess)
+        return fail(cuda_fail(e, "cudaMemsetAsync", __FILE__, __LINE__));
+    if ((rc = table_init(c))) return fail(rc);
+    c->stats.dp_kernel_kind = (c->packed_pre || c->packed_suf) ? 1 : ((c->align_pre || c->align_suf) ? 2 : 0);
+    *out = c;
+    return VFB_OK;
+}
+
+int vfb_destroy(vfb_ctx *c)
+{
+    if (!c) return VFB_OK;
+    cudaSetDevice(c->device);
+    if (c->st_compute) cudaStreamSynchronize(c->st_compute);
+    if (c->st_copy) cudaStreamSynchronize(c->st_copy);
+    for (auto &s : c->slots) {
+        s.d_text.release(); s.d_spans.release(); s.h_text.release(); s.h_spans.release();
+        if (s.copied) cudaEventDestroy(s.copied);
+        if (s.computed) cudaEventDestroy(s.computed);
+    }
+    DevBuf *bufs[] = {&c->d_code_pre, &c->d_code_suf, &c->d_generic_scratch, &c->d_start, &c->d_end, &c->d_list_a,
+                      &c->d_list_b, &c->d_fb_a, &c->d_fb_b, &c->d_c32, &c->d_t64, &c->d_keys, &c->d_koff, &c->d_klen,
+                      &c->d_khash, &c->d_owner, &c->d_diag_exact_pre, &c->d_diag_exact_suf, &c->d_diag_score_pre,
+                      &c->d_diag_len_pre, &c->d_diag_score_suf, &c->d_diag_len_suf, &c->t_slots, &c->t_counts,
+                      &c->t_row_hash, &c->t_row_off, &c->t_row_len, &c->t_arena, &c->t_counters, &c->t_row_count,
+                      &c->m_part_rows, &c->m_part_keys, &c->m_cursors, &c->m_chunk_off};
+    for (auto *b : bufs) b->release();
+    for (auto &ev : c->evpool) if (ev) cudaEventDestroy(ev);
+    if (c->st_compute && c->own_compute_stream) cudaStreamDestroy(c->st_compute);
+    if (c->st_copy) cudaStreamDestroy(c->st_copy);
+    delete c;
+    return VFB_OK;
+}
+
+int vfb_set_profiling(vfb_ctx *c, int enabled)
+{
+    if (!c) { set_error("null context"); return VFB_ERR_ARG; }
+    c->profiling = enabled != 0;
+    return VFB_OK;
+}
+
+int vfb_table_clear(vfb_ctx *c)
+{
+    if (!c) { set_error("null context"); return VFB_ERR_ARG; }
+    VFB_CUDA(cudaSetDevice(c->device));
+    VFB_CUDA(cudaMemsetAsync(c->tab.slots, 0, c->tab.capacity * 8, c->st_compute));
+    VFB_CUDA(cudaMemsetAsync(c->tab.counts, 0, c->tab.capacity * 8, c->st_compute));
+    VFB_CUDA(cudaMemsetAsync(c->tab.counters, 0, 8 * 8, c->st_compute));
+    c->ub_rows = 0;
+    c->ub_arena = 0;
+    return VFB_OK;
+}
+
+int vfb_reset(vfb_ctx *c)
+{
+    int rc = vfb_table_clear(c);
+    if (rc) return rc;
+    VFB_CUDA(cudaMemsetAsync(c->d_t64.p, 0, T_COUNT64 * 8, c->st_compute));
+    int kind = c->stats.dp_kernel_kind;
+    memset(&c->stats, 0, sizeof c->stats);
+    c->stats.dp_kernel_kind = kind;
+    c->diag_valid = false;
+    return VFB_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------ batch
+__global__ void k_accumulate(unsigned long long *t64, const uint32_t *c32)
+{
+    t64[T_DPPRE] += c32[C_NPRE];
+    t64[T_DPSUF] += c32[C_NSUF];
+}
+
+static int run_dp(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_spans, bool is_prefix)
+{
+    int rc;
+    DpJob job;
+    memset(&job, 0, sizeof job);
+    job.text = d_text;
+    job.spans = d_spans;
+    job.worklist = is_prefix ? c->d_list_a.as<uint32_t>() : c->d_list_b.as<uint32_t>();
+    job.n_items = c->d_c32.as<uint32_t>() + (is_prefix ? C_NPRE : C_NSUF);
+    job.bound = is_prefix ? c->d_start.as<uint32_t>() : c->d_end.as<uint32_t>();
+    if (c->prm.diagnostics) {
+        job.diag_score = is_prefix ? c->d_diag_score_pre.as<int32_t>() : c->d_diag_score_suf.as<int32_t>();
+        job.diag_len = is_prefix ? c->d_diag_len_pre.as<int32_t>() : c->d_diag_len_suf.as<int32_t>();
+    }
+    job.cells = c->d_t64.as<unsigned long long>() + T_CELLS;
+    job.is_prefix = is_prefix ? 1 : 0;
+    job.min_accept = is_prefix ? c->min_accept_pre : c->min_accept_suf;
+    const std::string &ad = is_prefix ? c->prefix : c->suffix;
+    job.adapter_len = (uint32_t)ad.size();
+    const bool packed = is_prefix ? c->packed_pre : c->packed_suf;
+    DpGenericJob gj;
+    gj.sc = c->sc;
+    gj.d_adapter_code = is_prefix ? c->d_code_pre.as<uint8_t>() : c->d_code_suf.as<uint8_t>();
+    gj.scratch = c->d_generic_scratch.as<int32_t>();
+    gj.n_threads = c->generic_threads;
+    if (packed) {
+        for (size_t i = 0; i < ad.size(); ++i) job.adapter_code[i] = (uint8_t)dp_code((uint8_t)ad[i]);
+        uint32_t *fb = is_prefix ? c->d_fb_a.as<uint32_t>() : c->d_fb_b.as<uint32_t>();
+        uint32_t *nfb = c->d_c32.as<uint32_t>() + (is_prefix ? C_FBPRE : C_FBSUF);
+        if ((rc = launch_dp_packed_ex(job, is_prefix ? c->lay_pre : c->lay_suf,
+                                      is_prefix ? c->lcap_pre : c->lcap_suf, fb, nfb, c->sm_count, c->st_compute)))
+            return rc;
+        // reads too long for the packed word (normally none): same rule set, unpacked
+        gj.base = job;
+        gj.base.worklist = fb;
+        gj.base.n_items = nfb;
+        gj.base.cells = nullptr;     // already counted by the packed kernel? no: it skipped them
+        gj.base.cells = job.cells;
+        if ((rc = launch_dp_generic(gj, c->sm_count, c->st_compute))) return rc;
+        c->stats.dp_kernel_launches += 2;
+    } else {
+        gj.base = job;
+        if ((rc = launch_dp_generic(gj, c->sm_count, c->st_compute))) return rc;
+        c->stats.dp_kernel_launches += 1;
+    }
+    return VFB_OK;
+}
+
+// The hot loop over one device-resident batch (all work queued on the compute stream).
+static int process_batch(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_spans, uint32_t n,
+                         uint64_t span_bytes_upper)
+{
+    int rc;
+    if (n == 0) return VFB_OK;
+    cudaStream_t st = c->st_compute;
+    const bool prof = c->profiling;
+    // scratch
+    if ((rc = c->d_start.ensure((size_t)n * 4))) return rc;
+    if ((rc = c->d_end.ensure((size_t)n * 4))) return rc;
+    if (c->align_pre) { if ((rc = c->d_list_a.ensure((size_t)n * 4))) return rc; if ((rc = c->d_fb_a.ensure((size_t)n * 4))) return rc; }
+    if (c->align_suf) { if ((rc = c->d_list_b.ensure((size_t)n * 4))) return rc; if ((rc = c->d_fb_b.ensure((size_t)n * 4))) return rc; }
+    // keys: sum of padded key lengths <= bytes/(3|1) + 16 per read
+    const uint64_t key_bytes_ub = (c->prm.skip_translation ? span_bytes_upper : span_bytes_upper / 3) + 16ull * n;
+    if ((rc = c->d_keys.ensure(key_bytes_ub))) return rc;
+    if ((rc = c->d_koff.ensure((size_t)n * 8))) return rc;
+    if ((rc = c->d_klen.ensure((size_t)n * 4))) return rc;
+    if ((rc = c->d_khash.ensure((size_t)n * 8))) return rc;
+    if ((rc = c->d_owner.ensure((size_t)n * 4))) return rc;
+    const bool diag = c->prm.diagnostics != 0;
+    if (diag) {
+        DevBuf *db[] = {&c->d_diag_exact_pre, &c->d_diag_exact_suf, &c->d_diag_score_pre, &c->d_diag_len_pre,
+                        &c->d_diag_score_suf, &c->d_diag_len_suf};
+        for (auto *b : db) if ((rc = b->ensure((size_t)n * 4))) return rc;
+    }
+    if ((rc = table_reserve(c, n, key_bytes_ub))) return rc;
+    cudaEvent_t *pev = nullptr;
+    if (prof && (rc = prof_events(c, &pev))) return rc;
+
+    if (prof) VFB_CUDA(cudaEventRecord(pev[0], st));
+    VFB_CUDA(cudaMemsetAsync(c->d_c32.p, 0, C_COUNT32 * 4, st));
+    VFB_CUDA(cudaMemsetAsync(c->d_t64.as<unsigned long long>() + T_KEYBYTES, 0, 8, st));
+    ScanJob sj{d_text, d_spans, n, c->d_start.as<uint32_t>(), c->d_end.as<uint32_t>()};
+    if ((rc = launch_scan(sj, c->ad_pre, c->ad_suf, c->sm_count, st))) return rc;
+    if (prof) VFB_CUDA(cudaEventRecord(pev[1], st));
+    if (diag) {
+        VFB_CUDA(cudaMemcpyAsync(c->d_diag_exact_pre.p, c->d_start.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        VFB_CUDA(cudaMemcpyAsync(c->d_diag_exact_suf.p, c->d_end.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        // "no DP ran" markers: score = INT32_MIN (0x80000000), len = -1
+        VFB_CUDA(cudaMemsetAsync(c->d_diag_len_pre.p, 0xFF, (size_t)n * 4, st));
+        VFB_CUDA(cudaMemsetAsync(c->d_diag_len_suf.p, 0xFF, (size_t)n * 4, st));
+        VFB_CUDA(cudaMemsetAsync(c->d_diag_score_pre.p, 0, (size_t)n * 4, st));
+        VFB_CUDA(cudaMemsetAsync(c->d_diag_score_suf.p, 0, (size_t)n * 4, st));
+    }
+    // worklists + DP.  The prefix runs first so that the suffix alignment can be skipped for
+    // reads whose prefix was rejected (no region either way, src/lib.rs:288).
+    if (c->align_pre) {
+        if ((rc = launch_worklist(c->d_start.as<uint32_t>(), nullptr, d_spans, n, c->d_list_a.as<uint32_t>(),
+                                  c->d_c32.as<uint32_t>() + C_NPRE, st))) return rc;
+    }
+    if (prof) VFB_CUDA(cudaEventRecord(pev[2], st));
+    if (c->align_pre) if ((rc = run_dp(c, d_text, d_spans, true))) return rc;
+    if (prof) VFB_CUDA(cudaEventRecord(pev[3], st));
+    if (c->align_suf) {
+        const uint32_t *require = (c->prm.dp_compute_all || diag) ? nullptr : c->d_start.as<uint32_t>();
+        if ((rc = launch_worklist(c->d_end.as<uint32_t>(), require, d_spans, n, c->d_list_b.as<uint32_t>(),
+                                  c->d_c32.as<uint32_t>() + C_NSUF, st))) return rc;
+    }
+    if (prof) VFB_CUDA(cudaEventRecord(pev[4], st));
+    if (c->align_suf) if ((rc = run_dp(c, d_text, d_spans, false))) return rc;
+    if (prof) VFB_CUDA(cudaEventRecord(pev[5], st));
+    k_accumulate<<<1, 1, 0, st>>>(c->d_t64.as<unsigned long long>(), c->d_c32.as<uint32_t>());
+    ++g_launches;
+
+    KeyJob kj;
+    kj.text = d_text; kj.spans = d_spans;
+    kj.start = c->d_start.as<uint32_t>(); kj.end = c->d_end.as<uint32_t>();
+    kj.n_reads = n; kj.skip_translation = c->prm.skip_translation;
+    kj.keys = c->d_keys.as<uint8_t>(); kj.koff = c->d_koff.as<uint64_t>();
+    kj.key_cursor = c->d_t64.as<unsigned long long>() + T_KEYBYTES;
+    kj.klen = c->d_klen.as<uint32_t>(); kj.khash = c->d_khash.as<uint64_t>();
+    kj.hash_bits = c->prm.debug_hash_bits;
+    if ((rc = launch_keys(kj, st))) return rc;
+    if (prof) VFB_CUDA(cudaEventRecord(pev[6], st));
+
+    InsertJob ij;
+    ij.keys = kj.keys; ij.klen = kj.klen; ij.khash = kj.khash; ij.kcount = nullptr; ij.koff = kj.koff;
+    ij.key_stride = 0; ij.n_keys = n; ij.owner_slot = c->d_owner.as<uint32_t>();
+    if ((rc = launch_insert(c->tab, ij, st))) return rc;
+    if (prof) VFB_CUDA(cudaEventRecord(pev[7], st));
+    c->stats.reads += n;
+    c->diag_n = n;
+    c->diag_valid = diag;
+    return VFB_OK;
+}
+
+extern "C" {
+
+int vfb_submit_device(vfb_ctx *c, const uint8_t *d_text, uint64_t text_bytes, const vfb_span *d_spans,
+                      uint64_t n_reads)
+{
+    if (!c || (n_reads && (!d_text || !d_spans))) { set_error("null argument"); return VFB_ERR_ARG; }
+    if (text_bytes > 0x100000000ull) { set_error("a text buffer is addressed with 32-bit offsets: at most 4 GiB per call"); return VFB_ERR_ARG; }
+    VFB_CUDA(cudaSetDevice(c->device));
+    const uint64_t before = g_launches;
+    uint64_t done = 0;
+    int rc = VFB_OK;
+    while (done < n_reads) {
+        const uint64_t n = n_reads - done < c->batch_reads ? n_reads - done : c->batch_reads;
+        // key space bound: this batch's share of the text, conservatively the whole buffer
+        const uint64_t share = n == n_reads ? text_bytes : text_bytes;
+        if ((rc = process_batch(c, d_text, d_spans + done, (uint32_t)n, share))) break;
+        done += n;
+    }
+    bump_launches(c, before);
+    return rc;
+}
+
+int vfb_submit_host(vfb_ctx *c, const uint8_t *text, uint64_t text_bytes, const vfb_span *spans, uint64_t n_reads)
+{
+    if (!c || (n_reads && (!text || !spans))) { set_error("null argument"); return VFB_ERR_ARG; }
+    if (text_bytes > 0x100000000ull) { set_error("a text buffer is addressed with 32-bit offsets: at most 4 GiB per call"); return VFB_ERR_ARG; }
+    VFB_CUDA(cudaSetDevice(c->device));
+    const uint64_t before = g_launches;
+    cudaPointerAttributes at;
+    bool pinned_text = false, pinned_spans = false;
+    if (cudaPointerGetAttributes(&at, text) == cudaSuccess) pinned_text = at.type == cudaMemoryTypeHost; else cudaGetLastError();
+    if (cudaPointerGetAttributes(&at, spans) == cudaSuccess) pinned_spans = at.type == cudaMemoryTypeHost; else cudaGetLastError();
+    int rc = VFB_OK;
+    uint64_t done = 0;
+    while (done < n_reads && rc == VFB_OK) {
+        // cut a batch: up to batch_reads reads whose text range fits batch_bytes
+        uint64_t n = 0, lo = UINT64_MAX, hi = 0;
+        while (done + n < n_reads && n < c->batch_reads) {
+            const vfb_span s = spans[done + n];
+            if ((uint64_t)s.off + s.len > text_bytes) { set_error("span outside the text buffer"); rc = VFB_ERR_ARG; break; }
+            const uint64_t nlo = s.off < lo ? s.off : lo, nhi = (uint64_t)s.off + s.len > hi ? (uint64_t)s.off + s.len : hi;
+            if (n > 0 && nhi - nlo > c->batch_bytes) break;
+            lo = nlo; hi = nhi; ++n;
+        }
+        if (rc) break;
+        if (n == 0) { set_error("a read is larger than batch_bytes"); rc = VFB_ERR_ARG; break; }
+        if (hi < lo) { lo = 0; hi = 0; }
+        const uint64_t bytes = hi - lo;
+        Slot &s = c->slots[c->batch_seq & 1];
+        if (s.busy) { VFB_CUDA(cudaEventSynchronize(s.computed)); s.busy = false; }
+        if ((rc = s.d_text.ensure(bytes + 16))) break;
+        if ((rc = s.d_spans.ensure(n * sizeof(vfb_span)))) break;
+        const uint8_t *src_text = text + lo;
+        const vfb_span *src_spans = spans + done;
+        if (!pinned_text) {
+            if ((rc = s.h_text.ensure(bytes))) break;
+            memcpy(s.h_text.p, src_text, bytes);
+            src_text = (const uint8_t *)s.h_text.p;
+        }
+        if (!pinned_spans) {
+            if ((rc = s.h_spans.ensure(n * sizeof(vfb_span)))) break;
+            memcpy(s.h_spans.p, src_spans, n * sizeof(vfb_span));
+            src_spans = (const vfb_span *)s.h_spans.p;
+        }
+        if (bytes) VFB_CUDA(cudaMemcpyAsync(s.d_text.p, src_text, bytes, cudaMemcpyHostToDevice, c->st_copy));
+        VFB_CUDA(cudaMemcpyAsync(s.d_spans.p, src_spans, n * sizeof(vfb_span), cudaMemcpyHostToDevice, c->st_copy));
+        VFB_CUDA(cudaEventRecord(s.copied, c->st_copy));
+        VFB_CUDA(cudaStreamWaitEvent(c->st_compute, s.copied, 0));
+        c->stats.h2d_bytes += bytes + n * sizeof(vfb_span);
+        // span offsets stay relative to the caller's buffer: bias the device base by -lo
+        const uint8_t *d_base = s.d_text.as<uint8_t>() - lo;
+        rc = process_batch(c, d_base, s.d_spans.as<vfb_span>(), (uint32_t)n, bytes);
+        if (rc) break;
+        VFB_CUDA(cudaEventRecord(s.computed, c->st_compute));
+        s.busy = true;
+        ++c->batch_seq;
+        done += n;
+    }
+    bump_launches(c, before);
+    return rc;
+}
+
+int vfb_sync(vfb_ctx *c)
+{
+    if (!c) { set_error("null context"); return VFB_ERR_ARG; }
+    VFB_CUDA(cudaSetDevice(c->device));
+    VFB_CUDA(cudaStreamSynchronize(c->st_copy));
+    VFB_CUDA(cudaStreamSynchronize(c->st_compute));
+    for (auto &s : c->slots) s.busy = false;
+    return prof_resolve(c);
+}
+
+int vfb_set_compute_stream(vfb_ctx *c, void *stream)
+{
+    if (!c) { set_error("null context"); return VFB_ERR_ARG; }
+    int rc = vfb_sync(c);
+    if (rc) return rc;
+    if (c->own_compute_stream && c->st_compute) cudaStreamDestroy(c->st_compute);
+    c->st_compute = (cudaStream_t)stream;
+    c->own_compute_stream = false;
+    return VFB_OK;
+}
+
+int vfb_get_stats(vfb_ctx *c, vfb_stats *out)
+{
+    if (!c || !out) { set_error("null argument"); return VFB_ERR_ARG; }
+    int rc = vfb_sync(c);
+    if (rc) return rc;
+    unsigned long long t64[T_COUNT64], ctr[3];
+    VFB_CUDA(cudaMemcpy(t64, c->d_t64.p, sizeof t64, cudaMemcpyDeviceToHost));
+    VFB_CUDA(cudaMemcpy(ctr, c->tab.counters, sizeof ctr, cudaMemcpyDeviceToHost));
+    c->stats.dp_cells = t64[T_CELLS];
+    c->stats.dp_prefix = t64[T_DPPRE];
+    c->stats.dp_suffix = t64[T_DPSUF];
+    c->stats.unique = ctr[0];
+    c->stats.counted = ctr[2];
+    *out = c->stats;
+    return VFB_OK;
+}
+
+int vfb_get_diag(vfb_ctx *c, vfb_read_diag *out, uint64_t n_reads)
+{
+    if (!c || !out) { set_error("null argument"); return VFB_ERR_ARG; }
+    if (!c->prm.diagnostics || !c->diag_valid) { set_error("diagnostics were not enabled for the last batch"); return VFB_ERR_ARG; }
+    if (n_reads != c->diag_n) { set_error("diagnostics cover exactly the last batch"); return VFB_ERR_ARG; }
+    int rc = vfb_sync(c);
+    if (rc) return rc;
+    const size_t n = (size_t)n_reads;
+    std::vector<uint32_t> ep(n), es(n), st(n), en(n);
+    std::vector<int32_t> sp(n), lp(n), ss(n), ls(n);
+    VFB_CUDA(cudaMemcpy(ep.data(), c->d_diag_exact_pre.p, n * 4, cudaMemcpyDeviceToHost));
+    VFB_CUDA(cudaMemcpy(es.data(), c->d_diag_exact_suf.p, n * 4, cudaMemcpyDeviceToHost));
+    VFB_CUDA(cudaMemcpy(st.data(), c->d_start.p, n * 4, cudaMemcpyDeviceToHost));
+    VFB_CUDA(cudaMemcpy(en.data(), c->d_end.p, n * 4, cudaMemcpyDeviceToHost));
+    VFB_CUDA(cudaMemcpy(sp.data(), c->d_diag_score_pre.p, n * 4, cudaMemcpyDeviceToHost));
+    VFB_CUDA(cudaMemcpy(lp.data(), c->d_diag_len_pre.p, n * 4, cudaMemcpyDeviceToHost));
+    VFB_CUDA(cudaMemcpy(ss.data(), c->d_diag_score_suf.p, n * 4, cudaMemcpyDeviceToHost));
+    VFB_CUDA(cudaMemcpy(ls.data(), c->d_diag_len_suf.p, n * 4, cudaMemcpyDeviceToHost));
+    c->stats.d2h_bytes += n * 32;
+    const uint32_t A = (uint32_t)c->prefix.size();
+    for (size_t i = 0; i < n; ++i) {
+        vfb_read_diag d;
+        d.exact_prefix = ep[i] == VFB_NONE ? -1 : (int32_t)(ep[i] - A);
+        d.exact_suffix = es[i] == VFB_NONE ? -1 : (int32_t)es[i];
+        d.score_prefix = lp[i] < 0 ? INT32_MIN : sp[i];
+        d.len_prefix = lp[i];
+        d.score_suffix = ls[i] < 0 ? INT32_MIN : ss[i];
+        d.len_suffix = ls[i];
+        d.start = st[i] == VFB_NONE ? -1 : (int32_t)st[i];
+        d.end = en[i] == VFB_NONE ? -1 : (int32_t)en[i];
+        out[i] = d;
+    }
+    return VFB_OK;
+}
+
+int vfb_finish(vfb_ctx *c, vfb_table *out)
+{
+    if (!c || !out) { set_error("null argument"); return VFB_ERR_ARG; }
+    memset(out, 0, sizeof *out);
+    int rc = vfb_sync(c);
+    if (rc) return rc;
+    const uint64_t before = g_launches;
+    unsigned long long ctr[3];
+    VFB_CUDA(cudaMemcpy(ctr, c->tab.counters, sizeof ctr, cudaMemcpyDeviceToHost));
+    const uint64_t rows = ctr[0], arena = ctr[1];
+    out->rows = rows;
+    out->offsets = (uint64_t *)malloc((rows + 1) * 8);
+    out->counts = (uint64_t *)malloc((rows ? rows : 1) * 8);
+    if (!out->offsets || !out->counts) { vfb_table_free(out); set_error("out of host memory"); return VFB_ERR_NOMEM; }
+    out->offsets[0] = 0;
+    if (rows == 0) {
+        out->data = (uint8_t *)malloc(1);
+        return VFB_OK;
+    }
+    if ((rc = c->t_row_count.ensure(rows * 8))) { vfb_table_free(out); return rc; }
+    if ((rc = launch_export_counts(c->tab, rows, c->t_row_count.as<unsigned long long>(), c->st_compute))) { vfb_table_free(out); return rc; }
+    std::vector<uint64_t> off(rows);
+    std::vector<uint32_t> len(rows);
+    std::vector<uint8_t> ar(arena);
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(out->counts, c->t_row_count.p, rows * 8, cudaMemcpyDeviceToHost, c->st_compute)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(off.data(), c->tab.row_off, rows * 8, cudaMemcpyDeviceToHost, c->st_compute)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(len.data(), c->tab.row_len, rows * 4, cudaMemcpyDeviceToHost, c->st_compute)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(ar.data(), c->tab.arena, arena, cudaMemcpyDeviceToHost, c->st_compute)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(c->st_compute)) != cudaSuccess) {
+        vfb_table_free(out);
+        return cuda_fail(e, "table download", __FILE__, __LINE__);
+    }
+    c->stats.d2h_bytes += rows * 20 + arena;
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < rows; ++i) { out->offsets[i] = total; total += len[i]; }
+    out->offsets[rows] = total;
+    out->key_bytes = total;
+    out->data = (uint8_t *)malloc(total ? total : 1);
+    if (!out->data) { vfb_table_free(out); set_error("out of host memory"); return VFB_ERR_NOMEM; }
+    for (uint64_t i = 0; i < rows; ++i) memcpy(out->data + out->offsets[i], ar.data() + off[i], len[i]);
+    bump_launches(c, before);
+    return VFB_OK;
+}
+
+void vfb_table_free(vfb_table *t)
+{
+    if (!t) return;
+    free(t->offsets);
+    free(t->data);
+    free(t->counts);
+    memset(t, 0, sizeof *t);
+}
+
+// ------------------------------------------------------------------------------------ merge
+int vfb_table_partition_sizes(vfb_ctx *c, uint32_t n_parts, uint64_t *chunk_bytes)
+{
+    if (!c || !chunk_bytes || n_parts == 0 || n_parts > 1024) { set_error("bad argument"); return VFB_ERR_ARG; }
+    int rc = vfb_sync(c);
+    if (rc) return rc;
+    const uint64_t before = g_launches;
+    unsigned long long ctr[3];
+    VFB_CUDA(cudaMemcpy(ctr, c->tab.counters, sizeof ctr, cudaMemcpyDeviceToHost));
+    const uint64_t rows = ctr[0];
+    if ((rc = c->m_part_rows.ensure(n_parts * 8))) return rc;
+    if ((rc = c->m_part_keys.ensure(n_parts * 8))) return rc;
+    VFB_CUDA(cudaMemsetAsync(c->m_part_rows.p, 0, n_parts * 8, c->st_compute));
+    VFB_CUDA(cudaMemsetAsync(c->m_part_keys.p, 0, n_parts * 8, c->st_compute));
+    if ((rc = launch_partition_count(c->tab, rows, n_parts, c->m_part_rows.as<unsigned long long>(),
+                                     c->m_part_keys.as<unsigned long long>(), c->st_compute))) return rc;
+    c->h_part_rows.assign(n_parts, 0);
+    c->h_part_keys.assign(n_parts, 0);
+    VFB_CUDA(cudaMemcpyAsync(c->h_part_rows.data(), c->m_part_rows.p, n_parts * 8, cudaMemcpyDeviceToHost, c->st_compute));
+    VFB_CUDA(cudaMemcpyAsync(c->h_part_keys.data(), c->m_part_keys.p, n_parts * 8, cudaMemcpyDeviceToHost, c->st_compute));
+    VFB_CUDA(cudaStreamSynchronize(c->st_compute));
+    for (uint32_t p = 0; p < n_parts; ++p) chunk_bytes[p] = chunk_bytes_for(c->h_part_rows[p], c->h_part_keys[p]);
+    bump_launches(c, before);
+    return VFB_OK;
+}
+
+int vfb_table_partition_fill(vfb_ctx *c, uint32_t n_parts, uint8_t *d_buf, const uint64_t *chunk_offsets)
+{
+    if (!c || !d_buf || !chunk_offsets || n_parts == 0 || c->h_part_rows.size() != n_parts) {
+        set_error("call vfb_table_partition_sizes with the same n_parts first");
+        return VFB_ERR_ARG;
+    }
+    VFB_CUDA(cudaSetDevice(c->device));
+    const uint64_t before = g_launches;
+    int rc;
+    uint64_t rows = 0;
+    for (auto r : c->h_part_rows) rows += r;
+    if ((rc = c->m_cursors.ensure(n_parts * 16))) return rc;
+    if ((rc = c->m_chunk_off.ensure(n_parts * 8))) return rc;
+    if ((rc = c->t_row_count.ensure((rows ? rows : 1) * 8))) return rc;
+    VFB_CUDA(cudaMemsetAsync(c->m_cursors.p, 0, n_parts * 16, c->st_compute));
+    VFB_CUDA(cudaMemcpyAsync(c->m_chunk_off.p, chunk_offsets, n_parts * 8, cudaMemcpyHostToDevice, c->st_compute));
+    for (uint32_t p = 0; p < n_parts; ++p) {
+        ChunkHeader h{VFB_CHUNK_MAGIC, c->h_part_rows[p], c->h_part_keys[p], 0};
+        VFB_CUDA(cudaMemcpyAsync(d_buf + chunk_offsets[p], &h, sizeof h, cudaMemcpyHostToDevice, c->st_compute));
+        VFB_CUDA(cudaStreamSynchronize(c->st_compute));   // h is a stack temporary
+    }
+    if ((rc = launch_export_counts(c->tab, rows, c->t_row_count.as<unsigned long long>(), c->st_compute))) return rc;
+    if ((rc = launch_partition_fill(c->tab, rows, n_parts, c->t_row_count.as<unsigned long long>(), d_buf,
+                                    c->m_chunk_off.as<uint64_t>(), c->m_part_rows.as<uint64_t>(),
+                                    c->m_part_keys.as<uint64_t>(), c->m_cursors.as<unsigned long long>(), c->st_compute)))
+        return rc;
+    VFB_CUDA(cudaStreamSynchronize(c->st_compute));
+    bump_launches(c, before);
+    return VFB_OK;
+}
+
+int vfb_chunk_rows(const uint8_t *h_chunk, uint64_t chunk_bytes, uint64_t *rows)
+{
+    if (!h_chunk || !rows || chunk_bytes < sizeof(ChunkHeader)) { set_error("bad chunk"); return VFB_ERR_ARG; }
+    ChunkHeader h;
+    memcpy(&h, h_chunk, sizeof h);
+    if (h.magic != VFB_CHUNK_MAGIC || chunk_bytes_for(h.rows, h.key_bytes) > chunk_bytes) { set_error("bad chunk header"); return VFB_ERR_FORMAT; }
+    *rows = h.rows;
+    return VFB_OK;
+}
+
+int vfb_table_absorb(vfb_ctx *c, const uint8_t *d_chunk, uint64_t chunk_bytes)
+{
+    if (!c || !d_chunk || chunk_bytes < sizeof(ChunkHeader)) { set_error("bad argument"); return VFB_ERR_ARG; }
+    VFB_CUDA(cudaSetDevice(c->device));
+    const uint64_t before = g_launches;
+    ChunkHeader h;
+    VFB_CUDA(cudaMemcpyAsync(&h, d_chunk, sizeof h, cudaMemcpyDeviceToHost, c->st_compute));
+    VFB_CUDA(cudaStreamSynchronize(c->st_compute));
+    if (h.magic != VFB_CHUNK_MAGIC || chunk_bytes_for(h.rows, h.key_bytes) > chunk_bytes) { set_error("bad chunk header"); return VFB_ERR_FORMAT; }
+    if (h.rows == 0) return VFB_OK;
+    if (h.rows > 0x7FFFFFFFull) { set_error("chunk too large"); return VFB_ERR_ARG; }
+    int rc;
+    if ((rc = table_reserve(c, h.rows, h.key_bytes))) return rc;
+    if ((rc = c->d_owner.ensure(h.rows * 4))) return rc;
+    const uint64_t n = h.rows;
+    const uint8_t *base = d_chunk + sizeof(ChunkHeader);
+    InsertJob ij;
+    ij.khash = reinterpret_cast<const uint64_t *>(base);
+    ij.kcount = reinterpret_cast<const unsigned long long *>(base + vfb_align16(n * 8));
+    ij.koff = reinterpret_cast<const uint64_t *>(base + vfb_align16(n * 8) * 2);
+    ij.klen = reinterpret_cast<const uint32_t *>(base + vfb_align16(n * 8) * 3);
+    ij.keys = base + vfb_align16(n * 8) * 3 + vfb_align16(n * 4);
+    ij.key_stride = 0;
+    ij.n_keys = (uint32_t)n;
+    ij.owner_slot = c->d_owner.as<uint32_t>();
+    if ((rc = launch_insert(c->tab, ij, c->st_compute))) return rc;
+    bump_launches(c, before);
+    return VFB_OK;
+}
+
+// ------------------------------------------------------------------------------------ synth + misc
+int vfb_synth_adapters(const vfb_synth_cfg *cfg, uint8_t *prefix, uint8_t *suffix)
+{
+    if (!cfg || !prefix || !suffix) { set_error("null argument"); return VFB_ERR_ARG; }
+    vfs_adapter(cfg->seed, 0, cfg->adapter_len, prefix);
+    vfs_adapter(cfg->seed, 1, cfg->adapter_len, suffix);
+    return VFB_OK;
+}
+
+int vfb_synth_host(const vfb_synth_cfg *cfg, uint64_t first, uint64_t n, uint8_t *text, vfb_span *spans)
+{
+    if (!cfg || (n && (!text || !spans))) { set_error("null argument"); return VFB_ERR_ARG; }
+    if (cfg->adapter_len > 61 || cfg->adapter_len == 0 || cfg->read_len == 0 || cfg->read_len > 700 ||
+        n * (uint64_t)cfg->read_len > 0xFFFFFFFFull) {
+        set_error("synth: adapter_len must be 1..61, read_len 1..700, at most 4 GiB per call");
+        return VFB_ERR_ARG;
+    }
+    uint8_t pre[64], suf[64];
+    vfs_adapter(cfg->seed, 0, cfg->adapter_len, pre);
+    vfs_adapter(cfg->seed, 1, cfg->adapter_len, suf);
+    for (uint64_t i = 0; i < n; ++i) {
+        vfs_read(cfg, first + i, pre, suf, text + i * cfg->read_len);
+        spans[i] = vfb_span{(uint32_t)(i * cfg->read_len), cfg->read_len};
+    }
+    return VFB_OK;
+}
+
+int vfb_synth_device(const vfb_synth_cfg *cfg, uint64_t first, uint64_t n, uint8_t *d_text, vfb_span *d_spans, int device)
+{
+    if (!cfg || (n && (!d_text || !d_spans))) { set_error("null argument"); return VFB_ERR_ARG; }
+    if (device >= 0) VFB_CUDA(cudaSetDevice(device));
+    int rc = launch_synth(*cfg, first, n, d_text, d_spans, 0);
+    if (rc) return rc;
+    VFB_CUDA(cudaStreamSynchronize(0));
+    return VFB_OK;
+}
+
+int vfb_measure_int_peak(int device, double *alu_gops, double *dual_gops)
+{
+    return measure_int_peak(device, alu_gops, dual_gops);
+}
+
+int vfb_host_alloc(void **p, uint64_t bytes)
+{
+    if (!p) { set_error("null argument"); return VFB_ERR_ARG; }
+    VFB_CUDA(cudaMallocHost(p, bytes ? bytes : 1));
+    return VFB_OK;
+}
+
+int vfb_host_free(void *p)
+{
+    if (p) VFB_CUDA(cudaFreeHost(p));
+    return VFB_OK;
+}
+
+}  // extern "C"

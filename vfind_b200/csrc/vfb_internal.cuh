@@ -1,0 +1,193 @@
+// Internal declarations shared by the kernels and the host API (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/vfind_b200.h"
+
+#define VFB_MAX_PACKED_ADAPTER 64   // longest adapter the register-resident DP kernel takes
+#define VFB_MAX_ADAPTER 1024        // longest adapter the fallback DP kernel takes
+#define VFB_MAX_SCAN_ADAPTER 256    // adapters are passed by value to the scan kernel
+
+namespace vfb {
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define VFB_CUDA(call)                                                         \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if (e__ != cudaSuccess) return vfb::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// ---------------------------------------------------------------- adapters
+struct AdapterBytes {
+    uint8_t b[VFB_MAX_SCAN_ADAPTER];
+    uint32_t len;
+};
+
+// Read-base / adapter-base codes of the alignment alphabet: parasail Matrix::create(b"ATCG")
+// (/root/reference/src/lib.rs:236) is case-insensitive; everything else is the wildcard.
+__host__ __device__ __forceinline__ int dp_code(uint8_t c)
+{
+    switch (c) {
+    case 'A': case 'a': return 0;
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': return 2;
+    case 'T': case 't': return 3;
+    default: return 4;
+    }
+}
+
+// ---------------------------------------------------------------- packed DP word layout
+// One 32-bit word carries (score | q | x | len), low to high: len [0,LB), x [LB,LB+XB),
+// q [LB+XB, LB+XB+2), score [S0,32).  Signed integer comparison of two words compares the
+// scores first, then the transient priority fields, so one VIMNMX3 / VIADDMNMX selects the
+// winner of a cell under parasail's tie rules and carries its alignment length along:
+//   q: source priority inside H = max(D,F,E): diag 2 > F 1 > E 0
+//   x: number of consecutive gap extensions; an extension (x>=1) beats an opening (x=0)
+//      at equal score ("tie -> extend").
+struct DpLayout {
+    int S0, LB, XB;
+    int c_eopen, c_eext;   // E: H_left + c_eopen  vs  E_left + c_eext
+    int c_fopen, c_fext;   // F: H_up + c_fopen    vs  F_up + c_fext   (both carry q=1)
+    int hmask;             // clears q and x after the H max
+    int lowmask;           // (1<<S0)-1
+    int lenmask;           // (1<<LB)-1
+    int neg_e, neg_f;      // border values of E and F ("-inf")
+    int w_match, w_mismatch, w_wild;   // diagonal increments incl. +1 length and q=2
+    int one;               // the constant 1 (opaque to the compiler: keeps adds on the FMA pipe)
+};
+
+struct DpScoring {
+    int match, mismatch, open, extend;
+};
+
+// Returns false if the parameters do not fit the packed layout (then the fallback runs).
+bool make_dp_layout(const DpScoring &s, uint32_t adapter_len, uint32_t max_read_len, DpLayout *out);
+
+struct DpJob {
+    const uint8_t *text;
+    const vfb_span *spans;
+    const uint32_t *worklist;     // read indices needing this alignment
+    const uint32_t *n_items;      // device counter
+    uint32_t *bound;              // start[] (prefix) or end[] (suffix): written on accept
+    int32_t *diag_score;          // nullable, indexed by read
+    int32_t *diag_len;
+    unsigned long long *cells;    // device counter: sum A*L over alignments
+    int is_prefix;
+    int min_accept;               // accept iff score >= min_accept
+    uint32_t adapter_len;
+    uint8_t adapter_code[VFB_MAX_PACKED_ADAPTER];
+};
+
+// Longest read the layout can take; longer items are appended to `fallback`.
+uint32_t dp_lcap(const DpLayout &lay, uint32_t adapter_len, int extend);
+int launch_dp_packed_ex(const DpJob &job, const DpLayout &lay, uint32_t lcap, uint32_t *fallback,
+                        uint32_t *n_fallback, int sm_count, cudaStream_t st);
+
+struct DpGenericJob {
+    DpJob base;
+    const uint8_t *d_adapter_code;   // adapter codes in device memory (any length)
+    DpScoring sc;
+    int32_t *scratch;                // 4 * adapter_len * n_threads ints
+    uint32_t n_threads;
+};
+int launch_dp_generic(const DpGenericJob &job, int sm_count, cudaStream_t st);
+uint32_t dp_generic_threads(int sm_count);
+
+// ---------------------------------------------------------------- scan + worklist
+struct ScanJob {
+    const uint8_t *text;
+    const vfb_span *spans;
+    uint32_t n_reads;
+    uint32_t *start;   // prefix boundary: pos + A, or VFB_NONE
+    uint32_t *end;     // suffix boundary: pos, or VFB_NONE
+};
+int launch_scan(const ScanJob &job, const AdapterBytes &prefix, const AdapterBytes &suffix,
+                int sm_count, cudaStream_t st);
+
+// Appends read indices whose boundary is VFB_NONE (and whose read is non-empty).
+// If `require` is non-null only reads with require[i] != VFB_NONE are listed.
+int launch_worklist(const uint32_t *bound, const uint32_t *require, const vfb_span *spans,
+                    uint32_t n_reads, uint32_t *list, uint32_t *count, cudaStream_t st);
+
+// ---------------------------------------------------------------- translate + count
+struct KeyJob {
+    const uint8_t *text;
+    const vfb_span *spans;
+    const uint32_t *start, *end;
+    uint32_t n_reads;
+    int skip_translation;
+    uint8_t *keys;            // key arena of the batch; keys are bump-allocated, 16-byte aligned
+    uint64_t *koff;           // per read: offset of its key in `keys`
+    unsigned long long *key_cursor;   // device bump pointer (zeroed per batch)
+    uint32_t *klen;           // 0 = no key
+    uint64_t *khash;
+    int hash_bits;            // 0 = 64
+};
+int launch_keys(const KeyJob &job, cudaStream_t st);
+
+// Open-addressing table in device memory.  A slot word is (tag << 32 | ref): tag = high 32
+// hash bits, ref = row id (bit31 clear) or, only inside the insert kernel of the batch that
+// created it, 0x80000000 | batch read index.  Equality is always decided on full key bytes.
+struct DevTable {
+    unsigned long long *slots;   // capacity words, 0 = empty
+    unsigned long long *counts;  // per slot
+    uint64_t capacity;           // power of two
+    // rows (distinct keys), append-only
+    uint64_t *row_hash;
+    uint64_t *row_off;           // into arena
+    uint32_t *row_len;
+    uint64_t row_capacity;
+    uint8_t *arena;              // keys, each padded to 16 bytes
+    uint64_t arena_capacity;
+    // device counters: [0] rows, [1] arena bytes, [2] counted reads
+    unsigned long long *counters;
+};
+
+struct InsertJob {
+    const uint8_t *keys;
+    const uint32_t *klen;
+    const uint64_t *khash;
+    const unsigned long long *kcount;   // nullable: per-key count (absorb); else 1
+    const uint64_t *koff;               // nullable: per-key byte offset into keys; else i * key_stride
+    uint32_t key_stride;
+    uint32_t n_keys;
+    uint32_t *owner_slot;               // scratch, n_keys: slot claimed by this key or VFB_NONE
+};
+int launch_insert(const DevTable &t, const InsertJob &job, cudaStream_t st);
+int launch_rehash(const DevTable &old_t, const DevTable &new_t, cudaStream_t st);
+int launch_export_counts(const DevTable &t, uint64_t rows, unsigned long long *row_count, cudaStream_t st);
+
+// ---------------------------------------------------------------- merge chunks
+// Chunk layout (all sections 16-byte aligned):
+//   header {magic, rows, key_area_bytes, reserved} u64 x4
+//   hash   u64 x rows | count u64 x rows | koff u64 x rows | klen u32 x rows | key area
+struct ChunkHeader {
+    uint64_t magic, rows, key_bytes, reserved;
+};
+#define VFB_CHUNK_MAGIC 0x5646423230304b31ull
+__host__ __device__ __forceinline__ uint64_t vfb_align16(uint64_t x) { return (x + 15) & ~15ull; }
+__host__ __device__ __forceinline__ uint64_t chunk_bytes_for(uint64_t rows, uint64_t key_bytes)
+{
+    return sizeof(ChunkHeader) + vfb_align16(rows * 8) * 3 + vfb_align16(rows * 4) + vfb_align16(key_bytes);
+}
+int launch_partition_count(const DevTable &t, uint64_t rows, uint32_t n_parts,
+                           unsigned long long *part_rows, unsigned long long *part_keybytes,
+                           cudaStream_t st);
+int launch_partition_fill(const DevTable &t, uint64_t rows, uint32_t n_parts,
+                          const unsigned long long *row_count, uint8_t *buf,
+                          const uint64_t *d_chunk_off, const uint64_t *d_part_rows,
+                          const uint64_t *d_part_keybytes, unsigned long long *cursors,
+                          cudaStream_t st);
+
+// ---------------------------------------------------------------- misc
+int launch_synth(const vfb_synth_cfg &cfg, uint64_t first, uint64_t n, uint8_t *d_text,
+                 vfb_span *d_spans, cudaStream_t st);
+int measure_int_peak(int device, double *alu_gops, double *dual_gops);
+
+extern thread_local uint64_t g_launches;   // kernels launched by this thread's calls
+}  // namespace vfb
