@@ -178,6 +178,9 @@ int vfb_table_partition_fill(vfb_ctx *ctx, uint32_t n_parts, uint8_t *d_buf,
                              const uint64_t *chunk_offsets /* n_parts */);
 int vfb_table_clear(vfb_ctx *ctx);
 int vfb_table_absorb(vfb_ctx *ctx, const uint8_t *d_chunk, uint64_t chunk_bytes);
+/* The key hash the table and the partitioning use, and the owner rule (host functions). */
+uint64_t vfb_hash_key(const uint8_t *key, uint32_t len);
+uint32_t vfb_key_owner(uint64_t hash, uint32_t n_parts);
 /* Host-side view of a chunk (for CPU tests of the exchange plumbing). */
 int vfb_chunk_rows(const uint8_t *h_chunk, uint64_t chunk_bytes, uint64_t *rows);
 

@@ -108,6 +108,10 @@ def load_library():
     L.vfb_table_clear.argtypes = [vp]
     L.vfb_table_absorb.argtypes = [vp, vp, u64]
     L.vfb_chunk_rows.argtypes = [vp, u64, C.POINTER(u64)]
+    L.vfb_hash_key.argtypes = [C.c_char_p, u32]
+    L.vfb_hash_key.restype = u64
+    L.vfb_key_owner.argtypes = [u64, u32]
+    L.vfb_key_owner.restype = u32
     L.vfb_synth_adapters.argtypes = [C.POINTER(SynthCfg), vp, vp]
     L.vfb_synth_host.argtypes = [C.POINTER(SynthCfg), u64, u64, vp, vp]
     L.vfb_synth_device.argtypes = [C.POINTER(SynthCfg), u64, u64, vp, vp, i32]
@@ -406,6 +410,14 @@ def synth_host(cfg: SynthCfg, first: int, n: int):
 
 def synth_device(cfg: SynthCfg, first: int, n: int, text_ptr: int, spans_ptr: int, device: int = -1):
     _check(load_library().vfb_synth_device(C.byref(cfg), first, n, text_ptr, spans_ptr, device))
+
+
+def hash_key(key: bytes) -> int:
+    return int(load_library().vfb_hash_key(key, len(key)))
+
+
+def key_owner(h: int, n_parts: int) -> int:
+    return int(load_library().vfb_key_owner(h, n_parts))
 
 
 def measure_int_peak(device: int = -1):

@@ -906,6 +906,9 @@ int vfb_table_partition_fill(vfb_ctx *c, uint32_t n_parts, uint8_t *d_buf, const
     return VFB_OK;
 }
 
+uint64_t vfb_hash_key(const uint8_t *key, uint32_t len) { return vfb_hash_bytes(key, len); }
+uint32_t vfb_key_owner(uint64_t hash, uint32_t n_parts) { return n_parts ? vfb_hash_owner(hash, n_parts) : 0; }
+
 int vfb_chunk_rows(const uint8_t *h_chunk, uint64_t chunk_bytes, uint64_t *rows)
 {
     if (!h_chunk || !rows || chunk_bytes < sizeof(ChunkHeader)) { set_error("bad chunk"); return VFB_ERR_ARG; }
