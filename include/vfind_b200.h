@@ -67,7 +67,7 @@ typedef struct vfb_params {
     int32_t dp_compute_all;           /* 1 = run the suffix DP even when the prefix failed
                                          (what the reference does, src/lib.rs:278-286; the
                                          result table is identical either way)              */
-    int32_t reserved;
+    int32_t force_general_scan;       /* tests only: use the byte-wise scan kernel          */
 } vfb_params;
 
 /* One read inside a text buffer: text[off .. off+len). */

@@ -196,6 +196,61 @@ def test_adapter_with_wildcard_bases():
     assert table == otable
 
 
+@pytest.mark.parametrize("pre,suf", [
+    (b"ACACACACACACACACACAC", b"GTGTGTGTGTGTGTGTGTGT"),      # one 4-mer at every offset
+    (b"AAAAAAAAAAAAAAAAAAAAAAAA", b"CCCCCCCCCCC"),            # homopolymers, stride 4 and 2
+    (b"ACGTACGT", b"TTGACCA"),                                # stride 1
+    (b"GGGCCCAGCCGGCCGGAT", b"GGGCCCAGCCGGCCGGATC"),          # one adapter contains the other
+])
+def test_scan_repetitive_and_nested_adapters(pre, suf):
+    rng = random.Random(len(pre) * 131 + len(suf))
+    seqs = []
+    for _ in range(1500):
+        parts = []
+        for _ in range(rng.randrange(1, 6)):
+            k = rng.randrange(5)
+            if k == 0:
+                parts.append(pre)
+            elif k == 1:
+                parts.append(suf)
+            elif k == 2:
+                parts.append(pre[:rng.randrange(len(pre))])
+            elif k == 3:
+                parts.append(bytes(rng.choice(pre + suf) for _ in range(rng.randrange(1, 30))))
+            else:
+                parts.append(bytes(rng.choice(b"ACGT") for _ in range(rng.randrange(1, 40))))
+        seqs.append(b"".join(parts))
+    kw = dict(accept_prefix_alignment=1.0, accept_suffix_alignment=1.0, skip_translation=True)
+    fast = gpu_run(seqs, (pre, suf), **kw)
+    slow = gpu_run(seqs, (pre, suf), force_general_scan=True, **kw)
+    otable, odiag, _ = oracle_run(seqs, (pre, suf), **kw)
+    assert_diag_equal(fast[1], odiag)
+    assert_diag_equal(slow[1], odiag)
+    assert fast[0] == slow[0] == otable
+
+
+def test_scan_unaligned_text_offsets():
+    # reads at every byte alignment inside a larger text buffer (as FASTQ text delivers them)
+    rng = random.Random(21)
+    chunks, off, ln, pos = [], [], [], 0
+    for i in range(3000):
+        junk = bytes(rng.choice(b"@+FFFFF:#rs0123456789\n") for _ in range(rng.randrange(0, 23)))
+        read = make_reads(rng, PREFIX, SUFFIX, 1)[0]
+        chunks += [junk, read]
+        off.append(pos + len(junk))
+        ln.append(len(read))
+        pos += len(junk) + len(read)
+    text = np.frombuffer(b"".join(chunks), dtype=np.uint8)
+    off, ln = np.array(off, np.uint32), np.array(ln, np.uint32)
+    with api.Context((PREFIX, SUFFIX), diagnostics=True) as ctx:
+        ctx.submit_host(text, spans_of(off, ln))
+        diag = ctx.diag(len(off))
+        got = ctx.finish_dict()
+    want, odiag, _ = oracle.process_reads(oracle.make_params((PREFIX, SUFFIX)), text, off, ln, want_diag=True)
+    assert_diag_equal(diag, odiag)
+    assert got == want
+
+
 def test_threshold_one_disables_alignment():
     rng = random.Random(8)
     seqs = make_reads(rng, PREFIX, SUFFIX, 800)

@@ -40,7 +40,7 @@ class Params(C.Structure):
                 ("batch_reads", C.c_uint64), ("batch_bytes", C.c_uint64),
                 ("table_capacity_hint", C.c_uint64),
                 ("debug_hash_bits", C.c_int32), ("force_generic_dp", C.c_int32),
-                ("dp_compute_all", C.c_int32), ("reserved", C.c_int32)]
+                ("dp_compute_all", C.c_int32), ("force_general_scan", C.c_int32)]
 
 
 class Table(C.Structure):
@@ -160,7 +160,7 @@ class Context:
                  n_threads=3, queue_len=2, skip_translation=False, show_progress=True, *,
                  device=None, diagnostics=False, batch_reads=0, batch_bytes=0,
                  table_capacity_hint=0, debug_hash_bits=0, force_generic_dp=False,
-                 dp_compute_all=False):
+                 dp_compute_all=False, force_general_scan=False):
         L = load_library()
         self._lib = L
         self._h = C.c_void_p()
@@ -184,6 +184,7 @@ class Context:
         p.debug_hash_bits = int(debug_hash_bits)
         p.force_generic_dp = 1 if force_generic_dp else 0
         p.dp_compute_all = 1 if dp_compute_all else 0
+        p.force_general_scan = 1 if force_general_scan else 0
         _check(L.vfb_create(C.byref(p), C.byref(self._h)))
 
     # -- lifetime

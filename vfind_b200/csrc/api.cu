@@ -520,6 +520,11 @@ static int run_dp(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_spans, bo
         job.diag_len = is_prefix ? c->d_diag_len_pre.as<int32_t>() : c->d_diag_len_suf.as<int32_t>();
     }
     job.cells = c->d_t64.as<unsigned long long>() + T_CELLS;
+    if (is_prefix && c->align_suf && !(c->prm.dp_compute_all || c->prm.diagnostics)) {
+        job.next_list = c->d_list_b.as<uint32_t>();
+        job.n_next = c->d_c32.as<uint32_t>() + C_NSUF;
+        job.other_bound = c->d_end.as<uint32_t>();
+    }
     job.is_prefix = is_prefix ? 1 : 0;
     job.min_accept = is_prefix ? c->min_accept_pre : c->min_accept_suf;
     const std::string &ad = is_prefix ? c->prefix : c->suffix;
@@ -586,7 +591,14 @@ static int process_batch(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_sp
     if (prof) VFB_CUDA(cudaEventRecord(pev[0], st));
     VFB_CUDA(cudaMemsetAsync(c->d_c32.p, 0, C_COUNT32 * 4, st));
     VFB_CUDA(cudaMemsetAsync(c->d_t64.as<unsigned long long>() + T_KEYBYTES, 0, 8, st));
-    ScanJob sj{d_text, d_spans, n, c->d_start.as<uint32_t>(), c->d_end.as<uint32_t>()};
+    ScanJob sj;
+    memset(&sj, 0, sizeof sj);
+    sj.text = d_text; sj.spans = d_spans; sj.n_reads = n;
+    sj.start = c->d_start.as<uint32_t>(); sj.end = c->d_end.as<uint32_t>();
+    if (c->align_pre) { sj.list_pre = c->d_list_a.as<uint32_t>(); sj.n_pre = c->d_c32.as<uint32_t>() + C_NPRE; }
+    if (c->align_suf) { sj.list_suf = c->d_list_b.as<uint32_t>(); sj.n_suf = c->d_c32.as<uint32_t>() + C_NSUF; }
+    sj.compute_all = (c->prm.dp_compute_all || diag) ? 1 : 0;
+    sj.force_general = c->prm.force_general_scan;
     if ((rc = launch_scan(sj, c->ad_pre, c->ad_suf, c->sm_count, st))) return rc;
     if (prof) VFB_CUDA(cudaEventRecord(pev[1], st));
     if (diag) {
@@ -598,20 +610,11 @@ static int process_batch(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_sp
         VFB_CUDA(cudaMemsetAsync(c->d_diag_score_pre.p, 0, (size_t)n * 4, st));
         VFB_CUDA(cudaMemsetAsync(c->d_diag_score_suf.p, 0, (size_t)n * 4, st));
     }
-    // worklists + DP.  The prefix runs first so that the suffix alignment can be skipped for
-    // reads whose prefix was rejected (no region either way, src/lib.rs:288).
-    if (c->align_pre) {
-        if ((rc = launch_worklist(c->d_start.as<uint32_t>(), nullptr, d_spans, n, c->d_list_a.as<uint32_t>(),
-                                  c->d_c32.as<uint32_t>() + C_NPRE, st))) return rc;
-    }
+    // DP.  The prefix pass runs first: reads it rejects need no suffix alignment (no region
+    // either way, src/lib.rs:288), reads it accepts join the suffix worklist if they need one.
     if (prof) VFB_CUDA(cudaEventRecord(pev[2], st));
     if (c->align_pre) if ((rc = run_dp(c, d_text, d_spans, true))) return rc;
     if (prof) VFB_CUDA(cudaEventRecord(pev[3], st));
-    if (c->align_suf) {
-        const uint32_t *require = (c->prm.dp_compute_all || diag) ? nullptr : c->d_start.as<uint32_t>();
-        if ((rc = launch_worklist(c->d_end.as<uint32_t>(), require, d_spans, n, c->d_list_b.as<uint32_t>(),
-                                  c->d_c32.as<uint32_t>() + C_NSUF, st))) return rc;
-    }
     if (prof) VFB_CUDA(cudaEventRecord(pev[4], st));
     if (c->align_suf) if ((rc = run_dp(c, d_text, d_spans, false))) return rc;
     if (prof) VFB_CUDA(cudaEventRecord(pev[5], st));

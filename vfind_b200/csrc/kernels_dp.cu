@@ -216,6 +216,7 @@ k2_dp_packed(const __grid_constant__ DpKernelArgs args)
             }
         }
 
+        bool want_next = false;
         if (run) {
             // last column: smallest i with the best score
             int cb = INT_MIN / 2, cbcap = INT_MIN / 2;
@@ -231,6 +232,16 @@ k2_dp_packed(const __grid_constant__ DpKernelArgs args)
             if (score >= job.min_accept) {
                 if (job.is_prefix) job.bound[r] = (uint32_t)len;
                 else if (len <= L) job.bound[r] = (uint32_t)(L - len);
+                want_next = job.next_list != nullptr && job.other_bound[r] == VFB_NONE;
+            }
+        }
+        if (job.next_list) {
+            const unsigned m = __ballot_sync(0xffffffffu, want_next);
+            if (m) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(job.n_next, (uint32_t)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (want_next) job.next_list[base + __popc(m & ((1u << lane) - 1))] = r;
             }
         }
     }
@@ -353,6 +364,7 @@ k2_dp_generic(const __grid_constant__ DpGenericJob gj)
         if (score >= job.min_accept) {
             if (job.is_prefix) job.bound[r] = (uint32_t)len;
             else if (len <= L) job.bound[r] = (uint32_t)(L - len);
+            if (job.next_list && job.other_bound[r] == VFB_NONE) job.next_list[atomicAdd(job.n_next, 1u)] = r;
         }
     }
 }

@@ -1,28 +1,290 @@
-// K1 — exact adapter scan, and the DP worklist builder.
+// K1 — exact adapter scan, fused with the DP worklist build.
 //
 // Replaces the two `memmem::find(seq, adapter)` calls per read of
 // /root/reference/src/lib.rs:148 (called from :278-286): leftmost byte-exact, case-sensitive
 // occurrence of each adapter over the whole read.  Output is the region boundary the exact
 // hit implies (:151-152): start = pos + A for the prefix, end = pos for the suffix, VFB_NONE
-// when there is no exact hit (the DP kernel may fill it in later).
+// when there is no exact hit (the DP kernel may fill it in later).  Reads that still need an
+// alignment (`aligner?.align`, :155) are appended to the prefix / suffix worklists here.
+//
+// Fast kernel (7 <= A <= 64): HBM-bound by design.  A half-warp owns a read; each lane pulls
+// 16-byte aligned chunks of the text with one LDG.128 and tests only every s-th aligned
+// 32-bit word (s = 4, 2 or 1 words, chosen so that every occurrence of the shorter adapter
+// fully contains a sampled word).  A sampled word is looked up in a 256-slot shared-memory
+// hash of the adapters' 4-mers; a hit names the adapter offsets it can sit at, and each
+// candidate start is verified against the adapter pre-shifted to the text's word alignment.
+// ~1 instruction per byte per lane on the common (miss) path.
 #include "vfb_internal.cuh"
 
 namespace vfb {
 
+#define SCAN_THREADS 256
+#define SCAN_WARPS (SCAN_THREADS / 32)
+#define SCAN_MAXC 5             // 16-byte chunks covering an adapter of <= 64 bytes at any alignment
+#define SCAN_SLOTS 512          // perfect hash of <= 32 four-mers: one probe, no chain
+#define WL_BUF 64               // per-warp worklist staging entries
+
+struct ScanTables {
+    // 4-mer hash: slot = {word, valid, maskP.lo, maskP.hi}, {maskS.lo, maskS.hi, -, -}
+    uint4 e0[SCAN_SLOTS];
+    uint4 e1[SCAN_SLOTS];
+    // adapters pre-shifted to every position s inside a 16-byte chunk: bytes and byte masks
+    uint4 pat[2][16][SCAN_MAXC];
+    uint4 msk[2][16][SCAN_MAXC];
+};
+
 struct ScanArgs {
     ScanJob job;
     AdapterBytes prefix, suffix;
+    uint32_t mult;      // hash multiplier under which the adapters' sampled 4-mers do not collide
 };
 
-#define SCAN_THREADS 256
+__host__ __device__ __forceinline__ uint32_t hash4(uint32_t w, uint32_t mult) { return (w * mult) >> 23; }
 
-// One warp per read; lanes test consecutive start positions and vote.
+__host__ __device__ __forceinline__ uint32_t load_word_le(const uint8_t *b, int i, int n)
+{
+    // bytes b[i..i+4) little endian, zero outside [0, n)
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int p = i + k;
+        if (p >= 0 && p < n) w |= (uint32_t)b[p] << (8 * k);
+    }
+    return w;
+}
+
+__device__ void build_tables(ScanTables *T, const AdapterBytes &pre, const AdapterBytes &suf, int max_k, uint32_t mult)
+{
+    for (int i = threadIdx.x; i < SCAN_SLOTS; i += blockDim.x) {
+        T->e0[i] = make_uint4(0, 0, 0, 0);
+        T->e1[i] = make_uint4(0, 0, 0, 0);
+    }
+    for (int i = threadIdx.x; i < 2 * 16 * SCAN_MAXC * 4; i += blockDim.x) {
+        // word m of chunk c of adapter x placed at chunk offset s
+        const int m = i & 3, c = (i >> 2) % SCAN_MAXC, s = ((i >> 2) / SCAN_MAXC) & 15, x = (i >> 2) / (SCAN_MAXC * 16);
+        const AdapterBytes &ad = x ? suf : pre;
+        uint32_t w = 0, k = 0;
+        for (int b = 0; b < 4; ++b) {
+            const int p = c * 16 + m * 4 + b - s;
+            if (p >= 0 && p < (int)ad.len) { w |= (uint32_t)ad.b[p] << (8 * b); k |= 0xFFu << (8 * b); }
+        }
+        reinterpret_cast<uint32_t *>(&T->pat[x][s][c])[m] = w;
+        reinterpret_cast<uint32_t *>(&T->msk[x][s][c])[m] = k;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // Serial insert (<= 32 entries).  Only offsets k < max_k = 4*stride are needed: the FIRST
+        // sampled word an occurrence fully contains sits at adapter offset (-p) mod 4*stride,
+        // so every occurrence yields exactly one candidate, in exactly one lane.  The same
+        // 4-mer at several offsets ORs into one slot.
+        for (int x = 0; x < 2; ++x) {
+            const AdapterBytes &ad = x ? suf : pre;
+            for (int k = 0; k < max_k && k + 4 <= (int)ad.len; ++k) {
+                const uint32_t w = load_word_le(ad.b, k, (int)ad.len);
+                const uint32_t h = hash4(w, mult);      // collision-free by choice of mult (host)
+                T->e0[h].x = w;
+                T->e0[h].y = 1;
+                const uint32_t lo = k < 32 ? 1u << k : 0u, hi = k >= 32 ? 1u << (k - 32) : 0u;
+                if (x == 0) { T->e0[h].z |= lo; T->e0[h].w |= hi; }
+                else { T->e1[h].x |= lo; T->e1[h].y |= hi; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// Per-read geometry shared by a lane group: 16-byte aligned base, bytes of the first chunk
+// that precede the read, read length.
+struct ReadGeom {
+    const uint4 *base16;
+    uint32_t lead, len;
+};
+
+// Verify a candidate start `rel` of adapter x: 16-byte aligned loads against the adapter
+// pre-shifted to the candidate's offset inside its chunk.
+__device__ __forceinline__ bool verify_at(const ScanTables *T, uint32_t x, uint32_t rel, uint32_t A, const ReadGeom &rg)
+{
+    const uint32_t abs0 = rg.lead + rel, s = abs0 & 15u;
+    const uint4 *src = rg.base16 + (abs0 >> 4);
+    const uint32_t nc = (s + A + 15) >> 4;
+    uint32_t diff = 0;
+    for (uint32_t k = 0; k < nc; ++k) {
+        const uint4 t = __ldg(src + k), pt = T->pat[x][s][k], mk = T->msk[x][s][k];
+        diff |= ((t.x ^ pt.x) & mk.x) | ((t.y ^ pt.y) & mk.y) | ((t.z ^ pt.z) & mk.z) | ((t.w ^ pt.w) & mk.w);
+    }
+    return diff == 0;
+}
+
+// A table hit: the sampled word at `relq` (bytes after the read start, may be negative) equals
+// the adapter 4-mer(s) of `slot`.  Expand to candidate starts and verify them.
+__device__ __forceinline__ void hit_expand(const ScanTables *T, uint32_t slot, int relq, const ReadGeom &rg,
+                                           uint32_t AP, uint32_t AS, uint32_t &bestP, uint32_t &bestS)
+{
+    // adapter offsets < 16 each (see build_tables): prefix in bits 0-15, suffix in bits 16-31
+    uint32_t m = (T->e0[slot].z & 0xFFFFu) | (T->e1[slot].x << 16);
+    while (m) {
+        const int b = __ffs((int)m) - 1;
+        m &= m - 1;
+        const uint32_t x = (uint32_t)b >> 4;
+        const int p = relq - (b & 15);
+        const uint32_t A = x ? AS : AP;
+        if (p < 0 || p + (int)A > (int)rg.len || (uint32_t)p >= (x ? bestS : bestP)) continue;
+        if (verify_at(T, x, (uint32_t)p, A, rg)) {
+            if (x) bestS = (uint32_t)p; else bestP = (uint32_t)p;
+        }
+    }
+}
+
+// Hits wait in a 3-deep per-lane queue and are expanded after the probes, all lanes together,
+// so that the divergent expand+verify code runs about once per trip instead of once per probe.
+struct Hits {
+    uint32_t s0, s1, s2;
+    int q0, q1, q2;
+};
+
+__device__ __forceinline__ void probe_word(const ScanTables *T, uint32_t mult, uint32_t w, int relq,
+                                           const ReadGeom &rg, uint32_t AP, uint32_t AS, Hits &hq,
+                                           uint32_t &bestP, uint32_t &bestS)
+{
+    const uint32_t h = hash4(w, mult);
+    const uint4 e = T->e0[h];
+    if (e.y && e.x == w) {
+        if (hq.s0 == VFB_NONE) { hq.s0 = h; hq.q0 = relq; }
+        else if (hq.s1 == VFB_NONE) { hq.s1 = h; hq.q1 = relq; }
+        else if (hq.s2 == VFB_NONE) { hq.s2 = h; hq.q2 = relq; }
+        else hit_expand(T, h, relq, rg, AP, AS, bestP, bestS);      // queue full: expand now
+    }
+}
+
+__device__ __forceinline__ void hits_drain(const ScanTables *T, Hits &hq, const ReadGeom &rg, uint32_t AP,
+                                           uint32_t AS, uint32_t &bestP, uint32_t &bestS)
+{
+    while (__any_sync(0xffffffffu, hq.s0 != VFB_NONE)) {
+        if (hq.s0 != VFB_NONE) {
+            hit_expand(T, hq.s0, hq.q0, rg, AP, AS, bestP, bestS);
+            hq.s0 = hq.s1; hq.q0 = hq.q1;
+            hq.s1 = hq.s2; hq.q1 = hq.q2;
+            hq.s2 = VFB_NONE;
+        }
+    }
+}
+
+template <int STRIDE_WORDS>
+__device__ __forceinline__ void probe_chunk(const ScanTables *T, uint32_t mult, const uint4 &v, int relq,
+                                            const ReadGeom &rg, uint32_t AP, uint32_t AS, Hits &hq,
+                                            uint32_t &bestP, uint32_t &bestS)
+{
+    probe_word(T, mult, v.x, relq, rg, AP, AS, hq, bestP, bestS);
+    if (STRIDE_WORDS <= 2) probe_word(T, mult, v.z, relq + 8, rg, AP, AS, hq, bestP, bestS);
+    if (STRIDE_WORDS == 1) {
+        probe_word(T, mult, v.y, relq + 4, rg, AP, AS, hq, bestP, bestS);
+        probe_word(T, mult, v.w, relq + 12, rg, AP, AS, hq, bestP, bestS);
+    }
+}
+
+// Per-warp staging of worklist appends: one global atomic per WL_BUF/2..WL_BUF entries.
+struct WlStage {
+    uint32_t buf[2][WL_BUF];
+};
+
+__device__ __forceinline__ void wl_flush(uint32_t *stage, uint32_t &cnt, uint32_t *list, uint32_t *counter, int lane)
+{
+    if (cnt == 0) return;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(counter, cnt);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (uint32_t i = lane; i < cnt; i += 32) list[base + i] = stage[i];
+    __syncwarp();
+    cnt = 0;
+}
+
+__device__ __forceinline__ void wl_push(uint32_t *stage, uint32_t &cnt, bool want, uint32_t value,
+                                        uint32_t *list, uint32_t *counter, int lane)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (!m) return;
+    if (cnt + __popc(m) > WL_BUF) wl_flush(stage, cnt, list, counter, lane);
+    if (want) stage[cnt + __popc(m & ((1u << lane) - 1))] = value;
+    cnt += __popc(m);
+    __syncwarp();
+}
+
+#define SCAN_GROUP 8                      // lanes per read
+#define SCAN_RPW (32 / SCAN_GROUP)        // reads per warp trip
+
+template <int STRIDE_WORDS>
+__global__ void __launch_bounds__(SCAN_THREADS)
+k1_scan_fast(const __grid_constant__ ScanArgs args)
+{
+    __shared__ ScanTables T;
+    __shared__ WlStage stage[SCAN_WARPS];
+    build_tables(&T, args.prefix, args.suffix, 4 * STRIDE_WORDS, args.mult);
+    const uint32_t mult = args.mult;
+    const ScanJob &job = args.job;
+    const uint32_t AP = args.prefix.len, AS = args.suffix.len;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane & (SCAN_GROUP - 1), grp = lane / SCAN_GROUP;
+    uint32_t cntP = 0, cntS = 0;
+    const uint32_t warps_total = gridDim.x * SCAN_WARPS;
+    const uint32_t n_units = (job.n_reads + SCAN_RPW - 1) / SCAN_RPW;
+    for (uint32_t unit = blockIdx.x * SCAN_WARPS + warp; unit < n_units; unit += warps_total) {
+        const uint32_t r = unit * SCAN_RPW + grp;
+        const bool have = r < job.n_reads;
+        const vfb_span sp = have ? job.spans[r] : vfb_span{0u, 0u};
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(job.text + sp.off);
+        ReadGeom rg;
+        rg.base16 = reinterpret_cast<const uint4 *>(addr & ~(uintptr_t)15);
+        rg.lead = (uint32_t)(addr & 15u);
+        rg.len = sp.len;
+        uint32_t bestP = VFB_NONE, bestS = VFB_NONE;
+        Hits hq{VFB_NONE, VFB_NONE, VFB_NONE, 0, 0, 0};
+        const uint32_t n_chunks = sp.len ? (rg.lead + sp.len + 15) >> 4 : 0;
+        // warp-uniform trip count: every lane takes part in the converged drain
+        const uint32_t max_chunks = __reduce_max_sync(0xffffffffu, n_chunks);
+        for (uint32_t cb = 0; cb < max_chunks; cb += 3 * SCAN_GROUP) {
+            // three chunks per lane per trip; all loads are issued before any probe
+            const uint32_t c0 = cb + g, c1 = c0 + SCAN_GROUP, c2 = c0 + 2 * SCAN_GROUP;
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            const uint4 v0 = c0 < n_chunks ? __ldg(rg.base16 + c0) : z;
+            const uint4 v1 = c1 < n_chunks ? __ldg(rg.base16 + c1) : z;
+            const uint4 v2 = c2 < n_chunks ? __ldg(rg.base16 + c2) : z;
+            if (c0 < n_chunks) probe_chunk<STRIDE_WORDS>(&T, mult, v0, (int)(c0 * 16) - (int)rg.lead, rg, AP, AS, hq, bestP, bestS);
+            if (c1 < n_chunks) probe_chunk<STRIDE_WORDS>(&T, mult, v1, (int)(c1 * 16) - (int)rg.lead, rg, AP, AS, hq, bestP, bestS);
+            if (c2 < n_chunks) probe_chunk<STRIDE_WORDS>(&T, mult, v2, (int)(c2 * 16) - (int)rg.lead, rg, AP, AS, hq, bestP, bestS);
+            hits_drain(&T, hq, rg, AP, AS, bestP, bestS);
+        }
+        // leftmost over the lane group
+#pragma unroll
+        for (int o = SCAN_GROUP / 2; o > 0; o >>= 1) {
+            bestP = min(bestP, __shfl_xor_sync(0xffffffffu, bestP, o));
+            bestS = min(bestS, __shfl_xor_sync(0xffffffffu, bestS, o));
+        }
+        const bool leader = g == 0 && have;
+        const uint32_t start = bestP == VFB_NONE ? VFB_NONE : bestP + AP;
+        if (leader) {
+            job.start[r] = start;
+            job.end[r] = bestS;
+        }
+        // worklists (`aligner?.align` only on an exact miss, src/lib.rs:155)
+        const bool needP = leader && job.list_pre && start == VFB_NONE && sp.len > 0;
+        const bool needS = leader && job.list_suf && bestS == VFB_NONE && sp.len > 0 &&
+                           (job.compute_all || start != VFB_NONE);
+        wl_push(stage[warp].buf[0], cntP, needP, r, job.list_pre, job.n_pre, lane);
+        wl_push(stage[warp].buf[1], cntS, needS, r, job.list_suf, job.n_suf, lane);
+    }
+    wl_flush(stage[warp].buf[0], cntP, job.list_pre, job.n_pre, lane);
+    wl_flush(stage[warp].buf[1], cntS, job.list_suf, job.n_suf, lane);
+}
+
+// ---------------------------------------------------------------------------------------
+// General kernel: any adapter length (including 0 and > 64).  One warp per read; lanes test
+// consecutive start positions byte by byte and vote.
 __device__ __forceinline__ uint32_t scan_one(const uint8_t *seq, uint32_t L, const uint8_t *ad,
                                             uint32_t A, int lane)
 {
     if (A == 0) return 0;              // an empty needle matches at 0 (memchr convention)
     if (A > L) return VFB_NONE;
-    const uint32_t last = L - A;       // last candidate start
+    const uint32_t last = L - A;
     const uint8_t a0 = ad[0];
     for (uint32_t base = 0; base <= last; base += 32) {
         const uint32_t p = base + lane;
@@ -40,25 +302,35 @@ __device__ __forceinline__ uint32_t scan_one(const uint8_t *seq, uint32_t L, con
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
-k1_scan(const __grid_constant__ ScanArgs args)
+k1_scan_general(const __grid_constant__ ScanArgs args)
 {
     __shared__ uint8_t s_pre[VFB_MAX_SCAN_ADAPTER], s_suf[VFB_MAX_SCAN_ADAPTER];
+    __shared__ WlStage stage[SCAN_WARPS];
     for (uint32_t i = threadIdx.x; i < args.prefix.len; i += blockDim.x) s_pre[i] = args.prefix.b[i];
     for (uint32_t i = threadIdx.x; i < args.suffix.len; i += blockDim.x) s_suf[i] = args.suffix.b[i];
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const uint32_t warps_total = gridDim.x * (SCAN_THREADS / 32);
-    for (uint32_t r = blockIdx.x * (SCAN_THREADS / 32) + (threadIdx.x >> 5); r < args.job.n_reads;
-         r += warps_total) {
-        const vfb_span sp = args.job.spans[r];
-        const uint8_t *seq = args.job.text + sp.off;
+    const ScanJob &job = args.job;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t cntP = 0, cntS = 0;
+    const uint32_t warps_total = gridDim.x * SCAN_WARPS;
+    for (uint32_t r = blockIdx.x * SCAN_WARPS + warp; r < job.n_reads; r += warps_total) {
+        const vfb_span sp = job.spans[r];
+        const uint8_t *seq = job.text + sp.off;
         const uint32_t pp = scan_one(seq, sp.len, s_pre, args.prefix.len, lane);
         const uint32_t ps = scan_one(seq, sp.len, s_suf, args.suffix.len, lane);
+        const uint32_t start = pp == VFB_NONE ? VFB_NONE : pp + args.prefix.len;
         if (lane == 0) {
-            args.job.start[r] = pp == VFB_NONE ? VFB_NONE : pp + args.prefix.len;
-            args.job.end[r] = ps;
+            job.start[r] = start;
+            job.end[r] = ps;
         }
+        const bool needP = lane == 0 && job.list_pre && start == VFB_NONE && sp.len > 0;
+        const bool needS = lane == 0 && job.list_suf && ps == VFB_NONE && sp.len > 0 &&
+                           (job.compute_all || start != VFB_NONE);
+        wl_push(stage[warp].buf[0], cntP, needP, r, job.list_pre, job.n_pre, lane);
+        wl_push(stage[warp].buf[1], cntS, needS, r, job.list_suf, job.n_suf, lane);
     }
+    wl_flush(stage[warp].buf[0], cntP, job.list_pre, job.n_pre, lane);
+    wl_flush(stage[warp].buf[1], cntS, job.list_suf, job.n_suf, lane);
 }
 
 int launch_scan(const ScanJob &job, const AdapterBytes &prefix, const AdapterBytes &suffix,
@@ -69,47 +341,40 @@ int launch_scan(const ScanJob &job, const AdapterBytes &prefix, const AdapterByt
     a.job = job;
     a.prefix = prefix;
     a.suffix = suffix;
-    uint32_t blocks = (job.n_reads + (SCAN_THREADS / 32) - 1) / (SCAN_THREADS / 32);
-    uint32_t cap = (uint32_t)sm_count * 8u;
-    if (blocks > cap) blocks = cap;
-    k1_scan<<<blocks, SCAN_THREADS, 0, st>>>(a);
-    ++g_launches;
-    VFB_CUDA(cudaGetLastError());
-    return VFB_OK;
-}
-
-// Worklist: warp-aggregated append of the reads that still need an alignment.
-__global__ void __launch_bounds__(256)
-k_worklist(const uint32_t *__restrict__ bound, const uint32_t *__restrict__ require,
-           const vfb_span *__restrict__ spans, uint32_t n, uint32_t *__restrict__ list,
-           uint32_t *__restrict__ count)
-{
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const int lane = threadIdx.x & 31;
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
-        const uint32_t i = base + lane;
-        bool need = false;
-        if (i < n) {
-            need = bound[i] == VFB_NONE && spans[i].len > 0;
-            if (need && require) need = require[i] != VFB_NONE;
+    const uint32_t amin = prefix.len < suffix.len ? prefix.len : suffix.len;
+    const uint32_t amax = prefix.len > suffix.len ? prefix.len : suffix.len;
+    bool fast = amin >= 7 && amax <= 64 && !job.force_general;
+    if (fast) {
+        // perfect hash: find a multiplier under which the sampled 4-mers of both adapters
+        // occupy distinct slots (<= 32 keys in 512 slots: a few tries)
+        const int max_k = amin >= 19 ? 16 : (amin >= 11 ? 8 : 4);
+        bool ok = false;
+        for (uint32_t t = 0; t < 4096 && !ok; ++t) {
+            const uint32_t mult = 0x9E3779B1u + 2u * t * 0x632BE5ABu;
+            uint32_t words[SCAN_SLOTS];
+            bool used[SCAN_SLOTS] = {false};
+            ok = true;
+            for (int x = 0; x < 2 && ok; ++x) {
+                const AdapterBytes &ad = x ? suffix : prefix;
+                for (int k = 0; k < max_k && k + 4 <= (int)ad.len; ++k) {
+                    const uint32_t w = load_word_le(ad.b, k, (int)ad.len), h = hash4(w, mult);
+                    if (used[h] && words[h] != w) { ok = false; break; }
+                    used[h] = true;
+                    words[h] = w;
+                }
+            }
+            if (ok) a.mult = mult;
         }
-        const unsigned m = __ballot_sync(0xffffffffu, need);
-        if (m) {
-            uint32_t pos = 0;
-            if (lane == 0) pos = atomicAdd(count, (uint32_t)__popc(m));
-            pos = __shfl_sync(0xffffffffu, pos, 0);
-            if (need) list[pos + __popc(m & ((1u << lane) - 1))] = i;
-        }
+        fast = ok;
     }
-}
-
-int launch_worklist(const uint32_t *bound, const uint32_t *require, const vfb_span *spans,
-                    uint32_t n_reads, uint32_t *list, uint32_t *count, cudaStream_t st)
-{
-    if (n_reads == 0) return VFB_OK;
-    uint32_t blocks = (n_reads + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    k_worklist<<<blocks, 256, 0, st>>>(bound, require, spans, n_reads, list, count);
+    const uint32_t units = fast ? (job.n_reads + SCAN_RPW - 1) / SCAN_RPW : job.n_reads;
+    uint32_t blocks = (units + SCAN_WARPS - 1) / SCAN_WARPS;
+    const uint32_t cap = (uint32_t)sm_count * 8u;
+    if (blocks > cap) blocks = cap;
+    if (!fast) k1_scan_general<<<blocks, SCAN_THREADS, 0, st>>>(a);
+    else if (amin >= 19) k1_scan_fast<4><<<blocks, SCAN_THREADS, 0, st>>>(a);
+    else if (amin >= 11) k1_scan_fast<2><<<blocks, SCAN_THREADS, 0, st>>>(a);
+    else k1_scan_fast<1><<<blocks, SCAN_THREADS, 0, st>>>(a);
     ++g_launches;
     VFB_CUDA(cudaGetLastError());
     return VFB_OK;

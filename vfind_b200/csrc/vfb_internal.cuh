@@ -77,6 +77,9 @@ struct DpJob {
     int32_t *diag_score;          // nullable, indexed by read
     int32_t *diag_len;
     unsigned long long *cells;    // device counter: sum A*L over alignments
+    // prefix pass only: reads it accepts whose suffix is still missing go on the suffix worklist
+    uint32_t *next_list, *n_next;
+    const uint32_t *other_bound;
     int is_prefix;
     int min_accept;               // accept iff score >= min_accept
     uint32_t adapter_len;
@@ -105,14 +108,14 @@ struct ScanJob {
     uint32_t n_reads;
     uint32_t *start;   // prefix boundary: pos + A, or VFB_NONE
     uint32_t *end;     // suffix boundary: pos, or VFB_NONE
+    // DP worklists built by the scan (null = that alignment is disabled)
+    uint32_t *list_pre, *n_pre;   // reads without an exact prefix
+    uint32_t *list_suf, *n_suf;   // reads without an exact suffix whose prefix is already located
+    int compute_all;              // 1: list every suffix miss (what the reference computes)
+    int force_general;            // tests: use the byte-wise kernel
 };
 int launch_scan(const ScanJob &job, const AdapterBytes &prefix, const AdapterBytes &suffix,
                 int sm_count, cudaStream_t st);
-
-// Appends read indices whose boundary is VFB_NONE (and whose read is non-empty).
-// If `require` is non-null only reads with require[i] != VFB_NONE are listed.
-int launch_worklist(const uint32_t *bound, const uint32_t *require, const vfb_span *spans,
-                    uint32_t n_reads, uint32_t *list, uint32_t *count, cudaStream_t st);
 
 // ---------------------------------------------------------------- translate + count
 struct KeyJob {
