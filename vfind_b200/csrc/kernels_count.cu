@@ -63,82 +63,161 @@ __device__ bool utf8_valid(const uint8_t *s, uint32_t n)
 }
 
 #define KEY_THREADS 256
+#define KEY_GROUP 8                 // lanes per read in the translate phase
+#define KEY_MULTS 128               // hash multipliers kept in shared memory
 
+struct KeyTables {
+    uint8_t lut[256];               // byte -> base index 0..4 (bytes >= 128 -> 4)
+    uint8_t aa[128];                // c0*25 + c1*5 + c2 -> amino acid, 'X' if any index is 4
+    uint64_t mult[KEY_MULTS];       // vfb_hash_mult(i)
+};
+
+__device__ __forceinline__ uint64_t key_mult(const KeyTables *T, uint32_t i)
+{
+    return i < KEY_MULTS ? T->mult[i] : vfb_hash_mult(i);
+}
+
+// 12 (or 4) consecutive text bytes starting at `a` as little-endian words, from aligned loads
+// that never touch a word at or beyond `limit` (the 4-aligned end of the region's last byte).
+template <int NW>
+__device__ __forceinline__ void load_unaligned(const uint8_t *a, const uint8_t *limit, uint32_t *out)
+{
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(a) & 3u) * 8u;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(a - (sh >> 3));
+    uint32_t t[NW + 1];
+#pragma unroll
+    for (int j = 0; j <= NW; ++j)
+        t[j] = reinterpret_cast<const uint8_t *>(w + j) < limit ? __ldg(w + j) : 0u;
+#pragma unroll
+    for (int j = 0; j < NW; ++j) out[j] = __funnelshift_r(t[j], t[j + 1], sh);
+}
+
+// Phase A: one lane per read decides the key length and claims key space (one atomic per
+// 32 reads).  Phase B: lane groups of 8 translate 4 reads at a time, one 32-bit word of key
+// (4 amino acids = 12 bases) per lane per step, hashing the words they hold.
 __global__ void __launch_bounds__(KEY_THREADS)
 k3_keys(const __grid_constant__ KeyJob job)
 {
-    __shared__ uint8_t s_lut[256];
-    __shared__ char s_aa[64];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = (uint8_t)(i >= 128 ? 4 : tr_index((uint8_t)i));
-    if (threadIdx.x < 64) s_aa[threadIdx.x] = c_aa[threadIdx.x];
+    __shared__ KeyTables T;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) T.lut[i] = (uint8_t)(i >= 128 ? 4 : tr_index((uint8_t)i));
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+        const int c0 = i / 25, c1 = (i / 5) % 5, c2 = i % 5;
+        T.aa[i] = (i >= 125 || c0 == 4 || c1 == 4 || c2 == 4) ? (uint8_t)'X' : (uint8_t)c_aa[c0 * 16 + c1 * 4 + c2];
+    }
+    for (int i = threadIdx.x; i < KEY_MULTS; i += blockDim.x) T.mult[i] = vfb_hash_mult((uint32_t)i);
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
+    const int g = lane & (KEY_GROUP - 1), grp = lane / KEY_GROUP;
     const uint32_t warps_total = gridDim.x * (KEY_THREADS / 32);
-    for (uint32_t r = blockIdx.x * (KEY_THREADS / 32) + (threadIdx.x >> 5); r < job.n_reads; r += warps_total) {
-        const uint32_t s = job.start[r], e = job.end[r];
-        const vfb_span sp = job.spans[r];
-        uint32_t klen = 0;
-        // src/lib.rs:288: both located and start < end (strict).  end <= len always holds for
-        // located suffix boundaries; a prefix boundary beyond it fails start < end.
-        const bool located = s != VFB_NONE && e != VFB_NONE && s < e && e <= sp.len;
-        const uint8_t *var = job.text + sp.off + s;
-        const uint32_t V = located ? e - s : 0;
-        if (located) {
-            if (!job.skip_translation) {
-                if (V % 3 == 0) klen = V / 3;                       // :17-19 partial codon -> None
-            } else {
-                bool high = false;
-                for (uint32_t c = lane; c < V; c += 32) high |= __ldg(var + c) >= 0x80;
-                klen = V;
-                if (__any_sync(0xffffffffu, high)) {
-                    int ok = 1;
-                    if (lane == 0) ok = utf8_valid(var, V) ? 1 : 0;
-                    ok = __shfl_sync(0xffffffffu, ok, 0);
-                    if (!ok) klen = 0;                              // :295 from_utf8 Err -> dropped
-                }
+    const uint32_t n_rounds = (job.n_reads + 31) / 32;
+    for (uint32_t round = blockIdx.x * (KEY_THREADS / 32) + (threadIdx.x >> 5); round < n_rounds; round += warps_total) {
+        // ---- phase A
+        const uint32_t r = round * 32 + lane;
+        uint32_t klen = 0, V = 0;
+        const uint8_t *var = job.text;
+        if (r < job.n_reads) {
+            const uint32_t s = job.start[r], e = job.end[r];
+            const vfb_span sp = job.spans[r];
+            // src/lib.rs:288: both located and start < end (strict).  end <= len always holds
+            // for located suffix boundaries; a prefix boundary beyond it fails start < end.
+            if (s != VFB_NONE && e != VFB_NONE && s < e && e <= sp.len) {
+                V = e - s;
+                var = job.text + sp.off + s;
+                if (job.skip_translation) klen = V;
+                else if (V % 3 == 0) klen = V / 3;                 // :17-19 partial codon -> None
             }
         }
-        if (klen) {
-            const uint32_t padded = (klen + 15u) & ~15u;
-            unsigned long long off = 0;
-            if (lane == 0) off = atomicAdd(job.key_cursor, (unsigned long long)padded);
-            off = __shfl_sync(0xffffffffu, off, 0);
-            uint8_t *key = job.keys + off;
-            if (!job.skip_translation) {
-                for (uint32_t c = lane; c < klen; c += 32) {
-                    const uint8_t b0 = __ldg(var + 3 * c), b1 = __ldg(var + 3 * c + 1), b2 = __ldg(var + 3 * c + 2);
-                    const uint32_t i0 = s_lut[b0], i1 = s_lut[b1], i2 = s_lut[b2];
-                    key[c] = (i0 | i1 | i2) & 4 ? (uint8_t)'X' : (uint8_t)s_aa[i0 * 16 + i1 * 4 + i2];
-                }
-            } else {
-                for (uint32_t c = lane; c < klen; c += 32) key[c] = __ldg(var + c);
-            }
-            for (uint32_t c = klen + lane; c < padded; c += 32) key[c] = 0;
-            __syncwarp();
-            uint64_t acc = 0;
-            const uint32_t nw = (klen + 3) / 4;
-            const uint32_t *kw = reinterpret_cast<const uint32_t *>(key);
-            for (uint32_t i = lane; i < nw; i += 32) acc += vfb_hash_term(kw[i], i);
+        const uint32_t padded = (klen + 15u) & ~15u;
+        uint32_t incl = padded;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) {
-                uint64_t h = vfb_hash_finish(acc, klen);
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        unsigned long long base = 0;
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 31 && total) base = atomicAdd(job.key_cursor, (unsigned long long)total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        const unsigned long long koff = base + (incl - padded);
+        if (r < job.n_reads && klen) job.koff[r] = koff;
+        uint32_t bad_mask = 0;       // reads whose raw region is not valid UTF-8 (skip_translation only)
+        // ---- phase B
+#pragma unroll 1
+        for (int sub = 0; sub < 32 / (32 / KEY_GROUP); ++sub) {
+            const int owner = sub * (32 / KEY_GROUP) + grp;
+            const uint32_t kl = __shfl_sync(0xffffffffu, klen, owner);
+            const uint32_t vv = __shfl_sync(0xffffffffu, V, owner);
+            const unsigned long long ko = __shfl_sync(0xffffffffu, koff, owner);
+            const uintptr_t va = __shfl_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(var), owner);
+            const uint32_t max_kl = __reduce_max_sync(0xffffffffu, kl);
+            if (max_kl == 0) continue;
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(va);
+            const uint8_t *limit = reinterpret_cast<const uint8_t *>((va + vv + 3) & ~(uintptr_t)3);
+            uint32_t *key = reinterpret_cast<uint32_t *>(job.keys + ko);
+            const uint32_t nw = (kl + 3) >> 2, npad = ((kl + 15u) & ~15u) >> 2;
+            uint64_t acc = 0;
+            uint32_t high = 0;
+            for (uint32_t wi = g; wi < npad; wi += KEY_GROUP) {
+                uint32_t word = 0;
+                if (wi < nw) {
+                    if (!job.skip_translation) {
+                        uint32_t x[3];
+                        load_unaligned<3>(src + 12 * wi, limit, x);
+                        const uint32_t n_aa = min(4u, kl - 4 * wi);
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) {
+                            // codon a = bytes 3a .. 3a+2 of the 12
+                            uint32_t b[3];
+#pragma unroll
+                            for (int t = 0; t < 3; ++t) {
+                                const int p = 3 * a + t;
+                                b[t] = (x[p >> 2] >> (8 * (p & 3))) & 0xFFu;
+                            }
+                            const uint32_t idx = T.lut[b[0]] * 25u + T.lut[b[1]] * 5u + T.lut[b[2]];
+                            const uint32_t aa = (uint32_t)a < n_aa ? T.aa[idx] : 0u;
+                            word |= aa << (8 * a);
+                        }
+                    } else {
+                        load_unaligned<1>(src + 4 * wi, limit, &word);
+                        const uint32_t nb = min(4u, kl - 4 * wi);
+                        if (nb < 4) word &= (1u << (8 * nb)) - 1u;
+                        high |= word & 0x80808080u;
+                    }
+                    acc += (uint64_t)(word ^ VFB_HASH_K) * key_mult(&T, wi);
+                }
+                key[wi] = word;
+            }
+#pragma unroll
+            for (int o = KEY_GROUP / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (g == 0 && kl) {
+                uint64_t h = vfb_hash_finish(acc, kl);
                 if (job.hash_bits > 0 && job.hash_bits < 64) h &= (1ull << job.hash_bits) - 1;
-                job.khash[r] = h;
-                job.koff[r] = off;
+                job.khash[round * 32 + owner] = h;
+            }
+            if (job.skip_translation) {
+                // String::from_utf8 (:295): only regions holding a byte >= 0x80 need the validator
+#pragma unroll
+                for (int o = KEY_GROUP / 2; o > 0; o >>= 1) high |= __shfl_xor_sync(0xffffffffu, high, o);
+                bool bad = false;
+                if (g == 0 && kl && high) bad = !utf8_valid(src, vv);
+                const unsigned bm = __ballot_sync(0xffffffffu, bad);
+#pragma unroll
+                for (int q = 0; q < 32 / KEY_GROUP; ++q)
+                    if (bm & (1u << (q * KEY_GROUP))) bad_mask |= 1u << (sub * (32 / KEY_GROUP) + q);
             }
         }
-        if (lane == 0) job.klen[r] = klen;
-        __syncwarp();
+        if (bad_mask & (1u << lane)) klen = 0;
+        if (r < job.n_reads) job.klen[r] = klen;
     }
 }
 
 int launch_keys(const KeyJob &job, cudaStream_t st)
 {
     if (job.n_reads == 0) return VFB_OK;
-    uint32_t blocks = (job.n_reads + (KEY_THREADS / 32) - 1) / (KEY_THREADS / 32);
+    uint32_t blocks = (job.n_reads / 32 + (KEY_THREADS / 32)) / (KEY_THREADS / 32);
     if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
     k3_keys<<<blocks, KEY_THREADS, 0, st>>>(job);
     ++g_launches;
     VFB_CUDA(cudaGetLastError());
