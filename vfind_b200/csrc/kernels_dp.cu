@@ -96,7 +96,7 @@ __host__ __device__ static inline uint32_t dp_layout_lcap(const DpLayout &l, uin
 
 #define DP_WARPS 4
 #define DP_THREADS (DP_WARPS * 32)
-#define DP_TL 64   // read columns per shared-memory tile
+#define DP_ROW 80   // bytes of ring buffer per lane: 4 slots x 16 B + 16 B pad (odd multiple of 16: no STS.128 conflicts beyond the 4-wavefront minimum)
 
 struct DpKernelArgs {
     DpJob job;
@@ -106,15 +106,18 @@ struct DpKernelArgs {
     uint32_t *n_fallback;
 };
 
+// Resident CTAs per SM the register budget is tuned for.
+template <int AMAX> struct DpOcc { static constexpr int value = AMAX <= 20 ? 6 : (AMAX <= 28 ? 4 : (AMAX <= 44 ? 3 : 2)); };
+
 template <int AMAX, bool USE_IMAD>
-__global__ void __launch_bounds__(DP_THREADS)
+__global__ void __launch_bounds__(DP_THREADS, DpOcc<AMAX>::value)
 k2_dp_packed(const __grid_constant__ DpKernelArgs args)
 {
     constexpr int NG = AMAX / 4;
     extern __shared__ __align__(16) unsigned char smem[];
     int4 *prof = reinterpret_cast<int4 *>(smem);                 // [NG][8] : rows 4g..4g+3 at code c
-    uint8_t *lut = smem + NG * 8 * sizeof(int4);                 // byte -> code
-    uint8_t *tiles = lut + 256;                                  // [warp][DP_TL][32]
+    uint8_t *lut = smem + NG * 8 * sizeof(int4);                 // byte -> 16 * code
+    uint8_t *rings = lut + 256;                                  // [warp][lane][DP_ROW]
 
     const DpJob &job = args.job;
     const DpLayout &lay = args.lay;
@@ -129,11 +132,11 @@ k2_dp_packed(const __grid_constant__ DpKernelArgs args)
         }
         reinterpret_cast<int *>(prof)[idx] = w;
     }
-    for (int idx = threadIdx.x; idx < 256; idx += blockDim.x) lut[idx] = (uint8_t)dp_code((uint8_t)idx);
+    for (int idx = threadIdx.x; idx < 256; idx += blockDim.x) lut[idx] = (uint8_t)(16 * dp_code((uint8_t)idx));
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint8_t *tile = tiles + warp * (DP_TL * 32);
+    uint8_t *ring = rings + (warp * 32 + lane) * DP_ROW;         // private to this lane
     const uint32_t n_items = *job.n_items;
     const uint32_t n_groups = (n_items + 31) / 32;
     const uint32_t warps_total = gridDim.x * DP_WARPS;
@@ -141,6 +144,7 @@ k2_dp_packed(const __grid_constant__ DpKernelArgs args)
     const int c_eopen = lay.c_eopen, c_eext = lay.c_eext, c_fopen = lay.c_fopen, c_fext = lay.c_fext;
     const int hmask = lay.hmask, lowmask = lay.lowmask, one = lay.one;
     const int S0 = lay.S0;
+    const unsigned char *profb = reinterpret_cast<const unsigned char *>(prof);
 
     for (uint32_t g = blockIdx.x * DP_WARPS + warp; g < n_groups; g += warps_total) {
         const uint32_t item = g * 32 + lane;
@@ -154,9 +158,7 @@ k2_dp_packed(const __grid_constant__ DpKernelArgs args)
             run = false;
         }
         const int L = run ? (int)sp.len : 0;
-        int Lmax = L;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) Lmax = max(Lmax, __shfl_xor_sync(0xffffffffu, Lmax, o));
+        const int Lmax = __reduce_max_sync(0xffffffffu, L);
         if (job.cells) {
             unsigned long long c = (unsigned long long)L * (unsigned long long)A;
 #pragma unroll
@@ -164,56 +166,62 @@ k2_dp_packed(const __grid_constant__ DpKernelArgs args)
             if (lane == 0 && c) atomicAdd(job.cells, c);
         }
 
+        // The read streams through the lane's own ring: 16-byte aligned chunks, chunk m+2 is
+        // in flight (registers) while the 16 columns of block m are computed.
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(job.text + sp.off);
+        const uint4 *base16 = reinterpret_cast<const uint4 *>(addr & ~(uintptr_t)15);
+        const int lead = (int)(addr & 15u);
+        const int nch = L ? (lead + L + 15) >> 4 : 0;
+        const uint4 z4 = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4 *>(ring) = nch > 0 ? __ldg(base16) : z4;
+        *reinterpret_cast<uint4 *>(ring + 16) = nch > 1 ? __ldg(base16 + 1) : z4;
+        uint4 nxt = nch > 2 ? __ldg(base16 + 2) : z4;
+
         int H[AMAX], E[AMAX];
 #pragma unroll
         for (int i = 0; i < AMAX; ++i) { H[i] = 0; E[i] = lay.neg_e; }
         int best = INT_MIN / 2, bestcap = INT_MIN / 2, bestj = 0;
 
-        for (int t0 = 0; t0 < Lmax; t0 += DP_TL) {
-            __syncwarp();
-            // cooperative, coalesced fill of the transposed tile: tile[k][lane'] = code(read_lane'[t0+k])
-            for (int rr = 0; rr < 32; ++rr) {
-                const uint32_t off_rr = __shfl_sync(0xffffffffu, sp.off, rr);
-                const int L_rr = __shfl_sync(0xffffffffu, L, rr);
-                if (L_rr <= t0) continue;
-                const uint8_t *src = job.text + off_rr + t0;
-                const int nk = min(DP_TL, L_rr - t0);
-#pragma unroll
-                for (int k = lane; k < DP_TL; k += 32)
-                    if (k < nk) tile[k * 32 + rr] = lut[__ldg(src + k)];
-            }
-            __syncwarp();
-            const int kend = min(DP_TL, L - t0);
+        for (int m = 0; m * 16 < Lmax; ++m) {
+            const int kend = min(16, L - m * 16);
+#pragma unroll 1
             for (int k = 0; k < kend; ++k) {
-                const int c = tile[k * 32 + lane];
-                const int4 *pc = prof + c;
-                int hd = 0;                 // H[0][j-1] = 0
+                const int c16 = lut[ring[(lead + m * 16 + k) & 63]];
+                const int4 *pc = reinterpret_cast<const int4 *>(profb + c16);
                 int hup = 0;                // H[0][j]   = 0
                 int F = lay.neg_f;
+                int4 W4 = pc[0];
+                int d = W4.x;               // row 1 diagonal: H[0][j-1] + W = W
 #pragma unroll
                 for (int gi = 0; gi < NG; ++gi) {
-                    const int4 W4 = pc[gi * 8];
-                    const int Wv[4] = {W4.x, W4.y, W4.z, W4.w};
+                    int4 Wn = W4;
+                    if (gi + 1 < NG) Wn = pc[(gi + 1) * 8];
+                    const int Wv[5] = {W4.x, W4.y, W4.z, W4.w, Wn.x};
 #pragma unroll
                     for (int rI = 0; rI < 4; ++rI) {
                         const int i = gi * 4 + rI;
                         const int hl = H[i];
+                        // next row's diagonal candidate, taken before H[i] is overwritten
+                        const int dn = USE_IMAD ? hl * one + Wv[rI + 1] : hl + Wv[rI + 1];
                         int ee = USE_IMAD ? E[i] * one + c_eext : E[i] + c_eext;
                         ee = __viaddmax_s32(hl, c_eopen, ee);
                         int ff = USE_IMAD ? F * one + c_fext : F + c_fext;
                         ff = __viaddmax_s32(hup, c_fopen, ff);
-                        const int d = USE_IMAD ? hd * one + Wv[rI] : hd + Wv[rI];
                         const int h = __vimax3_s32(d, ff, ee) & hmask;
-                        E[i] = ee; F = ff; hd = hl; H[i] = h; hup = h;
+                        E[i] = ee; F = ff; H[i] = h; hup = h; d = dn;
                     }
+                    W4 = Wn;
                 }
                 // last row (row A, which is one of the four bottom register rows)
                 int hA = H[AMAX - 1];
                 if (A == AMAX - 1) hA = H[AMAX - 2];
                 if (A == AMAX - 2) hA = H[AMAX - 3];
                 if (A == AMAX - 3) hA = H[AMAX - 4];
-                if (hA > bestcap) { best = hA; bestcap = hA | lowmask; bestj = t0 + k + 1; }
+                if (hA > bestcap) { best = hA; bestcap = hA | lowmask; bestj = m * 16 + k + 1; }
             }
+            // chunk m+2 lands in the ring, chunk m+3 takes off
+            *reinterpret_cast<uint4 *>(ring + (((m + 2) & 3) << 4)) = nxt;
+            nxt = m + 3 < nch ? __ldg(base16 + m + 3) : z4;
         }
 
         bool want_next = false;
@@ -251,7 +259,7 @@ template <int AMAX>
 static int launch_one(const DpKernelArgs &args, int sm_count, cudaStream_t st)
 {
     auto kern = k2_dp_packed<AMAX, true>;
-    size_t smem = (AMAX / 4) * 8 * sizeof(int4) + 256 + DP_WARPS * DP_TL * 32;
+    size_t smem = (AMAX / 4) * 8 * sizeof(int4) + 256 + DP_WARPS * 32 * DP_ROW;
     static int blocks_per_sm = 0;
     if (!blocks_per_sm) {
         VFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, DP_THREADS, smem));
