@@ -267,7 +267,7 @@ def main():
                     ctx.submit_host_ptr(ht.data_ptr(), ht.numel(), hs.data_ptr(), m)
                 if world > 1:
                     merge_tables(ctx, device=dev)
-                offsets, data, counts = ctx.finish_arrays()
+                offsets, data, counts = ctx.finish_arrays(copy=False)
                 rows = len(counts)
                 return offsets.nbytes + data.nbytes + counts.nbytes
 

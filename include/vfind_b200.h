@@ -96,6 +96,8 @@ typedef struct vfb_table {
     uint64_t *offsets;      /* rows + 1 */
     uint8_t *data;          /* key_bytes */
     uint64_t *counts;       /* rows */
+    void *owner;            /* non-null: the columns live in pinned memory owned by that context
+                               and stay valid until its next vfb_finish / vfb_destroy */
 } vfb_table;
 
 typedef struct vfb_stats {
@@ -158,8 +160,10 @@ int vfb_sync(vfb_ctx *ctx);
  * ownership of the stream. */
 int vfb_set_compute_stream(vfb_ctx *ctx, void *stream);
 
-/* `variants.into_iter().unzip()` (src/lib.rs:312): waits for all batches, copies the
- * table to the host.  Free with vfb_table_free.  The context stays usable. */
+/* `variants.into_iter().unzip()` (src/lib.rs:312): waits for all batches, compacts the
+ * table into Arrow-style columns on the device and copies them into pinned host buffers
+ * owned by the context (see vfb_table.owner).  Call vfb_table_free when done with the
+ * view.  The context stays usable. */
 int vfb_finish(vfb_ctx *ctx, vfb_table *out);
 void vfb_table_free(vfb_table *t);
 

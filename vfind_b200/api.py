@@ -46,7 +46,7 @@ class Params(C.Structure):
 class Table(C.Structure):
     _fields_ = [("rows", C.c_uint64), ("key_bytes", C.c_uint64),
                 ("offsets", C.POINTER(C.c_uint64)), ("data", C.POINTER(C.c_uint8)),
-                ("counts", C.POINTER(C.c_uint64))]
+                ("counts", C.POINTER(C.c_uint64)), ("owner", C.c_void_p)]
 
 
 class Stats(C.Structure):
@@ -250,15 +250,20 @@ class Context:
         return out
 
     # -- results
-    def finish_arrays(self):
-        """(offsets uint64[rows+1], data uint8[key_bytes], counts uint64[rows]) — host copies."""
+    def finish_arrays(self, copy=True):
+        """(offsets uint64[rows+1], data uint8[key_bytes], counts uint64[rows]) on the host.
+
+        copy=False returns views of the context's pinned buffers: valid only until the next
+        finish on this context or its close()."""
         t = Table()
         _check(self._lib.vfb_finish(self._h, C.byref(t)))
         try:
             rows, kb = int(t.rows), int(t.key_bytes)
-            offsets = np.ctypeslib.as_array(t.offsets, shape=(rows + 1,)).copy()
-            data = np.ctypeslib.as_array(t.data, shape=(kb,)).copy() if kb else np.zeros(0, np.uint8)
-            counts = np.ctypeslib.as_array(t.counts, shape=(rows,)).copy() if rows else np.zeros(0, np.uint64)
+            offsets = np.ctypeslib.as_array(t.offsets, shape=(rows + 1,))
+            data = np.ctypeslib.as_array(t.data, shape=(kb,)) if kb else np.zeros(0, np.uint8)
+            counts = np.ctypeslib.as_array(t.counts, shape=(rows,)) if rows else np.zeros(0, np.uint64)
+            if copy:
+                offsets, data, counts = offsets.copy(), data.copy(), counts.copy()
         finally:
             self._lib.vfb_table_free(C.byref(t))
         return offsets, data, counts

@@ -140,6 +140,10 @@ struct vfb_ctx {
     DevBuf t_slots, t_counts, t_row_hash, t_row_off, t_row_len, t_arena, t_counters, t_row_count;
     uint64_t ub_rows = 0, ub_arena = 0;   // host-side upper bounds of rows / arena bytes
 
+    // export: device-side Arrow compaction and pinned host columns
+    DevBuf x_block_sums, x_offsets, x_data;
+    PinBuf h_offsets, h_counts, h_data;
+
     // merge scratch
     DevBuf m_part_rows, m_part_keys, m_cursors, m_chunk_off;
     std::vector<uint64_t> h_part_rows, h_part_keys;
@@ -458,6 +462,8 @@ int vfb_destroy(vfb_ctx *c)
                       &c->t_row_hash, &c->t_row_off, &c->t_row_len, &c->t_arena, &c->t_counters, &c->t_row_count,
                       &c->m_part_rows, &c->m_part_keys, &c->m_cursors, &c->m_chunk_off};
     for (auto *b : bufs) b->release();
+    c->x_block_sums.release(); c->x_offsets.release(); c->x_data.release();
+    c->h_offsets.release(); c->h_counts.release(); c->h_data.release();
     for (auto &ev : c->evpool) if (ev) cudaEventDestroy(ev);
     if (c->st_compute && c->own_compute_stream) cudaStreamDestroy(c->st_compute);
     if (c->st_copy) cudaStreamDestroy(c->st_copy);
@@ -808,37 +814,40 @@ int vfb_finish(vfb_ctx *c, vfb_table *out)
     unsigned long long ctr[3];
     VFB_CUDA(cudaMemcpy(ctr, c->tab.counters, sizeof ctr, cudaMemcpyDeviceToHost));
     const uint64_t rows = ctr[0], arena = ctr[1];
+    // The columns are compacted on the device and land in pinned host buffers owned by the
+    // context (valid until the next vfb_finish / vfb_destroy on it).
+    if ((rc = c->h_offsets.ensure((rows + 1) * 8))) return rc;
+    if ((rc = c->h_counts.ensure((rows ? rows : 1) * 8))) return rc;
     out->rows = rows;
-    out->offsets = (uint64_t *)malloc((rows + 1) * 8);
-    out->counts = (uint64_t *)malloc((rows ? rows : 1) * 8);
-    if (!out->offsets || !out->counts) { vfb_table_free(out); set_error("out of host memory"); return VFB_ERR_NOMEM; }
+    out->offsets = (uint64_t *)c->h_offsets.p;
+    out->counts = (uint64_t *)c->h_counts.p;
     out->offsets[0] = 0;
+    out->owner = c;
     if (rows == 0) {
-        out->data = (uint8_t *)malloc(1);
+        if ((rc = c->h_data.ensure(16))) return rc;
+        out->data = (uint8_t *)c->h_data.p;
         return VFB_OK;
     }
-    if ((rc = c->t_row_count.ensure(rows * 8))) { vfb_table_free(out); return rc; }
-    if ((rc = launch_export_counts(c->tab, rows, c->t_row_count.as<unsigned long long>(), c->st_compute))) { vfb_table_free(out); return rc; }
-    std::vector<uint64_t> off(rows);
-    std::vector<uint32_t> len(rows);
-    std::vector<uint8_t> ar(arena);
-    cudaError_t e;
-    if ((e = cudaMemcpyAsync(out->counts, c->t_row_count.p, rows * 8, cudaMemcpyDeviceToHost, c->st_compute)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(off.data(), c->tab.row_off, rows * 8, cudaMemcpyDeviceToHost, c->st_compute)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(len.data(), c->tab.row_len, rows * 4, cudaMemcpyDeviceToHost, c->st_compute)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(ar.data(), c->tab.arena, arena, cudaMemcpyDeviceToHost, c->st_compute)) != cudaSuccess ||
-        (e = cudaStreamSynchronize(c->st_compute)) != cudaSuccess) {
-        vfb_table_free(out);
-        return cuda_fail(e, "table download", __FILE__, __LINE__);
-    }
-    c->stats.d2h_bytes += rows * 20 + arena;
-    uint64_t total = 0;
-    for (uint64_t i = 0; i < rows; ++i) { out->offsets[i] = total; total += len[i]; }
-    out->offsets[rows] = total;
+    const uint64_t nb = (rows + 1023) / 1024;
+    if ((rc = c->t_row_count.ensure(rows * 8))) return rc;
+    if ((rc = c->x_block_sums.ensure((nb + 1) * 8))) return rc;
+    if ((rc = c->x_offsets.ensure((rows + 1) * 8))) return rc;
+    if ((rc = c->x_data.ensure(arena ? arena : 16))) return rc;
+    unsigned long long *d_total = c->x_block_sums.as<unsigned long long>() + nb;
+    if ((rc = launch_export_counts(c->tab, rows, c->t_row_count.as<unsigned long long>(), c->st_compute))) return rc;
+    if ((rc = launch_export_arrow(c->tab, rows, c->x_block_sums.as<unsigned long long>(), d_total,
+                                  c->x_offsets.as<unsigned long long>(), c->x_data.as<uint8_t>(), c->st_compute))) return rc;
+    unsigned long long total = 0;
+    VFB_CUDA(cudaMemcpyAsync(out->counts, c->t_row_count.p, rows * 8, cudaMemcpyDeviceToHost, c->st_compute));
+    VFB_CUDA(cudaMemcpyAsync(out->offsets, c->x_offsets.p, (rows + 1) * 8, cudaMemcpyDeviceToHost, c->st_compute));
+    VFB_CUDA(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, c->st_compute));
+    VFB_CUDA(cudaStreamSynchronize(c->st_compute));
+    if ((rc = c->h_data.ensure(total ? total : 16))) return rc;
+    out->data = (uint8_t *)c->h_data.p;
     out->key_bytes = total;
-    out->data = (uint8_t *)malloc(total ? total : 1);
-    if (!out->data) { vfb_table_free(out); set_error("out of host memory"); return VFB_ERR_NOMEM; }
-    for (uint64_t i = 0; i < rows; ++i) memcpy(out->data + out->offsets[i], ar.data() + off[i], len[i]);
+    if (total) VFB_CUDA(cudaMemcpyAsync(out->data, c->x_data.p, total, cudaMemcpyDeviceToHost, c->st_compute));
+    VFB_CUDA(cudaStreamSynchronize(c->st_compute));
+    c->stats.d2h_bytes += rows * 16 + 8 + total;
     bump_launches(c, before);
     return VFB_OK;
 }
@@ -846,9 +855,11 @@ int vfb_finish(vfb_ctx *c, vfb_table *out)
 void vfb_table_free(vfb_table *t)
 {
     if (!t) return;
-    free(t->offsets);
-    free(t->data);
-    free(t->counts);
+    if (!t->owner) {
+        free(t->offsets);
+        free(t->data);
+        free(t->counts);
+    }
     memset(t, 0, sizeof *t);
 }
 

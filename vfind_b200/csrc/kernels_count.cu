@@ -306,20 +306,38 @@ k4_insert(const __grid_constant__ InsertArgs a)
 }
 
 // Owners of freshly claimed slots move their key into the arena and turn the slot's
-// batch reference into a row reference.
+// batch reference into a row reference.  Row ids and arena space are claimed once per warp.
 __global__ void __launch_bounds__(256)
 k4_publish(const __grid_constant__ InsertArgs a)
 {
     const InsertJob &j = a.job;
     const DevTable &t = a.t;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= j.n_keys) return;
-    const uint32_t slot = j.owner_slot[i];
-    if (slot == VFB_NONE) return;
-    const uint32_t klen = j.klen[i];
-    const uint32_t padded = (klen + 15u) & ~15u;
-    const unsigned long long row = atomicAdd(&t.counters[0], 1ull);
-    const unsigned long long off = atomicAdd(&t.counters[1], (unsigned long long)padded);
+    const int lane = threadIdx.x & 31;
+    uint32_t slot = VFB_NONE, klen = 0;
+    if (i < j.n_keys) slot = j.owner_slot[i];
+    const bool own = slot != VFB_NONE;
+    if (own) klen = j.klen[i];
+    const unsigned m = __ballot_sync(0xffffffffu, own);
+    if (!m) return;
+    const uint32_t padded = own ? (klen + 15u) & ~15u : 0u;
+    uint32_t incl = padded;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long row0 = 0, off0 = 0;
+    if (lane == 0) {
+        row0 = atomicAdd(&t.counters[0], (unsigned long long)__popc(m));
+        off0 = atomicAdd(&t.counters[1], (unsigned long long)total);
+    }
+    row0 = __shfl_sync(0xffffffffu, row0, 0);
+    off0 = __shfl_sync(0xffffffffu, off0, 0);
+    if (!own) return;
+    const unsigned long long row = row0 + __popc(m & ((1u << lane) - 1));
+    const unsigned long long off = off0 + (incl - padded);
     const uint4 *src = reinterpret_cast<const uint4 *>(job_key(j, i));
     uint4 *dst = reinterpret_cast<uint4 *>(t.arena + off);
     for (uint32_t c = 0; c < padded / 16; ++c) dst[c] = src[c];
@@ -389,6 +407,130 @@ int launch_export_counts(const DevTable &t, uint64_t rows, unsigned long long *r
     if (blocks > 148 * 16) blocks = 148 * 16;
     k4_export_counts<<<(uint32_t)blocks, 256, 0, st>>>(t, row_count);
     ++g_launches;
+    VFB_CUDA(cudaGetLastError());
+    return VFB_OK;
+}
+
+// ------------------------------------------------------------------------------------ export
+// Arrow-style compaction of the table on the device: offsets = exclusive scan of the row
+// lengths, data = the keys back to back (the arena pads every key to 16 bytes).
+#define EXP_ROWS 1024   // rows per block
+
+__global__ void __launch_bounds__(256)
+k_export_sums(const uint32_t *__restrict__ row_len, uint64_t rows, unsigned long long *__restrict__ block_sums)
+{
+    __shared__ unsigned long long s_part[8];
+    const uint64_t r0 = (uint64_t)blockIdx.x * EXP_ROWS;
+    unsigned long long acc = 0;
+    for (uint32_t k = threadIdx.x; k < EXP_ROWS; k += 256)
+        if (r0 + k < rows) acc += row_len[r0 + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 8; ++w) t += s_part[w];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+// exclusive scan of the block sums, in place, by one block
+__global__ void __launch_bounds__(1024)
+k_export_scan(unsigned long long *block_sums, uint64_t n_blocks, unsigned long long *total)
+{
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint64_t base = 0; base < n_blocks; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const unsigned long long v = i < n_blocks ? block_sums[i] : 0ull;
+        unsigned long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = s_warp[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long u = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += u;
+            }
+            s_warp[lane] = wi - w;      // exclusive over warps
+        }
+        __syncthreads();
+        const unsigned long long carry = s_carry;
+        if (i < n_blocks) block_sums[i] = carry + s_warp[warp] + (incl - v);
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_warp[warp] + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = s_carry;
+}
+
+__global__ void __launch_bounds__(256)
+k_export_gather(const DevTable t, uint64_t rows, const unsigned long long *__restrict__ block_off,
+                unsigned long long *__restrict__ offsets, uint8_t *__restrict__ data)
+{
+    __shared__ unsigned long long s_off[EXP_ROWS];
+    __shared__ unsigned long long s_warp[8];
+    const uint64_t r0 = (uint64_t)blockIdx.x * EXP_ROWS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // each thread owns 4 consecutive rows of the block
+    uint32_t len[4];
+    unsigned long long mine = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint64_t r = r0 + threadIdx.x * 4 + k;
+        len[k] = r < rows ? t.row_len[r] : 0u;
+        mine += len[k];
+    }
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned long long wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += s_warp[w];
+    unsigned long long o = block_off[blockIdx.x] + wbase + (incl - mine);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint64_t r = r0 + threadIdx.x * 4 + k;
+        s_off[threadIdx.x * 4 + k] = o;
+        if (r < rows) offsets[r] = o;
+        o += len[k];
+        if (r + 1 == rows) offsets[rows] = o;
+    }
+    __syncthreads();
+    // copy: one warp per row, lanes over bytes
+    for (uint32_t k = warp; k < EXP_ROWS; k += 8) {
+        const uint64_t r = r0 + k;
+        if (r >= rows) break;
+        const uint32_t n = t.row_len[r];
+        const uint8_t *src = t.arena + t.row_off[r];
+        uint8_t *dst = data + s_off[k];
+        for (uint32_t b = lane; b < n; b += 32) dst[b] = src[b];
+    }
+}
+
+int launch_export_arrow(const DevTable &t, uint64_t rows, unsigned long long *block_sums,
+                        unsigned long long *total, unsigned long long *offsets, uint8_t *data, cudaStream_t st)
+{
+    if (rows == 0) return VFB_OK;
+    const uint64_t nb = (rows + EXP_ROWS - 1) / EXP_ROWS;
+    k_export_sums<<<(uint32_t)nb, 256, 0, st>>>(t.row_len, rows, block_sums);
+    k_export_scan<<<1, 1024, 0, st>>>(block_sums, nb, total);
+    k_export_gather<<<(uint32_t)nb, 256, 0, st>>>(t, rows, block_sums, offsets, data);
+    g_launches += 3;
     VFB_CUDA(cudaGetLastError());
     return VFB_OK;
 }

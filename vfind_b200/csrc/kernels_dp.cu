@@ -109,11 +109,12 @@ struct DpKernelArgs {
 // Resident CTAs per SM the register budget is tuned for.
 template <int AMAX> struct DpOcc { static constexpr int value = AMAX <= 20 ? 6 : (AMAX <= 28 ? 4 : (AMAX <= 44 ? 3 : 2)); };
 
-template <int AMAX, bool USE_IMAD>
+template <int AMAX, bool EXACT>
 __global__ void __launch_bounds__(DP_THREADS, DpOcc<AMAX>::value)
 k2_dp_packed(const __grid_constant__ DpKernelArgs args)
 {
     constexpr int NG = AMAX / 4;
+    constexpr bool USE_IMAD = true;     // adds as IMAD (x*1+c): they issue on the FMA pipe, not the ALU pipe
     extern __shared__ __align__(16) unsigned char smem[];
     int4 *prof = reinterpret_cast<int4 *>(smem);                 // [NG][8] : rows 4g..4g+3 at code c
     uint8_t *lut = smem + NG * 8 * sizeof(int4);                 // byte -> 16 * code
@@ -214,9 +215,11 @@ k2_dp_packed(const __grid_constant__ DpKernelArgs args)
                 }
                 // last row (row A, which is one of the four bottom register rows)
                 int hA = H[AMAX - 1];
-                if (A == AMAX - 1) hA = H[AMAX - 2];
-                if (A == AMAX - 2) hA = H[AMAX - 3];
-                if (A == AMAX - 3) hA = H[AMAX - 4];
+                if (!EXACT) {
+                    if (A == AMAX - 1) hA = H[AMAX - 2];
+                    if (A == AMAX - 2) hA = H[AMAX - 3];
+                    if (A == AMAX - 3) hA = H[AMAX - 4];
+                }
                 if (hA > bestcap) { best = hA; bestcap = hA | lowmask; bestj = m * 16 + k + 1; }
             }
             // chunk m+2 lands in the ring, chunk m+3 takes off
@@ -258,14 +261,16 @@ k2_dp_packed(const __grid_constant__ DpKernelArgs args)
 template <int AMAX>
 static int launch_one(const DpKernelArgs &args, int sm_count, cudaStream_t st)
 {
-    auto kern = k2_dp_packed<AMAX, true>;
+    const bool exact = (int)args.job.adapter_len == AMAX;
+    auto kern = exact ? k2_dp_packed<AMAX, true> : k2_dp_packed<AMAX, false>;
     size_t smem = (AMAX / 4) * 8 * sizeof(int4) + 256 + DP_WARPS * 32 * DP_ROW;
-    static int blocks_per_sm = 0;
-    if (!blocks_per_sm) {
-        VFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, DP_THREADS, smem));
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    static int blocks_per_sm[2] = {0, 0};
+    int &bps = blocks_per_sm[exact ? 1 : 0];
+    if (!bps) {
+        VFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, DP_THREADS, smem));
+        if (bps < 1) bps = 1;
     }
-    kern<<<sm_count * blocks_per_sm, DP_THREADS, smem, st>>>(args);
+    kern<<<sm_count * bps, DP_THREADS, smem, st>>>(args);
     ++g_launches;
     VFB_CUDA(cudaGetLastError());
     return VFB_OK;

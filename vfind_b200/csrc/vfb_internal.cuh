@@ -164,6 +164,10 @@ struct InsertJob {
 int launch_insert(const DevTable &t, const InsertJob &job, cudaStream_t st);
 int launch_rehash(const DevTable &old_t, const DevTable &new_t, cudaStream_t st);
 int launch_export_counts(const DevTable &t, uint64_t rows, unsigned long long *row_count, cudaStream_t st);
+// offsets[rows+1] (exclusive scan of row lengths) and the keys back to back; block_sums holds
+// ceil(rows/1024) words of scratch, *total receives the number of key bytes.
+int launch_export_arrow(const DevTable &t, uint64_t rows, unsigned long long *block_sums,
+                        unsigned long long *total, unsigned long long *offsets, uint8_t *data, cudaStream_t st);
 
 // ---------------------------------------------------------------- merge chunks
 // Chunk layout (all sections 16-byte aligned):
