@@ -453,6 +453,29 @@ def test_file_ingest_variants(tmp_path, golden):
     got = rows(find_variants(str(p), (PREFIX.decode(), SUFFIX.decode()), accept_prefix_alignment=0.6))
     want = oracle.find_variants_file(str(p), (PREFIX, SUFFIX), n_threads=8, accept_prefix_alignment=0.6)
     assert {k.encode(): v for k, v in got.items()} == want
+    # chunked ingest: records straddling chunk boundaries are carried over (tiny chunks force it)
+    import os
+    for chunk in ("700", "4096", "100000"):
+        os.environ["VFB_INGEST_CHUNK"] = chunk
+        try:
+            got2 = rows(find_variants(str(p), (PREFIX.decode(), SUFFIX.decode()), accept_prefix_alignment=0.6))
+        finally:
+            del os.environ["VFB_INGEST_CHUNK"]
+        assert got2 == got, chunk
+    # a malformed record in the middle of a large file is reported with its index
+    recs2 = list(recs)
+    recs2[20000] = ("bad", "ACGT", "FFF")
+    pb = write_fastq_gz(tmp_path / "bigbad.fq.gz", recs2, members=2)
+    with pytest.raises(PanicException, match="record 20000"):
+        find_variants(str(pb), ad)
+    blank = tmp_path / "blank.fq.gz"
+    import gzip as _gz
+    blank.write_bytes(_gz.compress(b"@r\nACGT\n+\nFFFF\n\n\n\r\n"))
+    assert rows(find_variants(str(blank), ad)) == {}
+    mid = tmp_path / "mid.fq.gz"
+    mid.write_bytes(_gz.compress(b"@r\nACGT\n+\nFFFF\n\n@q\nACGT\n+\nFFFF\n"))
+    with pytest.raises(PanicException):
+        find_variants(str(mid), ad)
     # empty file -> empty table with both columns (Q12)
     e = tmp_path / "e.fq.gz"
     import gzip

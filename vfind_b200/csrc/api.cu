@@ -140,6 +140,10 @@ struct vfb_ctx {
     DevBuf t_slots, t_counts, t_row_hash, t_row_off, t_row_len, t_arena, t_counters, t_row_count;
     uint64_t ub_rows = 0, ub_arena = 0;   // host-side upper bounds of rows / arena bytes
 
+    // ingest: GPU FASTQ parse scratch and the first-malformed-record word
+    DevBuf p_tiles, p_line_end, p_err;      // p_err: u32 chunk-relative + u64 global (at +8)
+    bool p_err_init = false;
+
     // export: device-side Arrow compaction and pinned host columns
     DevBuf x_block_sums, x_offsets, x_data;
     PinBuf h_offsets, h_counts, h_data;
@@ -463,6 +467,7 @@ int vfb_destroy(vfb_ctx *c)
                       &c->m_part_rows, &c->m_part_keys, &c->m_cursors, &c->m_chunk_off};
     for (auto *b : bufs) b->release();
     c->x_block_sums.release(); c->x_offsets.release(); c->x_data.release();
+    c->p_tiles.release(); c->p_line_end.release(); c->p_err.release();
     c->h_offsets.release(); c->h_counts.release(); c->h_data.release();
     for (auto &ev : c->evpool) if (ev) cudaEventDestroy(ev);
     if (c->st_compute && c->own_compute_stream) cudaStreamDestroy(c->st_compute);
@@ -730,6 +735,74 @@ int vfb_submit_host(vfb_ctx *c, const uint8_t *text, uint64_t text_bytes, const 
     bump_launches(c, before);
     return rc;
 }
+
+}  // extern "C"
+
+__global__ void k_parse_err_fold(uint32_t *err32, unsigned long long base, unsigned long long *global)
+{
+    if (*err32 != 0xFFFFFFFFu) atomicMin(global, base + *err32);
+    *err32 = 0xFFFFFFFFu;
+}
+
+int vfb_internal_submit_fastq(vfb_ctx *c, const uint8_t *pinned_text, uint64_t n_bytes, uint64_t n_lines,
+                              uint64_t record_base, cudaEvent_t copied)
+{
+    if (n_bytes > 0xFFFFFFF0ull || n_lines > 0xFFFFFFF0ull) { set_error("ingest chunk too large"); return VFB_ERR_ARG; }
+    VFB_CUDA(cudaSetDevice(c->device));
+    const uint64_t before = g_launches;
+    const uint32_t n_rec = (uint32_t)(n_lines / 4);
+    int rc;
+    if (!c->p_err_init) {
+        if ((rc = c->p_err.ensure(16))) return rc;
+        VFB_CUDA(cudaMemsetAsync(c->p_err.p, 0xFF, 16, c->st_compute));
+        c->p_err_init = true;
+    }
+    Slot &s = c->slots[c->batch_seq & 1];
+    if (s.busy) { VFB_CUDA(cudaEventSynchronize(s.computed)); s.busy = false; }
+    if ((rc = s.d_text.ensure(n_bytes + 32))) return rc;
+    if ((rc = s.d_spans.ensure((size_t)(n_rec ? n_rec : 1) * sizeof(vfb_span)))) return rc;
+    if ((rc = c->p_tiles.ensure(parse_tile_words((uint32_t)n_bytes) * 8 + 8))) return rc;
+    if ((rc = c->p_line_end.ensure((n_lines ? n_lines : 1) * 4))) return rc;
+    VFB_CUDA(cudaMemcpyAsync(s.d_text.p, pinned_text, n_bytes, cudaMemcpyHostToDevice, c->st_copy));
+    if (copied) VFB_CUDA(cudaEventRecord(copied, c->st_copy));
+    VFB_CUDA(cudaEventRecord(s.copied, c->st_copy));
+    VFB_CUDA(cudaStreamWaitEvent(c->st_compute, s.copied, 0));
+    c->stats.h2d_bytes += n_bytes;
+    if (n_rec) {
+        if ((rc = launch_parse(s.d_text.as<uint8_t>(), (uint32_t)n_bytes, (uint32_t)n_lines, n_rec,
+                               c->p_tiles.as<unsigned long long>(), c->p_line_end.as<uint32_t>(),
+                               s.d_spans.as<vfb_span>(), c->p_err.as<uint32_t>(), c->st_compute))) return rc;
+        k_parse_err_fold<<<1, 1, 0, c->st_compute>>>(c->p_err.as<uint32_t>(), record_base,
+                                                     reinterpret_cast<unsigned long long *>(c->p_err.as<uint8_t>() + 8));
+        ++g_launches;
+        // batches inside the chunk
+        uint32_t done = 0;
+        while (done < n_rec) {
+            const uint32_t n = n_rec - done < c->batch_reads ? n_rec - done : (uint32_t)c->batch_reads;
+            if ((rc = process_batch(c, s.d_text.as<uint8_t>(), s.d_spans.as<vfb_span>() + done, n, n_bytes))) return rc;
+            done += n;
+        }
+    }
+    VFB_CUDA(cudaEventRecord(s.computed, c->st_compute));
+    s.busy = true;
+    ++c->batch_seq;
+    bump_launches(c, before);
+    return VFB_OK;
+}
+
+int vfb_internal_parse_error(vfb_ctx *c, uint64_t *first_bad)
+{
+    *first_bad = UINT64_MAX;
+    if (!c->p_err_init) return VFB_OK;
+    unsigned long long v = 0;
+    VFB_CUDA(cudaMemcpy(&v, c->p_err.as<uint8_t>() + 8, 8, cudaMemcpyDeviceToHost));
+    *first_bad = v;
+    // re-arm
+    VFB_CUDA(cudaMemset(c->p_err.p, 0xFF, 16));
+    return VFB_OK;
+}
+
+extern "C" {
 
 int vfb_sync(vfb_ctx *c)
 {

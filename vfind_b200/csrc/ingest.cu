@@ -1,16 +1,28 @@
-// Ingest: gzip (multi-member) FASTQ file -> inflate -> record parse -> vfb_submit_host.
+// Ingest: gzip (multi-member) FASTQ file -> inflate -> pinned chunks -> async H2D -> GPU parse
+// -> the hot loop.
 //
 // Replaces `File::open(fq_path).map(MultiGzDecoder::new)` + `seq_io::fastq::Reader` +
 // `parallel_fastq` of /root/reference/src/lib.rs:233-234, :271-308 (flate2 1.1.1 /
 // seq_io 0.3.4).  Grammar: gzip only; strict 4-line records — '@' header, one
 // sequence line, '+' line, quality of the same length; "\r\n" trimmed; a missing final
-// newline and trailing blank lines are tolerated.  Only the sequence line reaches the GPU:
-// the inflated text is uploaded as is and reads are (offset, length) spans into it.
+// newline and trailing blank lines are tolerated.
+//
+// Pipeline: a producer thread inflates straight into one of three pinned chunk buffers,
+// counts newlines as it goes and cuts the chunk at the last 4-line boundary (the remainder is
+// carried into the next chunk).  The calling thread queues each chunk on the GPU: H2D copy on
+// the copy stream, record framing / validation / span extraction on the device
+// (kernels_parse.cu), then K1..K4.  The host never looks at a record.
 #include <zlib.h>
 
+#include <cerrno>
+#include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "vfb_internal.cuh"
@@ -70,6 +82,35 @@ struct Inflater {
     }
 };
 
+size_t count_nl(const uint8_t *p, size_t n)
+{
+    size_t c = 0;
+    const uint8_t *e = p + n;
+    while (p < e) {
+        const uint8_t *q = (const uint8_t *)memchr(p, '\n', (size_t)(e - p));
+        if (!q) break;
+        ++c;
+        p = q + 1;
+    }
+    return c;
+}
+
+struct Chunk {
+    uint8_t *buf = nullptr;
+    size_t cut = 0;        // bytes to submit (ends at a record boundary)
+    size_t lines = 0;      // complete lines in [0, cut)
+    cudaEvent_t copied = nullptr;
+};
+
+struct Pipe {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<int> free_q, ready_q;
+    bool done = false, failed = false, abort = false;
+    std::string err;
+    int err_code = VFB_OK;
+};
+
 }  // namespace
 
 extern "C" int vfb_run_file(vfb_ctx *ctx, const char *path, uint64_t *n_reads_out)
@@ -81,79 +122,147 @@ extern "C" int vfb_run_file(vfb_ctx *ctx, const char *path, uint64_t *n_reads_ou
         set_error(std::string("cannot open ") + path + ": " + strerror(errno));
         return VFB_ERR_IO;
     }
-    // chunk size: large enough to amortise launches, small enough for toy files
     fseek(inf.f, 0, SEEK_END);
-    long fsz = ftell(inf.f);
+    const long fsz = ftell(inf.f);
     fseek(inf.f, 0, SEEK_SET);
-    size_t chunk = (size_t)1 << 28;
-    if (fsz >= 0 && (size_t)fsz * 8 + 4096 < chunk) chunk = (size_t)fsz * 8 + 4096;
-    std::vector<uint8_t> buf(chunk);
-    std::vector<vfb_span> spans;
-    size_t carry = 0;            // bytes of an incomplete record kept at the front of buf
-    uint64_t n_total = 0;
-    bool at_end = false;
-    std::string err;
-    while (!at_end) {
-        long long got = inf.read(buf.data() + carry, buf.size() - carry, &err);
-        if (got < 0) { set_error(err); return VFB_ERR_FORMAT; }
-        size_t have = carry + (size_t)got;
-        if ((size_t)got < buf.size() - carry) at_end = true;
-        // parse complete records
-        spans.clear();
-        size_t p = 0;
-        while (p < have) {
-            size_t ls[4], ll[4];
-            size_t q = p;
-            bool complete = true;
-            for (int l = 0; l < 4; ++l) {
-                if (q >= have && !(at_end && l == 3 && q == have)) { complete = false; break; }
-                const uint8_t *nl = q < have ? (const uint8_t *)memchr(buf.data() + q, '\n', have - q) : nullptr;
-                size_t e;
-                if (nl) e = (size_t)(nl - buf.data());
-                else if (at_end && l == 3) e = have;      // final newline missing
-                else { complete = false; break; }
-                size_t ee = e;
-                if (ee > q && buf[ee - 1] == '\r') --ee;
-                ls[l] = q; ll[l] = ee - q;
-                q = nl ? e + 1 : have;
+    size_t cap = (size_t)128 << 20;
+    if (const char *e = getenv("VFB_INGEST_CHUNK")) cap = (size_t)strtoull(e, nullptr, 10);
+    else if (fsz >= 0 && (size_t)fsz * 12 + 65536 < cap) cap = (size_t)fsz * 12 + 65536;
+    if (cap < 256) cap = 256;
+
+    constexpr int NCH = 3;
+    Chunk ch[NCH];
+    Pipe pp;
+    int rc = VFB_OK;
+    for (int i = 0; i < NCH; ++i) {
+        void *p = nullptr;
+        if (cudaMallocHost(&p, cap + 64) != cudaSuccess || cudaEventCreateWithFlags(&ch[i].copied, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("cannot allocate pinned ingest buffers");
+            rc = VFB_ERR_NOMEM;
+        }
+        ch[i].buf = (uint8_t *)p;
+        pp.free_q.push_back(i);
+    }
+
+    std::thread producer;
+    if (rc == VFB_OK) producer = std::thread([&]() {
+        std::vector<uint8_t> carry;
+        bool at_end = false;
+        auto fail = [&](int code, const std::string &m) {
+            std::lock_guard<std::mutex> lk(pp.mu);
+            pp.failed = true; pp.err = m; pp.err_code = code; pp.done = true;
+            pp.cv.notify_all();
+        };
+        while (!at_end) {
+            int k;
+            {
+                std::unique_lock<std::mutex> lk(pp.mu);
+                pp.cv.wait(lk, [&] { return !pp.free_q.empty() || pp.abort; });
+                if (pp.abort) return;
+                k = pp.free_q.front();
+                pp.free_q.pop_front();
             }
-            if (!complete) {
-                if (at_end) {
-                    // only blank lines may remain
-                    bool blank = true;
-                    for (size_t k = p; k < have; ++k) if (buf[k] != '\n' && buf[k] != '\r') { blank = false; break; }
-                    if (!blank) { set_error("truncated FASTQ record " + std::to_string(n_total + spans.size())); return VFB_ERR_FORMAT; }
-                    p = have;
-                }
-                break;
+            Chunk &c = ch[k];
+            if (carry.size() >= cap) { fail(VFB_ERR_FORMAT, "a FASTQ record is larger than the ingest chunk"); return; }
+            size_t used = carry.size();
+            if (used) memcpy(c.buf, carry.data(), used);
+            size_t lines = count_nl(c.buf, used);
+            std::string err;
+            while (used < cap && !at_end) {
+                const size_t want = cap - used < ((size_t)4 << 20) ? cap - used : ((size_t)4 << 20);
+                const long long got = inf.read(c.buf + used, want, &err);
+                if (got < 0) { fail(VFB_ERR_FORMAT, err); return; }
+                if ((size_t)got < want) at_end = true;
+                lines += count_nl(c.buf + used, (size_t)got);
+                used += (size_t)got;
             }
+            size_t cut = used, keep_lines = lines;
             if (at_end) {
-                // a tail made only of newlines is not a record
-                bool blank = true;
-                for (size_t k = p; k < have; ++k) if (buf[k] != '\n' && buf[k] != '\r') { blank = false; break; }
-                if (blank) { p = have; break; }
+                // trailing blank lines are tolerated, and so is a missing final newline
+                while (used && (c.buf[used - 1] == '\n' || c.buf[used - 1] == '\r')) --used;
+                if (used) c.buf[used++] = '\n';            // cap + 64 bytes were allocated
+                lines = count_nl(c.buf, used);
+                if (lines % 4) { fail(VFB_ERR_FORMAT, "truncated FASTQ record at the end of the input"); return; }
+                cut = used;
+                keep_lines = lines;
+                carry.clear();
+            } else {
+                const size_t rem = lines % 4;
+                keep_lines = lines - rem;
+                // cut just after newline number keep_lines: walk back over the last `rem` newlines
+                size_t end = used;
+                for (size_t s = 0; s <= rem && keep_lines; ++s) {
+                    const void *q = end ? memrchr(c.buf, '\n', end) : nullptr;
+                    end = q ? (size_t)((const uint8_t *)q - c.buf) : 0;
+                }
+                cut = keep_lines ? end + 1 : 0;
+                carry.assign(c.buf + cut, c.buf + used);
             }
-            const uint64_t rec = n_total + spans.size();
-            if (ll[0] == 0 || buf[ls[0]] != '@') { set_error("FASTQ record " + std::to_string(rec) + ": expected '@'"); return VFB_ERR_FORMAT; }
-            if (ll[2] == 0 || buf[ls[2]] != '+') { set_error("FASTQ record " + std::to_string(rec) + ": expected '+'"); return VFB_ERR_FORMAT; }
-            if (ll[1] != ll[3]) { set_error("FASTQ record " + std::to_string(rec) + ": sequence and quality lengths differ"); return VFB_ERR_FORMAT; }
-            spans.push_back(vfb_span{(uint32_t)ls[1], (uint32_t)ll[1]});
-            p = q;
+            c.cut = cut;
+            c.lines = keep_lines;
+            {
+                std::lock_guard<std::mutex> lk(pp.mu);
+                pp.ready_q.push_back(k);
+                if (at_end) pp.done = true;
+                pp.cv.notify_all();
+            }
         }
-        if (!spans.empty()) {
-            int rc = vfb_submit_host(ctx, buf.data(), p, spans.data(), spans.size());
-            if (rc) return rc;
-            // the submit staged the bytes into pinned memory; buf may be reused
-            n_total += spans.size();
+    });
+
+    uint64_t n_total = 0;
+    std::deque<int> in_flight;
+    while (rc == VFB_OK) {
+        int k = -1;
+        {
+            std::unique_lock<std::mutex> lk(pp.mu);
+            pp.cv.wait(lk, [&] { return !pp.ready_q.empty() || pp.done; });
+            if (!pp.ready_q.empty()) { k = pp.ready_q.front(); pp.ready_q.pop_front(); }
+            else if (pp.failed) { set_error(pp.err); rc = pp.err_code; break; }
+            else break;     // done and drained
         }
-        carry = have - p;
-        if (carry == buf.size()) {
-            // one record larger than the chunk: grow
-            buf.resize(buf.size() * 2);
+        Chunk &c = ch[k];
+        if (c.lines) {
+            rc = vfb_internal_submit_fastq(ctx, c.buf, c.cut, c.lines, n_total, c.copied);
+            n_total += c.lines / 4;
+        } else if (cudaEventRecord(c.copied, 0) != cudaSuccess) {
+            cudaGetLastError();
         }
-        if (carry && p) memmove(buf.data(), buf.data() + p, carry);
-        if (at_end && carry) { set_error("truncated FASTQ record " + std::to_string(n_total)); return VFB_ERR_FORMAT; }
+        in_flight.push_back(k);
+        // hand buffers back to the producer once their H2D copy has finished; keep at most one
+        // copy outstanding beyond the newest so the producer always has a buffer to fill
+        while (rc == VFB_OK && in_flight.size() > 1) {
+            const int o = in_flight.front();
+            if (cudaEventSynchronize(ch[o].copied) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "ingest event", __FILE__, __LINE__); break; }
+            in_flight.pop_front();
+            std::lock_guard<std::mutex> lk(pp.mu);
+            pp.free_q.push_back(o);
+            pp.cv.notify_all();
+        }
+    }
+    {
+        std::lock_guard<std::mutex> lk(pp.mu);
+        pp.abort = true;
+        pp.cv.notify_all();
+    }
+    if (producer.joinable()) producer.join();
+    if (rc == VFB_OK && pp.failed) { set_error(pp.err); rc = pp.err_code; }
+    // the malformed-record flag comes back from the device
+    int src = vfb_sync(ctx);
+    if (rc == VFB_OK) rc = src;
+    if (rc == VFB_OK) {
+        uint64_t bad = UINT64_MAX;
+        rc = vfb_internal_parse_error(ctx, &bad);
+        if (rc == VFB_OK && bad != UINT64_MAX) {
+            set_error("FASTQ record " + std::to_string(bad) +
+                      ": malformed (expected '@' header, '+' separator, sequence and quality of equal length)");
+            rc = VFB_ERR_FORMAT;
+        }
+    }
+    for (int i = 0; i < NCH; ++i) {
+        if (ch[i].buf) cudaFreeHost(ch[i].buf);
+        if (ch[i].copied) cudaEventDestroy(ch[i].copied);
     }
     if (n_reads_out) *n_reads_out = n_total;
-    return VFB_OK;
+    return rc;
 }

@@ -191,6 +191,14 @@ int launch_partition_fill(const DevTable &t, uint64_t rows, uint32_t n_parts,
                           const uint64_t *d_part_keybytes, unsigned long long *cursors,
                           cudaStream_t st);
 
+// ---------------------------------------------------------------- FASTQ parse (ingest)
+// d_text holds n_lines complete lines (n_records = n_lines / 4 records, text starts at a record
+// boundary, every line ends with a newline).  tile_scratch: parse_tile_words(n_bytes) u64.
+int launch_parse(const uint8_t *d_text, uint32_t n_bytes, uint32_t n_lines, uint32_t n_records,
+                 unsigned long long *tile_scratch, uint32_t *line_end, vfb_span *spans, uint32_t *err,
+                 cudaStream_t st);
+uint64_t parse_tile_words(uint32_t n_bytes);
+
 // ---------------------------------------------------------------- misc
 int launch_synth(const vfb_synth_cfg &cfg, uint64_t first, uint64_t n, uint8_t *d_text,
                  vfb_span *d_spans, cudaStream_t st);
@@ -198,3 +206,11 @@ int measure_int_peak(int device, double *alu_gops, double *dual_gops);
 
 extern thread_local uint64_t g_launches;   // kernels launched by this thread's calls
 }  // namespace vfb
+
+// Internal hooks between ingest.cu and api.cu (not part of the C ABI).
+// Queue one chunk of inflated FASTQ text held in PINNED host memory: H2D copy, GPU parse, the
+// hot loop.  `copied` is recorded on the copy stream once the host buffer may be reused.
+int vfb_internal_submit_fastq(vfb_ctx *ctx, const uint8_t *pinned_text, uint64_t n_bytes, uint64_t n_lines,
+                              uint64_t record_base, cudaEvent_t copied);
+// After vfb_sync: global index of the first malformed record, or UINT64_MAX.
+int vfb_internal_parse_error(vfb_ctx *ctx, uint64_t *first_bad_record);
