@@ -251,6 +251,26 @@ def test_scan_unaligned_text_offsets():
     assert got == want
 
 
+def test_submit_device_unaligned_buffer():
+    # a caller's device buffer whose ends are not 16-byte aligned: the library must not read
+    # outside it (it runs on an aligned copy) and results must not change
+    torch = pytest.importorskip("torch")
+    rng = random.Random(22)
+    seqs = make_reads(rng, PREFIX, SUFFIX, 4000)
+    text, off, ln = oracle.pack_reads(seqs)
+    want, odiag, _ = oracle_run(seqs, (PREFIX, SUFFIX))
+    for shift in (0, 1, 3, 7, 13):
+        big = torch.full((len(text) + 64,), ord("G"), dtype=torch.uint8, device="cuda")
+        big[shift:shift + len(text)] = torch.from_numpy(text.copy()).cuda()
+        sp = torch.from_numpy(np.stack([off, ln], 1).astype(np.uint32).view(np.int32).copy()).cuda()
+        with api.Context((PREFIX, SUFFIX), diagnostics=True) as ctx:
+            ctx.submit_device(big.data_ptr() + shift, len(text), sp.data_ptr(), len(seqs))
+            diag = ctx.diag(len(seqs))
+            got = ctx.finish_dict()
+        assert_diag_equal(diag, odiag)
+        assert got == want
+
+
 def test_threshold_one_disables_alignment():
     rng = random.Random(8)
     seqs = make_reads(rng, PREFIX, SUFFIX, 800)

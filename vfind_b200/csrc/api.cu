@@ -131,6 +131,7 @@ struct vfb_ctx {
     // per-batch scratch
     DevBuf d_start, d_end, d_list_a, d_list_b, d_fb_a, d_fb_b, d_c32, d_t64;
     DevBuf d_keys, d_koff, d_klen, d_khash, d_owner;
+    DevBuf d_aligned_text;     // aligned copy of an unaligned caller buffer (vfb_submit_device)
     DevBuf d_diag_exact_pre, d_diag_exact_suf, d_diag_score_pre, d_diag_len_pre, d_diag_score_suf, d_diag_len_suf;
     uint64_t diag_n = 0;
     bool diag_valid = false;
@@ -467,6 +468,7 @@ int vfb_destroy(vfb_ctx *c)
                       &c->m_part_rows, &c->m_part_keys, &c->m_cursors, &c->m_chunk_off};
     for (auto *b : bufs) b->release();
     c->x_block_sums.release(); c->x_offsets.release(); c->x_data.release();
+    c->d_aligned_text.release();
     c->p_tiles.release(); c->p_line_end.release(); c->p_err.release();
     c->h_offsets.release(); c->h_counts.release(); c->h_data.release();
     for (auto &ev : c->evpool) if (ev) cudaEventDestroy(ev);
@@ -665,11 +667,22 @@ int vfb_submit_device(vfb_ctx *c, const uint8_t *d_text, uint64_t text_bytes, co
     const uint64_t before = g_launches;
     uint64_t done = 0;
     int rc = VFB_OK;
+    // The kernels pull 16-byte ALIGNED chunks around each read.  That stays inside the caller's
+    // buffer iff both of its ends are 16-byte aligned; otherwise the text is first copied into
+    // an aligned, padded buffer of ours (one extra pass over it) so that no load can leave
+    // memory the caller handed over.
+    const uintptr_t a_lo = reinterpret_cast<uintptr_t>(d_text), a_hi = a_lo + text_bytes;
+    if ((a_lo | a_hi) & 15u) {
+        const size_t shift = a_lo & 15u;
+        if ((rc = c->d_aligned_text.ensure(text_bytes + 48))) return rc;
+        uint8_t *dst = c->d_aligned_text.as<uint8_t>() + shift;      // same alignment phase as the source
+        VFB_CUDA(cudaMemcpyAsync(dst, d_text, text_bytes, cudaMemcpyDeviceToDevice, c->st_compute));
+        d_text = dst;
+    }
     while (done < n_reads) {
         const uint64_t n = n_reads - done < c->batch_reads ? n_reads - done : c->batch_reads;
-        // key space bound: this batch's share of the text, conservatively the whole buffer
-        const uint64_t share = n == n_reads ? text_bytes : text_bytes;
-        if ((rc = process_batch(c, d_text, d_spans + done, (uint32_t)n, share))) break;
+        // key space bound: conservatively the whole buffer
+        if ((rc = process_batch(c, d_text, d_spans + done, (uint32_t)n, text_bytes))) break;
         done += n;
     }
     bump_launches(c, before);
@@ -704,7 +717,7 @@ int vfb_submit_host(vfb_ctx *c, const uint8_t *text, uint64_t text_bytes, const 
         const uint64_t bytes = hi - lo;
         Slot &s = c->slots[c->batch_seq & 1];
         if (s.busy) { VFB_CUDA(cudaEventSynchronize(s.computed)); s.busy = false; }
-        if ((rc = s.d_text.ensure(bytes + 16))) break;
+        if ((rc = s.d_text.ensure(bytes + 32))) break;     // aligned 16-byte loads may run past the last read
         if ((rc = s.d_spans.ensure(n * sizeof(vfb_span)))) break;
         const uint8_t *src_text = text + lo;
         const vfb_span *src_spans = spans + done;
