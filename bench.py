@@ -220,6 +220,22 @@ def main():
         for _ in range(args.warmup):
             step_device()
         barrier()
+        merge_check = None
+        if world > 1:
+            # untimed sanity check of the merge: partitions are disjoint by construction, so the
+            # counts summed over ranks must equal the reads counted over ranks before the merge
+            ctx.table_clear()
+            for t, s, n in chunks:
+                ctx.submit_device(t.data_ptr(), t.numel(), s.data_ptr(), n)
+            before = torch.tensor([ctx.stats()["counted"]], dtype=torch.int64, device=dev)
+            merge_tables(ctx, device=dev)
+            _, _, cnts = ctx.finish_arrays(copy=False)
+            after = torch.tensor([int(cnts.sum()), len(cnts)], dtype=torch.int64, device=dev)
+            dist.all_reduce(before)
+            dist.all_reduce(after)
+            merge_check = {"counted_before": int(before[0]), "counted_after": int(after[0]),
+                           "rows_total": int(after[1]), "ok": int(before[0]) == int(after[0])}
+            barrier()
         ctx.reset()
         ctx.set_profiling(True)
         sampler = ClockSampler(local)
@@ -351,7 +367,7 @@ def main():
         "roofline": roofline, "roofline_hbm": roofline_hbm, "stages_ms_per_step": stages,
         "dp": {"gcups": gcups, "cells_per_step": st["dp_cells"] // args.steps,
                "alignments_per_step": (st["dp_prefix"] + st["dp_suffix"]) // args.steps},
-        "table": {"unique": st["unique"], "counted_per_step": st["counted"]},
+        "table": {"unique": st["unique"], "counted_per_step": st["counted"], "merge_check": merge_check},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
