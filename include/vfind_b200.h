@@ -153,6 +153,13 @@ int vfb_submit_device(vfb_ctx *ctx, const uint8_t *d_text, uint64_t text_bytes,
  * opened, VFB_ERR_FORMAT on malformed gzip/FASTQ. */
 int vfb_run_file(vfb_ctx *ctx, const char *path, uint64_t *n_reads);
 
+/* Host-only front half of vfb_run_file (no GPU needed): inflate `path` chunk by chunk exactly as
+ * the ingest does (serial gzip, or member-parallel on n_threads for block-gzip/BGZF input) and
+ * return the submitted text, the complete lines in it and the number of chunks.  `out` may be
+ * NULL to only count.  For tests of the inflate / cut / carry logic. */
+int vfb_debug_inflate_file(const char *path, uint32_t n_threads, uint8_t *out, uint64_t out_cap,
+                           uint64_t *n_bytes, uint64_t *n_lines, uint64_t *n_chunks);
+
 int vfb_sync(vfb_ctx *ctx);
 
 /* Queue all kernels on the caller's CUDA stream (a cudaStream_t) instead of the context's

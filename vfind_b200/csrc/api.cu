@@ -803,6 +803,12 @@ int vfb_internal_submit_fastq(vfb_ctx *c, const uint8_t *pinned_text, uint64_t n
     return VFB_OK;
 }
 
+int vfb_internal_ingest_threads(vfb_ctx *c)
+{
+    // the reference's n_threads (src/lib.rs:228) are its worker threads; here they inflate
+    return c->prm.n_threads < 1 ? 1 : (int)(c->prm.n_threads > 256 ? 256 : c->prm.n_threads);
+}
+
 int vfb_internal_parse_error(vfb_ctx *c, uint64_t *first_bad)
 {
     *first_bad = UINT64_MAX;

@@ -7,14 +7,22 @@
 // sequence line, '+' line, quality of the same length; "\r\n" trimmed; a missing final
 // newline and trailing blank lines are tolerated.
 //
-// Pipeline: a producer thread inflates straight into one of three pinned chunk buffers,
+// Pipeline: a producer thread fills one of three pinned chunk buffers with inflated text,
 // counts newlines as it goes and cuts the chunk at the last 4-line boundary (the remainder is
 // carried into the next chunk).  The calling thread queues each chunk on the GPU: H2D copy on
 // the copy stream, record framing / validation / span extraction on the device
 // (kernels_parse.cu), then K1..K4.  The host never looks at a record.
+//
+// Inflate: a plain gzip stream is serial (one zlib stream, ~0.3 GB/s).  Block-gzip files
+// (BGZF: every member carries its compressed size in a "BC" extra field, as written by
+// bgzip / htslib and most sequencer pipelines) are inflated member-parallel on `n_threads`
+// host threads — the reference's n_threads knob (src/lib.rs:228) keeps its meaning of
+// "worker threads".
 #include <zlib.h>
 
+#include <atomic>
 #include <cerrno>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -31,6 +39,20 @@ using namespace vfb;
 
 namespace {
 
+size_t count_nl(const uint8_t *p, size_t n)
+{
+    size_t c = 0;
+    const uint8_t *e = p + n;
+    while (p < e) {
+        const uint8_t *q = (const uint8_t *)memchr(p, '\n', (size_t)(e - p));
+        if (!q) break;
+        ++c;
+        p = q + 1;
+    }
+    return c;
+}
+
+// Serial multi-member gzip stream (flate2 MultiGzDecoder semantics).
 struct Inflater {
     FILE *f = nullptr;
     z_stream z;
@@ -42,7 +64,6 @@ struct Inflater {
     ~Inflater()
     {
         if (z_open) inflateEnd(&z);
-        if (f) fclose(f);
     }
     // Fill out[0..cap) with inflated bytes; returns bytes produced (0 at end) or -1 on error.
     long long read(uint8_t *out, size_t cap, std::string *err)
@@ -82,17 +103,191 @@ struct Inflater {
     }
 };
 
-size_t count_nl(const uint8_t *p, size_t n)
+// One BGZF member read from the file but not yet inflated.
+struct Member {
+    size_t in_off = 0, in_len = 0;   // whole member inside the compressed staging buffer
+    size_t out_off = 0;
+    uint32_t isize = 0;
+    size_t lines = 0;
+};
+
+// Reads the next gzip member header at the current file position.  Returns 1 and the total
+// member size if it is a BGZF member, 0 if it is some other gzip member (position restored),
+// -1 at a clean end of file.
+int peek_bgzf(FILE *f, size_t *member_size)
 {
-    size_t c = 0;
-    const uint8_t *e = p + n;
-    while (p < e) {
-        const uint8_t *q = (const uint8_t *)memchr(p, '\n', (size_t)(e - p));
-        if (!q) break;
-        ++c;
-        p = q + 1;
+    const long pos = ftell(f);
+    uint8_t h[12];
+    const size_t got = fread(h, 1, 12, f);
+    if (got == 0) return -1;
+    int is_bgzf = 0;
+    if (got == 12 && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4)) {
+        const uint32_t xlen = h[10] | (h[11] << 8);
+        std::vector<uint8_t> x(xlen);
+        if (xlen >= 6 && fread(x.data(), 1, xlen, f) == xlen) {
+            for (uint32_t p = 0; p + 4 <= xlen;) {
+                const uint32_t slen = x[p + 2] | (x[p + 3] << 8);
+                if (x[p] == 'B' && x[p + 1] == 'C' && slen == 2 && p + 6 <= xlen) {
+                    *member_size = (size_t)(x[p + 4] | (x[p + 5] << 8)) + 1;
+                    is_bgzf = 1;
+                    break;
+                }
+                p += 4 + slen;
+            }
+        }
     }
-    return c;
+    fseek(f, pos, SEEK_SET);
+    return is_bgzf;
+}
+
+// Fills chunk buffers with inflated text and cuts them at record boundaries.
+struct ChunkProducer {
+    FILE *f = nullptr;
+    Inflater serial;
+    bool bgzf = false;          // still reading BGZF members
+    int threads = 1;
+    std::vector<uint8_t> carry;
+    std::vector<uint8_t> zbuf;  // compressed members of the current chunk
+    bool at_end = false;
+    std::string err;
+
+    ~ChunkProducer()
+    {
+        if (f) fclose(f);
+    }
+
+    bool open(const char *path, int n_threads, std::string *e)
+    {
+        f = fopen(path, "rb");
+        if (!f) { *e = std::string("cannot open ") + path + ": " + strerror(errno); return false; }
+        serial.f = f;
+        threads = n_threads < 1 ? 1 : n_threads;
+        size_t ms = 0;
+        bgzf = peek_bgzf(f, &ms) == 1;
+        return true;
+    }
+
+    // Member-parallel fill of buf[used..cap).  Returns false on error.
+    bool fill_bgzf(uint8_t *buf, size_t cap, size_t &used, size_t &lines)
+    {
+        std::vector<Member> ms;
+        zbuf.clear();
+        while (used < cap) {
+            size_t msize = 0;
+            const int k = peek_bgzf(f, &msize);
+            if (k < 0) { at_end = true; break; }
+            if (k == 0) { bgzf = false; break; }          // the rest is plain gzip: serial from here
+            if (msize < 26) { err = "invalid BGZF member"; return false; }
+            const size_t zo = zbuf.size();
+            zbuf.resize(zo + msize);
+            const long pos = ftell(f);
+            if (fread(zbuf.data() + zo, 1, msize, f) != msize) { err = "truncated gzip stream"; return false; }
+            const uint8_t *t = zbuf.data() + zo + msize - 4;
+            const uint32_t isize = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
+            if (isize > cap - used) {
+                fseek(f, pos, SEEK_SET);                   // does not fit: first member of the next chunk
+                zbuf.resize(zo);
+                if (ms.empty()) { err = "ingest chunk too small for a gzip member plus a carried record"; return false; }
+                break;
+            }
+            Member m;
+            m.in_off = zo; m.in_len = msize; m.out_off = used; m.isize = isize;
+            ms.push_back(m);
+            used += isize;
+        }
+        if (ms.empty()) return true;
+        std::atomic<size_t> next{0};
+        std::atomic<bool> bad{false};
+        auto work = [&]() {
+            z_stream z;
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= ms.size() || bad.load()) return;
+                Member &m = ms[i];
+                memset(&z, 0, sizeof z);
+                if (inflateInit2(&z, 15 + 16) != Z_OK) { bad = true; return; }
+                z.next_in = zbuf.data() + m.in_off;
+                z.avail_in = (uInt)m.in_len;
+                z.next_out = buf + m.out_off;
+                z.avail_out = m.isize;
+                const int rc = inflate(&z, Z_FINISH);
+                const bool ok = rc == Z_STREAM_END && z.avail_out == 0 && z.avail_in == 0;
+                inflateEnd(&z);
+                if (!ok) { bad = true; return; }
+                m.lines = count_nl(buf + m.out_off, m.isize);
+            }
+        };
+        const int nt = (int)std::min<size_t>((size_t)threads, ms.size());
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+        work();
+        for (auto &t : pool) t.join();
+        if (bad.load()) { err = "invalid gzip data in a BGZF member"; return false; }
+        for (const Member &m : ms) lines += m.lines;
+        return true;
+    }
+
+    // Produce the next chunk into buf (capacity cap, plus 64 spare bytes).  On success sets
+    // cut (bytes to submit) and keep_lines (complete lines in [0,cut)); *last when the input is
+    // exhausted.  Returns VFB_OK or an error code with `err` set.
+    int next(uint8_t *buf, size_t cap, size_t *cut_out, size_t *lines_out, bool *last)
+    {
+        if (carry.size() >= cap) { err = "a FASTQ record is larger than the ingest chunk"; return VFB_ERR_FORMAT; }
+        size_t used = carry.size();
+        if (used) memcpy(buf, carry.data(), used);
+        size_t lines = count_nl(buf, used);
+        while (used < cap && !at_end) {
+            if (bgzf) {
+                if (!fill_bgzf(buf, cap, used, lines)) return VFB_ERR_FORMAT;
+                if (bgzf && !at_end) break;                   // as full as whole members allow
+            } else {
+                const size_t want = cap - used < ((size_t)4 << 20) ? cap - used : ((size_t)4 << 20);
+                const long long got = serial.read(buf + used, want, &err);
+                if (got < 0) return VFB_ERR_FORMAT;
+                if ((size_t)got < want) at_end = true;
+                lines += count_nl(buf + used, (size_t)got);
+                used += (size_t)got;
+            }
+        }
+        size_t cut = used, keep = lines;
+        if (at_end) {
+            // trailing blank lines are tolerated, and so is a missing final newline
+            while (used && (buf[used - 1] == '\n' || buf[used - 1] == '\r')) --used;
+            if (used) buf[used++] = '\n';
+            lines = count_nl(buf, used);
+            if (lines % 4) { err = "truncated FASTQ record at the end of the input"; return VFB_ERR_FORMAT; }
+            cut = used;
+            keep = lines;
+            carry.clear();
+        } else {
+            const size_t rem = lines % 4;
+            keep = lines - rem;
+            // cut just after newline number `keep`: walk back over the last `rem` newlines
+            size_t end = used;
+            for (size_t s = 0; s <= rem && keep; ++s) {
+                const void *q = end ? memrchr(buf, '\n', end) : nullptr;
+                end = q ? (size_t)((const uint8_t *)q - buf) : 0;
+            }
+            cut = keep ? end + 1 : 0;
+            carry.assign(buf + cut, buf + used);
+        }
+        *cut_out = cut;
+        *lines_out = keep;
+        *last = at_end;
+        return VFB_OK;
+    }
+};
+
+size_t pick_chunk(FILE *f)
+{
+    fseek(f, 0, SEEK_END);
+    const long fsz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    size_t cap = (size_t)128 << 20;
+    if (const char *e = getenv("VFB_INGEST_CHUNK")) cap = (size_t)strtoull(e, nullptr, 10);
+    else if (fsz >= 0 && (size_t)fsz * 12 + 65536 < cap) cap = (size_t)fsz * 12 + 65536;
+    if (cap < 256) cap = 256;
+    return cap;
 }
 
 struct Chunk {
@@ -113,22 +308,48 @@ struct Pipe {
 
 }  // namespace
 
+// Host-only view of the ingest front half (no GPU): inflates `path` chunk by chunk exactly as
+// vfb_run_file does and returns the concatenated submitted text, the number of complete lines
+// and the number of chunks.  For CPU tests of the inflate / cut / carry logic.
+extern "C" int vfb_debug_inflate_file(const char *path, uint32_t n_threads, uint8_t *out, uint64_t out_cap,
+                                      uint64_t *n_bytes, uint64_t *n_lines, uint64_t *n_chunks)
+{
+    if (!path || !n_bytes || !n_lines) { set_error("null argument"); return VFB_ERR_ARG; }
+    ChunkProducer prod;
+    std::string e;
+    if (!prod.open(path, (int)n_threads, &e)) { set_error(e); return VFB_ERR_IO; }
+    const size_t cap = pick_chunk(prod.f);
+    std::vector<uint8_t> buf(cap + 64);
+    uint64_t total = 0, lines = 0, chunks = 0;
+    for (;;) {
+        size_t cut = 0, kl = 0;
+        bool last = false;
+        const int rc = prod.next(buf.data(), cap, &cut, &kl, &last);
+        if (rc) { set_error(prod.err); return rc; }
+        if (out) {
+            if (total + cut > out_cap) { set_error("output buffer too small"); return VFB_ERR_ARG; }
+            memcpy(out + total, buf.data(), cut);
+        }
+        total += cut;
+        lines += kl;
+        ++chunks;
+        if (last) break;
+    }
+    *n_bytes = total;
+    *n_lines = lines;
+    if (n_chunks) *n_chunks = chunks;
+    return VFB_OK;
+}
+
 extern "C" int vfb_run_file(vfb_ctx *ctx, const char *path, uint64_t *n_reads_out)
 {
     if (!ctx || !path) { set_error("null argument"); return VFB_ERR_ARG; }
-    Inflater inf;
-    inf.f = fopen(path, "rb");
-    if (!inf.f) {
-        set_error(std::string("cannot open ") + path + ": " + strerror(errno));
-        return VFB_ERR_IO;
+    ChunkProducer prod;
+    {
+        std::string e;
+        if (!prod.open(path, vfb_internal_ingest_threads(ctx), &e)) { set_error(e); return VFB_ERR_IO; }
     }
-    fseek(inf.f, 0, SEEK_END);
-    const long fsz = ftell(inf.f);
-    fseek(inf.f, 0, SEEK_SET);
-    size_t cap = (size_t)128 << 20;
-    if (const char *e = getenv("VFB_INGEST_CHUNK")) cap = (size_t)strtoull(e, nullptr, 10);
-    else if (fsz >= 0 && (size_t)fsz * 12 + 65536 < cap) cap = (size_t)fsz * 12 + 65536;
-    if (cap < 256) cap = 256;
+    const size_t cap = pick_chunk(prod.f);
 
     constexpr int NCH = 3;
     Chunk ch[NCH];
@@ -145,16 +366,16 @@ extern "C" int vfb_run_file(vfb_ctx *ctx, const char *path, uint64_t *n_reads_ou
         pp.free_q.push_back(i);
     }
 
+    const bool trace = getenv("VFB_INGEST_TRACE") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+    };
+    if (trace) fprintf(stderr, "[vfb ingest] %s: %s, chunk %zu bytes, %d inflate threads\n", path,
+                       prod.bgzf ? "block gzip (member-parallel)" : "gzip stream (serial)", cap, prod.threads);
     std::thread producer;
     if (rc == VFB_OK) producer = std::thread([&]() {
-        std::vector<uint8_t> carry;
-        bool at_end = false;
-        auto fail = [&](int code, const std::string &m) {
-            std::lock_guard<std::mutex> lk(pp.mu);
-            pp.failed = true; pp.err = m; pp.err_code = code; pp.done = true;
-            pp.cv.notify_all();
-        };
-        while (!at_end) {
+        for (;;) {
             int k;
             {
                 std::unique_lock<std::mutex> lk(pp.mu);
@@ -163,50 +384,21 @@ extern "C" int vfb_run_file(vfb_ctx *ctx, const char *path, uint64_t *n_reads_ou
                 k = pp.free_q.front();
                 pp.free_q.pop_front();
             }
-            Chunk &c = ch[k];
-            if (carry.size() >= cap) { fail(VFB_ERR_FORMAT, "a FASTQ record is larger than the ingest chunk"); return; }
-            size_t used = carry.size();
-            if (used) memcpy(c.buf, carry.data(), used);
-            size_t lines = count_nl(c.buf, used);
-            std::string err;
-            while (used < cap && !at_end) {
-                const size_t want = cap - used < ((size_t)4 << 20) ? cap - used : ((size_t)4 << 20);
-                const long long got = inf.read(c.buf + used, want, &err);
-                if (got < 0) { fail(VFB_ERR_FORMAT, err); return; }
-                if ((size_t)got < want) at_end = true;
-                lines += count_nl(c.buf + used, (size_t)got);
-                used += (size_t)got;
-            }
-            size_t cut = used, keep_lines = lines;
-            if (at_end) {
-                // trailing blank lines are tolerated, and so is a missing final newline
-                while (used && (c.buf[used - 1] == '\n' || c.buf[used - 1] == '\r')) --used;
-                if (used) c.buf[used++] = '\n';            // cap + 64 bytes were allocated
-                lines = count_nl(c.buf, used);
-                if (lines % 4) { fail(VFB_ERR_FORMAT, "truncated FASTQ record at the end of the input"); return; }
-                cut = used;
-                keep_lines = lines;
-                carry.clear();
-            } else {
-                const size_t rem = lines % 4;
-                keep_lines = lines - rem;
-                // cut just after newline number keep_lines: walk back over the last `rem` newlines
-                size_t end = used;
-                for (size_t s = 0; s <= rem && keep_lines; ++s) {
-                    const void *q = end ? memrchr(c.buf, '\n', end) : nullptr;
-                    end = q ? (size_t)((const uint8_t *)q - c.buf) : 0;
-                }
-                cut = keep_lines ? end + 1 : 0;
-                carry.assign(c.buf + cut, c.buf + used);
-            }
-            c.cut = cut;
-            c.lines = keep_lines;
-            {
-                std::lock_guard<std::mutex> lk(pp.mu);
-                pp.ready_q.push_back(k);
-                if (at_end) pp.done = true;
+            bool last = false;
+            const auto t0 = std::chrono::steady_clock::now();
+            const int prc = prod.next(ch[k].buf, cap, &ch[k].cut, &ch[k].lines, &last);
+            if (trace) fprintf(stderr, "[vfb ingest] chunk %zu bytes %zu lines inflated in %.1f ms\n", ch[k].cut, ch[k].lines,
+                               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+            std::lock_guard<std::mutex> lk(pp.mu);
+            if (prc) {
+                pp.failed = true; pp.err = prod.err; pp.err_code = prc; pp.done = true;
                 pp.cv.notify_all();
+                return;
             }
+            pp.ready_q.push_back(k);
+            if (last) pp.done = true;
+            pp.cv.notify_all();
+            if (last) return;
         }
     });
 
@@ -223,14 +415,16 @@ extern "C" int vfb_run_file(vfb_ctx *ctx, const char *path, uint64_t *n_reads_ou
         }
         Chunk &c = ch[k];
         if (c.lines) {
+            const auto t0 = std::chrono::steady_clock::now();
             rc = vfb_internal_submit_fastq(ctx, c.buf, c.cut, c.lines, n_total, c.copied);
+            if (trace) fprintf(stderr, "[vfb ingest] submit at %.1f ms took %.1f ms\n", ms_since(t_start), ms_since(t0));
             n_total += c.lines / 4;
         } else if (cudaEventRecord(c.copied, 0) != cudaSuccess) {
             cudaGetLastError();
         }
         in_flight.push_back(k);
-        // hand buffers back to the producer once their H2D copy has finished; keep at most one
-        // copy outstanding beyond the newest so the producer always has a buffer to fill
+        // hand buffers back to the producer once their H2D copy has finished; the newest copy
+        // stays outstanding so that inflating the next chunk overlaps it
         while (rc == VFB_OK && in_flight.size() > 1) {
             const int o = in_flight.front();
             if (cudaEventSynchronize(ch[o].copied) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "ingest event", __FILE__, __LINE__); break; }
@@ -248,8 +442,11 @@ extern "C" int vfb_run_file(vfb_ctx *ctx, const char *path, uint64_t *n_reads_ou
     if (producer.joinable()) producer.join();
     if (rc == VFB_OK && pp.failed) { set_error(pp.err); rc = pp.err_code; }
     // the malformed-record flag comes back from the device
-    int src = vfb_sync(ctx);
-    if (rc == VFB_OK) rc = src;
+    const std::string keep = rc ? std::string(vfb_last_error()) : std::string();
+    if (trace) fprintf(stderr, "[vfb ingest] all chunks queued at %.1f ms\n", ms_since(t_start));
+    const int src = vfb_sync(ctx);
+    if (trace) fprintf(stderr, "[vfb ingest] device drained at %.1f ms\n", ms_since(t_start));
+    if (rc == VFB_OK) rc = src; else set_error(keep);
     if (rc == VFB_OK) {
         uint64_t bad = UINT64_MAX;
         rc = vfb_internal_parse_error(ctx, &bad);
@@ -264,5 +461,7 @@ extern "C" int vfb_run_file(vfb_ctx *ctx, const char *path, uint64_t *n_reads_ou
         if (ch[i].copied) cudaEventDestroy(ch[i].copied);
     }
     if (n_reads_out) *n_reads_out = n_total;
+    if (trace) fprintf(stderr, "[vfb ingest] %llu records in %.1f ms\n", (unsigned long long)n_total,
+                       std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
     return rc;
 }

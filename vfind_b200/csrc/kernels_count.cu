@@ -258,14 +258,18 @@ k4_insert(const __grid_constant__ InsertArgs a)
     uint32_t klen = 0;
     if (i < j.n_keys) klen = j.klen[i];
     const unsigned active = __ballot_sync(0xffffffffu, klen != 0);
-    if ((threadIdx.x & 31) == 0 && active && !j.kcount)
-        atomicAdd(&t.counters[2], (unsigned long long)__popc(active));
+    if (active) {
+        // reads counted by this warp: one atomic per warp
+        unsigned long long add = klen ? (j.kcount ? j.kcount[i] : 1ull) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
+        if ((threadIdx.x & 31) == 0 && add) atomicAdd(&t.counters[2], add);
+    }
     if (i >= j.n_keys) return;
     uint32_t owner = VFB_NONE;
     if (klen) {
         const uint64_t h = j.khash[i];
         const unsigned long long cnt = j.kcount ? j.kcount[i] : 1ull;
-        if (j.kcount && cnt) atomicAdd(&t.counters[2], cnt);
         const uint32_t tag = (uint32_t)(h >> 32);
         const uint64_t mask = t.capacity - 1;
         uint64_t slot = h & mask;
@@ -536,15 +540,45 @@ int launch_export_arrow(const DevTable &t, uint64_t rows, unsigned long long *bl
 }
 
 // ------------------------------------------------------------------------------------ merge
+// Per warp and per destination part: number of rows, padded key bytes, and this lane's rank /
+// byte offset inside its part's group (one atomic per warp per part instead of one per row).
+__device__ __forceinline__ void part_group(uint32_t p, bool valid, uint32_t padded, unsigned &peers,
+                                           uint32_t &rank, uint32_t &byte_rank, uint32_t &group_bytes)
+{
+    const int lane = threadIdx.x & 31;
+    peers = __match_any_sync(0xffffffffu, valid ? p : 0xFFFFFFFFu);
+    rank = __popc(peers & ((1u << lane) - 1));
+    byte_rank = 0;
+    group_bytes = 0;
+    // the shuffles run for every lane (full mask); each lane keeps only its own group's terms
+#pragma unroll 1
+    for (int l = 0; l < 32; ++l) {
+        const uint32_t v = __shfl_sync(0xffffffffu, padded, l);
+        if (peers & (1u << l)) {
+            group_bytes += v;
+            if (l < lane) byte_rank += v;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k5_partition_count(const DevTable t, uint64_t rows, uint32_t n_parts,
                    unsigned long long *part_rows, unsigned long long *part_keybytes)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += stride) {
-        const uint32_t p = vfb_hash_owner(t.row_hash[r], n_parts);
-        atomicAdd(&part_rows[p], 1ull);
-        atomicAdd(&part_keybytes[p], (unsigned long long)((t.row_len[r] + 15u) & ~15u));
+    const int lane = threadIdx.x & 31;
+    for (uint64_t r0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); r0 < rows; r0 += stride) {
+        const uint64_t r = r0 + lane;
+        const bool valid = r < rows;
+        const uint32_t p = valid ? vfb_hash_owner(t.row_hash[r], n_parts) : 0u;
+        const uint32_t padded = valid ? (t.row_len[r] + 15u) & ~15u : 0u;
+        unsigned peers;
+        uint32_t rank, brank, gbytes;
+        part_group(p, valid, padded, peers, rank, brank, gbytes);
+        if (valid && rank == 0) {
+            atomicAdd(&part_rows[p], (unsigned long long)__popc(peers));
+            atomicAdd(&part_keybytes[p], (unsigned long long)gbytes);
+        }
     }
 }
 
@@ -568,13 +602,27 @@ k5_partition_fill(const DevTable t, uint64_t rows, uint32_t n_parts,
                   unsigned long long *cursors)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += stride) {
-        const uint64_t h = t.row_hash[r];
-        const uint32_t p = vfb_hash_owner(h, n_parts);
-        const uint32_t len = t.row_len[r];
+    const int lane = threadIdx.x & 31;
+    for (uint64_t r0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); r0 < rows; r0 += stride) {
+        const uint64_t r = r0 + lane;
+        const bool valid = r < rows;
+        const uint64_t h = valid ? t.row_hash[r] : 0ull;
+        const uint32_t p = valid ? vfb_hash_owner(h, n_parts) : 0u;
+        const uint32_t len = valid ? t.row_len[r] : 0u;
         const uint32_t padded = (len + 15u) & ~15u;
-        const unsigned long long idx = atomicAdd(&cursors[2 * p], 1ull);
-        const unsigned long long koff = atomicAdd(&cursors[2 * p + 1], (unsigned long long)padded);
+        unsigned peers;
+        uint32_t rank, brank, gbytes;
+        part_group(p, valid, valid ? padded : 0u, peers, rank, brank, gbytes);
+        unsigned long long idx0 = 0, koff0 = 0;
+        if (valid && rank == 0) {
+            idx0 = atomicAdd(&cursors[2 * p], (unsigned long long)__popc(peers));
+            koff0 = atomicAdd(&cursors[2 * p + 1], (unsigned long long)gbytes);
+        }
+        const int leader = __ffs((int)peers) - 1;
+        idx0 = __shfl_sync(0xffffffffu, idx0, leader);
+        koff0 = __shfl_sync(0xffffffffu, koff0, leader);
+        if (!valid) continue;
+        const unsigned long long idx = idx0 + rank, koff = koff0 + brank;
         const uint64_t n = part_rows[p];
         uint8_t *c = buf + chunk_off[p];
         uint64_t *c_hash = reinterpret_cast<uint64_t *>(c + sizeof(ChunkHeader));

@@ -212,5 +212,7 @@ extern thread_local uint64_t g_launches;   // kernels launched by this thread's 
 // hot loop.  `copied` is recorded on the copy stream once the host buffer may be reused.
 int vfb_internal_submit_fastq(vfb_ctx *ctx, const uint8_t *pinned_text, uint64_t n_bytes, uint64_t n_lines,
                               uint64_t record_base, cudaEvent_t copied);
+// Host threads the ingest may use to inflate block-gzip members in parallel (params.n_threads).
+int vfb_internal_ingest_threads(vfb_ctx *ctx);
 // After vfb_sync: global index of the first malformed record, or UINT64_MAX.
 int vfb_internal_parse_error(vfb_ctx *ctx, uint64_t *first_bad_record);
