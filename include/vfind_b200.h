@@ -225,6 +225,12 @@ int vfb_synth_device(const vfb_synth_cfg *cfg, uint64_t first, uint64_t n, uint8
  * pipe (IADD3/VIADDMNMX mix) and of ALU+FMA-pipe dual issue (IADD3 + IMAD).  Giga-ops/s. */
 int vfb_measure_int_peak(int device, double *alu_gops, double *dual_gops);
 
+/* Test hook for the GPU inflater: `members` holds n_members x {z_off, z_len, out_off, isize}
+ * (uint32 each) describing whole gzip members inside z; the text lands in out.  *first_bad is
+ * the first member that failed (bad deflate data, CRC-32 or ISIZE mismatch) or 0xFFFFFFFF. */
+int vfb_debug_gpu_inflate(const uint8_t *z, uint64_t z_bytes, const uint32_t *members, uint32_t n_members,
+                          uint8_t *out, uint64_t out_bytes, int device, uint32_t *first_bad, double *kernel_ms);
+
 /* Pinned host memory for callers without their own allocator. */
 int vfb_host_alloc(void **p, uint64_t bytes);
 int vfb_host_free(void *p);

@@ -141,6 +141,11 @@ struct vfb_ctx {
     DevBuf t_slots, t_counts, t_row_hash, t_row_off, t_row_len, t_arena, t_counters, t_row_count;
     uint64_t ub_rows = 0, ub_arena = 0;   // host-side upper bounds of rows / arena bytes
 
+    // ingest, GPU inflate path: compressed members, member table, text (double buffered), tail
+    DevBuf g_z, g_members, g_text[2], g_tail, g_info;
+    PinBuf g_pin;               // carry staging + tail/info landing zone
+    uint64_t g_seq = 0;
+
     // ingest: GPU FASTQ parse scratch and the first-malformed-record word
     DevBuf p_tiles, p_line_end, p_err;      // p_err: u32 chunk-relative + u64 global (at +8)
     bool p_err_init = false;
@@ -470,6 +475,8 @@ int vfb_destroy(vfb_ctx *c)
     c->x_block_sums.release(); c->x_offsets.release(); c->x_data.release();
     c->d_aligned_text.release();
     c->p_tiles.release(); c->p_line_end.release(); c->p_err.release();
+    c->g_z.release(); c->g_members.release(); c->g_text[0].release(); c->g_text[1].release();
+    c->g_tail.release(); c->g_info.release(); c->g_pin.release();
     c->h_offsets.release(); c->h_counts.release(); c->h_data.release();
     for (auto &ev : c->evpool) if (ev) cudaEventDestroy(ev);
     if (c->st_compute && c->own_compute_stream) cudaStreamDestroy(c->st_compute);
@@ -803,6 +810,94 @@ int vfb_internal_submit_fastq(vfb_ctx *c, const uint8_t *pinned_text, uint64_t n
     return VFB_OK;
 }
 
+int vfb_internal_submit_bgzf(vfb_ctx *c, const uint8_t *pinned_z, uint64_t z_bytes, vfb_member *members,
+                             uint32_t n_members, uint64_t text_bytes, const uint8_t *carry, uint64_t carry_len,
+                             uint64_t record_base, uint64_t *n_records, uint8_t *tail, uint64_t *tail_len,
+                             uint32_t *bad_member)
+{
+    *n_records = 0; *tail_len = 0; *bad_member = 0xFFFFFFFFu;
+    const uint64_t used = carry_len + text_bytes;
+    if (used > 0xFFFFFF00ull || z_bytes > 0xFFFFFF00ull) { set_error("ingest segment too large"); return VFB_ERR_ARG; }
+    VFB_CUDA(cudaSetDevice(c->device));
+    const uint64_t before = g_launches;
+    int rc;
+    if (!c->p_err_init) {
+        if ((rc = c->p_err.ensure(16))) return rc;
+        VFB_CUDA(cudaMemsetAsync(c->p_err.p, 0xFF, 16, c->st_compute));
+        c->p_err_init = true;
+    }
+    DevBuf &txt = c->g_text[c->g_seq & 1];
+    ++c->g_seq;
+    if ((rc = txt.ensure(used + 64))) return rc;
+    if ((rc = c->g_z.ensure(z_bytes + 64))) return rc;
+    if ((rc = c->g_members.ensure((size_t)(n_members ? n_members : 1) * sizeof(vfb_member)))) return rc;
+    if ((rc = c->g_tail.ensure(VFB_TAIL_CAP))) return rc;
+    if ((rc = c->g_info.ensure(64))) return rc;
+    if ((rc = c->g_pin.ensure(VFB_TAIL_CAP + 64))) return rc;
+    if ((rc = c->p_tiles.ensure(parse_tile_words((uint32_t)used) * 8 + 8))) return rc;
+    uint8_t *pin = (uint8_t *)c->g_pin.p;
+    // the text of this segment starts behind the carried bytes
+    for (uint32_t i = 0; i < n_members; ++i) members[i].out_off += (uint32_t)carry_len;
+    if (carry_len) {
+        memcpy(pin, carry, carry_len);
+        VFB_CUDA(cudaMemcpyAsync(txt.p, pin, carry_len, cudaMemcpyHostToDevice, c->st_compute));
+    }
+    if (z_bytes) VFB_CUDA(cudaMemcpyAsync(c->g_z.p, pinned_z, z_bytes, cudaMemcpyHostToDevice, c->st_compute));
+    if (n_members) VFB_CUDA(cudaMemcpyAsync(c->g_members.p, members, (size_t)n_members * sizeof(vfb_member), cudaMemcpyHostToDevice, c->st_compute));
+    c->stats.h2d_bytes += carry_len + z_bytes + (uint64_t)n_members * sizeof(vfb_member);
+    uint32_t *d_bad = c->g_info.as<uint32_t>() + 8;
+    VFB_CUDA(cudaMemsetAsync(d_bad, 0xFF, 4, c->st_compute));
+    if ((rc = launch_inflate(c->g_z.as<uint8_t>(), c->g_members.as<vfb_member>(), n_members, txt.as<uint8_t>(), d_bad, c->st_compute))) return rc;
+    unsigned long long lines = 0;
+    uint32_t bad = 0xFFFFFFFFu;
+    if (used) {
+        if ((rc = launch_parse_count(txt.as<uint8_t>(), (uint32_t)used, c->p_tiles.as<unsigned long long>(), c->st_compute))) return rc;
+        const uint64_t n_tiles = parse_tile_words((uint32_t)used) - 1;
+        VFB_CUDA(cudaMemcpyAsync(&lines, c->p_tiles.as<unsigned long long>() + n_tiles, 8, cudaMemcpyDeviceToHost, c->st_compute));
+    }
+    VFB_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, c->st_compute));
+    VFB_CUDA(cudaStreamSynchronize(c->st_compute));
+    c->stats.d2h_bytes += 12;
+    *bad_member = bad;
+    if (bad != 0xFFFFFFFFu || used == 0) { bump_launches(c, before); return VFB_OK; }
+    const uint32_t n_rec = (uint32_t)(lines / 4);
+    if ((rc = c->p_line_end.ensure((lines ? lines : 1) * 4))) return rc;
+    Slot &s = c->slots[0];      // spans live in the host-path slot buffers (not in use by this path)
+    if ((rc = s.d_spans.ensure((size_t)(n_rec ? n_rec : 1) * sizeof(vfb_span)))) return rc;
+    if ((rc = launch_parse_index(txt.as<uint8_t>(), (uint32_t)used, (uint32_t)lines, n_rec,
+                                 c->p_tiles.as<unsigned long long>(), c->p_line_end.as<uint32_t>(), s.d_spans.as<vfb_span>(),
+                                 c->p_err.as<uint32_t>(), c->g_tail.as<uint8_t>(), VFB_TAIL_CAP, c->g_info.as<uint32_t>(),
+                                 c->st_compute))) return rc;
+    uint32_t *h_info = reinterpret_cast<uint32_t *>(pin + VFB_TAIL_CAP);
+    VFB_CUDA(cudaMemcpyAsync(h_info, c->g_info.p, 8, cudaMemcpyDeviceToHost, c->st_compute));
+    // the tail is normally a fraction of one record: fetch a first page with the info, the rest if needed
+    VFB_CUDA(cudaMemcpyAsync(pin, c->g_tail.p, 65536, cudaMemcpyDeviceToHost, c->st_compute));
+    VFB_CUDA(cudaStreamSynchronize(c->st_compute));
+    const uint32_t tl = h_info[1];
+    if (tl > VFB_TAIL_CAP) { set_error("a FASTQ record is larger than 16 MiB"); return VFB_ERR_FORMAT; }
+    if (tl > 65536) {
+        VFB_CUDA(cudaMemcpyAsync(pin, c->g_tail.p, tl, cudaMemcpyDeviceToHost, c->st_compute));
+        VFB_CUDA(cudaStreamSynchronize(c->st_compute));
+    }
+    memcpy(tail, pin, tl);
+    *tail_len = tl;
+    c->stats.d2h_bytes += 8 + tl;
+    if (n_rec) {
+        k_parse_err_fold<<<1, 1, 0, c->st_compute>>>(c->p_err.as<uint32_t>(), record_base,
+                                                     reinterpret_cast<unsigned long long *>(c->p_err.as<uint8_t>() + 8));
+        ++g_launches;
+        uint32_t done = 0;
+        while (done < n_rec) {
+            const uint32_t n = n_rec - done < c->batch_reads ? n_rec - done : (uint32_t)c->batch_reads;
+            if ((rc = process_batch(c, txt.as<uint8_t>(), s.d_spans.as<vfb_span>() + done, n, used))) return rc;
+            done += n;
+        }
+    }
+    *n_records = n_rec;
+    bump_launches(c, before);
+    return VFB_OK;
+}
+
 int vfb_internal_ingest_threads(vfb_ctx *c)
 {
     // the reference's n_threads (src/lib.rs:228) are its worker threads; here they inflate
@@ -1090,6 +1185,39 @@ int vfb_synth_device(const vfb_synth_cfg *cfg, uint64_t first, uint64_t n, uint8
     if (rc) return rc;
     VFB_CUDA(cudaStreamSynchronize(0));
     return VFB_OK;
+}
+
+int vfb_debug_gpu_inflate(const uint8_t *z, uint64_t z_bytes, const uint32_t *members, uint32_t n_members,
+                          uint8_t *out, uint64_t out_bytes, int device, uint32_t *first_bad, double *kernel_ms)
+{
+    if (!z || !members || !out || !first_bad) { set_error("null argument"); return VFB_ERR_ARG; }
+    if (device >= 0) VFB_CUDA(cudaSetDevice(device));
+    uint8_t *d_z = nullptr, *d_out = nullptr;
+    vfb_member *d_m = nullptr;
+    uint32_t *d_bad = nullptr;
+    VFB_CUDA(cudaMalloc(&d_z, z_bytes + 16));
+    VFB_CUDA(cudaMalloc(&d_out, out_bytes + 16));
+    VFB_CUDA(cudaMalloc(&d_m, (size_t)n_members * sizeof(vfb_member) + 16));
+    VFB_CUDA(cudaMalloc(&d_bad, 4));
+    VFB_CUDA(cudaMemcpy(d_z, z, z_bytes, cudaMemcpyHostToDevice));
+    VFB_CUDA(cudaMemcpy(d_m, members, (size_t)n_members * sizeof(vfb_member), cudaMemcpyHostToDevice));
+    VFB_CUDA(cudaMemset(d_bad, 0xFF, 4));
+    VFB_CUDA(cudaMemset(d_out, 0, out_bytes));
+    cudaEvent_t e0, e1;
+    VFB_CUDA(cudaEventCreate(&e0));
+    VFB_CUDA(cudaEventCreate(&e1));
+    VFB_CUDA(cudaEventRecord(e0, 0));
+    int rc = launch_inflate(d_z, d_m, n_members, d_out, d_bad, 0);
+    VFB_CUDA(cudaEventRecord(e1, 0));
+    VFB_CUDA(cudaDeviceSynchronize());
+    float ms = 0;
+    VFB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (kernel_ms) *kernel_ms = ms;
+    VFB_CUDA(cudaMemcpy(out, d_out, out_bytes, cudaMemcpyDeviceToHost));
+    VFB_CUDA(cudaMemcpy(first_bad, d_bad, 4, cudaMemcpyDeviceToHost));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_z); cudaFree(d_out); cudaFree(d_m); cudaFree(d_bad);
+    return rc;
 }
 
 int vfb_measure_int_peak(int device, double *alu_gops, double *dual_gops)

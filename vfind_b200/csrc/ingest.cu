@@ -306,6 +306,124 @@ struct Pipe {
     int err_code = VFB_OK;
 };
 
+// ---- GPU inflate phase: block-gzip members are shipped compressed and inflated on the device.
+struct ZSegment {
+    uint8_t *z = nullptr;          // pinned: whole members back to back
+    vfb_member *members = nullptr; // pinned
+    size_t z_bytes = 0, text_bytes = 0;
+    uint32_t n = 0;
+    bool last = false;             // nothing more for the GPU phase after this segment
+};
+
+// Consumes BGZF members from prod.f until the end of the file or the first member that is not
+// BGZF.  On return prod.carry holds the text after the last complete record, prod.at_end /
+// prod.bgzf say what is left for the host path (which also applies the end-of-input rules).
+int run_bgzf_gpu(vfb_ctx *ctx, ChunkProducer &prod, size_t text_target, uint64_t *n_total, bool trace)
+{
+    const size_t zcap = text_target / 2 + (1u << 20), mcap = text_target / 512 + 4096;
+    constexpr int NSEG = 2;
+    ZSegment seg[NSEG];
+    int rc = VFB_OK;
+    for (auto &g : seg) {
+        void *a = nullptr, *b = nullptr;
+        if (cudaMallocHost(&a, zcap) != cudaSuccess || cudaMallocHost(&b, mcap * sizeof(vfb_member)) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("cannot allocate pinned ingest buffers");
+            rc = VFB_ERR_NOMEM;
+        }
+        g.z = (uint8_t *)a;
+        g.members = (vfb_member *)b;
+    }
+    Pipe pp;
+    for (int i = 0; i < NSEG; ++i) pp.free_q.push_back(i);
+    std::thread reader;
+    if (rc == VFB_OK) reader = std::thread([&]() {
+        for (;;) {
+            int k;
+            {
+                std::unique_lock<std::mutex> lk(pp.mu);
+                pp.cv.wait(lk, [&] { return !pp.free_q.empty() || pp.abort; });
+                if (pp.abort) return;
+                k = pp.free_q.front();
+                pp.free_q.pop_front();
+            }
+            ZSegment &g = seg[k];
+            g.z_bytes = g.text_bytes = 0; g.n = 0; g.last = false;
+            std::string err;
+            while (g.text_bytes < text_target && g.n < mcap) {
+                size_t msize = 0;
+                const int kind = peek_bgzf(prod.f, &msize);
+                if (kind < 0) { prod.at_end = true; g.last = true; break; }
+                if (kind == 0) { prod.bgzf = false; g.last = true; break; }
+                if (msize < 26) { err = "invalid BGZF member"; break; }
+                if (g.z_bytes + msize > zcap) break;
+                if (fread(g.z + g.z_bytes, 1, msize, prod.f) != msize) { err = "truncated gzip stream"; break; }
+                const uint8_t *t = g.z + g.z_bytes + msize - 4;
+                const uint32_t isize = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
+                g.members[g.n++] = vfb_member{(uint32_t)g.z_bytes, (uint32_t)msize, (uint32_t)g.text_bytes, isize};
+                g.z_bytes += msize;
+                g.text_bytes += isize;
+            }
+            std::lock_guard<std::mutex> lk(pp.mu);
+            if (!err.empty()) {
+                pp.failed = true; pp.err = err; pp.err_code = VFB_ERR_FORMAT; pp.done = true;
+                pp.cv.notify_all();
+                return;
+            }
+            pp.ready_q.push_back(k);
+            if (g.last) pp.done = true;
+            pp.cv.notify_all();
+            if (g.last) return;
+        }
+    });
+    std::vector<uint8_t> tail(VFB_TAIL_CAP);
+    while (rc == VFB_OK) {
+        int k = -1;
+        {
+            std::unique_lock<std::mutex> lk(pp.mu);
+            pp.cv.wait(lk, [&] { return !pp.ready_q.empty() || pp.done; });
+            if (!pp.ready_q.empty()) { k = pp.ready_q.front(); pp.ready_q.pop_front(); }
+            else if (pp.failed) { set_error(pp.err); rc = pp.err_code; break; }
+            else break;
+        }
+        ZSegment &g = seg[k];
+        const auto t0 = std::chrono::steady_clock::now();
+        uint64_t n_rec = 0, tail_len = 0;
+        uint32_t bad = 0xFFFFFFFFu;
+        rc = vfb_internal_submit_bgzf(ctx, g.z, g.z_bytes, g.members, g.n, g.text_bytes, prod.carry.data(),
+                                      prod.carry.size(), *n_total, &n_rec, tail.data(), &tail_len, &bad);
+        if (rc == VFB_OK && bad != 0xFFFFFFFFu) {
+            set_error("invalid gzip data in a BGZF member (deflate stream, CRC-32 or size mismatch)");
+            rc = VFB_ERR_FORMAT;
+        }
+        if (rc == VFB_OK) {
+            prod.carry.assign(tail.data(), tail.data() + tail_len);
+            *n_total += n_rec;
+            if (trace) fprintf(stderr, "[vfb ingest] gpu segment: %u members, %zu -> %zu bytes, %llu records, %.1f ms\n", g.n,
+                               g.z_bytes, g.text_bytes, (unsigned long long)n_rec,
+                               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        }
+        std::lock_guard<std::mutex> lk(pp.mu);
+        pp.free_q.push_back(k);
+        pp.cv.notify_all();
+    }
+    {
+        std::lock_guard<std::mutex> lk(pp.mu);
+        pp.abort = true;
+        pp.cv.notify_all();
+    }
+    if (reader.joinable()) reader.join();
+    if (rc == VFB_OK && pp.failed) { set_error(pp.err); rc = pp.err_code; }
+    const std::string keep = rc ? std::string(vfb_last_error()) : std::string();
+    vfb_sync(ctx);                 // the pinned buffers are about to go away
+    if (rc) set_error(keep);
+    for (auto &g : seg) {
+        if (g.z) cudaFreeHost(g.z);
+        if (g.members) cudaFreeHost(g.members);
+    }
+    return rc;
+}
+
 }  // namespace
 
 // Host-only view of the ingest front half (no GPU): inflates `path` chunk by chunk exactly as
@@ -350,11 +468,22 @@ extern "C" int vfb_run_file(vfb_ctx *ctx, const char *path, uint64_t *n_reads_ou
         if (!prod.open(path, vfb_internal_ingest_threads(ctx), &e)) { set_error(e); return VFB_ERR_IO; }
     }
     const size_t cap = pick_chunk(prod.f);
+    const bool trace = getenv("VFB_INGEST_TRACE") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    uint64_t n_total = 0;
+    int rc = VFB_OK;
+    // Block-gzip input is inflated on the GPU (VFB_GPU_INFLATE=0 keeps it on the host threads);
+    // whatever follows — plain gzip members, the end-of-input rules — goes through the host path.
+    const char *gi = getenv("VFB_GPU_INFLATE");
+    if (prod.bgzf && !(gi && gi[0] == '0')) {
+        if (trace) fprintf(stderr, "[vfb ingest] %s: block gzip, inflating on the GPU\n", path);
+        rc = run_bgzf_gpu(ctx, prod, getenv("VFB_INGEST_CHUNK") ? cap : ((size_t)256 << 20), &n_total, trace);
+        if (rc) return rc;
+    }
 
     constexpr int NCH = 3;
     Chunk ch[NCH];
     Pipe pp;
-    int rc = VFB_OK;
     for (int i = 0; i < NCH; ++i) {
         void *p = nullptr;
         if (cudaMallocHost(&p, cap + 64) != cudaSuccess || cudaEventCreateWithFlags(&ch[i].copied, cudaEventDisableTiming) != cudaSuccess) {
@@ -366,8 +495,6 @@ extern "C" int vfb_run_file(vfb_ctx *ctx, const char *path, uint64_t *n_reads_ou
         pp.free_q.push_back(i);
     }
 
-    const bool trace = getenv("VFB_INGEST_TRACE") != nullptr;
-    const auto t_start = std::chrono::steady_clock::now();
     auto ms_since = [&](std::chrono::steady_clock::time_point t) {
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
     };
@@ -402,7 +529,6 @@ extern "C" int vfb_run_file(vfb_ctx *ctx, const char *path, uint64_t *n_reads_ou
         }
     });
 
-    uint64_t n_total = 0;
     std::deque<int> in_flight;
     while (rc == VFB_OK) {
         int k = -1;

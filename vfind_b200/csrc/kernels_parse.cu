@@ -163,4 +163,51 @@ int launch_parse(const uint8_t *d_text, uint32_t n_bytes, uint32_t n_lines, uint
 
 uint64_t parse_tile_words(uint32_t n_bytes) { return (uint64_t)(n_bytes + PARSE_TILE - 1) / PARSE_TILE + 1; }
 
+// ---- the same passes, split for text that was inflated on the device: the host does not know
+// ---- the line count (it never sees the text), so it reads it back between the passes.
+int launch_parse_count(const uint8_t *d_text, uint32_t n_bytes, unsigned long long *tile_scratch, cudaStream_t st)
+{
+    if (n_bytes == 0) return VFB_OK;
+    const uint32_t n_tiles = (n_bytes + PARSE_TILE - 1) / PARSE_TILE;
+    uint32_t blocks = n_tiles < 148u * 8u ? n_tiles : 148u * 8u;
+    k_parse_count<<<blocks, PARSE_THREADS, 0, st>>>(d_text, n_bytes, tile_scratch);
+    k_parse_scan<<<1, 1024, 0, st>>>(tile_scratch, n_tiles, tile_scratch + n_tiles);   // total at [n_tiles]
+    g_launches += 2;
+    VFB_CUDA(cudaGetLastError());
+    return VFB_OK;
+}
+
+// info[0] = cut (bytes of complete records), info[1] = tail length; tail receives up to tail_cap
+// bytes of the text after the last complete record.
+__global__ void __launch_bounds__(256)
+k_parse_tail(const uint8_t *__restrict__ text, uint32_t n_bytes, const uint32_t *__restrict__ line_end,
+             uint32_t n_records, uint8_t *__restrict__ tail, uint32_t tail_cap, uint32_t *__restrict__ info)
+{
+    const uint32_t cut = n_records ? line_end[4 * n_records - 1] + 1 : 0u;
+    const uint32_t tl = n_bytes - cut;
+    if (threadIdx.x == 0) { info[0] = cut; info[1] = tl; }
+    const uint32_t n = tl < tail_cap ? tl : tail_cap;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) tail[i] = text[cut + i];
+}
+
+int launch_parse_index(const uint8_t *d_text, uint32_t n_bytes, uint32_t n_lines, uint32_t n_records,
+                       const unsigned long long *tile_scratch, uint32_t *line_end, vfb_span *spans, uint32_t *err,
+                       uint8_t *tail, uint32_t tail_cap, uint32_t *info, cudaStream_t st)
+{
+    const uint32_t n_tiles = (n_bytes + PARSE_TILE - 1) / PARSE_TILE;
+    uint32_t blocks = n_tiles < 148u * 8u ? n_tiles : 148u * 8u;
+    if (n_lines) {
+        k_parse_index<<<blocks, PARSE_THREADS, 0, st>>>(d_text, n_bytes, tile_scratch, line_end, n_lines);
+        ++g_launches;
+    }
+    if (n_records) {
+        k_parse_spans<<<(n_records + 255) / 256, 256, 0, st>>>(d_text, line_end, n_records, spans, err);
+        ++g_launches;
+    }
+    k_parse_tail<<<1, 256, 0, st>>>(d_text, n_bytes, line_end, n_records, tail, tail_cap, info);
+    ++g_launches;
+    VFB_CUDA(cudaGetLastError());
+    return VFB_OK;
+}
+
 }  // namespace vfb

@@ -198,6 +198,20 @@ int launch_parse(const uint8_t *d_text, uint32_t n_bytes, uint32_t n_lines, uint
                  unsigned long long *tile_scratch, uint32_t *line_end, vfb_span *spans, uint32_t *err,
                  cudaStream_t st);
 uint64_t parse_tile_words(uint32_t n_bytes);
+// Split form for text inflated on the device (the host learns the line count in between).
+int launch_parse_count(const uint8_t *d_text, uint32_t n_bytes, unsigned long long *tile_scratch, cudaStream_t st);
+int launch_parse_index(const uint8_t *d_text, uint32_t n_bytes, uint32_t n_lines, uint32_t n_records,
+                       const unsigned long long *tile_scratch, uint32_t *line_end, vfb_span *spans, uint32_t *err,
+                       uint8_t *tail, uint32_t tail_cap, uint32_t *info, cudaStream_t st);
+
+// ---------------------------------------------------------------- GPU inflate (ingest)
+// One block-gzip member: where it sits in the compressed buffer, where its text goes.
+struct vfb_member {
+    uint32_t z_off, z_len, out_off, isize;
+};
+// *d_first_bad must be 0xFFFFFFFF before the launch; it receives the smallest failing member.
+int launch_inflate(const uint8_t *d_z, const vfb_member *d_members, uint32_t n_members, uint8_t *d_out,
+                   uint32_t *d_first_bad, cudaStream_t st);
 
 // ---------------------------------------------------------------- misc
 int launch_synth(const vfb_synth_cfg &cfg, uint64_t first, uint64_t n, uint8_t *d_text,
@@ -212,6 +226,16 @@ extern thread_local uint64_t g_launches;   // kernels launched by this thread's 
 // hot loop.  `copied` is recorded on the copy stream once the host buffer may be reused.
 int vfb_internal_submit_fastq(vfb_ctx *ctx, const uint8_t *pinned_text, uint64_t n_bytes, uint64_t n_lines,
                               uint64_t record_base, cudaEvent_t copied);
+// One segment of block-gzip members held in PINNED host memory: H2D of the compressed bytes,
+// GPU inflate behind `carry` (text left over from the previous segment), GPU parse, the hot
+// loop over the complete records.  Synchronous for the values it returns: records processed,
+// the text after the last complete record (tail, at most tail_cap bytes), and the first member
+// that failed to inflate (UINT32_MAX = none).
+#define VFB_TAIL_CAP (16u << 20)
+int vfb_internal_submit_bgzf(vfb_ctx *ctx, const uint8_t *pinned_z, uint64_t z_bytes, vfb::vfb_member *pinned_members,
+                             uint32_t n_members, uint64_t text_bytes, const uint8_t *carry, uint64_t carry_len,
+                             uint64_t record_base, uint64_t *n_records, uint8_t *tail, uint64_t *tail_len,
+                             uint32_t *bad_member);
 // Host threads the ingest may use to inflate block-gzip members in parallel (params.n_threads).
 int vfb_internal_ingest_threads(vfb_ctx *ctx);
 // After vfb_sync: global index of the first malformed record, or UINT64_MAX.
