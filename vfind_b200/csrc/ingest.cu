@@ -18,6 +18,7 @@
 // bgzip / htslib and most sequencer pipelines) are inflated member-parallel on `n_threads`
 // host threads — the reference's n_threads knob (src/lib.rs:228) keeps its meaning of
 // "worker threads".
+#include <unistd.h>
 #include <zlib.h>
 
 #include <atomic>
@@ -336,6 +337,8 @@ int run_bgzf_gpu(vfb_ctx *ctx, ChunkProducer &prod, size_t text_target, uint64_t
     }
     Pipe pp;
     for (int i = 0; i < NSEG; ++i) pp.free_q.push_back(i);
+    const int fd = fileno(prod.f);
+    size_t pos = (size_t)ftell(prod.f);
     std::thread reader;
     if (rc == VFB_OK) reader = std::thread([&]() {
         for (;;) {
@@ -350,20 +353,48 @@ int run_bgzf_gpu(vfb_ctx *ctx, ChunkProducer &prod, size_t text_target, uint64_t
             ZSegment &g = seg[k];
             g.z_bytes = g.text_bytes = 0; g.n = 0; g.last = false;
             std::string err;
-            while (g.text_bytes < text_target && g.n < mcap) {
+            // one pread per segment straight into the pinned buffer, then walk the member headers
+            const ssize_t got = pread(fd, g.z, zcap, (off_t)pos);
+            if (got < 0) err = std::string("read error: ") + strerror(errno);
+            const size_t avail = got > 0 ? (size_t)got : 0;
+            size_t off = 0;
+            bool stop = false;
+            while (err.empty() && !stop && off < avail && g.n < mcap) {
+                const uint8_t *h = g.z + off;
                 size_t msize = 0;
-                const int kind = peek_bgzf(prod.f, &msize);
-                if (kind < 0) { prod.at_end = true; g.last = true; break; }
-                if (kind == 0) { prod.bgzf = false; g.last = true; break; }
+                bool is_bgzf = false;
+                if (avail - off >= 18 && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4)) {
+                    const uint32_t xlen = h[10] | (h[11] << 8);
+                    if (avail - off >= 12 + (size_t)xlen) {
+                        for (uint32_t x = 0; x + 4 <= xlen;) {
+                            const uint8_t *sf = h + 12 + x;
+                            const uint32_t slen = sf[2] | (sf[3] << 8);
+                            if (sf[0] == 'B' && sf[1] == 'C' && slen == 2 && x + 6 <= xlen) { msize = (size_t)(sf[4] | (sf[5] << 8)) + 1; is_bgzf = true; break; }
+                            x += 4 + slen;
+                        }
+                    } else if (avail == zcap) break;          // header cut by the buffer: next segment
+                } else if (avail - off < 18 && avail == zcap) break;
+                if (!is_bgzf) {
+                    if (avail - off < 18 && avail < zcap) { err = "truncated gzip stream"; break; }
+                    prod.bgzf = false; g.last = true; stop = true;       // plain gzip from here: host path
+                    break;
+                }
                 if (msize < 26) { err = "invalid BGZF member"; break; }
-                if (g.z_bytes + msize > zcap) break;
-                if (fread(g.z + g.z_bytes, 1, msize, prod.f) != msize) { err = "truncated gzip stream"; break; }
-                const uint8_t *t = g.z + g.z_bytes + msize - 4;
+                if (off + msize > avail) {
+                    if (avail < zcap) err = "truncated gzip stream";     // end of file inside a member
+                    else if (off == 0) err = "a gzip member does not fit the ingest buffer";
+                    break;
+                }
+                const uint8_t *t = h + msize - 4;
                 const uint32_t isize = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
-                g.members[g.n++] = vfb_member{(uint32_t)g.z_bytes, (uint32_t)msize, (uint32_t)g.text_bytes, isize};
-                g.z_bytes += msize;
+                if (g.n && g.text_bytes + isize > text_target) break;
+                g.members[g.n++] = vfb_member{(uint32_t)off, (uint32_t)msize, (uint32_t)g.text_bytes, isize};
+                off += msize;
                 g.text_bytes += isize;
             }
+            g.z_bytes = off;
+            pos += off;
+            if (err.empty() && !stop && avail < zcap && off == avail) { prod.at_end = true; g.last = true; }
             std::lock_guard<std::mutex> lk(pp.mu);
             if (!err.empty()) {
                 pp.failed = true; pp.err = err; pp.err_code = VFB_ERR_FORMAT; pp.done = true;
@@ -413,6 +444,7 @@ int run_bgzf_gpu(vfb_ctx *ctx, ChunkProducer &prod, size_t text_target, uint64_t
         pp.cv.notify_all();
     }
     if (reader.joinable()) reader.join();
+    fseek(prod.f, (long)pos, SEEK_SET);      // the host path continues where the GPU phase stopped
     if (rc == VFB_OK && pp.failed) { set_error(pp.err); rc = pp.err_code; }
     const std::string keep = rc ? std::string(vfb_last_error()) : std::string();
     vfb_sync(ctx);                 // the pinned buffers are about to go away
@@ -467,7 +499,7 @@ extern "C" int vfb_run_file(vfb_ctx *ctx, const char *path, uint64_t *n_reads_ou
         std::string e;
         if (!prod.open(path, vfb_internal_ingest_threads(ctx), &e)) { set_error(e); return VFB_ERR_IO; }
     }
-    const size_t cap = pick_chunk(prod.f);
+    size_t cap = pick_chunk(prod.f);
     const bool trace = getenv("VFB_INGEST_TRACE") != nullptr;
     const auto t_start = std::chrono::steady_clock::now();
     uint64_t n_total = 0;
@@ -479,6 +511,8 @@ extern "C" int vfb_run_file(vfb_ctx *ctx, const char *path, uint64_t *n_reads_ou
         if (trace) fprintf(stderr, "[vfb ingest] %s: block gzip, inflating on the GPU\n", path);
         rc = run_bgzf_gpu(ctx, prod, getenv("VFB_INGEST_CHUNK") ? cap : ((size_t)256 << 20), &n_total, trace);
         if (rc) return rc;
+        // only the text after the last complete record may be left: no need for big chunks
+        if (prod.at_end) cap = prod.carry.size() * 2 + 65536;
     }
 
     constexpr int NCH = 3;

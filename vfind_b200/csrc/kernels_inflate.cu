@@ -8,6 +8,8 @@
 // decoded length by length); per-thread tables live in local memory, the four base/extra
 // tables in shared memory.  Each member's CRC-32 and ISIZE (RFC 1952 trailer) are checked, as
 // flate2 does; the first bad member is reported.
+#include <cstdlib>
+
 #include "vfb_internal.cuh"
 
 namespace vfb {
@@ -102,6 +104,7 @@ struct InflateArgs {
     uint32_t n_members;
     uint8_t *out;
     uint32_t *first_bad;         // atomicMin of the first member that failed
+    uint32_t lanes;              // lanes of each warp that decode (1 = lane 0 only)
 };
 
 // error codes are only used to tell "ok" from "bad"
@@ -220,7 +223,7 @@ __device__ int inflate_member(const InfTables *T, const uint8_t *zin, uint32_t z
     return 0;
 }
 
-#define INF_THREADS 64
+#define INF_THREADS 128
 
 __global__ void __launch_bounds__(INF_THREADS)
 k_inflate_members(const __grid_constant__ InflateArgs a)
@@ -242,7 +245,12 @@ k_inflate_members(const __grid_constant__ InflateArgs a)
         T.crc[i] = c;
     }
     __syncthreads();
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    // Decoding is branchy and every stream takes its own path: lanes of a warp that decode
+    // different members serialise each other.  So only `lanes` lanes per warp decode (default 1:
+    // a warp is one independent decoder and the SM interleaves warps instead of lanes).
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (lane >= a.lanes) return;
+    const uint32_t i = warp * a.lanes + lane;
     if (i >= a.n_members) return;
     const vfb_member m = a.members[i];
     int rc = 0;
@@ -254,8 +262,15 @@ int launch_inflate(const uint8_t *d_z, const vfb_member *d_members, uint32_t n_m
                    uint32_t *d_first_bad, cudaStream_t st)
 {
     if (n_members == 0) return VFB_OK;
-    InflateArgs a{d_z, d_members, n_members, d_out, d_first_bad};
-    k_inflate_members<<<(n_members + INF_THREADS - 1) / INF_THREADS, INF_THREADS, 0, st>>>(a);
+    static int lanes = 0;
+    if (!lanes) {
+        const char *e = getenv("VFB_INFLATE_LANES");
+        lanes = e ? atoi(e) : 1;
+        if (lanes < 1 || lanes > 32) lanes = 1;
+    }
+    InflateArgs a{d_z, d_members, n_members, d_out, d_first_bad, (uint32_t)lanes};
+    const uint32_t warps = (n_members + lanes - 1) / lanes;
+    k_inflate_members<<<(warps + INF_THREADS / 32 - 1) / (INF_THREADS / 32), INF_THREADS, 0, st>>>(a);
     ++g_launches;
     VFB_CUDA(cudaGetLastError());
     return VFB_OK;
