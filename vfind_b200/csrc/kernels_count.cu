@@ -248,10 +248,20 @@ __device__ __forceinline__ bool keys_equal16(const uint8_t *a, const uint8_t *b,
     return true;
 }
 
-// One thread per key: probe, claim or match (full key compare), count.
-__global__ void __launch_bounds__(256)
+// One thread per key: probe, claim or match (full key compare), count.  Counts are first
+// combined per block in a small shared-memory table keyed by slot, so a popular variant costs
+// one global atomic per block instead of one per read (same-address atomics serialise in L2).
+#define INS_THREADS 256
+#define INS_AGG 512
+
+__global__ void __launch_bounds__(INS_THREADS)
 k4_insert(const __grid_constant__ InsertArgs a)
 {
+    __shared__ uint32_t agg_slot[INS_AGG];
+    __shared__ unsigned long long agg_cnt[INS_AGG];
+    for (int e = threadIdx.x; e < INS_AGG; e += INS_THREADS) { agg_slot[e] = VFB_NONE; agg_cnt[e] = 0ull; }
+    __syncthreads();
+
     const InsertJob &j = a.job;
     const DevTable &t = a.t;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -265,7 +275,6 @@ k4_insert(const __grid_constant__ InsertArgs a)
         for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
         if ((threadIdx.x & 31) == 0 && add) atomicAdd(&t.counters[2], add);
     }
-    if (i >= j.n_keys) return;
     uint32_t owner = VFB_NONE;
     if (klen) {
         const uint64_t h = j.khash[i];
@@ -281,7 +290,6 @@ k4_insert(const __grid_constant__ InsertArgs a)
                 cur = atomicCAS(&t.slots[slot], 0ull, mine);
                 if (cur == 0ull) {
                     owner = (uint32_t)slot;
-                    atomicAdd(&t.counts[slot], cnt);
                     break;
                 }
             }
@@ -298,15 +306,23 @@ k4_insert(const __grid_constant__ InsertArgs a)
                     okey = t.arena + t.row_off[row];
                     olen = t.row_len[row];
                 }
-                if (olen == klen && keys_equal16(okey, mykey, klen)) {
-                    atomicAdd(&t.counts[slot], cnt);
-                    break;
-                }
+                if (olen == klen && keys_equal16(okey, mykey, klen)) break;
             }
             slot = (slot + 1) & mask;
         }
+        // block-level combine: claim (or find) this slot's entry in the shared table
+        const uint32_t s32 = (uint32_t)slot;
+        uint32_t e = (s32 * 2654435761u) >> 23;
+        for (;;) {
+            const uint32_t old = atomicCAS(&agg_slot[e], VFB_NONE, s32);
+            if (old == VFB_NONE || old == s32) { atomicAdd(&agg_cnt[e], cnt); break; }
+            e = (e + 1) & (INS_AGG - 1);
+        }
     }
-    j.owner_slot[i] = owner;
+    if (i < j.n_keys) j.owner_slot[i] = owner;
+    __syncthreads();
+    for (int e = threadIdx.x; e < INS_AGG; e += INS_THREADS)
+        if (agg_slot[e] != VFB_NONE) atomicAdd(&t.counts[agg_slot[e]], agg_cnt[e]);
 }
 
 // Owners of freshly claimed slots move their key into the arena and turn the slot's
