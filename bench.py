@@ -202,12 +202,18 @@ def main():
     ctx = api.Context(adapters, device=local, table_capacity_hint=min(R, 40_000_000), batch_reads=args.chunk_reads)
     ctx.set_compute_stream(stream.cuda_stream)
 
+    merge_events = []
+
     def step_device():
         ctx.table_clear()
         for t, s, n in chunks:
             ctx.submit_device(t.data_ptr(), t.numel(), s.data_ptr(), n)
         if world > 1:
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record(stream)
             merge_tables(ctx, device=dev)
+            m1.record(stream)
+            merge_events.append((m0, m1))
 
     def barrier():
         stream.synchronize()
@@ -243,12 +249,14 @@ def main():
             sampler.start()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        merge_events.clear()
         e0.record(stream)
         for _ in range(args.steps):
             step_device()
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
+        merge_ms = sum(a.elapsed_time(b) for a, b in merge_events) / max(1, len(merge_events)) if merge_events else 0.0
         clocks = sampler.stop() if rank == 0 else None
         st = ctx.stats()
         ctx.set_profiling(False)
@@ -367,7 +375,7 @@ def main():
         "roofline": roofline, "roofline_hbm": roofline_hbm, "stages_ms_per_step": stages,
         "dp": {"gcups": gcups, "cells_per_step": st["dp_cells"] // args.steps,
                "alignments_per_step": (st["dp_prefix"] + st["dp_suffix"]) // args.steps},
-        "table": {"unique": st["unique"], "counted_per_step": st["counted"], "merge_check": merge_check},
+        "merge_ms_per_step": merge_ms, "table": {"unique": st["unique"], "counted_per_step": st["counted"], "merge_check": merge_check},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
