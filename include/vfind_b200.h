@@ -68,6 +68,11 @@ typedef struct vfb_params {
                                          (what the reference does, src/lib.rs:278-286; the
                                          result table is identical either way)              */
     int32_t force_general_scan;       /* tests only: use the byte-wise scan kernel          */
+    int32_t dp_mode;                  /* 0 = auto (windowed DP where its filter applies, full DP in
+                                         diagnostics mode), 1 = always the full DP, 2 = windowed DP even
+                                         in diagnostics mode (scores of rejected alignments are then
+                                         lower bounds or absent)                              */
+    int32_t debug_win_cap;            /* tests only: > 0 caps the window list of the windowed DP   */
 } vfb_params;
 
 /* One read inside a text buffer: text[off .. off+len). */
@@ -115,8 +120,10 @@ typedef struct vfb_stats {
      * batches; only filled when vfb_set_profiling(ctx, 1). */
     double ms_scan, ms_worklist, ms_dp, ms_translate, ms_count, ms_total;
     uint64_t dp_kernel_launches;
-    int32_t dp_kernel_kind;     /* 1 = packed DPX kernel, 2 = generic fallback          */
+    int32_t dp_kernel_kind;     /* 1 = packed DPX kernel, 2 = generic fallback, 3 = windowed packed DPX */
     int32_t reserved;
+    uint64_t dp_cells_computed; /* cells the DP kernels actually evaluated (== dp_cells for the full DP) */
+    uint64_t dp_windows;        /* windows the filter produced (windowed DP)            */
 } vfb_stats;
 
 typedef struct vfb_ctx vfb_ctx;

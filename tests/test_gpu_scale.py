@@ -65,6 +65,33 @@ def test_config_sample_matches_oracle(name):
         assert (diag[f] == odiag[f]).all(), f
     assert got == want and st["dp_cells"] == cells
     assert st["dp_kernel_kind"] == 1
+    # the default (non-diagnostics) context: windowed DP where its filter applies (20-nt adapters at 0.75)
+    with api.Context(ad, accept_prefix_alignment=THR[name], accept_suffix_alignment=THR[name]) as ctx:
+        ctx.submit_device(t.data_ptr(), t.numel(), s.data_ptr(), n)
+        got2 = ctx.finish_dict()
+        st2 = ctx.stats()
+    assert got2 == want
+    assert st2["dp_kernel_kind"] == (1 if name == "C5" else 3)
+    if name != "C5":
+        assert st2["dp_cells_computed"] < 0.3 * st2["dp_cells"]
+
+
+def test_c3_windowed_dp_equals_full_dp_at_size():
+    # 12.5 M alignment-heavy reads (one bench.py chunk): the windowed DP and the full DP give the same table
+    cfg = api.synth_cfg(**CFG["C3"])
+    n = 12_500_000
+    ad = api.synth_adapters(cfg)
+    t, s = device_reads(cfg, 40_000_000, n)
+    tabs = []
+    for mode in (0, 1):
+        with api.Context(ad, dp_mode=mode, table_capacity_hint=8_000_000) as ctx:
+            ctx.submit_device(t.data_ptr(), t.numel(), s.data_ptr(), n)
+            o, d, c = table_of(ctx)
+            st = ctx.stats()
+            assert st["dp_kernel_kind"] == (3 if mode == 0 else 1)
+            assert int(c.sum()) == st["counted"]
+            tabs.append((as_dict(o, d, c), st["dp_cells"], st["dp_prefix"], st["dp_suffix"]))
+    assert tabs[0] == tabs[1]
 
 
 def test_c2_full_size_properties():

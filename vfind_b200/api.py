@@ -40,7 +40,8 @@ class Params(C.Structure):
                 ("batch_reads", C.c_uint64), ("batch_bytes", C.c_uint64),
                 ("table_capacity_hint", C.c_uint64),
                 ("debug_hash_bits", C.c_int32), ("force_generic_dp", C.c_int32),
-                ("dp_compute_all", C.c_int32), ("force_general_scan", C.c_int32)]
+                ("dp_compute_all", C.c_int32), ("force_general_scan", C.c_int32),
+                ("dp_mode", C.c_int32), ("debug_win_cap", C.c_int32)]
 
 
 class Table(C.Structure):
@@ -57,7 +58,7 @@ class Stats(C.Structure):
                 ("ms_scan", C.c_double), ("ms_worklist", C.c_double), ("ms_dp", C.c_double),
                 ("ms_translate", C.c_double), ("ms_count", C.c_double), ("ms_total", C.c_double),
                 ("dp_kernel_launches", C.c_uint64), ("dp_kernel_kind", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32), ("dp_cells_computed", C.c_uint64), ("dp_windows", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -160,7 +161,7 @@ class Context:
                  n_threads=3, queue_len=2, skip_translation=False, show_progress=True, *,
                  device=None, diagnostics=False, batch_reads=0, batch_bytes=0,
                  table_capacity_hint=0, debug_hash_bits=0, force_generic_dp=False,
-                 dp_compute_all=False, force_general_scan=False):
+                 dp_compute_all=False, force_general_scan=False, dp_mode=0, debug_win_cap=0):
         L = load_library()
         self._lib = L
         self._h = C.c_void_p()
@@ -185,6 +186,8 @@ class Context:
         p.force_generic_dp = 1 if force_generic_dp else 0
         p.dp_compute_all = 1 if dp_compute_all else 0
         p.force_general_scan = 1 if force_general_scan else 0
+        p.dp_mode = int(dp_mode)
+        p.debug_win_cap = int(debug_win_cap)
         _check(L.vfb_create(C.byref(p), C.byref(self._h)))
 
     # -- lifetime

@@ -100,9 +100,9 @@ struct Slot {
 };
 
 // device counters of one batch
-enum { C_NPRE = 0, C_NSUF, C_FBPRE, C_FBSUF, C_COUNT32 };
+enum { C_NPRE = 0, C_NSUF, C_FBPRE, C_FBSUF, C_FB2PRE, C_FB2SUF, C_NWINPRE, C_NWINSUF, C_COUNT32 };
 // 64-bit device counters
-enum { T_CELLS = 0, T_DPPRE, T_DPSUF, T_KEYBYTES, T_COUNT64 };
+enum { T_CELLS = 0, T_DPPRE, T_DPSUF, T_KEYBYTES, T_CELLSCOMP, T_WINDOWS, T_COUNT64 };
 
 }  // namespace vfb
 
@@ -131,6 +131,9 @@ struct vfb_ctx {
     // per-batch scratch
     DevBuf d_start, d_end, d_list_a, d_list_b, d_fb_a, d_fb_b, d_c32, d_t64;
     DevBuf d_keys, d_koff, d_klen, d_khash, d_owner;
+    DevBuf d_wins, d_bestkey, d_cbval, d_fb2;   // windowed DP: window items, per-item results, second fallback list
+    uint32_t win_cap = 0;
+    int win_k_pre = -1, win_k_suf = -1;         // Myers thresholds (-1: the windowed DP does not apply)
     DevBuf d_aligned_text;     // aligned copy of an unaligned caller buffer (vfb_submit_device)
     DevBuf d_diag_exact_pre, d_diag_exact_suf, d_diag_score_pre, d_diag_len_pre, d_diag_score_suf, d_diag_len_suf;
     uint64_t diag_n = 0;
@@ -439,6 +442,9 @@ int vfb_create(const vfb_params *p, vfb_ctx **out)
     };
     if ((rc = setup_dp(c->prefix, c->align_pre, &c->packed_pre, &c->lay_pre, &c->lcap_pre, &c->d_code_pre))) return fail(rc);
     if ((rc = setup_dp(c->suffix, c->align_suf, &c->packed_suf, &c->lay_suf, &c->lcap_suf, &c->d_code_suf))) return fail(rc);
+    if (c->packed_pre) c->win_k_pre = dpw_max_edits(c->sc, (uint32_t)c->prefix.size(), c->min_accept_pre);
+    if (c->packed_suf) c->win_k_suf = dpw_max_edits(c->sc, (uint32_t)c->suffix.size(), c->min_accept_suf);
+    if (p->dp_mode == 1) c->win_k_pre = c->win_k_suf = -1;
     if (c->align_pre || c->align_suf) {
         c->generic_threads = dp_generic_threads(c->sm_count);
         size_t amax = c->prefix.size() > c->suffix.size() ? c->prefix.size() : c->suffix.size();
@@ -450,6 +456,7 @@ int vfb_create(const vfb_params *p, vfb_ctx **out)
         return fail(cuda_fail(e, "cudaMemsetAsync", __FILE__, __LINE__));
     if ((rc = table_init(c))) return fail(rc);
     c->stats.dp_kernel_kind = (c->packed_pre || c->packed_suf) ? 1 : ((c->align_pre || c->align_suf) ? 2 : 0);
+    if ((c->win_k_pre >= 0 || c->win_k_suf >= 0) && (!p->diagnostics || p->dp_mode == 2)) c->stats.dp_kernel_kind = 3;
     *out = c;
     return VFB_OK;
 }
@@ -470,7 +477,8 @@ int vfb_destroy(vfb_ctx *c)
                       &c->d_khash, &c->d_owner, &c->d_diag_exact_pre, &c->d_diag_exact_suf, &c->d_diag_score_pre,
                       &c->d_diag_len_pre, &c->d_diag_score_suf, &c->d_diag_len_suf, &c->t_slots, &c->t_counts,
                       &c->t_row_hash, &c->t_row_off, &c->t_row_len, &c->t_arena, &c->t_counters, &c->t_row_count,
-                      &c->m_part_rows, &c->m_part_keys, &c->m_cursors, &c->m_chunk_off};
+                      &c->m_part_rows, &c->m_part_keys, &c->m_cursors, &c->m_chunk_off,
+                      &c->d_wins, &c->d_bestkey, &c->d_cbval, &c->d_fb2};
     for (auto *b : bufs) b->release();
     c->x_block_sums.release(); c->x_offsets.release(); c->x_data.release();
     c->d_aligned_text.release();
@@ -519,13 +527,14 @@ int vfb_reset(vfb_ctx *c)
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------ batch
-__global__ void k_accumulate(unsigned long long *t64, const uint32_t *c32)
+__global__ void k_accumulate(unsigned long long *t64, const uint32_t *c32, uint32_t win_cap)
 {
     t64[T_DPPRE] += c32[C_NPRE];
     t64[T_DPSUF] += c32[C_NSUF];
+    t64[T_WINDOWS] += (c32[C_NWINPRE] < win_cap ? c32[C_NWINPRE] : win_cap) + (c32[C_NWINSUF] < win_cap ? c32[C_NWINSUF] : win_cap);
 }
 
-static int run_dp(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_spans, bool is_prefix)
+static int run_dp(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_spans, bool is_prefix, uint32_t n_batch)
 {
     int rc;
     DpJob job;
@@ -555,7 +564,33 @@ static int run_dp(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_spans, bo
     gj.d_adapter_code = is_prefix ? c->d_code_pre.as<uint8_t>() : c->d_code_suf.as<uint8_t>();
     gj.scratch = c->d_generic_scratch.as<int32_t>();
     gj.n_threads = c->generic_threads;
-    if (packed) {
+    const int K = is_prefix ? c->win_k_pre : c->win_k_suf;
+    const bool windowed = packed && K >= 0 && c->prm.dp_mode != 1 && (!c->prm.diagnostics || c->prm.dp_mode == 2);
+    if (windowed) {
+        // filter -> DP on the flagged windows -> resolve; reads the windowed path cannot take go
+        // to the full kernel, and from there (too long for the packed word) to the unpacked one
+        for (size_t i = 0; i < ad.size(); ++i) job.adapter_code[i] = (uint8_t)dp_code((uint8_t)ad[i]);
+        uint32_t *c32 = c->d_c32.as<uint32_t>();
+        uint32_t *fb = is_prefix ? c->d_fb_a.as<uint32_t>() : c->d_fb_b.as<uint32_t>();
+        uint32_t *nfb = c32 + (is_prefix ? C_FBPRE : C_FBSUF);
+        uint32_t *fb2 = c->d_fb2.as<uint32_t>();
+        uint32_t *nfb2 = c32 + (is_prefix ? C_FB2PRE : C_FB2SUF);
+        const DpLayout &lay = is_prefix ? c->lay_pre : c->lay_suf;
+        const uint32_t lcap = is_prefix ? c->lcap_pre : c->lcap_suf;
+        if ((rc = launch_dp_windowed(job, lay, K, lcap, n_batch, c->d_wins.p, c32 + (is_prefix ? C_NWINPRE : C_NWINSUF),
+                                     c->win_cap, c->d_bestkey.as<unsigned long long>(), c->d_cbval.as<unsigned long long>(),
+                                     fb, nfb, c->d_t64.as<unsigned long long>() + T_CELLSCOMP, c->sm_count, c->st_compute)))
+            return rc;
+        DpJob fj = job;
+        fj.worklist = fb;
+        fj.n_items = nfb;
+        if ((rc = launch_dp_packed_ex(fj, lay, lcap, fb2, nfb2, c->sm_count, c->st_compute))) return rc;
+        gj.base = fj;
+        gj.base.worklist = fb2;
+        gj.base.n_items = nfb2;
+        if ((rc = launch_dp_generic(gj, c->sm_count, c->st_compute))) return rc;
+        c->stats.dp_kernel_launches += 5;
+    } else if (packed) {
         for (size_t i = 0; i < ad.size(); ++i) job.adapter_code[i] = (uint8_t)dp_code((uint8_t)ad[i]);
         uint32_t *fb = is_prefix ? c->d_fb_a.as<uint32_t>() : c->d_fb_b.as<uint32_t>();
         uint32_t *nfb = c->d_c32.as<uint32_t>() + (is_prefix ? C_FBPRE : C_FBSUF);
@@ -598,6 +633,15 @@ static int process_batch(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_sp
     if ((rc = c->d_klen.ensure((size_t)n * 4))) return rc;
     if ((rc = c->d_khash.ensure((size_t)n * 8))) return rc;
     if ((rc = c->d_owner.ensure((size_t)n * 4))) return rc;
+    if (c->win_k_pre >= 0 || c->win_k_suf >= 0) {
+        const uint32_t cap = n < 0x3FFFFFFFu ? n * 2u + 1024u : 0x7FFFFFFFu;
+        if ((rc = c->d_wins.ensure((size_t)cap * dpw_item_bytes()))) return rc;
+        c->win_cap = (uint32_t)(c->d_wins.cap / dpw_item_bytes());
+        if (c->prm.debug_win_cap > 0 && (uint32_t)c->prm.debug_win_cap < c->win_cap) c->win_cap = (uint32_t)c->prm.debug_win_cap;
+        if ((rc = c->d_bestkey.ensure((size_t)n * 8))) return rc;
+        if ((rc = c->d_cbval.ensure((size_t)n * 8))) return rc;
+        if ((rc = c->d_fb2.ensure((size_t)n * 4))) return rc;
+    }
     const bool diag = c->prm.diagnostics != 0;
     if (diag) {
         DevBuf *db[] = {&c->d_diag_exact_pre, &c->d_diag_exact_suf, &c->d_diag_score_pre, &c->d_diag_len_pre,
@@ -633,12 +677,12 @@ static int process_batch(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_sp
     // DP.  The prefix pass runs first: reads it rejects need no suffix alignment (no region
     // either way, src/lib.rs:288), reads it accepts join the suffix worklist if they need one.
     if (prof) VFB_CUDA(cudaEventRecord(pev[2], st));
-    if (c->align_pre) if ((rc = run_dp(c, d_text, d_spans, true))) return rc;
+    if (c->align_pre) if ((rc = run_dp(c, d_text, d_spans, true, n))) return rc;
     if (prof) VFB_CUDA(cudaEventRecord(pev[3], st));
     if (prof) VFB_CUDA(cudaEventRecord(pev[4], st));
-    if (c->align_suf) if ((rc = run_dp(c, d_text, d_spans, false))) return rc;
+    if (c->align_suf) if ((rc = run_dp(c, d_text, d_spans, false, n))) return rc;
     if (prof) VFB_CUDA(cudaEventRecord(pev[5], st));
-    k_accumulate<<<1, 1, 0, st>>>(c->d_t64.as<unsigned long long>(), c->d_c32.as<uint32_t>());
+    k_accumulate<<<1, 1, 0, st>>>(c->d_t64.as<unsigned long long>(), c->d_c32.as<uint32_t>(), c->win_cap);
     ++g_launches;
 
     KeyJob kj;
@@ -950,6 +994,8 @@ int vfb_get_stats(vfb_ctx *c, vfb_stats *out)
     c->stats.dp_cells = t64[T_CELLS];
     c->stats.dp_prefix = t64[T_DPPRE];
     c->stats.dp_suffix = t64[T_DPSUF];
+    c->stats.dp_cells_computed = t64[T_CELLSCOMP];
+    c->stats.dp_windows = t64[T_WINDOWS];
     c->stats.unique = ctr[0];
     c->stats.counted = ctr[2];
     *out = c->stats;

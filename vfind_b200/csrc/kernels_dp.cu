@@ -34,7 +34,7 @@ bool make_dp_layout(const DpScoring &s, uint32_t A, uint32_t /*max_read_len*/, D
     if (s.mismatch > wmax) wmax = s.mismatch;
     long long smax = (long long)A * wmax, smin = (long long)A * wmin;
     long long neg = smin - s.open - 1;           // border "-inf": below every real candidate
-    long long lowest = neg - s.extend;           // the lowest value ever formed
+    long long lowest = neg - (s.open > s.extend ? s.open : s.extend);   // the lowest value ever formed
     long long need = smax + 1 > -lowest ? smax + 1 : -lowest;
     if (need > (1 << 20)) return false;
     int SB = bits_for((uint64_t)need) + 1;       // signed field holding [-need, need]

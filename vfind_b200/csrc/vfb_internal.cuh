@@ -91,6 +91,15 @@ uint32_t dp_lcap(const DpLayout &lay, uint32_t adapter_len, int extend);
 int launch_dp_packed_ex(const DpJob &job, const DpLayout &lay, uint32_t lcap, uint32_t *fallback,
                         uint32_t *n_fallback, int sm_count, cudaStream_t st);
 
+// Windowed DP (kernels_dpw.cu): bit-parallel filter -> DP on the flagged windows -> resolve.
+// K = dpw_max_edits(...) >= 0 when the filter applies to this adapter / scoring / bound.
+int dpw_max_edits(const DpScoring &s, uint32_t adapter_len, int min_accept);
+uint32_t dpw_item_bytes();
+int launch_dp_windowed(const DpJob &job, const DpLayout &lay, int K, uint32_t lcap, uint32_t max_items,
+                       void *wins, uint32_t *n_wins, uint32_t win_cap, unsigned long long *best_key,
+                       unsigned long long *cb_val, uint32_t *fallback, uint32_t *n_fallback,
+                       unsigned long long *cells_computed, int sm_count, cudaStream_t st);
+
 struct DpGenericJob {
     DpJob base;
     const uint8_t *d_adapter_code;   // adapter codes in device memory (any length)
