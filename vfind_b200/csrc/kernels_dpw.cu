@@ -95,26 +95,55 @@ __device__ __forceinline__ void win_emit(const DpwArgs &a, uint32_t r, uint32_t 
     else overflow = true;
 }
 
-__global__ void __launch_bounds__(DPW_THREADS)
+// One column of Myers' bit-vector recurrence.  The adapter occupies the HIGH A bits of the word
+// (row A = bit 31, so the score delta is the top bit of Ph / Mh); the 32-A low bits are rows
+// that match every byte and start at D = 0, which leaves the adapter rows' values unchanged
+// (a free text start already gives them D[0][j] = 0 underneath).
+__device__ __forceinline__ void myers_col(uint32_t Eq, uint32_t &Pv, uint32_t &Mv, int &score)
+{
+    const uint32_t Xv = Eq | Mv;
+    const uint32_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+    uint32_t Ph = Mv | ~(Xh | Pv);
+    uint32_t Mh = Pv & Xh;
+    score += (int)(Ph >> 31);
+    score += ((int)Mh >> 31);
+    Ph <<= 1;
+    Mh <<= 1;
+    Pv = Mh | ~(Xv | Ph);
+    Mv = Ph & Xv;
+}
+
+// Filter: one lane = one read, streamed as 16-byte aligned chunks (LDG.128, next chunk prefetched).
+// The <= 15 bytes of the first chunk that precede the read are run through the recurrence as
+// well: extra text on the left can only lower ed(j), so the flagged set stays a superset.  Each
+// chunk first runs 16 unrolled columns tracking only the minimum of ed; the (few) chunks whose
+// minimum reaches K are replayed from the saved state with the per-column window bookkeeping.
+// Byte -> Eq goes through a 64-entry table keyed by byte & 0x3F (entries OR-ed over the four
+// bytes that share a key: again a superset, and exact for every letter).
+__global__ void __launch_bounds__(DPW_THREADS, 8)
 k2_filter(const __grid_constant__ DpwArgs a)
 {
-    __shared__ uint32_t lutEq[256];
+    __shared__ uint32_t lutEq[64];
     const DpJob &job = a.job;
     const int A = (int)job.adapter_len;
-    for (int b = threadIdx.x; b < 256; b += blockDim.x) {
-        const int c = dp_code((uint8_t)b);
-        uint32_t m = 0;
-        if (c < 4)
-            for (int i = 0; i < A; ++i)
-                if (job.adapter_code[i] == c) m |= 1u << i;
-        lutEq[b] = m;
+    const int sh = 32 - A;
+    if (threadIdx.x < 64) {
+        uint32_t m = sh ? (1u << sh) - 1u : 0u;
+        for (int b = threadIdx.x; b < 256; b += 64) {
+            const int c = dp_code((uint8_t)b);
+            if (c < 4)
+                for (int i = 0; i < A; ++i)
+                    if (job.adapter_code[i] == c) m |= 1u << (i + sh);
+        }
+        lutEq[threadIdx.x] = m;
     }
     __syncthreads();
+    const unsigned char *lutb = reinterpret_cast<const unsigned char *>(lutEq);
     const int lane = threadIdx.x & 31;
     const uint32_t n_items = *job.n_items;
     const uint32_t stride = gridDim.x * blockDim.x;
     const int span = A + a.K;
-    const int topsh = A - 1;
+    const int K = a.K;
     unsigned long long cells = 0;
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_items; base += stride) {
         const uint32_t item = base + lane;
@@ -127,29 +156,58 @@ k2_filter(const __grid_constant__ DpwArgs a)
             a.fallback[atomicAdd(a.n_fallback, 1u)] = r;       // full kernel (it counts its own cells)
             continue;
         }
-        const uint8_t *seq = job.text + sp.off;
-        uint32_t Pv = 0xFFFFFFFFu, Mv = 0;
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(job.text + sp.off);
+        const uint4 *base16 = reinterpret_cast<const uint4 *>(addr & ~(uintptr_t)15);
+        const int lead = (int)(addr & 15u);
+        const int n_chunks = (lead + L + 15) >> 4;
+        uint32_t Pv = 0xFFFFFFFFu << sh, Mv = 0;
         int score = A;
         int first = 0, last = 0;          // current group of flagged columns (0 = none)
         bool overflow = false;
-        for (int j = 1; j <= L; ++j) {
-            const uint32_t Eq = lutEq[__ldg(seq + j - 1)];
-            const uint32_t Xv = Eq | Mv;
-            const uint32_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
-            uint32_t Ph = Mv | ~(Xh | Pv);
-            uint32_t Mh = Pv & Xh;
-            score += (int)((Ph >> topsh) & 1u) - (int)((Mh >> topsh) & 1u);
-            Ph <<= 1;
-            Mh <<= 1;
-            Pv = Mh | ~(Xv | Ph);
-            Mv = Ph & Xv;
-            if (score <= a.K) {
-                if (first && j - last > span) {             // far from the previous group: close it
-                    win_emit(a, r, item, first, last, span, L, overflow);
-                    first = 0;
+        uint4 nx = __ldg(base16);
+        for (int c = 0; c < n_chunks; ++c) {
+            const uint4 v = nx;
+            if (c + 1 < n_chunks) nx = __ldg(base16 + c + 1);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            const uint32_t Pv0 = Pv, Mv0 = Mv;
+            const int score0 = score;
+            int mn = INT_MAX;
+#pragma unroll
+            for (int wi = 0; wi < 4; ++wi) {
+                const uint32_t w4 = (w[wi] & 0x3F3F3F3Fu) << 2;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const uint32_t key = __byte_perm(w4, 0, 0x4440 + b);
+                    myers_col(*reinterpret_cast<const uint32_t *>(lutb + key), Pv, Mv, score);
+                    mn = min(mn, score);
                 }
-                if (!first) first = j;
-                last = j;
+            }
+            if (mn <= K) {
+                // replay this chunk from the saved state, collecting the flagged columns
+                Pv = Pv0; Mv = Mv0; score = score0;
+                uint32_t flags = 0;
+#pragma unroll
+                for (int wi = 0; wi < 4; ++wi) {
+                    const uint32_t w4 = (w[wi] & 0x3F3F3F3Fu) << 2;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const uint32_t key = __byte_perm(w4, 0, 0x4440 + b);
+                        myers_col(*reinterpret_cast<const uint32_t *>(lutb + key), Pv, Mv, score);
+                        if (score <= K) flags |= 1u << (wi * 4 + b);
+                    }
+                }
+                const int jbase = c * 16 - lead + 1;      // column (1-based) of the chunk's first byte
+                while (flags) {
+                    const int j = jbase + __ffs((int)flags) - 1;
+                    flags &= flags - 1;
+                    if (j < 1 || j > L) continue;
+                    if (first && j - last > span) {             // far from the previous group: close it
+                        win_emit(a, r, item, first, last, span, L, overflow);
+                        first = 0;
+                    }
+                    if (!first) first = j;
+                    last = j;
+                }
             }
         }
         if (first) win_emit(a, r, item, first, last, span, L, overflow);
@@ -350,7 +408,7 @@ int launch_dp_windowed(const DpJob &job, const DpLayout &lay, int K, uint32_t lc
     a.cells_computed = cells_computed;
     VFB_CUDA(cudaMemsetAsync(best_key, 0, (size_t)max_items * 8, st));
     VFB_CUDA(cudaMemsetAsync(cb_val, 0, (size_t)max_items * 8, st));
-    k2_filter<<<sm_count * 8, DPW_THREADS, 0, st>>>(a);
+    k2_filter<<<sm_count * 12, DPW_THREADS, 0, st>>>(a);
     ++g_launches;
     int rc;
     switch (((int)job.adapter_len + 3) & ~3) {
