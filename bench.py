@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = "C3: 250-bp synthetic merged amplicon reads, 20-nt adapters, 30% adapters mutated (>=1 indel), seed 1003"
 ALU_OPS_PER_CELL = 4    # VIADDMNMX x2 + VIMNMX3 + LOP3 on the INT32 ALU pipe (3 IMAD ride the FMA pipe)
+FILTER_ALU_OPS_PER_COL = 11   # k2_filter: 7 LOP3 + PRMT + 2 LEA.HI (score) + VIMNMX per read column
 
 
 def c3_cfg(api):
@@ -331,20 +332,40 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     dp_s = st["ms_dp"] * 1e-3
-    gcups = st["dp_cells"] / dp_s / 1e9 if dp_s > 0 else 0.0
-    dp_achieved = gcups * ALU_OPS_PER_CELL            # G lane-ops/s on the ALU pipe
+    gcups = st["dp_cells"] / dp_s / 1e9 if dp_s > 0 else 0.0      # effective: full A x L matrices / DP stage time
+    windowed = st["dp_kernel_kind"] == 3
+    if windowed:
+        # the DP stage = k2_filter (Myers bit-vector, every column of every aligned read) + k2_dp_window
+        # (packed Gotoh cells on the flagged windows only) + k2_resolve.  Roofline of the window kernel:
+        # cells it actually evaluated x 4 ALU-pipe ops, against the measured ALU-pipe peak.
+        win_s = st["ms_dp_window"] * 1e-3
+        kernel_gcups = st["dp_cells_computed"] / win_s / 1e9 if win_s > 0 else 0.0
+        dp_kernel, dp_ms = "k2_dp_window", st["ms_dp_window"]
+    else:
+        kernel_gcups, dp_kernel, dp_ms = gcups, "k2_dp_packed", st["ms_dp"]
+    dp_achieved = kernel_gcups * ALU_OPS_PER_CELL     # G lane-ops/s on the ALU pipe
     scan_bytes = st["reads"] * (L + 12)               # N*(L+12)
     scan_gbs = scan_bytes / (st["ms_scan"] * 1e-3) / 1e9 if st["ms_scan"] > 0 else 0.0
     key_bytes = st["counted"] * args.steps * (cfg.region_len + cfg.region_len // 3 + 8)
-    roofline = {"bound": "int32", "kernel": "k2_dp_packed", "achieved": dp_achieved, "peak": alu_gops,
+    roofline = {"bound": "int32", "kernel": dp_kernel, "achieved": dp_achieved, "peak": alu_gops,
                 "unit": "Gop/s", "frac": dp_achieved / alu_gops if alu_gops else None, "traffic": None,
-                "gcups": gcups, "alu_ops_per_cell": ALU_OPS_PER_CELL,
+                "gcups": kernel_gcups, "alu_ops_per_cell": ALU_OPS_PER_CELL,
                 "peak_source": "vfb_measure_int_peak (VIADDMNMX stream, measured in this run); ALU+FMA dual-issue peak %.0f Gop/s" % dual_gops,
-                "share_of_step": st["ms_dp"] / st["ms_total"] if st["ms_total"] else None}
+                "share_of_step": dp_ms / st["ms_total"] if st["ms_total"] else None}
+    roofline_filter = None
+    if windowed and st["ms_dp_filter"] > 0:
+        # Myers column: 7 LOP3 + 1 PRMT + 3 score/min ops on the ALU pipe (3 IMAD adds/shifts on the FMA pipe, 1 LDS)
+        cols = st["dp_cells"] / cfg.adapter_len       # one column per read base of every aligned read
+        f_ach = cols * FILTER_ALU_OPS_PER_COL / (st["ms_dp_filter"] * 1e-3) / 1e9
+        roofline_filter = {"bound": "int32", "kernel": "k2_filter", "achieved": f_ach, "peak": alu_gops, "unit": "Gop/s",
+                           "frac": f_ach / alu_gops if alu_gops else None, "traffic": None,
+                           "columns_per_s": cols / (st["ms_dp_filter"] * 1e-3), "alu_ops_per_column": FILTER_ALU_OPS_PER_COL,
+                           "share_of_step": st["ms_dp_filter"] / st["ms_total"] if st["ms_total"] else None}
     roofline_hbm = {"bound": "hbm", "kernel": "k1_scan", "achieved": scan_gbs, "peak": hbm_peak, "unit": "GB/s",
                     "frac": scan_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
                     "share_of_step": st["ms_scan"] / st["ms_total"] if st["ms_total"] else None}
-    stages = {k: st[k] / args.steps for k in ("ms_scan", "ms_worklist", "ms_dp", "ms_translate", "ms_count", "ms_total")}
+    stages = {k: st[k] / args.steps for k in ("ms_scan", "ms_worklist", "ms_dp", "ms_dp_filter", "ms_dp_window",
+                                              "ms_translate", "ms_count", "ms_total")}
     stages["translate_gbs"] = key_bytes / (st["ms_translate"] * 1e-3) / 1e9 if st["ms_translate"] > 0 else 0.0
 
     cpu = None
@@ -372,8 +393,12 @@ def main():
                    "scoring": [3, -2, 5, 2], "l2": "inputs (%.1f GB per GPU) are larger than L2" % (R * L / 1e9),
                    "parallelism": "reads sharded over %d GPU(s), NCCL all-to-all table merge" % world},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(st["kernel_launches"]),
-        "roofline": roofline, "roofline_hbm": roofline_hbm, "stages_ms_per_step": stages,
-        "dp": {"gcups": gcups, "cells_per_step": st["dp_cells"] // args.steps,
+        "roofline": roofline, "roofline_filter": roofline_filter, "roofline_hbm": roofline_hbm,
+        "stages_ms_per_step": stages,
+        "dp": {"effective_gcups": gcups, "mode": "windowed (filter + windows)" if windowed else "full matrices",
+               "cells_per_step": st["dp_cells"] // args.steps,
+               "cells_computed_per_step": st["dp_cells_computed"] // args.steps,
+               "windows_per_step": st["dp_windows"] // args.steps,
                "alignments_per_step": (st["dp_prefix"] + st["dp_suffix"]) // args.steps},
         "merge_ms_per_step": merge_ms, "table": {"unique": st["unique"], "counted_per_step": st["counted"], "merge_check": merge_check},
         "cpu_baseline": cpu,

@@ -124,6 +124,7 @@ typedef struct vfb_stats {
     int32_t reserved;
     uint64_t dp_cells_computed; /* cells the DP kernels actually evaluated (== dp_cells for the full DP) */
     uint64_t dp_windows;        /* windows the filter produced (windowed DP)            */
+    double ms_dp_filter, ms_dp_window;   /* parts of ms_dp: k2_filter and k2_dp_window (profiling only) */
 } vfb_stats;
 
 typedef struct vfb_ctx vfb_ctx;

@@ -21,25 +21,36 @@ rows = list(csv.reader(io.StringIO(raw)))
 heads = [i for i, r in enumerate(rows) if r and r[0] == "Line No"]
 if not heads:
     raise SystemExit("no source page for " + a.kernel)
-h0 = heads[min(a.launch, len(heads) - 1)]
-end = heads[heads.index(h0) + 1] - 2 if heads.index(h0) + 1 < len(heads) else len(rows)
-H = rows[h0]
+# one section per source file of a launch; a launch's sections are consecutive and a new launch
+# starts when a file path repeats
+launches, cur_files = [[]], set()
+for h in heads:
+    f = rows[h - 2][1] if h >= 2 else "?"
+    if f in cur_files:
+        launches.append([]); cur_files = set()
+    cur_files.add(f); launches[-1].append(h)
+secs = launches[min(a.launch, len(launches) - 1)]
+H = rows[secs[0]]
 iS, iE, iT = H.index("# Samples"), H.index("Instructions Executed"), H.index("Thread Instructions Executed")
-print("kernel:", rows[h0 - 1][1] if h0 else "?")
+print("kernel:", rows[secs[0] - 1][1], " files:", len(secs))
 lines, sass = [], []
-cur = None
-for r in rows[h0 + 1:end]:
-    if len(r) <= iT or r[2] == "...":
-        continue
-    try:
-        s, e, t = int(r[iS]), int(r[iE]), int(r[iT])
-    except ValueError:
-        continue
-    if r[0]:
-        cur = (r[0], r[1].strip())
-        lines.append((s, e, t, r[0], r[1].strip()))
-    else:
-        sass.append((r[2], s, e, t, r[3].strip(), cur[0] if cur else "?"))
+for h0 in secs:
+    nxt = [x for x in heads if x > h0]
+    end = nxt[0] - 2 if nxt else len(rows)
+    fname = rows[h0 - 2][1].split("/")[-1] if h0 >= 2 else "?"
+    cur = None
+    for r in rows[h0 + 1:end]:
+        if len(r) <= iT or r[2] == "...":
+            continue
+        try:
+            s, e, t = int(r[iS]), int(r[iE]), int(r[iT])
+        except ValueError:
+            continue
+        if r[0]:
+            cur = (fname[:10] + ":" + r[0], r[1].strip())
+            lines.append((s, e, t, cur[0], r[1].strip()))
+        else:
+            sass.append((r[2], s, e, t, r[3].strip(), cur[0] if cur else "?"))
 # the same address can appear under several source lines (inlining): keep each address once
 seen, uniq = set(), []
 for x in sass:
@@ -50,7 +61,7 @@ totE = sum(x[2] for x in uniq); totS = sum(x[1] for x in uniq); totT = sum(x[3] 
 print("warp instructions executed: %d   thread instructions: %d   samples: %d" % (totE, totT, totS))
 print("-- hottest source lines (samples%, warp-inst%)")
 for s, e, t, ln, src in sorted(lines, key=lambda x: -x[0])[:a.top]:
-    print("  %5.1f%% %5.1f%%  L%-4s %s" % (100.0 * s / max(1, totS), 100.0 * e / max(1, totE), ln, src[:110]))
+    print("  %5.1f%% %5.1f%%  %-16s %s" % (100.0 * s / max(1, totS), 100.0 * e / max(1, totE), ln, src[:110]))
 if a.sass:
     print("-- SASS in address order (>= %.1f%% of executed warp instructions or of samples)" % (100 * a.min_share))
     for ad, s, e, t, txt, ln in sorted(uniq, key=lambda x: x[0]):

@@ -163,7 +163,7 @@ struct vfb_ctx {
 
     bool profiling = false;
     bool own_compute_stream = true;
-    std::vector<cudaEvent_t> evpool;   // 8 events per profiled batch, resolved at sync time
+    std::vector<cudaEvent_t> evpool;   // 12 events per profiled batch, resolved at sync time
     size_t ev_used = 0;
     vfb_stats stats{};
 };
@@ -172,19 +172,19 @@ struct vfb_ctx {
 // times are accumulated when the stream is next synchronised.
 static int prof_events(vfb_ctx *c, cudaEvent_t **out)
 {
-    if (c->ev_used + 8 > c->evpool.size()) {
+    if (c->ev_used + 12 > c->evpool.size()) {
         size_t old = c->evpool.size();
-        c->evpool.resize(old + 64, nullptr);
+        c->evpool.resize(old + 96, nullptr);
         for (size_t i = old; i < c->evpool.size(); ++i) VFB_CUDA(cudaEventCreate(&c->evpool[i]));
     }
     *out = &c->evpool[c->ev_used];
-    c->ev_used += 8;
+    c->ev_used += 12;
     return VFB_OK;
 }
 
 static int prof_resolve(vfb_ctx *c)
 {
-    for (size_t b = 0; b + 8 <= c->ev_used; b += 8) {
+    for (size_t b = 0; b + 12 <= c->ev_used; b += 12) {
         cudaEvent_t *ev = &c->evpool[b];
         float ms;
         VFB_CUDA(cudaEventElapsedTime(&ms, ev[0], ev[1])); c->stats.ms_scan += ms;
@@ -195,6 +195,17 @@ static int prof_resolve(vfb_ctx *c)
         VFB_CUDA(cudaEventElapsedTime(&ms, ev[5], ev[6])); c->stats.ms_translate += ms;
         VFB_CUDA(cudaEventElapsedTime(&ms, ev[6], ev[7])); c->stats.ms_count += ms;
         VFB_CUDA(cudaEventElapsedTime(&ms, ev[0], ev[7])); c->stats.ms_total += ms;
+        if (c->stats.dp_kernel_kind == 3) {
+            // windowed DP: [2] filter [8] windows [9] resolve + fallbacks [3], same for the suffix pass
+            if (c->win_k_pre >= 0 && c->align_pre) {
+                VFB_CUDA(cudaEventElapsedTime(&ms, ev[2], ev[8])); c->stats.ms_dp_filter += ms;
+                VFB_CUDA(cudaEventElapsedTime(&ms, ev[8], ev[9])); c->stats.ms_dp_window += ms;
+            }
+            if (c->win_k_suf >= 0 && c->align_suf) {
+                VFB_CUDA(cudaEventElapsedTime(&ms, ev[4], ev[10])); c->stats.ms_dp_filter += ms;
+                VFB_CUDA(cudaEventElapsedTime(&ms, ev[10], ev[11])); c->stats.ms_dp_window += ms;
+            }
+        }
     }
     c->ev_used = 0;
     return VFB_OK;
@@ -534,7 +545,8 @@ __global__ void k_accumulate(unsigned long long *t64, const uint32_t *c32, uint3
     t64[T_WINDOWS] += (c32[C_NWINPRE] < win_cap ? c32[C_NWINPRE] : win_cap) + (c32[C_NWINSUF] < win_cap ? c32[C_NWINSUF] : win_cap);
 }
 
-static int run_dp(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_spans, bool is_prefix, uint32_t n_batch)
+static int run_dp(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_spans, bool is_prefix, uint32_t n_batch,
+                  cudaEvent_t *pev)
 {
     int rc;
     DpJob job;
@@ -579,7 +591,8 @@ static int run_dp(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_spans, bo
         const uint32_t lcap = is_prefix ? c->lcap_pre : c->lcap_suf;
         if ((rc = launch_dp_windowed(job, lay, K, lcap, n_batch, c->d_wins.p, c32 + (is_prefix ? C_NWINPRE : C_NWINSUF),
                                      c->win_cap, c->d_bestkey.as<unsigned long long>(), c->d_cbval.as<unsigned long long>(),
-                                     fb, nfb, c->d_t64.as<unsigned long long>() + T_CELLSCOMP, c->sm_count, c->st_compute)))
+                                     fb, nfb, c->d_t64.as<unsigned long long>() + T_CELLSCOMP, c->sm_count, c->st_compute,
+                                     pev ? pev[is_prefix ? 8 : 10] : nullptr, pev ? pev[is_prefix ? 9 : 11] : nullptr)))
             return rc;
         DpJob fj = job;
         fj.worklist = fb;
@@ -677,10 +690,10 @@ static int process_batch(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_sp
     // DP.  The prefix pass runs first: reads it rejects need no suffix alignment (no region
     // either way, src/lib.rs:288), reads it accepts join the suffix worklist if they need one.
     if (prof) VFB_CUDA(cudaEventRecord(pev[2], st));
-    if (c->align_pre) if ((rc = run_dp(c, d_text, d_spans, true, n))) return rc;
+    if (c->align_pre) if ((rc = run_dp(c, d_text, d_spans, true, n, prof ? pev : nullptr))) return rc;
     if (prof) VFB_CUDA(cudaEventRecord(pev[3], st));
     if (prof) VFB_CUDA(cudaEventRecord(pev[4], st));
-    if (c->align_suf) if ((rc = run_dp(c, d_text, d_spans, false, n))) return rc;
+    if (c->align_suf) if ((rc = run_dp(c, d_text, d_spans, false, n, prof ? pev : nullptr))) return rc;
     if (prof) VFB_CUDA(cudaEventRecord(pev[5], st));
     k_accumulate<<<1, 1, 0, st>>>(c->d_t64.as<unsigned long long>(), c->d_c32.as<uint32_t>(), c->win_cap);
     ++g_launches;

@@ -63,13 +63,17 @@ __device__ bool utf8_valid(const uint8_t *s, uint32_t n)
 }
 
 #define KEY_THREADS 256
-#define KEY_GROUP 8                 // lanes per read in the translate phase
+#define KEY_WARPS (KEY_THREADS / 32)
+#define KEY_GROUP 4                 // lanes per read in the translate phase
+#define KEY_RPS (32 / KEY_GROUP)    // reads per sub-step of the translate phase
 #define KEY_MULTS 128               // hash multipliers kept in shared memory
 
 struct KeyTables {
-    uint8_t lut[256];               // byte -> base index 0..4 (bytes >= 128 -> 4)
+    // byte -> base index 0..4 (bytes >= 128 -> 4), premultiplied for the three codon positions
+    uint8_t lut25[256], lut5[256], lut1[256];
     uint8_t aa[128];                // c0*25 + c1*5 + c2 -> amino acid, 'X' if any index is 4
     uint64_t mult[KEY_MULTS];       // vfb_hash_mult(i)
+    uint8_t order[KEY_WARPS][32];   // per warp: lanes that own a key, compacted
 };
 
 __device__ __forceinline__ uint64_t key_mult(const KeyTables *T, uint32_t i)
@@ -93,13 +97,17 @@ __device__ __forceinline__ void load_unaligned(const uint8_t *a, const uint8_t *
 }
 
 // Phase A: one lane per read decides the key length and claims key space (one atomic per
-// 32 reads).  Phase B: lane groups of 8 translate 4 reads at a time, one 32-bit word of key
-// (4 amino acids = 12 bases) per lane per step, hashing the words they hold.
+// 32 reads); the lanes that own a key are compacted.  Phase B: lane groups of 4 translate 8
+// of those reads at a time, one 32-bit word of key (4 amino acids = 12 bases) per lane per
+// step, hashing the words they hold.
 __global__ void __launch_bounds__(KEY_THREADS)
 k3_keys(const __grid_constant__ KeyJob job)
 {
     __shared__ KeyTables T;
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) T.lut[i] = (uint8_t)(i >= 128 ? 4 : tr_index((uint8_t)i));
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const uint32_t c = i >= 128 ? 4u : tr_index((uint8_t)i);
+        T.lut25[i] = (uint8_t)(25u * c); T.lut5[i] = (uint8_t)(5u * c); T.lut1[i] = (uint8_t)c;
+    }
     for (int i = threadIdx.x; i < 128; i += blockDim.x) {
         const int c0 = i / 25, c1 = (i / 5) % 5, c2 = i % 5;
         T.aa[i] = (i >= 125 || c0 == 4 || c1 == 4 || c2 == 4) ? (uint8_t)'X' : (uint8_t)c_aa[c0 * 16 + c1 * 4 + c2];
@@ -107,26 +115,33 @@ k3_keys(const __grid_constant__ KeyJob job)
     for (int i = threadIdx.x; i < KEY_MULTS; i += blockDim.x) T.mult[i] = vfb_hash_mult((uint32_t)i);
     __syncthreads();
 
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane & (KEY_GROUP - 1), grp = lane / KEY_GROUP;
-    const uint32_t warps_total = gridDim.x * (KEY_THREADS / 32);
+    const uint32_t warps_total = gridDim.x * KEY_WARPS;
     const uint32_t n_rounds = (job.n_reads + 31) / 32;
-    for (uint32_t round = blockIdx.x * (KEY_THREADS / 32) + (threadIdx.x >> 5); round < n_rounds; round += warps_total) {
+    for (uint32_t round = blockIdx.x * KEY_WARPS + warp; round < n_rounds; round += warps_total) {
         // ---- phase A
         const uint32_t r = round * 32 + lane;
         uint32_t klen = 0, V = 0;
         const uint8_t *var = job.text;
         if (r < job.n_reads) {
             const uint32_t s = job.start[r], e = job.end[r];
-            const vfb_span sp = job.spans[r];
             // src/lib.rs:288: both located and start < end (strict).  end <= len always holds
             // for located suffix boundaries; a prefix boundary beyond it fails start < end.
-            if (s != VFB_NONE && e != VFB_NONE && s < e && e <= sp.len) {
-                V = e - s;
-                var = job.text + sp.off + s;
-                if (job.skip_translation) klen = V;
-                else if (V % 3 == 0) klen = V / 3;                 // :17-19 partial codon -> None
+            if (s != VFB_NONE && e != VFB_NONE && s < e) {
+                const vfb_span sp = job.spans[r];
+                if (e <= sp.len) {
+                    V = e - s;
+                    var = job.text + sp.off + s;
+                    if (job.skip_translation) klen = V;
+                    else if (V % 3 == 0) klen = V / 3;                 // :17-19 partial codon -> None
+                }
             }
+        }
+        const unsigned owners = __ballot_sync(0xffffffffu, klen != 0);
+        if (owners == 0) {
+            if (r < job.n_reads) job.klen[r] = 0;
+            continue;
         }
         const uint32_t padded = (klen + 15u) & ~15u;
         uint32_t incl = padded;
@@ -137,21 +152,27 @@ k3_keys(const __grid_constant__ KeyJob job)
         }
         unsigned long long base = 0;
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        if (lane == 31 && total) base = atomicAdd(job.key_cursor, (unsigned long long)total);
+        if (lane == 31) base = atomicAdd(job.key_cursor, (unsigned long long)total);
         base = __shfl_sync(0xffffffffu, base, 31);
         const unsigned long long koff = base + (incl - padded);
-        if (r < job.n_reads && klen) job.koff[r] = koff;
+        if (klen) {
+            job.koff[r] = koff;
+            T.order[warp][__popc(owners & ((1u << lane) - 1u))] = (uint8_t)lane;
+        }
+        __syncwarp();
+        const int n_own = __popc(owners);
         uint32_t bad_mask = 0;       // reads whose raw region is not valid UTF-8 (skip_translation only)
         // ---- phase B
 #pragma unroll 1
-        for (int sub = 0; sub < 32 / (32 / KEY_GROUP); ++sub) {
-            const int owner = sub * (32 / KEY_GROUP) + grp;
-            const uint32_t kl = __shfl_sync(0xffffffffu, klen, owner);
+        for (int sub = 0; sub * KEY_RPS < n_own; ++sub) {
+            const int k = sub * KEY_RPS + grp;
+            const bool have = k < n_own;
+            const int owner = have ? T.order[warp][k] : 0;
+            const uint32_t kl_owner = __shfl_sync(0xffffffffu, klen, owner);
+            const uint32_t kl = have ? kl_owner : 0u;
             const uint32_t vv = __shfl_sync(0xffffffffu, V, owner);
             const unsigned long long ko = __shfl_sync(0xffffffffu, koff, owner);
             const uintptr_t va = __shfl_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(var), owner);
-            const uint32_t max_kl = __reduce_max_sync(0xffffffffu, kl);
-            if (max_kl == 0) continue;
             const uint8_t *src = reinterpret_cast<const uint8_t *>(va);
             const uint8_t *limit = reinterpret_cast<const uint8_t *>((va + vv + 3) & ~(uintptr_t)3);
             uint32_t *key = reinterpret_cast<uint32_t *>(job.keys + ko);
@@ -164,20 +185,14 @@ k3_keys(const __grid_constant__ KeyJob job)
                     if (!job.skip_translation) {
                         uint32_t x[3];
                         load_unaligned<3>(src + 12 * wi, limit, x);
-                        const uint32_t n_aa = min(4u, kl - 4 * wi);
-#pragma unroll
-                        for (int a = 0; a < 4; ++a) {
-                            // codon a = bytes 3a .. 3a+2 of the 12
-                            uint32_t b[3];
-#pragma unroll
-                            for (int t = 0; t < 3; ++t) {
-                                const int p = 3 * a + t;
-                                b[t] = (x[p >> 2] >> (8 * (p & 3))) & 0xFFu;
-                            }
-                            const uint32_t idx = T.lut[b[0]] * 25u + T.lut[b[1]] * 5u + T.lut[b[2]];
-                            const uint32_t aa = (uint32_t)a < n_aa ? T.aa[idx] : 0u;
-                            word |= aa << (8 * a);
-                        }
+                        // codon a = bytes 3a .. 3a+2 of the 12
+                        const uint32_t i0 = T.lut25[x[0] & 0xFFu] + T.lut5[(x[0] >> 8) & 0xFFu] + T.lut1[(x[0] >> 16) & 0xFFu];
+                        const uint32_t i1 = T.lut25[x[0] >> 24] + T.lut5[x[1] & 0xFFu] + T.lut1[(x[1] >> 8) & 0xFFu];
+                        const uint32_t i2 = T.lut25[(x[1] >> 16) & 0xFFu] + T.lut5[x[1] >> 24] + T.lut1[x[2] & 0xFFu];
+                        const uint32_t i3 = T.lut25[(x[2] >> 8) & 0xFFu] + T.lut5[(x[2] >> 16) & 0xFFu] + T.lut1[x[2] >> 24];
+                        word = (uint32_t)T.aa[i0] | ((uint32_t)T.aa[i1] << 8) | ((uint32_t)T.aa[i2] << 16) | ((uint32_t)T.aa[i3] << 24);
+                        const uint32_t n_aa = kl - 4 * wi;             // >= 1
+                        if (n_aa < 4) word &= (1u << (8 * n_aa)) - 1u;
                     } else {
                         load_unaligned<1>(src + 4 * wi, limit, &word);
                         const uint32_t nb = min(4u, kl - 4 * wi);
@@ -203,10 +218,13 @@ k3_keys(const __grid_constant__ KeyJob job)
                 if (g == 0 && kl && high) bad = !utf8_valid(src, vv);
                 const unsigned bm = __ballot_sync(0xffffffffu, bad);
 #pragma unroll
-                for (int q = 0; q < 32 / KEY_GROUP; ++q)
-                    if (bm & (1u << (q * KEY_GROUP))) bad_mask |= 1u << (sub * (32 / KEY_GROUP) + q);
+                for (int q = 0; q < KEY_RPS; ++q) {
+                    const uint32_t q_owner = __shfl_sync(0xffffffffu, (uint32_t)owner, q * KEY_GROUP);
+                    if (bm & (1u << (q * KEY_GROUP))) bad_mask |= 1u << q_owner;
+                }
             }
         }
+        __syncwarp();
         if (bad_mask & (1u << lane)) klen = 0;
         if (r < job.n_reads) job.klen[r] = klen;
     }

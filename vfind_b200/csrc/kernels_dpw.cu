@@ -399,7 +399,8 @@ static int launch_window(const DpwArgs &args, int sm_count, cudaStream_t st)
 int launch_dp_windowed(const DpJob &job, const DpLayout &lay, int K, uint32_t lcap, uint32_t max_items,
                        void *wins, uint32_t *n_wins, uint32_t win_cap, unsigned long long *best_key,
                        unsigned long long *cb_val, uint32_t *fallback, uint32_t *n_fallback,
-                       unsigned long long *cells_computed, int sm_count, cudaStream_t st)
+                       unsigned long long *cells_computed, int sm_count, cudaStream_t st,
+                       cudaEvent_t ev_filter_done, cudaEvent_t ev_windows_done)
 {
     DpwArgs a;
     a.job = job; a.lay = lay; a.K = K; a.lcap = lcap;
@@ -410,6 +411,7 @@ int launch_dp_windowed(const DpJob &job, const DpLayout &lay, int K, uint32_t lc
     VFB_CUDA(cudaMemsetAsync(cb_val, 0, (size_t)max_items * 8, st));
     k2_filter<<<sm_count * 12, DPW_THREADS, 0, st>>>(a);
     ++g_launches;
+    if (ev_filter_done) VFB_CUDA(cudaEventRecord(ev_filter_done, st));
     int rc;
     switch (((int)job.adapter_len + 3) & ~3) {
     case 4: rc = launch_window<4>(a, sm_count, st); break;
@@ -423,6 +425,7 @@ int launch_dp_windowed(const DpJob &job, const DpLayout &lay, int K, uint32_t lc
     default: set_error("adapter too long for the windowed DP"); return VFB_ERR_ARG;
     }
     if (rc) return rc;
+    if (ev_windows_done) VFB_CUDA(cudaEventRecord(ev_windows_done, st));
     k2_resolve<<<(max_items + 255) / 256, 256, 0, st>>>(a);
     ++g_launches;
     VFB_CUDA(cudaGetLastError());

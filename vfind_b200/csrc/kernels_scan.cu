@@ -25,9 +25,13 @@ namespace vfb {
 #define WL_BUF 64               // per-warp worklist staging entries
 
 struct ScanTables {
-    // 4-mer hash: slot = {word, valid, maskP.lo, maskP.hi}, {maskS.lo, maskS.hi, -, -}
+    // 4-mer hash.  e0 slot = {word, kind | adapter << 8 | offset << 16, next word, next-word mask}:
+    // kind 1 = the 4-mer sits at ONE (adapter, offset); the word after it in the text must then
+    // match the adapter's next bytes (cuts the 1-in-8 false 4-mer hits before any verification);
+    // kind 2 = several (adapter, offset) pairs share the 4-mer: their offsets are bit sets in
+    // e1 (prefix in bits 0-15, suffix in bits 16-31) and the next-word mask is 0.
     uint4 e0[SCAN_SLOTS];
-    uint4 e1[SCAN_SLOTS];
+    uint32_t e1[SCAN_SLOTS];
     // adapters pre-shifted to every position s inside a 16-byte chunk: bytes and byte masks
     uint4 pat[2][16][SCAN_MAXC];
     uint4 msk[2][16][SCAN_MAXC];
@@ -37,9 +41,15 @@ struct ScanArgs {
     ScanJob job;
     AdapterBytes prefix, suffix;
     uint32_t mult;      // hash multiplier under which the adapters' sampled 4-mers do not collide
+    int multi;          // a sampled 4-mer occurs at more than one (adapter, offset)
 };
 
 __host__ __device__ __forceinline__ uint32_t hash4(uint32_t w, uint32_t mult) { return (w * mult) >> 23; }
+// 8-byte keys (two consecutive text words)
+__host__ __device__ __forceinline__ uint32_t hash8(uint32_t w0, uint32_t w1, uint32_t mult)
+{
+    return (w0 * mult + w1 * (mult * 0x85EBCA6Bu + 2u)) >> 23;
+}
 
 __host__ __device__ __forceinline__ uint32_t load_word_le(const uint8_t *b, int i, int n)
 {
@@ -53,11 +63,12 @@ __host__ __device__ __forceinline__ uint32_t load_word_le(const uint8_t *b, int 
     return w;
 }
 
-__device__ void build_tables(ScanTables *T, const AdapterBytes &pre, const AdapterBytes &suf, int max_k, uint32_t mult)
+__device__ void build_tables(ScanTables *T, const AdapterBytes &pre, const AdapterBytes &suf, int max_k, uint32_t mult,
+                             bool next_word, bool key8)
 {
     for (int i = threadIdx.x; i < SCAN_SLOTS; i += blockDim.x) {
         T->e0[i] = make_uint4(0, 0, 0, 0);
-        T->e1[i] = make_uint4(0, 0, 0, 0);
+        T->e1[i] = 0;
     }
     for (int i = threadIdx.x; i < 2 * 16 * SCAN_MAXC * 4; i += blockDim.x) {
         // word m of chunk c of adapter x placed at chunk offset s
@@ -79,14 +90,29 @@ __device__ void build_tables(ScanTables *T, const AdapterBytes &pre, const Adapt
         // 4-mer at several offsets ORs into one slot.
         for (int x = 0; x < 2; ++x) {
             const AdapterBytes &ad = x ? suf : pre;
-            for (int k = 0; k < max_k && k + 4 <= (int)ad.len; ++k) {
+            for (int k = 0; k < max_k && k + (key8 ? 8 : 4) <= (int)ad.len; ++k) {
                 const uint32_t w = load_word_le(ad.b, k, (int)ad.len);
-                const uint32_t h = hash4(w, mult);      // collision-free by choice of mult (host)
-                T->e0[h].x = w;
-                T->e0[h].y = 1;
-                const uint32_t lo = k < 32 ? 1u << k : 0u, hi = k >= 32 ? 1u << (k - 32) : 0u;
-                if (x == 0) { T->e0[h].z |= lo; T->e0[h].w |= hi; }
-                else { T->e1[h].x |= lo; T->e1[h].y |= hi; }
+                const uint32_t w1 = load_word_le(ad.b, k + 4, (int)ad.len);
+                const uint32_t h = key8 ? hash8(w, w1, mult) : hash4(w, mult);      // collision-free by choice of mult (host)
+                uint4 e = T->e0[h];
+                if (e.y == 0) {
+                    e.x = w;
+                    e.y = 1u | ((uint32_t)x << 8) | ((uint32_t)k << 16);
+                    e.z = e.w = 0;
+                    if (key8) {
+                        e.z = w1;
+                        e.w = 0xFFFFFFFFu;
+                    } else if (next_word) {
+                        e.z = w1;
+                        for (int b = 0; b < 4; ++b)
+                            if (k + 4 + b < (int)ad.len) e.w |= 0xFFu << (8 * b);
+                    }
+                } else {
+                    e.y = 2u;
+                    if (!key8) e.z = e.w = 0;
+                }
+                T->e0[h] = e;
+                T->e1[h] |= 1u << (k + 16 * x);
             }
         }
     }
@@ -115,13 +141,13 @@ __device__ __forceinline__ bool verify_at(const ScanTables *T, uint32_t x, uint3
     return diff == 0;
 }
 
-// A table hit: the sampled word at `relq` (bytes after the read start, may be negative) equals
-// the adapter 4-mer(s) of `slot`.  Expand to candidate starts and verify them.
+// A hit on a kind-2 slot: the sampled word at `relq` (bytes after the read start, may be
+// negative) equals an adapter 4-mer that sits at several (adapter, offset) pairs.  Expand to
+// candidate starts and verify them.
 __device__ __forceinline__ void hit_expand(const ScanTables *T, uint32_t slot, int relq, const ReadGeom &rg,
                                            uint32_t AP, uint32_t AS, uint32_t &bestP, uint32_t &bestS)
 {
-    // adapter offsets < 16 each (see build_tables): prefix in bits 0-15, suffix in bits 16-31
-    uint32_t m = (T->e0[slot].z & 0xFFFFu) | (T->e1[slot].x << 16);
+    uint32_t m = T->e1[slot];
     while (m) {
         const int b = __ffs((int)m) - 1;
         m &= m - 1;
@@ -135,50 +161,82 @@ __device__ __forceinline__ void hit_expand(const ScanTables *T, uint32_t slot, i
     }
 }
 
-// Hits wait in a 3-deep per-lane queue and are expanded after the probes, all lanes together,
-// so that the divergent expand+verify code runs about once per trip instead of once per probe.
+// Out-of-line copy of the verification for the (practically never taken) queue-overflow path.
+__device__ __noinline__ uint32_t verify_cold(const ScanTables *T, uint32_t x, uint32_t rel, uint32_t A,
+                                             const uint4 *base16, uint32_t lead, uint32_t len)
+{
+    ReadGeom rg;
+    rg.base16 = base16; rg.lead = lead; rg.len = len;
+    return verify_at(T, x, rel, A, rg) ? 1u : 0u;
+}
+
+// One candidate: adapter x starting at p.
+__device__ __forceinline__ void hit_check(const ScanTables *T, uint32_t x, int p, const ReadGeom &rg,
+                                          uint32_t AP, uint32_t AS, uint32_t &bestP, uint32_t &bestS)
+{
+    const uint32_t A = x ? AS : AP;
+    if (p < 0 || (uint32_t)p + A > rg.len || (uint32_t)p >= (x ? bestS : bestP)) return;
+    if (verify_at(T, x, (uint32_t)p, A, rg)) {
+        if (x) bestS = (uint32_t)p; else bestP = (uint32_t)p;
+    }
+}
+
+// A candidate waits in ONE per-lane slot as ((p + 64) << 1 | adapter) and is verified after the
+// trip's probes, all lanes together, so that the divergent verify code runs once per trip
+// instead of once per probe.  A second candidate in the same lane and trip (rare: a lane's
+// three chunks are 128 bytes apart) sends the waiting one through the out-of-line copy.
 struct Hits {
-    uint32_t s0, s1, s2;
-    int q0, q1, q2;
+    uint32_t pend;
 };
 
-__device__ __forceinline__ void probe_word(const ScanTables *T, uint32_t mult, uint32_t w, int relq,
+template <bool MULTI, bool KEY8>
+__device__ __forceinline__ void probe_word(const ScanTables *T, uint32_t mult, uint32_t w, uint32_t wnext, int relq,
                                            const ReadGeom &rg, uint32_t AP, uint32_t AS, Hits &hq,
                                            uint32_t &bestP, uint32_t &bestS)
 {
-    const uint32_t h = hash4(w, mult);
+    const uint32_t h = KEY8 ? hash8(w, wnext, mult) : hash4(w, mult);
     const uint4 e = T->e0[h];
-    if (e.y && e.x == w) {
-        if (hq.s0 == VFB_NONE) { hq.s0 = h; hq.q0 = relq; }
-        else if (hq.s1 == VFB_NONE) { hq.s1 = h; hq.q1 = relq; }
-        else if (hq.s2 == VFB_NONE) { hq.s2 = h; hq.q2 = relq; }
-        else hit_expand(T, h, relq, rg, AP, AS, bestP, bestS);      // queue full: expand now
+    if (e.y && e.x == w && ((wnext ^ e.z) & e.w) == 0) {
+        if (MULTI && (e.y & 0xFFu) != 1u) { hit_expand(T, h, relq, rg, AP, AS, bestP, bestS); return; }
+        if (hq.pend != VFB_NONE) {
+            const uint32_t x = hq.pend & 1u, A = x ? AS : AP;
+            const int p = (int)(hq.pend >> 1) - 64;
+            if (p >= 0 && (uint32_t)p + A <= rg.len && (uint32_t)p < (x ? bestS : bestP) &&
+                verify_cold(T, x, (uint32_t)p, A, rg.base16, rg.lead, rg.len)) {
+                if (x) bestS = (uint32_t)p; else bestP = (uint32_t)p;
+            }
+        }
+        // (p + 64 < 2^31: reads of 2 GiB and more never reach the probes, see the kernel)
+        hq.pend = ((uint32_t)(relq - (int)(e.y >> 16) + 64) << 1) | ((e.y >> 8) & 1u);
     }
 }
 
 __device__ __forceinline__ void hits_drain(const ScanTables *T, Hits &hq, const ReadGeom &rg, uint32_t AP,
                                            uint32_t AS, uint32_t &bestP, uint32_t &bestS)
 {
-    while (__any_sync(0xffffffffu, hq.s0 != VFB_NONE)) {
-        if (hq.s0 != VFB_NONE) {
-            hit_expand(T, hq.s0, hq.q0, rg, AP, AS, bestP, bestS);
-            hq.s0 = hq.s1; hq.q0 = hq.q1;
-            hq.s1 = hq.s2; hq.q1 = hq.q2;
-            hq.s2 = VFB_NONE;
+    if (__any_sync(0xffffffffu, hq.pend != VFB_NONE)) {
+        if (hq.pend != VFB_NONE) {
+            hit_check(T, hq.pend & 1u, (int)(hq.pend >> 1) - 64, rg, AP, AS, bestP, bestS);
+            hq.pend = VFB_NONE;
         }
     }
 }
 
-template <int STRIDE_WORDS>
+// KEY8: the table is keyed by 8 text bytes (two words), probed at chunk offset 0 (and 8 when
+// STRIDE_WORDS == 2): no false hits to speak of, and duplicates among the adapters' keys are
+// rare.  Otherwise 4-byte keys probed every STRIDE_WORDS words, with the next-word check.
+template <int STRIDE_WORDS, bool MULTI, bool KEY8>
 __device__ __forceinline__ void probe_chunk(const ScanTables *T, uint32_t mult, const uint4 &v, int relq,
                                             const ReadGeom &rg, uint32_t AP, uint32_t AS, Hits &hq,
                                             uint32_t &bestP, uint32_t &bestS)
 {
-    probe_word(T, mult, v.x, relq, rg, AP, AS, hq, bestP, bestS);
-    if (STRIDE_WORDS <= 2) probe_word(T, mult, v.z, relq + 8, rg, AP, AS, hq, bestP, bestS);
+    // (with STRIDE_WORDS == 1 the word after v.w is in the next chunk: the tables carry no
+    // next-word check then, the argument is ignored)
+    probe_word<MULTI, KEY8>(T, mult, v.x, v.y, relq, rg, AP, AS, hq, bestP, bestS);
+    if (STRIDE_WORDS <= 2) probe_word<MULTI, KEY8>(T, mult, v.z, v.w, relq + 8, rg, AP, AS, hq, bestP, bestS);
     if (STRIDE_WORDS == 1) {
-        probe_word(T, mult, v.y, relq + 4, rg, AP, AS, hq, bestP, bestS);
-        probe_word(T, mult, v.w, relq + 12, rg, AP, AS, hq, bestP, bestS);
+        probe_word<MULTI, KEY8>(T, mult, v.y, v.z, relq + 4, rg, AP, AS, hq, bestP, bestS);
+        probe_word<MULTI, KEY8>(T, mult, v.w, 0u, relq + 12, rg, AP, AS, hq, bestP, bestS);
     }
 }
 
@@ -209,16 +267,46 @@ __device__ __forceinline__ void wl_push(uint32_t *stage, uint32_t &cnt, bool wan
     __syncwarp();
 }
 
+__device__ __forceinline__ uint32_t scan_one(const uint8_t *seq, uint32_t L, const uint8_t *ad,
+                                            uint32_t A, int lane)
+{
+    if (A == 0) return 0;              // an empty needle matches at 0 (memchr convention)
+    if (A > L) return VFB_NONE;
+    const uint32_t last = L - A;
+    const uint8_t a0 = ad[0];
+    for (uint32_t base = 0; base <= last; base += 32) {
+        const uint32_t p = base + lane;
+        bool hit = false;
+        if (p <= last && __ldg(seq + p) == a0) {
+            hit = true;
+            for (uint32_t t = 1; t < A; ++t) {
+                if (__ldg(seq + p + t) != ad[t]) { hit = false; break; }
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m) return base + (uint32_t)(__ffs((int)m) - 1);
+    }
+    return VFB_NONE;
+}
+
+__device__ __noinline__ uint2 scan_giant(const uint8_t *seq, uint32_t L, const ScanArgs &args, int lane)
+{
+    return make_uint2(scan_one(seq, L, args.prefix.b, args.prefix.len, lane),
+                      scan_one(seq, L, args.suffix.b, args.suffix.len, lane));
+}
+
 #define SCAN_GROUP 8                      // lanes per read
 #define SCAN_RPW (32 / SCAN_GROUP)        // reads per warp trip
 
-template <int STRIDE_WORDS>
-__global__ void __launch_bounds__(SCAN_THREADS)
+// MULTI = some 4-mer sits at several (adapter, offset) pairs (repetitive or overlapping
+// adapters; decided on the host): only then is the kind-2 expansion compiled in.
+template <int STRIDE_WORDS, bool MULTI, bool KEY8>
+__global__ void __launch_bounds__(SCAN_THREADS, MULTI ? 3 : 4)
 k1_scan_fast(const __grid_constant__ ScanArgs args)
 {
     __shared__ ScanTables T;
     __shared__ WlStage stage[SCAN_WARPS];
-    build_tables(&T, args.prefix, args.suffix, 4 * STRIDE_WORDS, args.mult);
+    build_tables(&T, args.prefix, args.suffix, 4 * STRIDE_WORDS, args.mult, STRIDE_WORDS >= 2, KEY8);
     const uint32_t mult = args.mult;
     const ScanJob &job = args.job;
     const uint32_t AP = args.prefix.len, AS = args.suffix.len;
@@ -237,8 +325,20 @@ k1_scan_fast(const __grid_constant__ ScanArgs args)
         rg.lead = (uint32_t)(addr & 15u);
         rg.len = sp.len;
         uint32_t bestP = VFB_NONE, bestS = VFB_NONE;
-        Hits hq{VFB_NONE, VFB_NONE, VFB_NONE, 0, 0, 0};
-        const uint32_t n_chunks = sp.len ? (rg.lead + sp.len + 15) >> 4 : 0;
+        // candidate starts are queued in 31 bits: a read of 2 GiB or more (there can be one in a
+        // 4 GiB buffer) is scanned byte-wise by the whole warp instead
+        const bool giant = sp.len >= 0x7FFFFF00u;
+        if (__any_sync(0xffffffffu, giant)) {
+            for (int q = 0; q < SCAN_RPW; ++q) {
+                if (!__shfl_sync(0xffffffffu, (int)giant, q * SCAN_GROUP)) continue;
+                const uint32_t off = __shfl_sync(0xffffffffu, sp.off, q * SCAN_GROUP);
+                const uint32_t ln = __shfl_sync(0xffffffffu, sp.len, q * SCAN_GROUP);
+                const uint2 b = scan_giant(job.text + off, ln, args, lane);
+                if (grp == q) { bestP = b.x; bestS = b.y; }
+            }
+        }
+        Hits hq{VFB_NONE};
+        const uint32_t n_chunks = sp.len && !giant ? (rg.lead + sp.len + 15) >> 4 : 0;
         // warp-uniform trip count: every lane takes part in the converged drain
         const uint32_t max_chunks = __reduce_max_sync(0xffffffffu, n_chunks);
         for (uint32_t cb = 0; cb < max_chunks; cb += 3 * SCAN_GROUP) {
@@ -248,9 +348,9 @@ k1_scan_fast(const __grid_constant__ ScanArgs args)
             const uint4 v0 = c0 < n_chunks ? __ldg(rg.base16 + c0) : z;
             const uint4 v1 = c1 < n_chunks ? __ldg(rg.base16 + c1) : z;
             const uint4 v2 = c2 < n_chunks ? __ldg(rg.base16 + c2) : z;
-            if (c0 < n_chunks) probe_chunk<STRIDE_WORDS>(&T, mult, v0, (int)(c0 * 16) - (int)rg.lead, rg, AP, AS, hq, bestP, bestS);
-            if (c1 < n_chunks) probe_chunk<STRIDE_WORDS>(&T, mult, v1, (int)(c1 * 16) - (int)rg.lead, rg, AP, AS, hq, bestP, bestS);
-            if (c2 < n_chunks) probe_chunk<STRIDE_WORDS>(&T, mult, v2, (int)(c2 * 16) - (int)rg.lead, rg, AP, AS, hq, bestP, bestS);
+            if (c0 < n_chunks) probe_chunk<STRIDE_WORDS, MULTI, KEY8>(&T, mult, v0, (int)(c0 * 16) - (int)rg.lead, rg, AP, AS, hq, bestP, bestS);
+            if (c1 < n_chunks) probe_chunk<STRIDE_WORDS, MULTI, KEY8>(&T, mult, v1, (int)(c1 * 16) - (int)rg.lead, rg, AP, AS, hq, bestP, bestS);
+            if (c2 < n_chunks) probe_chunk<STRIDE_WORDS, MULTI, KEY8>(&T, mult, v2, (int)(c2 * 16) - (int)rg.lead, rg, AP, AS, hq, bestP, bestS);
             hits_drain(&T, hq, rg, AP, AS, bestP, bestS);
         }
         // leftmost over the lane group
@@ -279,28 +379,6 @@ k1_scan_fast(const __grid_constant__ ScanArgs args)
 // ---------------------------------------------------------------------------------------
 // General kernel: any adapter length (including 0 and > 64).  One warp per read; lanes test
 // consecutive start positions byte by byte and vote.
-__device__ __forceinline__ uint32_t scan_one(const uint8_t *seq, uint32_t L, const uint8_t *ad,
-                                            uint32_t A, int lane)
-{
-    if (A == 0) return 0;              // an empty needle matches at 0 (memchr convention)
-    if (A > L) return VFB_NONE;
-    const uint32_t last = L - A;
-    const uint8_t a0 = ad[0];
-    for (uint32_t base = 0; base <= last; base += 32) {
-        const uint32_t p = base + lane;
-        bool hit = false;
-        if (p <= last && __ldg(seq + p) == a0) {
-            hit = true;
-            for (uint32_t t = 1; t < A; ++t) {
-                if (__ldg(seq + p + t) != ad[t]) { hit = false; break; }
-            }
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (m) return base + (uint32_t)(__ffs((int)m) - 1);
-    }
-    return VFB_NONE;
-}
-
 __global__ void __launch_bounds__(SCAN_THREADS)
 k1_scan_general(const __grid_constant__ ScanArgs args)
 {
@@ -344,37 +422,58 @@ int launch_scan(const ScanJob &job, const AdapterBytes &prefix, const AdapterByt
     const uint32_t amin = prefix.len < suffix.len ? prefix.len : suffix.len;
     const uint32_t amax = prefix.len > suffix.len ? prefix.len : suffix.len;
     bool fast = amin >= 7 && amax <= 64 && !job.force_general;
+    bool key8 = false;
+    int stride_words = 1;
     if (fast) {
         // perfect hash: find a multiplier under which the sampled 4-mers of both adapters
         // occupy distinct slots (<= 32 keys in 512 slots: a few tries)
-        const int max_k = amin >= 19 ? 16 : (amin >= 11 ? 8 : 4);
+        // amin >= 23: 8-byte keys every 16 bytes; >= 15: 8-byte keys every 8 bytes; >= 11: 4-byte keys
+        // every 8 bytes; else 4-byte keys every 4 bytes (every occurrence of the shorter adapter
+        // fully contains a sampled key)
+        key8 = amin >= 15;
+        stride_words = amin >= 23 ? 4 : (amin >= 11 ? 2 : 1);
+        const int max_k = 4 * stride_words, klen = key8 ? 8 : 4;
         bool ok = false;
+        bool multi = false;
         for (uint32_t t = 0; t < 4096 && !ok; ++t) {
             const uint32_t mult = 0x9E3779B1u + 2u * t * 0x632BE5ABu;
-            uint32_t words[SCAN_SLOTS];
+            uint32_t w0s[SCAN_SLOTS], w1s[SCAN_SLOTS];
             bool used[SCAN_SLOTS] = {false};
             ok = true;
+            multi = false;
             for (int x = 0; x < 2 && ok; ++x) {
                 const AdapterBytes &ad = x ? suffix : prefix;
-                for (int k = 0; k < max_k && k + 4 <= (int)ad.len; ++k) {
-                    const uint32_t w = load_word_le(ad.b, k, (int)ad.len), h = hash4(w, mult);
-                    if (used[h] && words[h] != w) { ok = false; break; }
+                for (int k = 0; k < max_k && k + klen <= (int)ad.len; ++k) {
+                    const uint32_t w = load_word_le(ad.b, k, (int)ad.len);
+                    const uint32_t w1 = key8 ? load_word_le(ad.b, k + 4, (int)ad.len) : 0u;
+                    const uint32_t h = key8 ? hash8(w, w1, mult) : hash4(w, mult);
+                    if (used[h] && (w0s[h] != w || w1s[h] != w1)) { ok = false; break; }
+                    if (used[h]) multi = true;
                     used[h] = true;
-                    words[h] = w;
+                    w0s[h] = w;
+                    w1s[h] = w1;
                 }
             }
             if (ok) a.mult = mult;
         }
         fast = ok;
+        a.multi = multi ? 1 : 0;
     }
     const uint32_t units = fast ? (job.n_reads + SCAN_RPW - 1) / SCAN_RPW : job.n_reads;
     uint32_t blocks = (units + SCAN_WARPS - 1) / SCAN_WARPS;
     const uint32_t cap = (uint32_t)sm_count * 8u;
     if (blocks > cap) blocks = cap;
+#define VFB_SCAN_LAUNCH(S, K8)                                                              \
+    do {                                                                                    \
+        if (a.multi) k1_scan_fast<S, true, K8><<<blocks, SCAN_THREADS, 0, st>>>(a);         \
+        else k1_scan_fast<S, false, K8><<<blocks, SCAN_THREADS, 0, st>>>(a);                \
+    } while (0)
     if (!fast) k1_scan_general<<<blocks, SCAN_THREADS, 0, st>>>(a);
-    else if (amin >= 19) k1_scan_fast<4><<<blocks, SCAN_THREADS, 0, st>>>(a);
-    else if (amin >= 11) k1_scan_fast<2><<<blocks, SCAN_THREADS, 0, st>>>(a);
-    else k1_scan_fast<1><<<blocks, SCAN_THREADS, 0, st>>>(a);
+    else if (key8 && stride_words == 4) VFB_SCAN_LAUNCH(4, true);
+    else if (key8) VFB_SCAN_LAUNCH(2, true);
+    else if (stride_words == 2) VFB_SCAN_LAUNCH(2, false);
+    else VFB_SCAN_LAUNCH(1, false);
+#undef VFB_SCAN_LAUNCH
     ++g_launches;
     VFB_CUDA(cudaGetLastError());
     return VFB_OK;
