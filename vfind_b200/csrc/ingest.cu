@@ -21,6 +21,7 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cerrno>
 #include <chrono>
@@ -339,6 +340,7 @@ int run_bgzf_gpu(vfb_ctx *ctx, ChunkProducer &prod, size_t text_target, uint64_t
     for (int i = 0; i < NSEG; ++i) pp.free_q.push_back(i);
     const int fd = fileno(prod.f);
     size_t pos = (size_t)ftell(prod.f);
+    size_t z_estimate = std::min(zcap, text_target / 4 + (1u << 20));     // compressed bytes a segment is expected to need
     std::thread reader;
     if (rc == VFB_OK) reader = std::thread([&]() {
         for (;;) {
@@ -353,48 +355,67 @@ int run_bgzf_gpu(vfb_ctx *ctx, ChunkProducer &prod, size_t text_target, uint64_t
             ZSegment &g = seg[k];
             g.z_bytes = g.text_bytes = 0; g.n = 0; g.last = false;
             std::string err;
-            // one pread per segment straight into the pinned buffer, then walk the member headers
-            const ssize_t got = pread(fd, g.z, zcap, (off_t)pos);
-            if (got < 0) err = std::string("read error: ") + strerror(errno);
-            const size_t avail = got > 0 ? (size_t)got : 0;
-            size_t off = 0;
-            bool stop = false;
-            while (err.empty() && !stop && off < avail && g.n < mcap) {
-                const uint8_t *h = g.z + off;
-                size_t msize = 0;
-                bool is_bgzf = false;
-                if (avail - off >= 18 && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4)) {
-                    const uint32_t xlen = h[10] | (h[11] << 8);
-                    if (avail - off >= 12 + (size_t)xlen) {
-                        for (uint32_t x = 0; x + 4 <= xlen;) {
-                            const uint8_t *sf = h + 12 + x;
-                            const uint32_t slen = sf[2] | (sf[3] << 8);
-                            if (sf[0] == 'B' && sf[1] == 'C' && slen == 2 && x + 6 <= xlen) { msize = (size_t)(sf[4] | (sf[5] << 8)) + 1; is_bgzf = true; break; }
-                            x += 4 + slen;
-                        }
-                    } else if (avail == zcap) break;          // header cut by the buffer: next segment
-                } else if (avail - off < 18 && avail == zcap) break;
-                if (!is_bgzf) {
-                    if (avail - off < 18 && avail < zcap) { err = "truncated gzip stream"; break; }
-                    prod.bgzf = false; g.last = true; stop = true;       // plain gzip from here: host path
-                    break;
+            // pread straight into the pinned buffer — about as much as the last segment needed,
+            // topped up while whole members are still missing — then walk the member headers
+            size_t avail = 0, off = 0;
+            bool eof = false, stop = false, full = false;
+            size_t step = z_estimate;
+            while (err.empty() && !stop && !full) {
+                if (!eof && avail < zcap) {
+                    const size_t want = std::min(zcap - avail, step);
+                    const ssize_t got = pread(fd, g.z + avail, want, (off_t)(pos + avail));
+                    if (got < 0) { err = std::string("read error: ") + strerror(errno); break; }
+                    if ((size_t)got < want) eof = true;
+                    avail += (size_t)got;
+                    step = std::max<size_t>((size_t)4 << 20, z_estimate / 4);
                 }
-                if (msize < 26) { err = "invalid BGZF member"; break; }
-                if (off + msize > avail) {
-                    if (avail < zcap) err = "truncated gzip stream";     // end of file inside a member
-                    else if (off == 0) err = "a gzip member does not fit the ingest buffer";
-                    break;
+                bool need_more = false;
+                while (off < avail && g.n < mcap) {
+                    const uint8_t *h = g.z + off;
+                    size_t msize = 0;
+                    bool is_bgzf = false, cut = false;
+                    if (avail - off >= 18 && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4)) {
+                        const uint32_t xlen = h[10] | (h[11] << 8);
+                        if (avail - off >= 12 + (size_t)xlen) {
+                            for (uint32_t x = 0; x + 4 <= xlen;) {
+                                const uint8_t *sf = h + 12 + x;
+                                const uint32_t slen = sf[2] | (sf[3] << 8);
+                                if (sf[0] == 'B' && sf[1] == 'C' && slen == 2 && x + 6 <= xlen) { msize = (size_t)(sf[4] | (sf[5] << 8)) + 1; is_bgzf = true; break; }
+                                x += 4 + slen;
+                            }
+                        } else cut = true;                          // header cut by what has been read so far
+                    } else if (avail - off < 18) cut = true;
+                    if (cut && !eof) { need_more = true; break; }
+                    if (!is_bgzf) {
+                        if (cut) { err = "truncated gzip stream"; break; }     // end of file inside a header
+                        prod.bgzf = false; g.last = true; stop = true;       // plain gzip from here: host path
+                        break;
+                    }
+                    if (msize < 26) { err = "invalid BGZF member"; break; }
+                    if (off + msize > avail) {
+                        if (eof) err = "truncated gzip stream";              // end of file inside a member
+                        else need_more = true;
+                        break;
+                    }
+                    const uint8_t *t = h + msize - 4;
+                    const uint32_t isize = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
+                    if (g.n && g.text_bytes + isize > text_target) { full = true; break; }
+                    g.members[g.n++] = vfb_member{(uint32_t)off, (uint32_t)msize, (uint32_t)g.text_bytes, isize};
+                    off += msize;
+                    g.text_bytes += isize;
                 }
-                const uint8_t *t = h + msize - 4;
-                const uint32_t isize = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
-                if (g.n && g.text_bytes + isize > text_target) break;
-                g.members[g.n++] = vfb_member{(uint32_t)off, (uint32_t)msize, (uint32_t)g.text_bytes, isize};
-                off += msize;
-                g.text_bytes += isize;
+                if (!err.empty() || stop || full) break;
+                if (g.n >= mcap) break;
+                if (avail >= zcap) {
+                    if (need_more && off == 0) err = "a gzip member does not fit the ingest buffer";
+                    break;                                           // the buffer is full: next segment
+                }
+                if (eof) break;                                      // everything read and consumed
             }
+            if (off) z_estimate = off + off / 16 + 65536;
             g.z_bytes = off;
             pos += off;
-            if (err.empty() && !stop && avail < zcap && off == avail) { prod.at_end = true; g.last = true; }
+            if (err.empty() && !stop && eof && off == avail) { prod.at_end = true; g.last = true; }
             std::lock_guard<std::mutex> lk(pp.mu);
             if (!err.empty()) {
                 pp.failed = true; pp.err = err; pp.err_code = VFB_ERR_FORMAT; pp.done = true;
