@@ -243,6 +243,11 @@ int vfb_debug_gpu_inflate(const uint8_t *z, uint64_t z_bytes, const uint32_t *me
 int vfb_host_alloc(void **p, uint64_t bytes);
 int vfb_host_free(void *p);
 
+/* Pinned staging buffers (ingest segments, result columns) are cached process-wide between calls,
+ * because page-locking costs more than a small run; this frees the cache (VFB_PINNED_POOL_MB caps it,
+ * default 1024). */
+int vfb_pinned_pool_trim(void);
+
 #ifdef __cplusplus
 }
 #endif

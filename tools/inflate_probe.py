@@ -3,7 +3,7 @@ import ctypes, os, struct, sys, time, subprocess
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from vfind_b200 import api
-path = "/tmp/synth_4000000.fq.bgzf.gz"
+path = sys.argv[2] if len(sys.argv) > 2 else "/tmp/synth_4000000.fq.bgzf.gz"
 raw = np.fromfile(path, dtype=np.uint8)
 blob = raw.tobytes()
 tab, p, oo = [], 0, 0

@@ -120,6 +120,7 @@ def load_library():
     L.vfb_measure_int_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.vfb_host_alloc.argtypes = [C.POINTER(vp), u64]
     L.vfb_host_free.argtypes = [vp]
+    L.vfb_pinned_pool_trim.argtypes = []
     _lib = L
     return L
 
@@ -428,6 +429,11 @@ def hash_key(key: bytes) -> int:
 
 def key_owner(h: int, n_parts: int) -> int:
     return int(load_library().vfb_key_owner(h, n_parts))
+
+
+def pinned_pool_trim():
+    """Free the process-wide cache of pinned staging buffers."""
+    _check(load_library().vfb_pinned_pool_trim())
 
 
 def measure_int_peak(device: int = -1):

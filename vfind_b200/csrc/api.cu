@@ -30,6 +30,33 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
     return VFB_ERR_CUDA;
 }
 
+}  // namespace vfb (reopened below)
+
+#include <chrono>
+#include <cstdarg>
+#include <mutex>
+#include <utility>
+#include <vector>
+namespace vfb {
+bool trace_on()
+{
+    static int on = -1;
+    if (on < 0) on = getenv("VFB_TRACE") ? 1 : 0;
+    return on == 1;
+}
+void trace(const char *fmt, ...)
+{
+    if (!trace_on()) return;
+    static const auto t0 = std::chrono::steady_clock::now();
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "[vfb %9.1f ms] ", ms);
+    va_list ap;
+    va_start(ap, fmt);
+    vfprintf(stderr, fmt, ap);
+    va_end(ap);
+    fputc('\n', stderr);
+}
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -38,6 +65,7 @@ struct DevBuf {
         if (bytes <= cap) return VFB_OK;
         size_t ncap = bytes + bytes / 4 + 256;
         void *np = nullptr;
+        if (ncap >= (8u << 20)) trace("cudaMalloc %zu MB (was %zu MB)", ncap >> 20, cap >> 20);
         cudaError_t e = cudaMalloc(&np, ncap);
         if (e != cudaSuccess) {
             set_error("out of device memory allocating " + std::to_string(ncap) + " bytes");
@@ -64,29 +92,95 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// Process-wide cache of pinned host buffers: page-locking costs about 1 ms per MB, more than a
+// whole small run.  Buffers released by a context / an ingest are kept (up to VFB_PINNED_POOL_MB,
+// default 1024) and handed to the next one; vfb_pinned_pool_trim() frees them.
+struct PinnedPool {
+    std::mutex mu;
+    std::vector<std::pair<void *, size_t>> idle;
+    size_t bytes = 0;
+};
+static PinnedPool &pinned_pool()
+{
+    static PinnedPool *p = new PinnedPool;      // never destroyed: the driver may be gone at exit
+    return *p;
+}
+void *pinned_acquire(size_t want, size_t *cap_out)
+{
+    PinnedPool &pp = pinned_pool();
+    {
+        std::lock_guard<std::mutex> lk(pp.mu);
+        int best = -1;
+        for (size_t i = 0; i < pp.idle.size(); ++i)
+            if (pp.idle[i].second >= want && pp.idle[i].second <= 2 * want + (1u << 20) &&
+                (best < 0 || pp.idle[i].second < pp.idle[(size_t)best].second)) best = (int)i;
+        if (best >= 0) {
+            void *p = pp.idle[(size_t)best].first;
+            *cap_out = pp.idle[(size_t)best].second;
+            pp.bytes -= *cap_out;
+            pp.idle.erase(pp.idle.begin() + best);
+            return p;
+        }
+    }
+    void *p = nullptr;
+    if (want >= (8u << 20)) trace("cudaMallocHost %zu MB", want >> 20);
+    if (cudaMallocHost(&p, want) != cudaSuccess) {
+        cudaGetLastError();
+        pinned_pool_trim();                      // give the cache back and try once more
+        if (cudaMallocHost(&p, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    *cap_out = want;
+    return p;
+}
+void pinned_release(void *p, size_t cap)
+{
+    if (!p) return;
+    static size_t limit = 0;
+    if (!limit) {
+        const char *e = getenv("VFB_PINNED_POOL_MB");
+        limit = ((size_t)(e ? strtoull(e, nullptr, 10) : 1024ull) << 20) + 1;
+    }
+    PinnedPool &pp = pinned_pool();
+    {
+        std::lock_guard<std::mutex> lk(pp.mu);
+        if (pp.bytes + cap < limit) {
+            pp.idle.emplace_back(p, cap);
+            pp.bytes += cap;
+            return;
+        }
+    }
+    cudaFreeHost(p);
+}
+void pinned_pool_trim()
+{
+    PinnedPool &pp = pinned_pool();
+    std::vector<std::pair<void *, size_t>> all;
+    {
+        std::lock_guard<std::mutex> lk(pp.mu);
+        all.swap(pp.idle);
+        pp.bytes = 0;
+    }
+    for (auto &b : all) cudaFreeHost(b.first);
+}
+
 struct PinBuf {
     void *p = nullptr;
     size_t cap = 0;
     int ensure(size_t bytes)
     {
         if (bytes <= cap) return VFB_OK;
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        cap = 0;
-        size_t ncap = bytes + bytes / 8 + 4096;
-        cudaError_t e = cudaMallocHost(&p, ncap);
-        if (e != cudaSuccess) {
-            p = nullptr;
-            cudaGetLastError();
+        release();
+        p = pinned_acquire(bytes + bytes / 8 + 4096, &cap);
+        if (!p) {
+            cap = 0;
             set_error("cannot allocate pinned host memory");
             return VFB_ERR_NOMEM;
         }
-        cap = ncap;
         return VFB_OK;
     }
     void release()
     {
-        if (p) cudaFreeHost(p);
+        pinned_release(p, cap);
         p = nullptr;
         cap = 0;
     }
@@ -275,6 +369,8 @@ static int table_reserve(vfb_ctx *c, uint64_t new_keys, uint64_t new_bytes)
         return VFB_OK;
     }
     // tighten the bounds with the true counters, then grow if still needed
+    trace("table_reserve: bounds exceeded (rows %llu + %llu, capacity %llu): sync", (unsigned long long)c->ub_rows,
+          (unsigned long long)new_keys, (unsigned long long)c->tab.capacity);
     unsigned long long ctr[2];
     VFB_CUDA(cudaMemcpyAsync(ctr, c->tab.counters, sizeof ctr, cudaMemcpyDeviceToHost, c->st_compute));
     VFB_CUDA(cudaStreamSynchronize(c->st_compute));
@@ -294,6 +390,7 @@ static int table_reserve(vfb_ctx *c, uint64_t new_keys, uint64_t new_bytes)
     if (want_rows * 2 > c->tab.capacity) {
         // rehash into a larger slot array
         uint64_t ncap = pow2_at_least(want_rows * 3);
+        trace("table rehash %llu -> %llu slots", (unsigned long long)c->tab.capacity, (unsigned long long)ncap);
         DevBuf nslots, ncounts;
         if ((rc = nslots.ensure(ncap * 8))) return rc;
         if ((rc = ncounts.ensure(ncap * 8))) { nslots.release(); return rc; }
@@ -369,6 +466,7 @@ static int preflight(double thr, bool *skip)
 
 int vfb_create(const vfb_params *p, vfb_ctx **out)
 {
+    trace("vfb_create");
     if (!p || !out) { set_error("null argument"); return VFB_ERR_ARG; }
     if (p->struct_size != sizeof(vfb_params)) { set_error("vfb_params size mismatch"); return VFB_ERR_ARG; }
     if ((p->prefix_len && !p->prefix) || (p->suffix_len && !p->suffix)) { set_error("null adapter"); return VFB_ERR_ARG; }
@@ -913,7 +1011,9 @@ int vfb_internal_submit_bgzf(vfb_ctx *c, const uint8_t *pinned_z, uint64_t z_byt
         VFB_CUDA(cudaMemcpyAsync(&lines, c->p_tiles.as<unsigned long long>() + n_tiles, 8, cudaMemcpyDeviceToHost, c->st_compute));
     }
     VFB_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, c->st_compute));
+    trace("submit_bgzf: H2D + inflate + line count queued");
     VFB_CUDA(cudaStreamSynchronize(c->st_compute));
+    trace("submit_bgzf: inflated, %llu lines", lines);
     c->stats.d2h_bytes += 12;
     *bad_member = bad;
     if (bad != 0xFFFFFFFFu || used == 0) { bump_launches(c, before); return VFB_OK; }
@@ -938,6 +1038,7 @@ int vfb_internal_submit_bgzf(vfb_ctx *c, const uint8_t *pinned_z, uint64_t z_byt
     }
     memcpy(tail, pin, tl);
     *tail_len = tl;
+    trace("submit_bgzf: parsed, tail %u bytes", tl);
     c->stats.d2h_bytes += 8 + tl;
     if (n_rec) {
         k_parse_err_fold<<<1, 1, 0, c->st_compute>>>(c->p_err.as<uint32_t>(), record_base,
@@ -952,6 +1053,7 @@ int vfb_internal_submit_bgzf(vfb_ctx *c, const uint8_t *pinned_z, uint64_t z_byt
     }
     *n_records = n_rec;
     bump_launches(c, before);
+    trace("submit_bgzf: hot loop queued (%u records)", n_rec);
     return VFB_OK;
 }
 
@@ -1294,6 +1396,12 @@ int vfb_host_alloc(void **p, uint64_t bytes)
 int vfb_host_free(void *p)
 {
     if (p) VFB_CUDA(cudaFreeHost(p));
+    return VFB_OK;
+}
+
+int vfb_pinned_pool_trim(void)
+{
+    pinned_pool_trim();
     return VFB_OK;
 }
 

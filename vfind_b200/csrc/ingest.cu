@@ -113,6 +113,43 @@ struct Member {
     size_t lines = 0;
 };
 
+// pread of a large range split over `threads` threads (page-cache copies into pinned memory run
+// at a few GB/s per core).  Returns the bytes read from `off` on (short only at end of file), -1 on error.
+ssize_t pread_parallel(int fd, uint8_t *buf, size_t want, off_t off, int threads)
+{
+    const size_t min_part = (size_t)4 << 20;
+    int parts = threads < 1 ? 1 : threads;
+    if ((size_t)parts > want / min_part) parts = (int)(want / min_part);
+    if (parts <= 1) {
+        size_t done = 0;
+        while (done < want) {
+            const ssize_t got = pread(fd, buf + done, want - done, off + (off_t)done);
+            if (got < 0) { if (errno == EINTR) continue; return -1; }
+            if (got == 0) break;
+            done += (size_t)got;
+        }
+        return (ssize_t)done;
+    }
+    const size_t part = ((want / (size_t)parts) + 4095) & ~(size_t)4095;
+    std::vector<ssize_t> got((size_t)parts, 0);
+    std::vector<std::thread> pool;
+    auto run = [&](int i) {
+        const size_t lo = (size_t)i * part, hi = std::min(want, lo + part);
+        got[(size_t)i] = lo < hi ? pread_parallel(fd, buf + lo, hi - lo, off + (off_t)lo, 1) : 0;
+    };
+    for (int i = 1; i < parts; ++i) pool.emplace_back(run, i);
+    run(0);
+    for (auto &t : pool) t.join();
+    size_t total = 0;
+    for (int i = 0; i < parts; ++i) {
+        if (got[(size_t)i] < 0) return -1;
+        const size_t lo = (size_t)i * part, hi = std::min(want, lo + part);
+        total += (size_t)got[(size_t)i];
+        if ((size_t)got[(size_t)i] < hi - lo) break;       // end of file inside this part
+    }
+    return (ssize_t)total;
+}
+
 // Reads the next gzip member header at the current file position.  Returns 1 and the total
 // member size if it is a BGZF member, 0 if it is some other gzip member (position restored),
 // -1 at a clean end of file.
@@ -294,6 +331,7 @@ size_t pick_chunk(FILE *f)
 
 struct Chunk {
     uint8_t *buf = nullptr;
+    size_t buf_cap = 0;
     size_t cut = 0;        // bytes to submit (ends at a record boundary)
     size_t lines = 0;      // complete lines in [0, cut)
     cudaEvent_t copied = nullptr;
@@ -312,6 +350,7 @@ struct Pipe {
 struct ZSegment {
     uint8_t *z = nullptr;          // pinned: whole members back to back
     vfb_member *members = nullptr; // pinned
+    size_t z_cap = 0, m_cap = 0;   // pinned capacities (for the pool)
     size_t z_bytes = 0, text_bytes = 0;
     uint32_t n = 0;
     bool last = false;             // nothing more for the GPU phase after this segment
@@ -322,20 +361,30 @@ struct ZSegment {
 // prod.bgzf say what is left for the host path (which also applies the end-of-input rules).
 int run_bgzf_gpu(vfb_ctx *ctx, ChunkProducer &prod, size_t text_target, uint64_t *n_total, bool trace)
 {
-    const size_t zcap = text_target / 2 + (1u << 20), mcap = text_target / 512 + 4096;
+    // pinned staging for the compressed members of one segment: sized for a 3.2x ratio (a segment
+    // closes early when the buffer fills first) and never beyond what is left of the file
+    size_t zcap = text_target / 16 * 5 + (1u << 20);
+    {
+        const long here = ftell(prod.f);
+        fseek(prod.f, 0, SEEK_END);
+        const long fsz = ftell(prod.f);
+        fseek(prod.f, here, SEEK_SET);
+        if (fsz > here && (size_t)(fsz - here) + 65536 < zcap) zcap = (size_t)(fsz - here) + 65536;
+    }
+    const size_t mcap = text_target / 512 + 4096;
     constexpr int NSEG = 2;
     ZSegment seg[NSEG];
     int rc = VFB_OK;
     for (auto &g : seg) {
-        void *a = nullptr, *b = nullptr;
-        if (cudaMallocHost(&a, zcap) != cudaSuccess || cudaMallocHost(&b, mcap * sizeof(vfb_member)) != cudaSuccess) {
-            cudaGetLastError();
+        void *a = pinned_acquire(zcap, &g.z_cap), *b = pinned_acquire(mcap * sizeof(vfb_member), &g.m_cap);
+        if (!a || !b) {
             set_error("cannot allocate pinned ingest buffers");
             rc = VFB_ERR_NOMEM;
         }
         g.z = (uint8_t *)a;
         g.members = (vfb_member *)b;
     }
+    vfb::trace("ingest: pinned segment buffers ready (2 x %zu MB)", zcap >> 20);
     Pipe pp;
     for (int i = 0; i < NSEG; ++i) pp.free_q.push_back(i);
     const int fd = fileno(prod.f);
@@ -363,7 +412,7 @@ int run_bgzf_gpu(vfb_ctx *ctx, ChunkProducer &prod, size_t text_target, uint64_t
             while (err.empty() && !stop && !full) {
                 if (!eof && avail < zcap) {
                     const size_t want = std::min(zcap - avail, step);
-                    const ssize_t got = pread(fd, g.z + avail, want, (off_t)(pos + avail));
+                    const ssize_t got = pread_parallel(fd, g.z + avail, want, (off_t)(pos + avail), prod.threads);
                     if (got < 0) { err = std::string("read error: ") + strerror(errno); break; }
                     if ((size_t)got < want) eof = true;
                     avail += (size_t)got;
@@ -413,6 +462,7 @@ int run_bgzf_gpu(vfb_ctx *ctx, ChunkProducer &prod, size_t text_target, uint64_t
                 if (eof) break;                                      // everything read and consumed
             }
             if (off) z_estimate = off + off / 16 + 65536;
+            vfb::trace("ingest reader: segment of %u members, %zu compressed bytes read", g.n, off);
             g.z_bytes = off;
             pos += off;
             if (err.empty() && !stop && eof && off == avail) { prod.at_end = true; g.last = true; }
@@ -471,8 +521,8 @@ int run_bgzf_gpu(vfb_ctx *ctx, ChunkProducer &prod, size_t text_target, uint64_t
     vfb_sync(ctx);                 // the pinned buffers are about to go away
     if (rc) set_error(keep);
     for (auto &g : seg) {
-        if (g.z) cudaFreeHost(g.z);
-        if (g.members) cudaFreeHost(g.members);
+        pinned_release(g.z, g.z_cap);
+        pinned_release(g.members, g.m_cap);
     }
     return rc;
 }
@@ -540,8 +590,8 @@ extern "C" int vfb_run_file(vfb_ctx *ctx, const char *path, uint64_t *n_reads_ou
     Chunk ch[NCH];
     Pipe pp;
     for (int i = 0; i < NCH; ++i) {
-        void *p = nullptr;
-        if (cudaMallocHost(&p, cap + 64) != cudaSuccess || cudaEventCreateWithFlags(&ch[i].copied, cudaEventDisableTiming) != cudaSuccess) {
+        void *p = pinned_acquire(cap + 64, &ch[i].buf_cap);
+        if (!p || cudaEventCreateWithFlags(&ch[i].copied, cudaEventDisableTiming) != cudaSuccess) {
             cudaGetLastError();
             set_error("cannot allocate pinned ingest buffers");
             rc = VFB_ERR_NOMEM;
@@ -638,7 +688,7 @@ extern "C" int vfb_run_file(vfb_ctx *ctx, const char *path, uint64_t *n_reads_ou
         }
     }
     for (int i = 0; i < NCH; ++i) {
-        if (ch[i].buf) cudaFreeHost(ch[i].buf);
+        pinned_release(ch[i].buf, ch[i].buf_cap);
         if (ch[i].copied) cudaEventDestroy(ch[i].copied);
     }
     if (n_reads_out) *n_reads_out = n_total;

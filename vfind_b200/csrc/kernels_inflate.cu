@@ -258,6 +258,415 @@ k_inflate_members(const __grid_constant__ InflateArgs a)
     if (rc != 0) atomicMin(a.first_bad, i);
 }
 
+// =====================================================================================
+// v2: one WARP per member, table-driven.
+//
+// All 32 lanes run the same decode (same bit buffer, same tables: no divergence, no broadcasts);
+// the lanes differ only where a warp helps: the compressed input arrives through a 512-byte
+// shared-memory ring that the lanes top up with coalesced 128-byte loads three lines ahead of
+// the bit reader, Huffman decode is one shared-memory lookup per symbol (10-bit table for
+// literal/length codes, 8-bit for distances, built by all lanes from the canonical code; longer
+// codes fall back to the bit-by-bit canonical decode), a match is copied by all lanes at once
+// (period `dist` when it overlaps itself), and the CRC-32 is computed after the decode, each
+// lane over 1/32 of the output, the partial CRCs combined with x^(8n) mod P multiplications.
+#define INFW_WARPS 4
+#define INFW_LBITS 10
+#define INFW_DBITS 8
+
+struct InfWarp {
+    uint32_t ltab[1 << INFW_LBITS];   // nbits | kind << 4 | value << 8 | extra << 24 ; 0 = long / unused code
+    uint32_t dtab[1 << INFW_DBITS];   // nbits | extra << 4 | base << 8
+    uint16_t lcount[16], dcount[16];  // canonical code: symbols per length
+    uint16_t lsym[INF_MAXL], dsym[32];
+    uint8_t lens[32 + INF_MAXL + 32];   // code lengths being read (staged 32 bytes up while the code-length code is in use)
+    uint32_t ring[128];               // 4 lines of 32 compressed words
+};
+
+struct InfShared {
+    InfTables T;
+    uint32_t x2n[32];                 // x^(2^n) mod P (reflected CRC-32 polynomial)
+    InfWarp w[INFW_WARPS];
+};
+
+__device__ __forceinline__ uint32_t crc_multmodp(uint32_t a, uint32_t b)
+{
+    uint32_t m = 1u << 31, p = 0;
+    for (;;) {
+        if (a & m) {
+            p ^= b;
+            if ((a & (m - 1)) == 0) break;
+        }
+        m >>= 1;
+        b = (b & 1u) ? (b >> 1) ^ 0xEDB88320u : b >> 1;
+    }
+    return p;
+}
+
+// x^(n * 2^k) mod P
+__device__ uint32_t crc_x2nmodp(const uint32_t *x2n, uint32_t n, uint32_t k)
+{
+    uint32_t p = 1u << 31;
+    while (n) {
+        if (n & 1u) p = crc_multmodp(x2n[k & 31], p);
+        n >>= 1;
+        ++k;
+    }
+    return p;
+}
+
+struct WBits {
+    uint64_t buf;
+    int cnt;
+    uint32_t rw;          // next word (relative to `words`) to enter the bit buffer
+    uint32_t next_line;   // next 32-word line to load into the ring
+    const uint32_t *words;
+    uint32_t nwords;
+};
+
+__device__ __forceinline__ void wb_refill(WBits &b, InfWarp *W, int lane)
+{
+    if (b.cnt > 32) return;
+    while (b.next_line <= (b.rw >> 5) + 3) {
+        const uint32_t w = b.next_line * 32u + (uint32_t)lane;
+        W->ring[w & 127u] = w < b.nwords ? __ldg(b.words + w) : 0u;
+        ++b.next_line;
+        __syncwarp();
+    }
+    b.buf |= (uint64_t)W->ring[b.rw & 127u] << b.cnt;
+    b.cnt += 32;
+    ++b.rw;
+}
+
+// Start reading at byte `bytepos` (relative to `words`).
+__device__ __forceinline__ void wb_seek(WBits &b, InfWarp *W, int lane, uint32_t bytepos)
+{
+    __syncwarp();
+    b.rw = bytepos >> 2;
+    b.next_line = b.rw >> 5;
+    b.buf = 0;
+    b.cnt = 0;
+    wb_refill(b, W, lane);
+    const int skip = (int)(bytepos & 3u) * 8;
+    b.buf >>= skip;
+    b.cnt -= skip;
+}
+
+__device__ __forceinline__ uint32_t wb_bits(WBits &b, InfWarp *W, int lane, int n)   // n <= 16
+{
+    wb_refill(b, W, lane);
+    const uint32_t v = (uint32_t)b.buf & ((1u << n) - 1u);
+    b.buf >>= n;
+    b.cnt -= n;
+    return v;
+}
+
+// bytes consumed so far, rounded up to whole bytes
+__device__ __forceinline__ uint32_t wb_bytepos(const WBits &b) { return b.rw * 4u - (uint32_t)(b.cnt >> 3); }
+
+// bit-by-bit canonical decode from the low bits of `bits` (codes are MSB first); returns the
+// symbol and its length, or -1
+__device__ __forceinline__ int canon_decode(uint32_t bits, const uint16_t *count, const uint16_t *symbol, int maxlen, int *len_out)
+{
+    int code = 0, first = 0, index = 0;
+    for (int len = 1; len <= maxlen; ++len) {
+        code |= (int)(bits & 1u);
+        bits >>= 1;
+        const int c = count[len];
+        if (code - c < first) {
+            *len_out = len;
+            return symbol[index + (code - first)];
+        }
+        index += c;
+        first += c;
+        first <<= 1;
+        code <<= 1;
+    }
+    return -1;
+}
+
+// canonical code from code lengths (one lane); <0 over-subscribed, >0 incomplete, 0 complete
+__device__ int canon_construct(uint16_t *count, uint16_t *symbol, const uint8_t *length, int n)
+{
+    uint16_t offs[INF_MAXBITS + 1];
+    for (int len = 0; len <= INF_MAXBITS; ++len) count[len] = 0;
+    for (int s = 0; s < n; ++s) count[length[s]]++;
+    if (count[0] == n) return 0;
+    int left = 1;
+    for (int len = 1; len <= INF_MAXBITS; ++len) {
+        left <<= 1;
+        left -= count[len];
+        if (left < 0) return left;
+    }
+    offs[1] = 0;
+    for (int len = 1; len < INF_MAXBITS; ++len) offs[len + 1] = offs[len] + count[len];
+    for (int s = 0; s < n; ++s)
+        if (length[s] != 0) symbol[offs[length[s]]++] = (uint16_t)s;
+    return left;
+}
+
+__device__ __forceinline__ uint32_t lit_entry(const InfTables *T, int sym, int nbits)
+{
+    if (sym < 256) return (uint32_t)nbits | ((uint32_t)sym << 8);
+    if (sym == 256) return (uint32_t)nbits | (2u << 4);
+    if (sym > 285) return (uint32_t)nbits | (3u << 4);                         // invalid length symbol
+    return (uint32_t)nbits | (1u << 4) | ((uint32_t)T->lbase[sym - 257] << 8) | ((uint32_t)T->lext[sym - 257] << 24);
+}
+
+__device__ __forceinline__ uint32_t dist_entry(const InfTables *T, int sym, int nbits)
+{
+    if (sym > 29) return (uint32_t)nbits | (15u << 4);                         // invalid distance symbol (extra 15 never occurs)
+    return (uint32_t)nbits | ((uint32_t)T->dext[sym] << 4) | ((uint32_t)T->dbase[sym] << 8);
+}
+
+// lengths of the literal/length code in W->lens[0..nlen), of the distance code behind them
+__device__ int infw_build(const InfTables *T, InfWarp *W, int nlen, int ndist, int lane, bool fixed)
+{
+    int e1 = 0, e2 = 0;
+    if (lane == 0) {
+        e1 = canon_construct(W->lcount, W->lsym, W->lens, nlen);
+        if (!(e1 < 0 || (e1 > 0 && nlen - W->lcount[0] != 1))) e1 = 0; else e1 = 1;
+        e2 = canon_construct(W->dcount, W->dsym, W->lens + nlen, ndist);
+        if (!(e2 < 0 || (e2 > 0 && ndist - W->dcount[0] != 1))) e2 = 0; else e2 = 1;
+        if (fixed) e1 = e2 = 0;            // the fixed distance code leaves two codes unused (RFC 1951 3.2.6)
+    }
+    e1 = __shfl_sync(0xffffffffu, e1, 0);
+    e2 = __shfl_sync(0xffffffffu, e2, 0);
+    if (e1) return -11;
+    if (e2) return -12;
+    __syncwarp();
+    for (int e = lane; e < (1 << INFW_LBITS); e += 32) {
+        int len = 0;
+        const int sym = canon_decode((uint32_t)e, W->lcount, W->lsym, INFW_LBITS, &len);
+        W->ltab[e] = sym < 0 ? 0u : lit_entry(T, sym, len);
+    }
+    for (int e = lane; e < (1 << INFW_DBITS); e += 32) {
+        int len = 0;
+        const int sym = canon_decode((uint32_t)e, W->dcount, W->dsym, INFW_DBITS, &len);
+        W->dtab[e] = sym < 0 ? 0u : dist_entry(T, sym, len);
+    }
+    __syncwarp();
+    return 0;
+}
+
+__device__ int inflate_member_warp(const InfShared *S, InfWarp *W, const uint8_t *zin, uint32_t zlen, uint8_t *out,
+                                   uint32_t isize, int lane)
+{
+    const InfTables *T = &S->T;
+    if (zlen < 18 || zin[0] != 0x1f || zin[1] != 0x8b || zin[2] != 8) return -1;
+    const uint32_t flg = zin[3];
+    uint32_t p = 10;
+    if (flg & 4) { if (p + 2 > zlen) return -1; p += 2 + (zin[p] | (zin[p + 1] << 8)); }
+    if (flg & 8) { while (p < zlen && zin[p]) ++p; ++p; }
+    if (flg & 16) { while (p < zlen && zin[p]) ++p; ++p; }
+    if (flg & 2) p += 2;
+    if (p + 8 > zlen) return -1;
+    const uint8_t *tr = zin + zlen - 8;
+    const uint32_t want_crc = tr[0] | (tr[1] << 8) | (tr[2] << 16) | ((uint32_t)tr[3] << 24);
+    const uint32_t want_len = tr[4] | (tr[5] << 8) | (tr[6] << 16) | ((uint32_t)tr[7] << 24);
+    if (want_len != isize) return -2;
+
+    WBits b;
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(zin + p);
+    b.words = reinterpret_cast<const uint32_t *>(a0 & ~(uintptr_t)3);
+    const uint32_t lead = (uint32_t)(a0 & 3u);
+    const uint32_t data_len = zlen - 8 - p;                  // deflate stream bytes
+    b.nwords = (lead + data_len + 8 + 3) >> 2;               // (the trailer may be looked at, never beyond)
+    wb_seek(b, W, lane, lead);
+    uint32_t n_out = 0;
+    int last;
+    do {
+        last = (int)wb_bits(b, W, lane, 1);
+        const uint32_t type = wb_bits(b, W, lane, 2);
+        if (type == 0) {
+            const int drop = b.cnt & 7;
+            b.buf >>= drop; b.cnt -= drop;
+            const uint32_t len = wb_bits(b, W, lane, 16), nlen = wb_bits(b, W, lane, 16);
+            if ((len ^ 0xFFFFu) != nlen) return -3;
+            if (n_out + len > isize) return -4;
+            const uint32_t src = wb_bytepos(b);              // byte aligned here
+            if (src + len > lead + data_len) return -19;
+            const uint8_t *sp = reinterpret_cast<const uint8_t *>(b.words) + src;
+            for (uint32_t i = lane; i < len; i += 32) out[n_out + i] = __ldg(sp + i);
+            n_out += len;
+            wb_seek(b, W, lane, src + len);
+        } else if (type == 1 || type == 2) {
+            int nl, nd;
+            if (type == 1) {
+                nl = 288; nd = 30;
+                for (int s = lane; s < 288; s += 32) W->lens[s] = (uint8_t)(s < 144 ? 8 : (s < 256 ? 9 : (s < 280 ? 7 : 8)));
+                if (lane < 30) W->lens[288 + lane] = 5;
+                __syncwarp();
+            } else {
+                nl = (int)wb_bits(b, W, lane, 5) + 257;
+                nd = (int)wb_bits(b, W, lane, 5) + 1;
+                const int ncode = (int)wb_bits(b, W, lane, 4) + 4;
+                if (nl > 286 || nd > 30) return -5;
+                __syncwarp();
+                if (lane < 19) W->lens[lane] = 0;
+                __syncwarp();
+                for (int idx = 0; idx < ncode; ++idx) {
+                    const uint32_t v = wb_bits(b, W, lane, 3);
+                    if (lane == 0) W->lens[T->order[idx]] = (uint8_t)v;
+                }
+                __syncwarp();
+                int e0 = 0;
+                if (lane == 0) e0 = canon_construct(W->lcount, W->lsym, W->lens, 19);
+                e0 = __shfl_sync(0xffffffffu, e0, 0);
+                if (e0 != 0) return -6;                          // must be complete
+                __syncwarp();
+                int idx = 0;
+                while (idx < nl + nd) {
+                    wb_refill(b, W, lane);
+                    int cl = 0;
+                    const int sym = canon_decode((uint32_t)b.buf, W->lcount, W->lsym, 7, &cl);
+                    if (sym < 0) return -7;
+                    b.buf >>= cl; b.cnt -= cl;
+                    if (sym < 16) {
+                        if (lane == 0) W->lens[32 + idx] = (uint8_t)sym;      // (kept clear of the 19 code-length lengths)
+                        ++idx;
+                    } else {
+                        int len = 0, rep;
+                        if (sym == 16) {
+                            if (idx == 0) return -8;
+                            __syncwarp();
+                            len = W->lens[32 + idx - 1];
+                            rep = 3 + (int)wb_bits(b, W, lane, 2);
+                        } else if (sym == 17) rep = 3 + (int)wb_bits(b, W, lane, 3);
+                        else rep = 11 + (int)wb_bits(b, W, lane, 7);
+                        if (idx + rep > nl + nd) return -9;
+                        if (lane < rep) W->lens[32 + idx + lane] = (uint8_t)len;
+                        if (lane + 32 < rep) W->lens[32 + idx + lane + 32] = (uint8_t)len;
+                        if (lane + 64 < rep) W->lens[32 + idx + lane + 64] = (uint8_t)len;
+                        if (lane + 96 < rep) W->lens[32 + idx + lane + 96] = (uint8_t)len;
+                        if (lane + 128 < rep) W->lens[32 + idx + lane + 128] = (uint8_t)len;
+                        idx += rep;
+                    }
+                    __syncwarp();
+                }
+                // move the lengths down to lens[0..nl+nd)
+                uint8_t t[10];
+#pragma unroll
+                for (int k = 0; k < 10; ++k) t[k] = lane + 32 * k < nl + nd ? W->lens[32 + lane + 32 * k] : (uint8_t)0;
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 10; ++k) if (lane + 32 * k < nl + nd) W->lens[lane + 32 * k] = t[k];
+                __syncwarp();
+                if (W->lens[256] == 0) return -10;
+            }
+            const int brc = infw_build(T, W, nl, nd, lane, type == 1);
+            if (brc) return brc;
+            for (;;) {
+                wb_refill(b, W, lane);
+                uint32_t e = W->ltab[(uint32_t)b.buf & ((1u << INFW_LBITS) - 1u)];
+                if (e == 0) {
+                    int cl = 0;
+                    const int sym = canon_decode((uint32_t)b.buf, W->lcount, W->lsym, INF_MAXBITS, &cl);
+                    if (sym < 0) return -13;
+                    e = lit_entry(T, sym, cl);
+                }
+                const int nb = (int)(e & 15u);
+                b.buf >>= nb; b.cnt -= nb;
+                const uint32_t kind = (e >> 4) & 3u;
+                if (kind == 0) {
+                    if (n_out >= isize) return -14;
+                    if (lane == 0) out[n_out] = (uint8_t)(e >> 8);
+                    ++n_out;
+                } else if (kind == 2) {
+                    break;
+                } else if (kind == 3) {
+                    return -15;
+                } else {
+                    const int xb = (int)(e >> 24);
+                    const uint32_t len = ((e >> 8) & 0xFFFFu) + ((uint32_t)b.buf & ((1u << xb) - 1u));
+                    b.buf >>= xb; b.cnt -= xb;
+                    wb_refill(b, W, lane);
+                    uint32_t d = W->dtab[(uint32_t)b.buf & ((1u << INFW_DBITS) - 1u)];
+                    if (d == 0) {
+                        int cl = 0;
+                        const int ds = canon_decode((uint32_t)b.buf, W->dcount, W->dsym, INF_MAXBITS, &cl);
+                        if (ds < 0) return -16;
+                        d = dist_entry(T, ds, cl);
+                    }
+                    const int db = (int)(d & 15u), dx = (int)((d >> 4) & 15u);
+                    if (dx == 15) return -16;
+                    b.buf >>= db; b.cnt -= db;
+                    const uint32_t dist = (d >> 8) + ((uint32_t)b.buf & ((1u << dx) - 1u));
+                    b.buf >>= dx; b.cnt -= dx;
+                    if (dist > n_out) return -17;
+                    if (n_out + len > isize) return -18;
+                    __syncwarp();                                 // earlier stores of all lanes are visible
+                    const uint8_t *from = out + n_out - dist;
+                    if (dist >= len) {
+                        for (uint32_t i = lane; i < len; i += 32) out[n_out + i] = __ldcg(from + i);
+                    } else {
+                        for (uint32_t i = lane; i < len; i += 32) out[n_out + i] = __ldcg(from + i % dist);
+                    }
+                    n_out += len;
+                }
+            }
+        } else {
+            return -20;
+        }
+    } while (!last);
+    if (n_out != isize) return -21;
+    // the gzip trailer follows the deflate stream at the next byte boundary (RFC 1952)
+    if (wb_bytepos(b) != lead + data_len) return -19;
+    // CRC-32 of the output: one slice per lane, then combine
+    __syncwarp();
+    const uint32_t chunk = (isize + 31u) / 32u;
+    const uint32_t lo = min(isize, (uint32_t)lane * chunk), hi = min(isize, lo + chunk);
+    uint32_t crc = 0xFFFFFFFFu;
+    for (uint32_t i = lo; i < hi; ++i) crc = T->crc[(crc ^ __ldcg(out + i)) & 0xFFu] ^ (crc >> 8);
+    crc ^= 0xFFFFFFFFu;
+    uint32_t total = __shfl_sync(0xffffffffu, crc, 0);
+    if (chunk) {
+        const uint32_t q_full = crc_x2nmodp(S->x2n, chunk, 3);
+        for (int l = 1; l < 32; ++l) {
+            const uint32_t c_l = __shfl_sync(0xffffffffu, crc, l);
+            const uint32_t l_lo = min(isize, (uint32_t)l * chunk), l_len = min(isize, l_lo + chunk) - l_lo;
+            if (l_len == 0) break;
+            const uint32_t q = l_len == chunk ? q_full : crc_x2nmodp(S->x2n, l_len, 3);
+            total = crc_multmodp(q, total) ^ c_l;
+        }
+    }
+    if (total != want_crc) return -22;
+    return 0;
+}
+
+__global__ void __launch_bounds__(INFW_WARPS * 32)
+k_inflate_warp(const __grid_constant__ InflateArgs a)
+{
+    __shared__ InfShared S;
+    if (threadIdx.x == 0) {
+        const unsigned short lb[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+        const unsigned short le[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+        const unsigned short db[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+        const unsigned short de[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+        const unsigned char od[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+        for (int i = 0; i < 29; ++i) { S.T.lbase[i] = lb[i]; S.T.lext[i] = le[i]; }
+        for (int i = 0; i < 30; ++i) { S.T.dbase[i] = db[i]; S.T.dext[i] = de[i]; }
+        for (int i = 0; i < 19; ++i) S.T.order[i] = od[i];
+        uint32_t p = 1u << 30;                     // x^1
+        S.x2n[0] = p;
+        for (int n = 1; n < 32; ++n) S.x2n[n] = p = crc_multmodp(p, p);
+    }
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        uint32_t c = (uint32_t)i;
+        for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+        S.T.crc[i] = c;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t warps_total = gridDim.x * INFW_WARPS;
+    for (uint32_t i = blockIdx.x * INFW_WARPS + warp; i < a.n_members; i += warps_total) {
+        const vfb_member m = a.members[i];
+        int rc = 0;
+        if (m.isize || m.z_len) rc = inflate_member_warp(&S, &S.w[warp], a.z + m.z_off, m.z_len, a.out + m.out_off, m.isize, lane);
+        if (rc != 0 && lane == 0) atomicMin(a.first_bad, i);
+        __syncwarp();
+    }
+}
+
 int launch_inflate(const uint8_t *d_z, const vfb_member *d_members, uint32_t n_members, uint8_t *d_out,
                    uint32_t *d_first_bad, cudaStream_t st)
 {
@@ -269,6 +678,24 @@ int launch_inflate(const uint8_t *d_z, const vfb_member *d_members, uint32_t n_m
         if (lanes < 1 || lanes > 32) lanes = 1;
     }
     InflateArgs a{d_z, d_members, n_members, d_out, d_first_bad, (uint32_t)lanes};
+    static int v1 = -1;
+    if (v1 < 0) v1 = getenv("VFB_INFLATE_V1") ? 1 : 0;
+    if (!v1) {
+        static int bps = 0, sms = 0;
+        if (!bps) {
+            int dev = 0;
+            VFB_CUDA(cudaGetDevice(&dev));
+            VFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            VFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_inflate_warp, INFW_WARPS * 32, 0));
+            if (bps < 1) bps = 1;
+        }
+        uint32_t blocks = (n_members + INFW_WARPS - 1) / INFW_WARPS;
+        if (blocks > (uint32_t)(sms * bps)) blocks = (uint32_t)(sms * bps);
+        k_inflate_warp<<<blocks, INFW_WARPS * 32, 0, st>>>(a);
+        ++g_launches;
+        VFB_CUDA(cudaGetLastError());
+        return VFB_OK;
+    }
     const uint32_t warps = (n_members + lanes - 1) / lanes;
     k_inflate_members<<<(warps + INF_THREADS / 32 - 1) / (INF_THREADS / 32), INF_THREADS, 0, st>>>(a);
     ++g_launches;

@@ -14,7 +14,14 @@
 namespace vfb {
 
 void set_error(const std::string &msg);
+// VFB_TRACE=1: timestamped lines on stderr (allocations, table growth, ingest phases)
+bool trace_on();
+void trace(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+// process-wide cache of pinned host buffers (api.cu)
+void *pinned_acquire(size_t want, size_t *cap_out);
+void pinned_release(void *p, size_t cap);
+void pinned_pool_trim();
 
 #define VFB_CUDA(call)                                                         \
     do {                                                                       \
