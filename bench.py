@@ -88,6 +88,29 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+FULL_AFFINITY = None
+
+
+def bind_to_gpu_cpus(gpu_index):
+    """Run this rank on the CPUs NVML names as local to its GPU (the socket its PCIe root hangs off), so that the
+    pinned host buffers of the e2e leg are allocated on that NUMA node.  Best effort: containers may forbid it."""
+    if os.environ.get("VFB_BENCH_NO_AFFINITY"):
+        return "off"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        global FULL_AFFINITY
+        if FULL_AFFINITY is None:
+            FULL_AFFINITY = os.sched_getaffinity(0)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        after = sorted(os.sched_getaffinity(0))
+        return "nvml ideal CPUs of GPU %d: %d of %d allowed (%d..%d)" % (gpu_index, len(after), before, after[0], after[-1])
+    except Exception as e:
+        return "unchanged (%s)" % type(e).__name__
+
+
 def oracle_sample(api, oracle, cfg, adapters, text, spans, threads, target_s):
     """Time the CPU oracle (all host threads) on a bounded prefix of the workload."""
     n_all = len(spans)
@@ -181,6 +204,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_cpus(local)          # before any pinned allocation: first touch decides the NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node = --gpus"
@@ -374,6 +398,8 @@ def main():
     if world == 1 and not args.no_cpu:
         import oracle
         oracle.build()
+        if FULL_AFFINITY is not None:
+            os.sched_setaffinity(0, FULL_AFFINITY)      # the CPU baseline gets every host core
         threads = os.cpu_count() or 1
         t, s, n = chunks[0]
         m = min(n, 4_000_000)
@@ -391,6 +417,7 @@ def main():
     # FASTQ parse, K1..K4, table hand-off; whole call, best of 3 after one warm-up call
     ingest = None
     if world == 1 and args.ingest_reads > 0:
+        bind_to_gpu_cpus(local)
         try:
             import tempfile
             sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -425,7 +452,8 @@ def main():
         "config": {"workload": WORKLOAD, "reads_per_gpu": R, "read_len": L, "adapter_len": cfg.adapter_len,
                    "region_len": cfg.region_len, "library": cfg.n_variants, "thresholds": [0.75, 0.75],
                    "scoring": [3, -2, 5, 2], "l2": "inputs (%.1f GB per GPU) are larger than L2" % (R * L / 1e9),
-                   "parallelism": "reads sharded over %d GPU(s), NCCL all-to-all table merge" % world},
+                   "parallelism": "reads sharded over %d GPU(s), NCCL all-to-all table merge" % world,
+                   "cpu_affinity": affinity},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(st["kernel_launches"]),
         "roofline": roofline, "roofline_filter": roofline_filter, "roofline_hbm": roofline_hbm,
         "stages_ms_per_step": stages,

@@ -105,6 +105,23 @@ typedef struct vfb_table {
                                and stay valid until its next vfb_finish / vfb_destroy */
 } vfb_table;
 
+/* Arrow C Data Interface structs (the stable ABI of the Apache Arrow specification), declared here so that
+ * callers need no Arrow headers. */
+typedef struct vfb_arrow_schema {
+    const char *format, *name, *metadata;
+    int64_t flags, n_children;
+    struct vfb_arrow_schema **children, *dictionary;
+    void (*release)(struct vfb_arrow_schema *);
+    void *private_data;
+} vfb_arrow_schema;
+typedef struct vfb_arrow_array {
+    int64_t length, null_count, offset, n_buffers, n_children;
+    const void **buffers;
+    struct vfb_arrow_array **children, *dictionary;
+    void (*release)(struct vfb_arrow_array *);
+    void *private_data;
+} vfb_arrow_array;
+
 typedef struct vfb_stats {
     uint64_t reads;             /* reads submitted since create/reset                  */
     uint64_t dp_prefix;         /* prefix alignments performed                         */
@@ -181,6 +198,11 @@ int vfb_set_compute_stream(vfb_ctx *ctx, void *stream);
  * view.  The context stays usable. */
 int vfb_finish(vfb_ctx *ctx, vfb_table *out);
 void vfb_table_free(vfb_table *t);
+
+/* vfb_finish, exported as one Arrow struct array {sequence: large_utf8, count: uint64} (= the DataFrame of
+ * src/lib.rs:312-319) over the pinned host columns themselves: zero copies.  The pinned buffers leave the context
+ * and are released (to the pinned pool) by the array's release callback, so the result outlives the context. */
+int vfb_finish_arrow(vfb_ctx *ctx, vfb_arrow_array *out_array, vfb_arrow_schema *out_schema);
 
 int vfb_get_stats(vfb_ctx *ctx, vfb_stats *out);
 

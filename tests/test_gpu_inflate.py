@@ -159,6 +159,19 @@ def test_find_variants_on_block_gzip_files(tmp_path):
     p.write_bytes(bytes(bad))
     with pytest.raises(PanicException):
         find_variants(str(p), ad)
+    # a file cut inside a member, and inside a member header
+    whole = variants["bgzf"]
+    second = whole.find(b"\x1f\x8b\x08\x04", 100)
+    for cut in (len(whole) - 40, second + 9, second + 300):
+        p.write_bytes(whole[:cut])
+        for chunk in (None, "200000"):
+            if chunk:
+                os.environ["VFB_INGEST_CHUNK"] = chunk
+            try:
+                with pytest.raises(PanicException, match="truncated|invalid"):
+                    find_variants(str(p), ad)
+            finally:
+                os.environ.pop("VFB_INGEST_CHUNK", None)
     p.write_bytes(bgzf_file(text + b"@q\nACGT\n"))
     with pytest.raises(PanicException, match="truncated"):
         find_variants(str(p), ad)

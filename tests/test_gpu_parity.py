@@ -515,3 +515,37 @@ def test_file_ingest_variants(tmp_path, golden):
     trunc.write_bytes(gzip.compress(b"@r\nACGT\n+\nFFFF\n@q\nAC"))
     with pytest.raises(PanicException):
         find_variants(str(trunc), ad)
+
+
+def test_arrow_c_data_export_is_zero_copy_and_outlives_the_context():
+    # the result table leaves through the Arrow C Data Interface
+    import gc
+    import pyarrow as pa
+    rng = random.Random(21)
+    seqs = make_reads(rng, PREFIX, SUFFIX, 6000, lib=700)
+    text, off, ln = oracle.pack_reads(seqs)
+    want = oracle_run(seqs, (PREFIX, SUFFIX))[0]
+    with api.Context((PREFIX, SUFFIX)) as ctx:
+        ctx.submit_host(text, spans_of(off, ln))
+        batch = ctx.finish_arrow()
+        # the context stays usable and hands out fresh columns next time
+        ctx.submit_host(text, spans_of(off, ln))
+        twice = ctx.finish_dict()
+    assert batch.schema.names == ["sequence", "count"]
+    assert batch.schema.field("sequence").type == pa.large_string() and batch.schema.field("count").type == pa.uint64()
+    assert batch.num_rows == len(want)
+    got = {k.encode(): v for k, v in zip(batch.column(0).to_pylist(), batch.column(1).to_pylist())}
+    assert got == want                                   # read after the context is gone
+    assert twice == {k: 2 * v for k, v in want.items()}
+    frame = api.batch_to_frame(batch)
+    cols = frame.to_pydict() if hasattr(frame, "to_pydict") else frame.to_dict(as_series=False)
+    assert {k.encode(): v for k, v in zip(cols["sequence"], cols["count"])} == want
+    # zero-copy: the Arrow buffers are not owned by Python (they are the pinned columns)
+    data_buf = batch.column(0).buffers()[2]
+    assert data_buf.size >= sum(len(k) for k in want) and data_buf.address != 0
+    del batch, frame, cols, data_buf
+    gc.collect()                                         # release callback -> pinned pool, no crash
+    # empty result (Q12): both columns, zero rows
+    with api.Context((PREFIX, SUFFIX)) as ctx:
+        empty = ctx.finish_arrow()
+    assert empty.num_rows == 0 and empty.schema.names == ["sequence", "count"]

@@ -50,6 +50,20 @@ class Table(C.Structure):
                 ("counts", C.POINTER(C.c_uint64)), ("owner", C.c_void_p)]
 
 
+class ArrowSchema(C.Structure):
+    """struct ArrowSchema of the Arrow C Data Interface (72 bytes)."""
+    _fields_ = [("format", C.c_char_p), ("name", C.c_char_p), ("metadata", C.c_char_p), ("flags", C.c_int64),
+                ("n_children", C.c_int64), ("children", C.c_void_p), ("dictionary", C.c_void_p),
+                ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+
+class ArrowArray(C.Structure):
+    """struct ArrowArray of the Arrow C Data Interface (80 bytes)."""
+    _fields_ = [("length", C.c_int64), ("null_count", C.c_int64), ("offset", C.c_int64), ("n_buffers", C.c_int64),
+                ("n_children", C.c_int64), ("buffers", C.c_void_p), ("children", C.c_void_p),
+                ("dictionary", C.c_void_p), ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+
 class Stats(C.Structure):
     _fields_ = [("reads", C.c_uint64), ("dp_prefix", C.c_uint64), ("dp_suffix", C.c_uint64),
                 ("dp_cells", C.c_uint64), ("counted", C.c_uint64), ("unique", C.c_uint64),
@@ -120,6 +134,7 @@ def load_library():
     L.vfb_measure_int_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.vfb_host_alloc.argtypes = [C.POINTER(vp), u64]
     L.vfb_host_free.argtypes = [vp]
+    L.vfb_finish_arrow.argtypes = [vp, vp, vp]
     L.vfb_pinned_pool_trim.argtypes = []
     _lib = L
     return L
@@ -273,6 +288,16 @@ class Context:
             self._lib.vfb_table_free(C.byref(t))
         return offsets, data, counts
 
+    def finish_arrow(self):
+        """The table as a pyarrow.RecordBatch {sequence: large_string, count: uint64} imported through the
+        Arrow C Data Interface: its buffers are the pinned host columns the device wrote, nothing is copied.
+        The batch owns them (they return to the pinned pool when it is garbage-collected) and outlives
+        this context."""
+        import pyarrow as pa
+        arr, sch = ArrowArray(), ArrowSchema()
+        _check(self._lib.vfb_finish_arrow(self._h, C.byref(arr), C.byref(sch)))
+        return pa.RecordBatch._import_from_c(C.addressof(arr), C.addressof(sch))
+
     def finish_dict(self) -> dict:
         offsets, data, counts = self.finish_arrays()
         raw = data.tobytes()
@@ -293,6 +318,18 @@ class Context:
 
     def absorb(self, chunk_ptr: int, chunk_bytes: int):
         _check(self._lib.vfb_table_absorb(self._h, chunk_ptr, chunk_bytes))
+
+
+def batch_to_frame(batch):
+    """pyarrow.RecordBatch -> polars.DataFrame when polars is importable (zero-copy: polars' String is
+    large_utf8), else a pyarrow.Table with columns `sequence` and `count` (src/lib.rs:312-317)."""
+    import pyarrow as pa
+    tbl = pa.Table.from_batches([batch])
+    try:
+        import polars as pl
+    except ImportError:
+        return tbl
+    return pl.from_arrow(tbl)
 
 
 def table_to_frame(offsets, data, counts):
@@ -392,7 +429,7 @@ def find_variants(fq_path, adapters, match_score=3, mismatch_score=-2, gap_open_
                  skip_translation, show_progress, device=device, batch_reads=batch_reads,
                  table_capacity_hint=table_capacity_hint) as ctx:
         ctx.run_file(fq_path)
-        return table_to_frame(*ctx.finish_arrays())
+        return batch_to_frame(ctx.finish_arrow())
 
 
 # ---- synthetic reads (bench + tests) ----------------------------------------------------

@@ -32,6 +32,7 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 
 }  // namespace vfb (reopened below)
 
+#include <atomic>
 #include <chrono>
 #include <cstdarg>
 #include <mutex>
@@ -1197,6 +1198,94 @@ int vfb_finish(vfb_ctx *c, vfb_table *out)
     VFB_CUDA(cudaStreamSynchronize(c->st_compute));
     c->stats.d2h_bytes += rows * 16 + 8 + total;
     bump_launches(c, before);
+    return VFB_OK;
+}
+
+// ---- Arrow C Data Interface (https://arrow.apache.org/docs/format/CDataInterface.html): the result as a struct
+// array {sequence: large_utf8, count: uint64} whose buffers ARE the pinned host columns — nothing is copied on the
+// way to pyarrow / polars.  Ownership of the pinned buffers moves from the context into the exported array; its
+// release callback hands them back to the pinned pool.
+namespace {
+struct ArrowHolder {
+    std::atomic<int> refs{0};
+    PinBuf offsets, data, counts;
+    vfb_arrow_array children[2];
+    vfb_arrow_array *child_ptrs[2];
+    const void *seq_bufs[3], *cnt_bufs[2], *top_bufs[1];
+};
+void holder_unref(ArrowHolder *h)
+{
+    if (h->refs.fetch_sub(1) == 1) {
+        h->offsets.release(); h->data.release(); h->counts.release();
+        delete h;
+    }
+}
+void arrow_child_release(vfb_arrow_array *a)
+{
+    if (!a || !a->release) return;
+    ArrowHolder *h = static_cast<ArrowHolder *>(a->private_data);
+    a->release = nullptr;
+    holder_unref(h);
+}
+void arrow_top_release(vfb_arrow_array *a)
+{
+    if (!a || !a->release) return;
+    ArrowHolder *h = static_cast<ArrowHolder *>(a->private_data);
+    for (int i = 0; i < 2; ++i)                     // children the consumer has not moved out
+        if (h->children[i].release) h->children[i].release(&h->children[i]);
+    a->release = nullptr;
+    holder_unref(h);
+}
+struct SchemaHolder {
+    vfb_arrow_schema children[2];
+    vfb_arrow_schema *child_ptrs[2];
+};
+void schema_child_release(vfb_arrow_schema *s) { if (s) s->release = nullptr; }
+void schema_top_release(vfb_arrow_schema *s)
+{
+    if (!s || !s->release) return;
+    SchemaHolder *h = static_cast<SchemaHolder *>(s->private_data);
+    for (int i = 0; i < 2; ++i)
+        if (h->children[i].release) h->children[i].release(&h->children[i]);
+    s->release = nullptr;
+    delete h;
+}
+}  // namespace
+
+int vfb_finish_arrow(vfb_ctx *c, vfb_arrow_array *out_array, vfb_arrow_schema *out_schema)
+{
+    if (!c || !out_array || !out_schema) { set_error("null argument"); return VFB_ERR_ARG; }
+    vfb_table t;
+    int rc = vfb_finish(c, &t);
+    if (rc) return rc;
+    ArrowHolder *h = new ArrowHolder;
+    // the context gives its pinned columns away; its next vfb_finish takes fresh ones from the pool
+    h->offsets = c->h_offsets; h->data = c->h_data; h->counts = c->h_counts;
+    c->h_offsets = PinBuf(); c->h_data = PinBuf(); c->h_counts = PinBuf();
+    h->refs = 3;
+    h->seq_bufs[0] = nullptr; h->seq_bufs[1] = t.offsets; h->seq_bufs[2] = t.data;
+    h->cnt_bufs[0] = nullptr; h->cnt_bufs[1] = t.counts;
+    h->top_bufs[0] = nullptr;
+    vfb_arrow_array &seq = h->children[0], &cnt = h->children[1];
+    memset(&seq, 0, sizeof seq); memset(&cnt, 0, sizeof cnt);
+    seq.length = (int64_t)t.rows; seq.n_buffers = 3; seq.buffers = h->seq_bufs;
+    seq.release = arrow_child_release; seq.private_data = h;
+    cnt.length = (int64_t)t.rows; cnt.n_buffers = 2; cnt.buffers = h->cnt_bufs;
+    cnt.release = arrow_child_release; cnt.private_data = h;
+    h->child_ptrs[0] = &seq; h->child_ptrs[1] = &cnt;
+    memset(out_array, 0, sizeof *out_array);
+    out_array->length = (int64_t)t.rows; out_array->n_buffers = 1; out_array->buffers = h->top_bufs;
+    out_array->n_children = 2; out_array->children = h->child_ptrs;
+    out_array->release = arrow_top_release; out_array->private_data = h;
+
+    SchemaHolder *sh = new SchemaHolder;
+    memset(sh->children, 0, sizeof sh->children);
+    sh->children[0].format = "U"; sh->children[0].name = "sequence"; sh->children[0].release = schema_child_release;
+    sh->children[1].format = "L"; sh->children[1].name = "count"; sh->children[1].release = schema_child_release;
+    sh->child_ptrs[0] = &sh->children[0]; sh->child_ptrs[1] = &sh->children[1];
+    memset(out_schema, 0, sizeof *out_schema);
+    out_schema->format = "+s"; out_schema->name = ""; out_schema->n_children = 2; out_schema->children = sh->child_ptrs;
+    out_schema->release = schema_top_release; out_schema->private_data = sh;
     return VFB_OK;
 }
 
