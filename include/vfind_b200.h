@@ -162,6 +162,13 @@ int vfb_destroy(vfb_ctx *ctx);
 int vfb_reset(vfb_ctx *ctx);
 int vfb_set_profiling(vfb_ctx *ctx, int enabled);
 
+/* Progress of vfb_run_file (the reference creates an indicatif spinner when show_progress is set but never
+ * ticks it, src/lib.rs:265-269, :310; here the flag can mean something).  The callback runs on the thread that
+ * is inside vfb_run_file, at most about ten times per second and once at the end: records queued so far,
+ * compressed bytes consumed so far, compressed size of the file. */
+typedef void (*vfb_progress_fn)(uint64_t records, uint64_t bytes_done, uint64_t bytes_total, void *user);
+int vfb_set_progress(vfb_ctx *ctx, vfb_progress_fn fn, void *user);
+
 /* The per-read hot loop (worker + reducer closures, src/lib.rs:275-306) over a batch of
  * reads held in HOST memory: host->device copies happen inside.  `text`/`spans` may be
  * pageable or pinned (pinned is copied directly).  Asynchronous: returns once the batch
@@ -177,6 +184,13 @@ int vfb_submit_device(vfb_ctx *ctx, const uint8_t *d_text, uint64_t text_bytes,
  * file -> inflate -> parse -> batches -> the hot loop.  VFB_ERR_IO if it cannot be
  * opened, VFB_ERR_FORMAT on malformed gzip/FASTQ. */
 int vfb_run_file(vfb_ctx *ctx, const char *path, uint64_t *n_reads);
+
+/* vfb_run_file with input options.  VFB_INPUT_ALLOW_TEXT: a file that does not start with the gzip magic is read
+ * as uncompressed FASTQ text (the reference accepts gzip only and panics on anything else, src/lib.rs:233, :308 —
+ * which is what vfb_run_file and flags = 0 do).  May be called for several files on one context: the table
+ * accumulates across calls (plain-text and multi-file front-ends). */
+#define VFB_INPUT_ALLOW_TEXT 1u
+int vfb_run_file_ex(vfb_ctx *ctx, const char *path, uint32_t flags, uint64_t *n_reads_out);
 
 /* Host-only front half of vfb_run_file (no GPU needed): inflate `path` chunk by chunk exactly as
  * the ingest does (serial gzip, or member-parallel on n_threads for block-gzip/BGZF input) and

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 
 import numpy as np
 
@@ -62,6 +63,9 @@ class ArrowArray(C.Structure):
     _fields_ = [("length", C.c_int64), ("null_count", C.c_int64), ("offset", C.c_int64), ("n_buffers", C.c_int64),
                 ("n_children", C.c_int64), ("buffers", C.c_void_p), ("children", C.c_void_p),
                 ("dictionary", C.c_void_p), ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+
+PROGRESS_FN = C.CFUNCTYPE(None, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p)
 
 
 class Stats(C.Structure):
@@ -135,6 +139,8 @@ def load_library():
     L.vfb_host_alloc.argtypes = [C.POINTER(vp), u64]
     L.vfb_host_free.argtypes = [vp]
     L.vfb_finish_arrow.argtypes = [vp, vp, vp]
+    L.vfb_run_file_ex.argtypes = [vp, C.c_char_p, u32, C.POINTER(u64)]
+    L.vfb_set_progress.argtypes = [vp, vp, vp]
     L.vfb_pinned_pool_trim.argtypes = []
     _lib = L
     return L
@@ -242,9 +248,11 @@ class Context:
     def submit_device(self, text_ptr, text_bytes, spans_ptr, n):
         _check(self._lib.vfb_submit_device(self._h, text_ptr, text_bytes, spans_ptr, n))
 
-    def run_file(self, path) -> int:
+    def run_file(self, path, allow_text=False) -> int:
+        """Ingest one FASTQ file; the table accumulates over calls.  allow_text: a file without the gzip
+        magic is read as uncompressed text instead of failing like the reference."""
         n = C.c_uint64(0)
-        _check(self._lib.vfb_run_file(self._h, os.fsencode(path), C.byref(n)))
+        _check(self._lib.vfb_run_file_ex(self._h, os.fsencode(path), 1 if allow_text else 0, C.byref(n)))
         return int(n.value)
 
     def sync(self):
@@ -255,6 +263,16 @@ class Context:
 
     def set_compute_stream(self, stream_ptr: int):
         _check(self._lib.vfb_set_compute_stream(self._h, stream_ptr))
+
+    def set_progress(self, fn):
+        """fn(records, bytes_done, bytes_total) is called from run_file about ten times per second and once at
+        the end (None removes it)."""
+        if fn is None:
+            self._progress_cb = None
+            _check(self._lib.vfb_set_progress(self._h, None, None))
+            return
+        self._progress_cb = PROGRESS_FN(lambda r, d, t, _u: fn(int(r), int(d), int(t)))
+        _check(self._lib.vfb_set_progress(self._h, C.cast(self._progress_cb, C.c_void_p), None))
 
     def set_profiling(self, on: bool):
         _check(self._lib.vfb_set_profiling(self._h, 1 if on else 0))
@@ -382,7 +400,7 @@ def _bool_arg(v, name):
 def find_variants(fq_path, adapters, match_score=3, mismatch_score=-2, gap_open_penalty=5,
                   gap_extend_penalty=2, accept_prefix_alignment=0.75, accept_suffix_alignment=0.75,
                   n_threads=3, queue_len=2, skip_translation=False, show_progress=True, *,
-                  device=None, batch_reads=0, table_capacity_hint=0):
+                  device=None, batch_reads=0, table_capacity_hint=0, progress=None, allow_text=False):
     """Find variable regions flanked by adapters in a gzipped FASTQ dataset.
 
     Drop-in for `vfind.find_variants` (/root/reference/src/lib.rs:168-232): same positional
@@ -392,13 +410,41 @@ def find_variants(fq_path, adapters, match_score=3, mismatch_score=-2, gap_open_
     polars.DataFrame when polars is installed, else a pyarrow.Table.  Row order is
     unspecified (as in the reference, src/lib.rs:312).
 
-    Extra keyword-only arguments: device (CUDA ordinal), batch_reads, table_capacity_hint.
+    Extra keyword-only arguments: device (CUDA ordinal), batch_reads, table_capacity_hint,
+    progress (callable(records, bytes_done, bytes_total), called about ten times per second),
+    allow_text (read a file without the gzip magic as uncompressed FASTQ; the reference panics on it).
+    With show_progress (the default) and a terminal on stderr a one-line progress display is shown
+    and cleared at the end, like the reference's spinner (src/lib.rs:265-269, :310).
     """
     if isinstance(fq_path, os.PathLike):
         fq_path = os.fspath(fq_path)
     if not isinstance(fq_path, str):
         raise TypeError("argument 'fq_path': '%s' object cannot be converted to 'PyString'"
                         % type(fq_path).__name__)
+    return _find_variants([fq_path], adapters, match_score, mismatch_score, gap_open_penalty, gap_extend_penalty,
+                          accept_prefix_alignment, accept_suffix_alignment, n_threads, queue_len, skip_translation,
+                          show_progress, device, batch_reads, table_capacity_hint, progress, allow_text)
+
+
+def find_variants_multi(fq_paths, adapters, match_score=3, mismatch_score=-2, gap_open_penalty=5,
+                        gap_extend_penalty=2, accept_prefix_alignment=0.75, accept_suffix_alignment=0.75,
+                        n_threads=3, queue_len=2, skip_translation=False, show_progress=True, *,
+                        device=None, batch_reads=0, table_capacity_hint=0, progress=None, allow_text=False):
+    """find_variants over several FASTQ files (lanes, split runs) counted into ONE table, on one context
+    (SURVEY §8(f) next-4).  Same arguments as find_variants; fq_paths is a non-empty sequence of paths."""
+    if isinstance(fq_paths, (str, bytes, os.PathLike)) or not hasattr(fq_paths, "__iter__"):
+        raise TypeError("argument 'fq_paths': expected a sequence of paths")
+    paths = [os.fspath(p) if isinstance(p, os.PathLike) else p for p in fq_paths]
+    if not paths or not all(isinstance(p, str) for p in paths):
+        raise TypeError("argument 'fq_paths': expected a non-empty sequence of str / os.PathLike")
+    return _find_variants(paths, adapters, match_score, mismatch_score, gap_open_penalty, gap_extend_penalty,
+                          accept_prefix_alignment, accept_suffix_alignment, n_threads, queue_len, skip_translation,
+                          show_progress, device, batch_reads, table_capacity_hint, progress, allow_text)
+
+
+def _find_variants(paths, adapters, match_score, mismatch_score, gap_open_penalty, gap_extend_penalty,
+                   accept_prefix_alignment, accept_suffix_alignment, n_threads, queue_len, skip_translation,
+                   show_progress, device, batch_reads, table_capacity_hint, progress, allow_text):
     if not isinstance(adapters, (tuple, list)):
         raise TypeError("argument 'adapters': '%s' object cannot be converted to 'PyTuple'"
                         % type(adapters).__name__)
@@ -422,14 +468,80 @@ def find_variants(fq_path, adapters, match_score=3, mismatch_score=-2, gap_open_
     show_progress = _bool_arg(show_progress, "show_progress")
 
     # The reference opens the file before validating thresholds (src/lib.rs:233 vs :239).
-    with open(fq_path, "rb"):
-        pass
+    for p in paths:
+        with open(p, "rb"):
+            pass
     with Context(adapters, match_score, mismatch_score, gap_open_penalty, gap_extend_penalty,
                  accept_prefix_alignment, accept_suffix_alignment, n_threads, queue_len,
                  skip_translation, show_progress, device=device, batch_reads=batch_reads,
                  table_capacity_hint=table_capacity_hint) as ctx:
-        ctx.run_file(fq_path)
+        shown = show_progress and progress is None and sys.stderr.isatty()
+        if progress is not None:
+            ctx.set_progress(progress)
+        elif shown:
+            def spin(records, done, total, _f="|/-\\", _i=[0]):
+                _i[0] += 1
+                pct = " %3d%%" % (100 * done // total) if total else ""
+                sys.stderr.write("\r%s Finding variants... %d reads%s" % (_f[_i[0] % 4], records, pct))
+                sys.stderr.flush()
+            ctx.set_progress(spin)
+        try:
+            for p in paths:
+                ctx.run_file(p, allow_text=allow_text)
+        finally:
+            if shown:
+                sys.stderr.write("\r" + " " * 60 + "\r")       # finish_and_clear
+                sys.stderr.flush()
         return batch_to_frame(ctx.finish_arrow())
+
+
+def read_diagnostics(reads, adapters, match_score=3, mismatch_score=-2, gap_open_penalty=5, gap_extend_penalty=2,
+                     accept_prefix_alignment=0.75, accept_suffix_alignment=0.75, skip_translation=False, *,
+                     device=None):
+    """What find_variants decides for each read, as a pyarrow.Table with one row per read:
+
+    exact_prefix / exact_suffix  leftmost exact adapter position, null when absent      (src/lib.rs:148)
+    score_* / len_*              semi-global alignment score and length statistic of the
+                                 alignments the reference computes, null where none ran  (src/lib.rs:155-160)
+    accept_prefix / accept_suffix  the adapter was located (exactly or by an accepted alignment)
+    start / end                  region boundaries, null when not located               (src/lib.rs:278-286)
+    region                       the variable region (null unless both located and start < end, src/lib.rs:288)
+
+    `reads` is a sequence of str / bytes.  Runs the full DP (exact scores also for rejected alignments)."""
+    import pyarrow as pa
+    seqs = [r if isinstance(r, bytes) else r.encode() for r in reads]
+    n = len(seqs)
+    length = np.array([len(s) for s in seqs], dtype=np.uint64)
+    if int(length.sum()) >= 2 ** 32:
+        raise ValueError("read_diagnostics takes at most 4 GiB of reads per call")
+    spans = np.zeros(n, dtype=SPAN_DTYPE)
+    spans["len"] = length
+    if n:
+        spans["off"][1:] = np.cumsum(length[:-1])
+    text = np.frombuffer(b"".join(seqs), dtype=np.uint8)
+    if n == 0:
+        d = np.zeros(0, dtype=DIAG_DTYPE)
+    else:
+        ad = tuple(a if isinstance(a, bytes) else a.encode() for a in adapters)
+        with Context(ad, match_score, mismatch_score, gap_open_penalty, gap_extend_penalty, accept_prefix_alignment,
+                     accept_suffix_alignment, skip_translation=skip_translation, device=device, diagnostics=True,
+                     batch_reads=max(n, 1)) as ctx:
+            ctx.submit_host(text, spans)
+            d = ctx.diag(n)
+    cols = {}
+    for f in ("exact_prefix", "exact_suffix"):
+        cols[f] = pa.array(d[f], mask=d[f] < 0, type=pa.int32())
+    for side in ("prefix", "suffix"):
+        ran = d["len_" + side] >= 0
+        cols["score_" + side] = pa.array(d["score_" + side], mask=~ran, type=pa.int32())
+        cols["len_" + side] = pa.array(d["len_" + side], mask=~ran, type=pa.int32())
+    cols["accept_prefix"] = pa.array(d["start"] >= 0)
+    cols["accept_suffix"] = pa.array(d["end"] >= 0)
+    cols["start"] = pa.array(d["start"], mask=d["start"] < 0, type=pa.int32())
+    cols["end"] = pa.array(d["end"], mask=d["end"] < 0, type=pa.int32())
+    ok = (d["start"] >= 0) & (d["end"] >= 0) & (d["start"] < d["end"])
+    cols["region"] = pa.array([seqs[i][d["start"][i]:d["end"][i]] if ok[i] else None for i in range(n)], type=pa.binary())
+    return pa.table(cols)
 
 
 # ---- synthetic reads (bench + tests) ----------------------------------------------------

@@ -257,6 +257,9 @@ struct vfb_ctx {
     std::vector<uint64_t> h_part_rows, h_part_keys;
 
     bool profiling = false;
+    vfb_progress_fn progress_fn = nullptr;
+    void *progress_user = nullptr;
+    std::chrono::steady_clock::time_point progress_last{};
     bool own_compute_stream = true;
     std::vector<cudaEvent_t> evpool;   // 12 events per profiled batch, resolved at sync time
     size_t ev_used = 0;
@@ -607,6 +610,15 @@ int vfb_set_profiling(vfb_ctx *c, int enabled)
 {
     if (!c) { set_error("null context"); return VFB_ERR_ARG; }
     c->profiling = enabled != 0;
+    return VFB_OK;
+}
+
+int vfb_set_progress(vfb_ctx *c, vfb_progress_fn fn, void *user)
+{
+    if (!c) { set_error("null context"); return VFB_ERR_ARG; }
+    c->progress_fn = fn;
+    c->progress_user = user;
+    c->progress_last = std::chrono::steady_clock::time_point{};
     return VFB_OK;
 }
 
@@ -1056,6 +1068,15 @@ int vfb_internal_submit_bgzf(vfb_ctx *c, const uint8_t *pinned_z, uint64_t z_byt
     bump_launches(c, before);
     trace("submit_bgzf: hot loop queued (%u records)", n_rec);
     return VFB_OK;
+}
+
+void vfb_internal_progress(vfb_ctx *c, uint64_t records, uint64_t bytes_done, uint64_t bytes_total, bool final)
+{
+    if (!c->progress_fn) return;
+    const auto now = std::chrono::steady_clock::now();
+    if (!final && std::chrono::duration<double>(now - c->progress_last).count() < 0.1) return;
+    c->progress_last = now;
+    c->progress_fn(records, bytes_done, bytes_total, c->progress_user);
 }
 
 int vfb_internal_ingest_threads(vfb_ctx *c)

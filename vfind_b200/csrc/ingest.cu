@@ -182,8 +182,11 @@ int peek_bgzf(FILE *f, size_t *member_size)
 // Fills chunk buffers with inflated text and cuts them at record boundaries.
 struct ChunkProducer {
     FILE *f = nullptr;
+    uint64_t file_size = 0;
+    std::atomic<uint64_t> consumed{0};   // compressed bytes read so far (progress only)
     Inflater serial;
     bool bgzf = false;          // still reading BGZF members
+    bool plain = false;         // uncompressed FASTQ text (vfb_run_file_ex with VFB_INPUT_ALLOW_TEXT only)
     int threads = 1;
     std::vector<uint8_t> carry;
     std::vector<uint8_t> zbuf;  // compressed members of the current chunk
@@ -195,14 +198,23 @@ struct ChunkProducer {
         if (f) fclose(f);
     }
 
-    bool open(const char *path, int n_threads, std::string *e)
+    bool open(const char *path, int n_threads, std::string *e, bool allow_text = false)
     {
         f = fopen(path, "rb");
         if (!f) { *e = std::string("cannot open ") + path + ": " + strerror(errno); return false; }
         serial.f = f;
+        fseek(f, 0, SEEK_END);
+        file_size = (uint64_t)ftell(f);
+        fseek(f, 0, SEEK_SET);
         threads = n_threads < 1 ? 1 : n_threads;
         size_t ms = 0;
         bgzf = peek_bgzf(f, &ms) == 1;
+        if (allow_text && !bgzf) {
+            uint8_t m[2] = {0, 0};
+            const size_t got = fread(m, 1, 2, f);
+            fseek(f, 0, SEEK_SET);
+            plain = !(got == 2 && m[0] == 0x1f && m[1] == 0x8b);
+        }
         return true;
     }
 
@@ -281,7 +293,7 @@ struct ChunkProducer {
                 if (bgzf && !at_end) break;                   // as full as whole members allow
             } else {
                 const size_t want = cap - used < ((size_t)4 << 20) ? cap - used : ((size_t)4 << 20);
-                const long long got = serial.read(buf + used, want, &err);
+                const long long got = plain ? (long long)fread(buf + used, 1, want, f) : serial.read(buf + used, want, &err);
                 if (got < 0) return VFB_ERR_FORMAT;
                 if ((size_t)got < want) at_end = true;
                 lines += count_nl(buf + used, (size_t)got);
@@ -313,6 +325,7 @@ struct ChunkProducer {
         *cut_out = cut;
         *lines_out = keep;
         *last = at_end;
+        consumed = (uint64_t)ftell(f);
         return VFB_OK;
     }
 };
@@ -479,6 +492,7 @@ int run_bgzf_gpu(vfb_ctx *ctx, ChunkProducer &prod, size_t text_target, uint64_t
         }
     });
     std::vector<uint8_t> tail(VFB_TAIL_CAP);
+    uint64_t seg_bytes_done = pos;
     while (rc == VFB_OK) {
         int k = -1;
         {
@@ -501,6 +515,8 @@ int run_bgzf_gpu(vfb_ctx *ctx, ChunkProducer &prod, size_t text_target, uint64_t
         if (rc == VFB_OK) {
             prod.carry.assign(tail.data(), tail.data() + tail_len);
             *n_total += n_rec;
+            seg_bytes_done += g.z_bytes;
+            vfb_internal_progress(ctx, *n_total, seg_bytes_done, prod.file_size, false);
             if (trace) fprintf(stderr, "[vfb ingest] gpu segment: %u members, %zu -> %zu bytes, %llu records, %.1f ms\n", g.n,
                                g.z_bytes, g.text_bytes, (unsigned long long)n_rec,
                                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
@@ -564,11 +580,16 @@ extern "C" int vfb_debug_inflate_file(const char *path, uint32_t n_threads, uint
 
 extern "C" int vfb_run_file(vfb_ctx *ctx, const char *path, uint64_t *n_reads_out)
 {
+    return vfb_run_file_ex(ctx, path, 0, n_reads_out);
+}
+
+extern "C" int vfb_run_file_ex(vfb_ctx *ctx, const char *path, uint32_t flags, uint64_t *n_reads_out)
+{
     if (!ctx || !path) { set_error("null argument"); return VFB_ERR_ARG; }
     ChunkProducer prod;
     {
         std::string e;
-        if (!prod.open(path, vfb_internal_ingest_threads(ctx), &e)) { set_error(e); return VFB_ERR_IO; }
+        if (!prod.open(path, vfb_internal_ingest_threads(ctx), &e, (flags & VFB_INPUT_ALLOW_TEXT) != 0)) { set_error(e); return VFB_ERR_IO; }
     }
     size_t cap = pick_chunk(prod.f);
     const bool trace = getenv("VFB_INGEST_TRACE") != nullptr;
@@ -604,7 +625,7 @@ extern "C" int vfb_run_file(vfb_ctx *ctx, const char *path, uint64_t *n_reads_ou
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
     };
     if (trace) fprintf(stderr, "[vfb ingest] %s: %s, chunk %zu bytes, %d inflate threads\n", path,
-                       prod.bgzf ? "block gzip (member-parallel)" : "gzip stream (serial)", cap, prod.threads);
+                       prod.plain ? "plain text" : (prod.bgzf ? "block gzip (member-parallel)" : "gzip stream (serial)"), cap, prod.threads);
     std::thread producer;
     if (rc == VFB_OK) producer = std::thread([&]() {
         for (;;) {
@@ -650,6 +671,7 @@ extern "C" int vfb_run_file(vfb_ctx *ctx, const char *path, uint64_t *n_reads_ou
             rc = vfb_internal_submit_fastq(ctx, c.buf, c.cut, c.lines, n_total, c.copied);
             if (trace) fprintf(stderr, "[vfb ingest] submit at %.1f ms took %.1f ms\n", ms_since(t_start), ms_since(t0));
             n_total += c.lines / 4;
+            vfb_internal_progress(ctx, n_total, prod.consumed.load(), prod.file_size, false);
         } else if (cudaEventRecord(c.copied, 0) != cudaSuccess) {
             cudaGetLastError();
         }
@@ -692,6 +714,7 @@ extern "C" int vfb_run_file(vfb_ctx *ctx, const char *path, uint64_t *n_reads_ou
         if (ch[i].copied) cudaEventDestroy(ch[i].copied);
     }
     if (n_reads_out) *n_reads_out = n_total;
+    if (rc == VFB_OK) vfb_internal_progress(ctx, n_total, prod.file_size, prod.file_size, true);
     if (trace) fprintf(stderr, "[vfb ingest] %llu records in %.1f ms\n", (unsigned long long)n_total,
                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
     return rc;

@@ -255,5 +255,6 @@ int vfb_internal_submit_bgzf(vfb_ctx *ctx, const uint8_t *pinned_z, uint64_t z_b
                              uint32_t *bad_member);
 // Host threads the ingest may use to inflate block-gzip members in parallel (params.n_threads).
 int vfb_internal_ingest_threads(vfb_ctx *ctx);
+void vfb_internal_progress(vfb_ctx *ctx, uint64_t records, uint64_t bytes_done, uint64_t bytes_total, bool final);
 // After vfb_sync: global index of the first malformed record, or UINT64_MAX.
 int vfb_internal_parse_error(vfb_ctx *ctx, uint64_t *first_bad_record);
