@@ -165,10 +165,23 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else libraries print on fd 1 (NCCL's version banner,
+    for one) was sent to stderr by main()."""
+    os.write(REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+REAL_STDOUT = 1
 
 
 def main():
+    global REAL_STDOUT
+    sys.stdout.flush()
+    REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -465,7 +478,7 @@ def main():
         "merge_ms_per_step": merge_ms, "table": {"unique": st["unique"], "counted_per_step": st["counted"], "merge_check": merge_check},
         "cpu_baseline": cpu, "ingest": ingest,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
