@@ -370,6 +370,13 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        if traffic.get("reads_per_launch") != min(args.chunk_reads, R):
+            traffic = {}                    # captured at another batch size: not comparable per launch
+    except (OSError, ValueError):
+        pass
     dp_s = st["ms_dp"] * 1e-3
     gcups = st["dp_cells"] / dp_s / 1e9 if dp_s > 0 else 0.0      # effective: full A x L matrices / DP stage time
     windowed = st["dp_kernel_kind"] == 3
@@ -387,7 +394,8 @@ def main():
     scan_gbs = scan_bytes / (st["ms_scan"] * 1e-3) / 1e9 if st["ms_scan"] > 0 else 0.0
     key_bytes = st["counted"] * args.steps * (cfg.region_len + cfg.region_len // 3 + 8)
     roofline = {"bound": "int32", "kernel": dp_kernel, "achieved": dp_achieved, "peak": alu_gops,
-                "unit": "Gop/s", "frac": dp_achieved / alu_gops if alu_gops else None, "traffic": None,
+                "unit": "Gop/s", "frac": dp_achieved / alu_gops if alu_gops else None,
+                "traffic": traffic.get(dp_kernel), "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_ncu_traffic.json)",
                 "gcups": kernel_gcups, "alu_ops_per_cell": ALU_OPS_PER_CELL,
                 "peak_source": "vfb_measure_int_peak (VIADDMNMX stream, measured in this run); ALU+FMA dual-issue peak %.0f Gop/s" % dual_gops,
                 "share_of_step": dp_ms / st["ms_total"] if st["ms_total"] else None}
@@ -397,11 +405,12 @@ def main():
         cols = st["dp_cells"] / cfg.adapter_len       # one column per read base of every aligned read
         f_ach = cols * FILTER_ALU_OPS_PER_COL / (st["ms_dp_filter"] * 1e-3) / 1e9
         roofline_filter = {"bound": "int32", "kernel": "k2_filter", "achieved": f_ach, "peak": alu_gops, "unit": "Gop/s",
-                           "frac": f_ach / alu_gops if alu_gops else None, "traffic": None,
+                           "frac": f_ach / alu_gops if alu_gops else None, "traffic": traffic.get("k2_filter"),
                            "columns_per_s": cols / (st["ms_dp_filter"] * 1e-3), "alu_ops_per_column": FILTER_ALU_OPS_PER_COL,
                            "share_of_step": st["ms_dp_filter"] / st["ms_total"] if st["ms_total"] else None}
     roofline_hbm = {"bound": "hbm", "kernel": "k1_scan", "achieved": scan_gbs, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": scan_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                    "frac": scan_gbs / hbm_peak, "traffic": traffic.get("k1_scan"),
+                    "algorithmic_bytes_per_launch": min(args.chunk_reads, R) * (L + 12), "peak_source": hbm_src,
                     "share_of_step": st["ms_scan"] / st["ms_total"] if st["ms_total"] else None}
     stages = {k: st[k] / args.steps for k in ("ms_scan", "ms_worklist", "ms_dp", "ms_dp_filter", "ms_dp_window",
                                               "ms_translate", "ms_count", "ms_total")}
