@@ -46,9 +46,10 @@ struct ScanArgs {
 
 __host__ __device__ __forceinline__ uint32_t hash4(uint32_t w, uint32_t mult) { return (w * mult) >> 23; }
 // 8-byte keys (two consecutive text words)
-__host__ __device__ __forceinline__ uint32_t hash8(uint32_t w0, uint32_t w1, uint32_t mult)
+__host__ __device__ __forceinline__ uint32_t hash8_mult2(uint32_t mult) { return mult * 0x85EBCA6Bu + 2u; }
+__host__ __device__ __forceinline__ uint32_t hash8(uint32_t w0, uint32_t w1, uint32_t mult, uint32_t mult2)
 {
-    return (w0 * mult + w1 * (mult * 0x85EBCA6Bu + 2u)) >> 23;
+    return (w0 * mult + w1 * mult2) >> 23;
 }
 
 __host__ __device__ __forceinline__ uint32_t load_word_le(const uint8_t *b, int i, int n)
@@ -93,7 +94,7 @@ __device__ void build_tables(ScanTables *T, const AdapterBytes &pre, const Adapt
             for (int k = 0; k < max_k && k + (key8 ? 8 : 4) <= (int)ad.len; ++k) {
                 const uint32_t w = load_word_le(ad.b, k, (int)ad.len);
                 const uint32_t w1 = load_word_le(ad.b, k + 4, (int)ad.len);
-                const uint32_t h = key8 ? hash8(w, w1, mult) : hash4(w, mult);      // collision-free by choice of mult (host)
+                const uint32_t h = key8 ? hash8(w, w1, mult, hash8_mult2(mult)) : hash4(w, mult);      // collision-free by choice of mult (host)
                 uint4 e = T->e0[h];
                 if (e.y == 0) {
                     e.x = w;
@@ -115,6 +116,15 @@ __device__ void build_tables(ScanTables *T, const AdapterBytes &pre, const Adapt
                 T->e1[h] |= 1u << (k + 16 * x);
             }
         }
+    }
+    __syncthreads();
+    // An empty slot gets a key that does not hash to it: a text key equal to it is looked up in
+    // another slot, so the probe needs no "occupied" test — one compare decides.
+    for (int i = threadIdx.x; i < SCAN_SLOTS; i += blockDim.x) {
+        if (T->e0[i].y != 0) continue;
+        uint32_t t = 0;
+        while ((key8 ? hash8(t, 0u, mult, hash8_mult2(mult)) : hash4(t, mult)) == (uint32_t)i) ++t;
+        T->e0[i] = make_uint4(t, 0u, 0u, 0xFFFFFFFFu);
     }
     __syncthreads();
 }
@@ -190,13 +200,14 @@ struct Hits {
 };
 
 template <bool MULTI, bool KEY8>
-__device__ __forceinline__ void probe_word(const ScanTables *T, uint32_t mult, uint32_t w, uint32_t wnext, int relq,
+__device__ __forceinline__ void probe_word(const ScanTables *T, uint32_t mult, uint32_t mult2, uint32_t w, uint32_t wnext, int relq,
                                            const ReadGeom &rg, uint32_t AP, uint32_t AS, Hits &hq,
                                            uint32_t &bestP, uint32_t &bestS)
 {
-    const uint32_t h = KEY8 ? hash8(w, wnext, mult) : hash4(w, mult);
+    const uint32_t h = KEY8 ? hash8(w, wnext, mult, mult2) : hash4(w, mult);
     const uint4 e = T->e0[h];
-    if (e.y && e.x == w && ((wnext ^ e.z) & e.w) == 0) {
+    const uint32_t diff = KEY8 ? ((e.x ^ w) | (e.z ^ wnext)) : ((e.x ^ w) | ((e.z ^ wnext) & e.w));
+    if (diff == 0) {
         if (MULTI && (e.y & 0xFFu) != 1u) { hit_expand(T, h, relq, rg, AP, AS, bestP, bestS); return; }
         if (hq.pend != VFB_NONE) {
             const uint32_t x = hq.pend & 1u, A = x ? AS : AP;
@@ -226,17 +237,17 @@ __device__ __forceinline__ void hits_drain(const ScanTables *T, Hits &hq, const 
 // STRIDE_WORDS == 2): no false hits to speak of, and duplicates among the adapters' keys are
 // rare.  Otherwise 4-byte keys probed every STRIDE_WORDS words, with the next-word check.
 template <int STRIDE_WORDS, bool MULTI, bool KEY8>
-__device__ __forceinline__ void probe_chunk(const ScanTables *T, uint32_t mult, const uint4 &v, int relq,
+__device__ __forceinline__ void probe_chunk(const ScanTables *T, uint32_t mult, uint32_t mult2, const uint4 &v, int relq,
                                             const ReadGeom &rg, uint32_t AP, uint32_t AS, Hits &hq,
                                             uint32_t &bestP, uint32_t &bestS)
 {
     // (with STRIDE_WORDS == 1 the word after v.w is in the next chunk: the tables carry no
     // next-word check then, the argument is ignored)
-    probe_word<MULTI, KEY8>(T, mult, v.x, v.y, relq, rg, AP, AS, hq, bestP, bestS);
-    if (STRIDE_WORDS <= 2) probe_word<MULTI, KEY8>(T, mult, v.z, v.w, relq + 8, rg, AP, AS, hq, bestP, bestS);
+    probe_word<MULTI, KEY8>(T, mult, mult2, v.x, v.y, relq, rg, AP, AS, hq, bestP, bestS);
+    if (STRIDE_WORDS <= 2) probe_word<MULTI, KEY8>(T, mult, mult2, v.z, v.w, relq + 8, rg, AP, AS, hq, bestP, bestS);
     if (STRIDE_WORDS == 1) {
-        probe_word<MULTI, KEY8>(T, mult, v.y, v.z, relq + 4, rg, AP, AS, hq, bestP, bestS);
-        probe_word<MULTI, KEY8>(T, mult, v.w, 0u, relq + 12, rg, AP, AS, hq, bestP, bestS);
+        probe_word<MULTI, KEY8>(T, mult, mult2, v.y, v.z, relq + 4, rg, AP, AS, hq, bestP, bestS);
+        probe_word<MULTI, KEY8>(T, mult, mult2, v.w, 0u, relq + 12, rg, AP, AS, hq, bestP, bestS);
     }
 }
 
@@ -307,7 +318,7 @@ k1_scan_fast(const __grid_constant__ ScanArgs args)
     __shared__ ScanTables T;
     __shared__ WlStage stage[SCAN_WARPS];
     build_tables(&T, args.prefix, args.suffix, 4 * STRIDE_WORDS, args.mult, STRIDE_WORDS >= 2, KEY8);
-    const uint32_t mult = args.mult;
+    const uint32_t mult = args.mult, mult2 = hash8_mult2(args.mult);
     const ScanJob &job = args.job;
     const uint32_t AP = args.prefix.len, AS = args.suffix.len;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -348,9 +359,13 @@ k1_scan_fast(const __grid_constant__ ScanArgs args)
             const uint4 v0 = c0 < n_chunks ? __ldg(rg.base16 + c0) : z;
             const uint4 v1 = c1 < n_chunks ? __ldg(rg.base16 + c1) : z;
             const uint4 v2 = c2 < n_chunks ? __ldg(rg.base16 + c2) : z;
-            if (c0 < n_chunks) probe_chunk<STRIDE_WORDS, MULTI, KEY8>(&T, mult, v0, (int)(c0 * 16) - (int)rg.lead, rg, AP, AS, hq, bestP, bestS);
-            if (c1 < n_chunks) probe_chunk<STRIDE_WORDS, MULTI, KEY8>(&T, mult, v1, (int)(c1 * 16) - (int)rg.lead, rg, AP, AS, hq, bestP, bestS);
-            if (c2 < n_chunks) probe_chunk<STRIDE_WORDS, MULTI, KEY8>(&T, mult, v2, (int)(c2 * 16) - (int)rg.lead, rg, AP, AS, hq, bestP, bestS);
+            probe_chunk<STRIDE_WORDS, MULTI, KEY8>(&T, mult, mult2, v0, (int)(c0 * 16) - (int)rg.lead, rg, AP, AS, hq, bestP, bestS);
+            // (chunks past a read's end were loaded as zeros and cannot pass the bounds check of a hit:
+            // the probes need no per-lane guard, only these warp-uniform ones)
+            if (cb + SCAN_GROUP < max_chunks)
+                probe_chunk<STRIDE_WORDS, MULTI, KEY8>(&T, mult, mult2, v1, (int)(c1 * 16) - (int)rg.lead, rg, AP, AS, hq, bestP, bestS);
+            if (cb + 2 * SCAN_GROUP < max_chunks)
+                probe_chunk<STRIDE_WORDS, MULTI, KEY8>(&T, mult, mult2, v2, (int)(c2 * 16) - (int)rg.lead, rg, AP, AS, hq, bestP, bestS);
             hits_drain(&T, hq, rg, AP, AS, bestP, bestS);
         }
         // leftmost over the lane group
@@ -446,7 +461,7 @@ int launch_scan(const ScanJob &job, const AdapterBytes &prefix, const AdapterByt
                 for (int k = 0; k < max_k && k + klen <= (int)ad.len; ++k) {
                     const uint32_t w = load_word_le(ad.b, k, (int)ad.len);
                     const uint32_t w1 = key8 ? load_word_le(ad.b, k + 4, (int)ad.len) : 0u;
-                    const uint32_t h = key8 ? hash8(w, w1, mult) : hash4(w, mult);
+                    const uint32_t h = key8 ? hash8(w, w1, mult, hash8_mult2(mult)) : hash4(w, mult);
                     if (used[h] && (w0s[h] != w || w1s[h] != w1)) { ok = false; break; }
                     if (used[h]) multi = true;
                     used[h] = true;
