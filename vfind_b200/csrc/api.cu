@@ -236,7 +236,7 @@ struct vfb_ctx {
 
     // table
     DevTable tab{};
-    DevBuf t_slots, t_counts, t_row_hash, t_row_off, t_row_len, t_arena, t_counters, t_row_count;
+    DevBuf t_slots, t_row_hash, t_row_off, t_row_len, t_arena, t_counters, t_row_count;
     uint64_t ub_rows = 0, ub_arena = 0;   // host-side upper bounds of rows / arena bytes
 
     // ingest, GPU inflate path: compressed members, member table, text (double buffered), tail
@@ -319,14 +319,12 @@ static int bump_launches(vfb_ctx *c, uint64_t before)
 static int table_alloc(vfb_ctx *c, uint64_t capacity, uint64_t rows_cap, uint64_t arena_cap)
 {
     int rc;
-    if ((rc = c->t_slots.ensure(capacity * 8))) return rc;
-    if ((rc = c->t_counts.ensure(capacity * 8))) return rc;
+    if ((rc = c->t_slots.ensure(capacity * 8 * VFB_SLOT_WORDS))) return rc;
     if ((rc = c->t_row_hash.ensure(rows_cap * 8, true, c->st_compute))) return rc;
     if ((rc = c->t_row_off.ensure(rows_cap * 8, true, c->st_compute))) return rc;
     if ((rc = c->t_row_len.ensure(rows_cap * 4, true, c->st_compute))) return rc;
     if ((rc = c->t_arena.ensure(arena_cap, true, c->st_compute))) return rc;
     c->tab.slots = c->t_slots.as<unsigned long long>();
-    c->tab.counts = c->t_counts.as<unsigned long long>();
     c->tab.capacity = capacity;
     c->tab.row_hash = c->t_row_hash.as<uint64_t>();
     c->tab.row_off = c->t_row_off.as<uint64_t>();
@@ -353,8 +351,7 @@ static int table_init(vfb_ctx *c)
     uint64_t cap = pow2_at_least(hint ? hint * 2 : (1u << 16));
     uint64_t rows = hint ? hint : (1u << 15);
     if ((rc = table_alloc(c, cap, rows, rows * 32))) return rc;
-    VFB_CUDA(cudaMemsetAsync(c->tab.slots, 0, cap * 8, c->st_compute));
-    VFB_CUDA(cudaMemsetAsync(c->tab.counts, 0, cap * 8, c->st_compute));
+    VFB_CUDA(cudaMemsetAsync(c->tab.slots, 0, cap * 8 * VFB_SLOT_WORDS, c->st_compute));
     VFB_CUDA(cudaMemsetAsync(c->tab.counters, 0, 8 * 8, c->st_compute));
     c->ub_rows = 0;
     c->ub_arena = 0;
@@ -395,21 +392,16 @@ static int table_reserve(vfb_ctx *c, uint64_t new_keys, uint64_t new_bytes)
         // rehash into a larger slot array
         uint64_t ncap = pow2_at_least(want_rows * 3);
         trace("table rehash %llu -> %llu slots", (unsigned long long)c->tab.capacity, (unsigned long long)ncap);
-        DevBuf nslots, ncounts;
-        if ((rc = nslots.ensure(ncap * 8))) return rc;
-        if ((rc = ncounts.ensure(ncap * 8))) { nslots.release(); return rc; }
-        VFB_CUDA(cudaMemsetAsync(nslots.p, 0, ncap * 8, c->st_compute));
-        VFB_CUDA(cudaMemsetAsync(ncounts.p, 0, ncap * 8, c->st_compute));
+        DevBuf nslots;
+        if ((rc = nslots.ensure(ncap * 8 * VFB_SLOT_WORDS))) return rc;
+        VFB_CUDA(cudaMemsetAsync(nslots.p, 0, ncap * 8 * VFB_SLOT_WORDS, c->st_compute));
         DevTable nt = c->tab;
         nt.slots = nslots.as<unsigned long long>();
-        nt.counts = ncounts.as<unsigned long long>();
         nt.capacity = ncap;
         if ((rc = launch_rehash(c->tab, nt, c->st_compute))) return rc;
         VFB_CUDA(cudaStreamSynchronize(c->st_compute));
         c->t_slots.release();
-        c->t_counts.release();
         c->t_slots = nslots;
-        c->t_counts = ncounts;
         c->tab.capacity = ncap;
     }
     if ((rc = table_alloc(c, c->tab.capacity, rows_cap, arena_cap))) return rc;
@@ -588,7 +580,7 @@ int vfb_destroy(vfb_ctx *c)
     DevBuf *bufs[] = {&c->d_code_pre, &c->d_code_suf, &c->d_generic_scratch, &c->d_start, &c->d_end, &c->d_list_a,
                       &c->d_list_b, &c->d_fb_a, &c->d_fb_b, &c->d_c32, &c->d_t64, &c->d_keys, &c->d_koff, &c->d_klen,
                       &c->d_khash, &c->d_owner, &c->d_diag_exact_pre, &c->d_diag_exact_suf, &c->d_diag_score_pre,
-                      &c->d_diag_len_pre, &c->d_diag_score_suf, &c->d_diag_len_suf, &c->t_slots, &c->t_counts,
+                      &c->d_diag_len_pre, &c->d_diag_score_suf, &c->d_diag_len_suf, &c->t_slots,
                       &c->t_row_hash, &c->t_row_off, &c->t_row_len, &c->t_arena, &c->t_counters, &c->t_row_count,
                       &c->m_part_rows, &c->m_part_keys, &c->m_cursors, &c->m_chunk_off,
                       &c->d_wins, &c->d_bestkey, &c->d_cbval, &c->d_fb2};
@@ -626,8 +618,7 @@ int vfb_table_clear(vfb_ctx *c)
 {
     if (!c) { set_error("null context"); return VFB_ERR_ARG; }
     VFB_CUDA(cudaSetDevice(c->device));
-    VFB_CUDA(cudaMemsetAsync(c->tab.slots, 0, c->tab.capacity * 8, c->st_compute));
-    VFB_CUDA(cudaMemsetAsync(c->tab.counts, 0, c->tab.capacity * 8, c->st_compute));
+    VFB_CUDA(cudaMemsetAsync(c->tab.slots, 0, c->tab.capacity * 8 * VFB_SLOT_WORDS, c->st_compute));
     VFB_CUDA(cudaMemsetAsync(c->tab.counters, 0, 8 * 8, c->st_compute));
     c->ub_rows = 0;
     c->ub_arena = 0;

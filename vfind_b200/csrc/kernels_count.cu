@@ -303,9 +303,10 @@ k4_insert(const __grid_constant__ InsertArgs a)
         const unsigned long long mine = ((unsigned long long)tag << 32) | REF_BATCH | i;
         const uint8_t *mykey = job_key(j, i);
         for (;;) {
-            unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&t.slots[slot]);
+            unsigned long long *ent = t.slots + slot * VFB_SLOT_WORDS;
+            unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(ent);
             if (cur == 0ull) {
-                cur = atomicCAS(&t.slots[slot], 0ull, mine);
+                cur = atomicCAS(ent, 0ull, mine);
                 if (cur == 0ull) {
                     owner = (uint32_t)slot;
                     break;
@@ -320,9 +321,10 @@ k4_insert(const __grid_constant__ InsertArgs a)
                     okey = job_key(j, o);
                     olen = j.klen[o];
                 } else {
-                    const uint32_t row = ref - 1;
-                    okey = t.arena + t.row_off[row];
-                    olen = t.row_len[row];
+                    // a row published by an earlier batch: its arena offset and length sit in the slot
+                    const ulonglong2 m = *reinterpret_cast<const ulonglong2 *>(ent + 2);
+                    okey = t.arena + m.x;
+                    olen = (uint32_t)m.y;
                 }
                 if (olen == klen && keys_equal16(okey, mykey, klen)) break;
             }
@@ -340,7 +342,7 @@ k4_insert(const __grid_constant__ InsertArgs a)
     if (i < j.n_keys) j.owner_slot[i] = owner;
     __syncthreads();
     for (int e = threadIdx.x; e < INS_AGG; e += INS_THREADS)
-        if (agg_slot[e] != VFB_NONE) atomicAdd(&t.counts[agg_slot[e]], agg_cnt[e]);
+        if (agg_slot[e] != VFB_NONE) atomicAdd(&t.slots[(uint64_t)agg_slot[e] * VFB_SLOT_WORDS + 1], agg_cnt[e]);
 }
 
 // Owners of freshly claimed slots move their key into the arena and turn the slot's
@@ -383,7 +385,10 @@ k4_publish(const __grid_constant__ InsertArgs a)
     t.row_hash[row] = h;
     t.row_off[row] = off;
     t.row_len[row] = klen;
-    t.slots[slot] = ((unsigned long long)(uint32_t)(h >> 32) << 32) | (unsigned long long)(row + 1);
+    unsigned long long *ent = t.slots + (uint64_t)slot * VFB_SLOT_WORDS;
+    ent[2] = off;
+    ent[3] = klen;
+    ent[0] = ((unsigned long long)(uint32_t)(h >> 32) << 32) | (unsigned long long)(row + 1);
 }
 
 int launch_insert(const DevTable &t, const InsertJob &job, cudaStream_t st)
@@ -406,15 +411,19 @@ k4_rehash(const DevTable o, const DevTable n)
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t mask = n.capacity - 1;
     for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < o.capacity; s += stride) {
-        const unsigned long long w = o.slots[s];
+        const unsigned long long *oe = o.slots + s * VFB_SLOT_WORDS;
+        const unsigned long long w = oe[0];
         if (!w) continue;
         const uint32_t row = (uint32_t)w - 1;
         uint64_t slot = o.row_hash[row] & mask;
         for (;;) {
-            if (atomicCAS(&n.slots[slot], 0ull, w) == 0ull) break;
+            if (atomicCAS(&n.slots[slot * VFB_SLOT_WORDS], 0ull, w) == 0ull) break;
             slot = (slot + 1) & mask;
         }
-        n.counts[slot] = o.counts[s];
+        unsigned long long *ne = n.slots + slot * VFB_SLOT_WORDS;
+        ne[1] = oe[1];
+        ne[2] = oe[2];
+        ne[3] = oe[3];
     }
 }
 
@@ -433,8 +442,8 @@ k4_export_counts(const DevTable t, unsigned long long *row_count)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < t.capacity; s += stride) {
-        const unsigned long long w = t.slots[s];
-        if (w) row_count[(uint32_t)w - 1] = t.counts[s];
+        const ulonglong2 e = *reinterpret_cast<const ulonglong2 *>(t.slots + s * VFB_SLOT_WORDS);
+        if (e.x) row_count[(uint32_t)e.x - 1] = e.y;
     }
 }
 

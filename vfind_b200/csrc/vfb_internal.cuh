@@ -150,12 +150,16 @@ struct KeyJob {
 };
 int launch_keys(const KeyJob &job, cudaStream_t st);
 
-// Open-addressing table in device memory.  A slot word is (tag << 32 | ref): tag = high 32
-// hash bits, ref = row id (bit31 clear) or, only inside the insert kernel of the batch that
-// created it, 0x80000000 | batch read index.  Equality is always decided on full key bytes.
+// Open-addressing table in device memory.  A slot is ONE 32-byte sector of four words:
+//   [0] (tag << 32 | ref)   tag = high 32 hash bits, ref = row id + 1 (bit31 clear) or, only inside the
+//                           insert kernel of the batch that created it, 0x80000000 | batch read index; 0 = empty
+//   [1] count               the atomicAdd lands in the sector the probe has just pulled into L2
+//   [2] arena offset, [3] key length of the row (written by k4_publish): the key compare needs no
+//                           row_off[] / row_len[] look-ups
+// Equality is always decided on full key bytes.
+#define VFB_SLOT_WORDS 4
 struct DevTable {
-    unsigned long long *slots;   // capacity words, 0 = empty
-    unsigned long long *counts;  // per slot
+    unsigned long long *slots;   // capacity * VFB_SLOT_WORDS words
     uint64_t capacity;           // power of two
     // rows (distinct keys), append-only
     uint64_t *row_hash;
