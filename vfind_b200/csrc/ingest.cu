@@ -35,6 +35,7 @@
 #include <thread>
 #include <vector>
 
+#include "pgunzip.h"
 #include "vfb_internal.cuh"
 
 using namespace vfb;
@@ -182,6 +183,8 @@ int peek_bgzf(FILE *f, size_t *member_size)
 // Fills chunk buffers with inflated text and cuts them at record boundaries.
 struct ChunkProducer {
     FILE *f = nullptr;
+    ParallelGunzip pgz;         // plain gzip streams on `threads` > 1 host threads
+    int pgz_state = 0;          // 0 = not decided, 1 = in use, -1 = zlib stream
     uint64_t file_size = 0;
     std::atomic<uint64_t> consumed{0};   // compressed bytes read so far (progress only)
     Inflater serial;
@@ -293,7 +296,13 @@ struct ChunkProducer {
                 if (bgzf && !at_end) break;                   // as full as whole members allow
             } else {
                 const size_t want = cap - used < ((size_t)4 << 20) ? cap - used : ((size_t)4 << 20);
-                const long long got = plain ? (long long)fread(buf + used, 1, want, f) : serial.read(buf + used, want, &err);
+                if (!plain && pgz_state == 0) {
+                    const char *e = getenv("VFB_PGUNZIP");
+                    pgz_state = threads > 1 && !(e && e[0] == '0') ? 1 : -1;
+                    if (pgz_state == 1) pgz.init(f, threads);
+                }
+                const long long got = plain ? (long long)fread(buf + used, 1, want, f)
+                                            : (pgz_state == 1 ? pgz.read(buf + used, want, &err) : serial.read(buf + used, want, &err));
                 if (got < 0) return VFB_ERR_FORMAT;
                 if ((size_t)got < want) at_end = true;
                 lines += count_nl(buf + used, (size_t)got);
