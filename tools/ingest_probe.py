@@ -57,7 +57,9 @@ if not os.path.exists(path + ".gz"):
         path, os.path.getsize(path + ".gz") / 1e6, os.path.getsize(path + ".bgzf.gz") / 1e6, time.time() - t0))
 
 results = {}
-for name, p, threads, gpu in (("gzip", path + ".gz", 3, "1"), ("bgzf host x3", path + ".bgzf.gz", 3, "0"),
+for name, p, threads, gpu in (("gzip zlib x1", path + ".gz", 1, "1"), ("gzip pgunzip x3", path + ".gz", 3, "1"),
+                              ("gzip pgunzip x%d" % os.cpu_count(), path + ".gz", os.cpu_count(), "1"),
+                              ("bgzf host x3", path + ".bgzf.gz", 3, "0"),
                               ("bgzf host x%d" % os.cpu_count(), path + ".bgzf.gz", os.cpu_count(), "0"),
                               ("bgzf GPU inflate", path + ".bgzf.gz", 3, "1")):
     if "--bgzf-only" in sys.argv and "bgzf" not in name:

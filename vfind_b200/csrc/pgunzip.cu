@@ -422,8 +422,13 @@ struct ParallelGunzip::Impl {
     std::vector<uint8_t> window;      // last <= 32 KiB of text of the current member
     uint64_t member_out = 0;          // bytes the current member has produced
     uint32_t member_crc = 0;
-    uint8_t *text = nullptr;          // decoded text of the current segment (malloc'd, never zero-filled)
+    uint8_t *text = nullptr;          // text of the segment being decoded (malloc'd, never zero-filled)
     size_t text_cap = 0, text_len = 0, text_pos = 0;
+    // the segment being handed out by read(), while the next one is decoded in the background
+    uint8_t *cur = nullptr;
+    size_t cur_cap = 0, cur_len = 0, cur_pos = 0;
+    std::thread bg;
+    bool bg_running = false, bg_ok = true, drained = false;
     size_t seg_bytes = (size_t)24 << 20;
     std::vector<OutBuf *> bufs;       // one symbol buffer per worker slot
     double ratio = 0;                 // text bytes per compressed byte, last segment
@@ -730,8 +735,10 @@ bool ParallelGunzip::Impl::segment()
 ParallelGunzip::ParallelGunzip() : impl_(new Impl) {}
 ParallelGunzip::~ParallelGunzip()
 {
+    if (impl_->bg_running) impl_->bg.join();
     for (OutBuf *b : impl_->bufs) delete b;
     free(impl_->text);
+    free(impl_->cur);
     delete impl_;
 }
 
@@ -744,17 +751,36 @@ void ParallelGunzip::init(FILE *f, int threads)
 
 long long ParallelGunzip::read(uint8_t *out, size_t cap, std::string *err)
 {
+    Impl &m = *impl_;
     size_t produced = 0;
     while (produced < cap) {
-        Impl &m = *impl_;
-        if (m.text_pos == m.text_len) {
-            if (m.finished) break;
-            if (!m.segment()) { *err = m.err; return -1; }
-            continue;
+        if (m.cur_pos == m.cur_len) {
+            if (m.drained) break;
+            if (!m.bg_running) {
+                m.bg = std::thread([&m] { m.bg_ok = m.segment(); });
+                m.bg_running = true;
+            }
+            m.bg.join();
+            m.bg_running = false;
+            if (!m.bg_ok) { *err = m.err; m.drained = true; return -1; }
+            std::swap(m.cur, m.text);
+            std::swap(m.cur_cap, m.text_cap);
+            m.cur_len = m.text_len;
+            m.cur_pos = 0;
+            m.text_len = 0;
+            if (m.finished) {
+                if (m.cur_len == 0) { m.drained = true; break; }
+                m.drained = true;                 // this is the last text; nothing left to decode
+            } else {
+                // decode the next segment while the caller consumes this one
+                m.bg = std::thread([&m] { m.bg_ok = m.segment(); });
+                m.bg_running = true;
+            }
+            if (m.cur_len == 0) { if (m.drained) break; continue; }
         }
-        const size_t n = std::min(cap - produced, m.text_len - m.text_pos);
-        memcpy(out + produced, m.text + m.text_pos, n);
-        m.text_pos += n;
+        const size_t n = std::min(cap - produced, m.cur_len - m.cur_pos);
+        memcpy(out + produced, m.cur + m.cur_pos, n);
+        m.cur_pos += n;
         produced += n;
     }
     return (long long)produced;
