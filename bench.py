@@ -463,6 +463,25 @@ def main():
                       "seconds_best_of_3": best, "seconds_first_call": times[0], "table_rows": rows,
                       "text_gbs": tb / best / 1e9}
             os.remove(fq)
+            # the same call on ONE plain gzip stream (what `gzip` / fastp write): decoded by the parallel
+            # host gunzip (pgunzip.cu) on the ingest threads
+            n_gz = min(args.ingest_reads, 2_000_000)
+            txt = os.path.join(tmp, "c3_plain.fq")
+            gz = txt + ".gz"
+            tb2 = synth_fastq.write_fastq(txt, cfg, 0, n_gz, api)
+            with open(gz, "wb") as g:
+                subprocess.check_call(["gzip", "-1", "-c", txt], stdout=g)
+            os.remove(txt)
+            times = []
+            for rep in range(3):
+                t0 = time.perf_counter()
+                find_variants(gz, ads, show_progress=False)
+                times.append(time.perf_counter() - t0)
+            ingest["plain_gzip"] = {"value": n_gz / min(times), "unit": "reads/s",
+                                    "input": "single gzip stream (gzip -1), %d reads, %.0f MB text, %.0f MB compressed"
+                                             % (n_gz, tb2 / 1e6, os.path.getsize(gz) / 1e6),
+                                    "seconds_best_of_3": min(times), "host_threads": min(os.cpu_count() or 1, 16)}
+            os.remove(gz)
             os.rmdir(tmp)
         except Exception as e:          # the ingest leg never fails the bench line
             ingest = {"error": repr(e)}

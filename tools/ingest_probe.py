@@ -65,6 +65,7 @@ for name, p, threads, gpu in (("gzip zlib x1", path + ".gz", 1, "1"), ("gzip pgu
     if "--bgzf-only" in sys.argv and "bgzf" not in name:
         continue
     os.environ["VFB_GPU_INFLATE"] = gpu
+    os.environ["VFB_INGEST_THREADS"] = str(threads)
     if gpu == "1" and "bgzf" in name:
         pass
     best = 1e9

@@ -36,6 +36,7 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 #include <chrono>
 #include <cstdarg>
 #include <mutex>
+#include <thread>
 #include <utility>
 #include <vector>
 namespace vfb {
@@ -1072,8 +1073,17 @@ void vfb_internal_progress(vfb_ctx *c, uint64_t records, uint64_t bytes_done, ui
 
 int vfb_internal_ingest_threads(vfb_ctx *c)
 {
-    // the reference's n_threads (src/lib.rs:228) are its worker threads; here they inflate
-    return c->prm.n_threads < 1 ? 1 : (int)(c->prm.n_threads > 256 ? 256 : c->prm.n_threads);
+    // The reference's n_threads (src/lib.rs:228, default 3) are its worker threads; here they inflate /
+    // read.  A B200 host has cores to spare and the GPU side is never the bottleneck of a gzip file, so the
+    // ingest takes at least min(hardware threads, 16) unless VFB_INGEST_THREADS says otherwise.
+    int t = c->prm.n_threads < 1 ? 1 : (int)(c->prm.n_threads > 256 ? 256 : c->prm.n_threads);
+    if (const char *e = getenv("VFB_INGEST_THREADS")) {
+        const int v = atoi(e);
+        if (v >= 1) return v > 256 ? 256 : v;
+    }
+    int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 16) hw = 16;
+    return t > hw ? t : hw;
 }
 
 int vfb_internal_parse_error(vfb_ctx *c, uint64_t *first_bad)
