@@ -480,7 +480,7 @@ def main():
             ingest["plain_gzip"] = {"value": n_gz / min(times), "unit": "reads/s",
                                     "input": "single gzip stream (gzip -1), %d reads, %.0f MB text, %.0f MB compressed"
                                              % (n_gz, tb2 / 1e6, os.path.getsize(gz) / 1e6),
-                                    "seconds_best_of_3": min(times), "host_threads": min(os.cpu_count() or 1, 16)}
+                                    "seconds_best_of_3": min(times), "host_threads": min(os.cpu_count() or 1, 32)}
             os.remove(gz)
             os.rmdir(tmp)
         except Exception as e:          # the ingest leg never fails the bench line

@@ -1075,14 +1075,14 @@ int vfb_internal_ingest_threads(vfb_ctx *c)
 {
     // The reference's n_threads (src/lib.rs:228, default 3) are its worker threads; here they inflate /
     // read.  A B200 host has cores to spare and the GPU side is never the bottleneck of a gzip file, so the
-    // ingest takes at least min(hardware threads, 16) unless VFB_INGEST_THREADS says otherwise.
+    // ingest takes at least min(hardware threads, 32) unless VFB_INGEST_THREADS says otherwise.
     int t = c->prm.n_threads < 1 ? 1 : (int)(c->prm.n_threads > 256 ? 256 : c->prm.n_threads);
     if (const char *e = getenv("VFB_INGEST_THREADS")) {
         const int v = atoi(e);
         if (v >= 1) return v > 256 ? 256 : v;
     }
     int hw = (int)std::thread::hardware_concurrency();
-    if (hw > 16) hw = 16;
+    if (hw > 32) hw = 32;
     return t > hw ? t : hw;
 }
 

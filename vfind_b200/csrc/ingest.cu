@@ -44,14 +44,19 @@ namespace {
 
 size_t count_nl(const uint8_t *p, size_t n)
 {
-    size_t c = 0;
-    const uint8_t *e = p + n;
-    while (p < e) {
-        const uint8_t *q = (const uint8_t *)memchr(p, '\n', (size_t)(e - p));
-        if (!q) break;
-        ++c;
-        p = q + 1;
+    // eight bytes at a time: x = word ^ 0x0A.. has a zero byte where the text has '\n'; ((x & 0x7F..) + 0x7F..) | x
+    // sets the high bit of every NON-zero byte without carries between bytes, so the cleared high bits count
+    size_t c = 0, i = 0;
+    const uint64_t k = 0x0A0A0A0A0A0A0A0Aull, lo7 = 0x7F7F7F7F7F7F7F7Full;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t w;
+        memcpy(&w, p + i, 8);
+        const uint64_t x = w ^ k;
+        // per byte: high bit set iff the byte of x is non-zero (no cross-byte carries)
+        const uint64_t nz = ((x & lo7) + lo7) | x;
+        c += (size_t)__builtin_popcountll(~nz & ~lo7);
     }
+    for (; i < n; ++i) c += p[i] == '\n';
     return c;
 }
 

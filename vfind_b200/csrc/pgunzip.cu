@@ -681,7 +681,25 @@ bool ParallelGunzip::Impl::segment()
             const uint16_t *src = w.outp->p;
             // history available in front of this worker (for the range check of its markers)
             const uint64_t avail = std::min<uint64_t>(avail0 + w.out_off, WSIZE);
-            for (size_t i = 0; i < w.outp->n; ++i) {
+            // 64 symbols at a time: narrow them all (vectorises), and only if one of them was a marker
+            // go over the block again symbol by symbol
+            const size_t n = w.outp->n;
+            size_t i = 0;
+            for (; i + 64 <= n; i += 64) {
+                uint16_t any = 0;
+                for (int k = 0; k < 64; ++k) { any |= src[i + k]; dst[i + k] = (uint8_t)src[i + k]; }
+                if (any >= 256) {
+                    for (int k = 0; k < 64; ++k) {
+                        const uint16_t s = src[i + k];
+                        if (s >= 256) {
+                            const uint32_t p = s - 256u;
+                            if ((uint64_t)(WSIZE - p) > avail) { bad = true; return; }
+                            dst[i + k] = win[p];
+                        }
+                    }
+                }
+            }
+            for (; i < n; ++i) {
                 const uint16_t s = src[i];
                 if (s < 256) dst[i] = (uint8_t)s;
                 else {
