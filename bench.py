@@ -337,6 +337,19 @@ def main():
 
             step_e2e()
             barrier()
+            # the link itself: one pinned chunk copied alone (best of 3) — what `e2e` is bounded by
+            link_gbs = 0.0
+            if host:
+                ht0 = host[0][0]
+                scratch = torch.empty(ht0.numel(), dtype=torch.uint8, device=dev)
+                for _ in range(3):
+                    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    c0.record(stream)
+                    scratch.copy_(ht0, non_blocking=True)
+                    c1.record(stream)
+                    stream.synchronize()
+                    link_gbs = max(link_gbs, ht0.numel() / (c0.elapsed_time(c1) * 1e-3) / 1e9)
+                del scratch
             d2h = 0
             t0 = time.perf_counter()
             f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -353,7 +366,10 @@ def main():
             e2e = {"value": world * got * esteps / (float(ems.item()) * 1e-3), "unit": "reads/s",
                    "h2d_bytes_per_step": int(sum(h[0].numel() + h[1].numel() * 4 for h in host)),
                    "d2h_bytes_per_step": int(d2h), "reads_per_step": got, "steps": esteps,
-                   "table_rows": rows, "ms_per_step": float(ems.item()) / esteps}
+                   "table_rows": rows, "ms_per_step": float(ems.item()) / esteps,
+                   "h2d_gbs_achieved": world * sum(h[0].numel() + h[1].numel() * 4 for h in host) * esteps / (float(ems.item()) * 1e-3) / 1e9,
+                   "h2d_gbs_link_alone": link_gbs,
+                   "bound": "host->device link: the step moves 258 B per read over PCIe"}
             del host
 
     if rank != 0:
