@@ -300,14 +300,24 @@ struct ChunkProducer {
                 if (!fill_bgzf(buf, cap, used, lines)) return VFB_ERR_FORMAT;
                 if (bgzf && !at_end) break;                   // as full as whole members allow
             } else {
-                const size_t want = cap - used < ((size_t)4 << 20) ? cap - used : ((size_t)4 << 20);
                 if (!plain && pgz_state == 0) {
                     const char *e = getenv("VFB_PGUNZIP");
                     pgz_state = threads > 1 && !(e && e[0] == '0') ? 1 : -1;
                     if (pgz_state == 1) pgz.init(f, threads);
                 }
-                const long long got = plain ? (long long)fread(buf + used, 1, want, f)
-                                            : (pgz_state == 1 ? pgz.read(buf + used, want, &err) : serial.read(buf + used, want, &err));
+                if (!plain && pgz_state == 1) {
+                    // already decoded in the background: take all the chunk has room for, copied and counted in parallel
+                    const size_t want = cap - used;
+                    size_t nl = 0;
+                    const long long got = pgz.read_counting(buf + used, want, &nl, &err);
+                    if (got < 0) return VFB_ERR_FORMAT;
+                    if ((size_t)got < want) at_end = true;
+                    lines += nl;
+                    used += (size_t)got;
+                    continue;
+                }
+                const size_t want = cap - used < ((size_t)4 << 20) ? cap - used : ((size_t)4 << 20);
+                const long long got = plain ? (long long)fread(buf + used, 1, want, f) : serial.read(buf + used, want, &err);
                 if (got < 0) return VFB_ERR_FORMAT;
                 if ((size_t)got < want) at_end = true;
                 lines += count_nl(buf + used, (size_t)got);

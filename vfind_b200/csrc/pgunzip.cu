@@ -681,39 +681,37 @@ bool ParallelGunzip::Impl::segment()
             const uint16_t *src = w.outp->p;
             // history available in front of this worker (for the range check of its markers)
             const uint64_t avail = std::min<uint64_t>(avail0 + w.out_off, WSIZE);
-            // 64 symbols at a time: narrow them all (vectorises), and only if one of them was a marker
-            // go over the block again symbol by symbol
+            // cache-sized pieces: narrow 64 symbols at a time (vectorises; a block that held a marker is gone
+            // over again symbol by symbol), then CRC the piece while it is still in cache
             const size_t n = w.outp->n;
-            size_t i = 0;
-            for (; i + 64 <= n; i += 64) {
-                uint16_t any = 0;
-                for (int k = 0; k < 64; ++k) { any |= src[i + k]; dst[i + k] = (uint8_t)src[i + k]; }
-                if (any >= 256) {
-                    for (int k = 0; k < 64; ++k) {
-                        const uint16_t s = src[i + k];
-                        if (s >= 256) {
-                            const uint32_t p = s - 256u;
-                            if ((uint64_t)(WSIZE - p) > avail) { bad = true; return; }
-                            dst[i + k] = win[p];
+            uLong c32 = crc32(0L, Z_NULL, 0);
+            for (size_t p0 = 0; p0 < n; p0 += (size_t)1 << 16) {
+                const size_t p1 = std::min(n, p0 + ((size_t)1 << 16));
+                size_t i = p0;
+                for (; i + 64 <= p1; i += 64) {
+                    uint16_t any = 0;
+                    for (int k = 0; k < 64; ++k) { any |= src[i + k]; dst[i + k] = (uint8_t)src[i + k]; }
+                    if (any >= 256) {
+                        for (int k = 0; k < 64; ++k) {
+                            const uint16_t s = src[i + k];
+                            if (s >= 256) {
+                                const uint32_t p = s - 256u;
+                                if ((uint64_t)(WSIZE - p) > avail) { bad = true; return; }
+                                dst[i + k] = win[p];
+                            }
                         }
                     }
                 }
-            }
-            for (; i < n; ++i) {
-                const uint16_t s = src[i];
-                if (s < 256) dst[i] = (uint8_t)s;
-                else {
-                    const uint32_t p = s - 256u;
-                    if ((uint64_t)(WSIZE - p) > avail) { bad = true; return; }
-                    dst[i] = win[p];
+                for (; i < p1; ++i) {
+                    const uint16_t s = src[i];
+                    if (s < 256) dst[i] = (uint8_t)s;
+                    else {
+                        const uint32_t p = s - 256u;
+                        if ((uint64_t)(WSIZE - p) > avail) { bad = true; return; }
+                        dst[i] = win[p];
+                    }
                 }
-            }
-            size_t done = 0;
-            uLong c32 = crc32(0L, Z_NULL, 0);
-            while (done < w.outp->n) {
-                const size_t part = std::min<size_t>(w.outp->n - done, (size_t)1 << 30);
-                c32 = crc32(c32, dst + done, (uInt)part);
-                done += part;
+                c32 = crc32(c32, dst + p0, (uInt)(p1 - p0));
             }
             w.crc = (uint32_t)c32;
         };
@@ -767,10 +765,30 @@ void ParallelGunzip::init(FILE *f, int threads)
     if (const char *e = getenv("VFB_PGUNZIP_SEGMENT")) impl_->seg_bytes = std::max<size_t>(4096, (size_t)strtoull(e, nullptr, 10));
 }
 
-long long ParallelGunzip::read(uint8_t *out, size_t cap, std::string *err)
+namespace {
+size_t copy_count(uint8_t *dst, const uint8_t *src, size_t n)
+{
+    memcpy(dst, src, n);
+    size_t c = 0, i = 0;
+    const uint64_t k = 0x0A0A0A0A0A0A0A0Aull, lo7 = 0x7F7F7F7F7F7F7F7Full;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t w;
+        memcpy(&w, dst + i, 8);
+        const uint64_t x = w ^ k, nz = ((x & lo7) + lo7) | x;      // high bit of every non-'\n' byte
+        c += (size_t)__builtin_popcountll(~nz & ~lo7);
+    }
+    for (; i < n; ++i) c += dst[i] == '\n';
+    return c;
+}
+}  // namespace
+
+long long ParallelGunzip::read(uint8_t *out, size_t cap, std::string *err) { return read_counting(out, cap, nullptr, err); }
+
+long long ParallelGunzip::read_counting(uint8_t *out, size_t cap, size_t *newlines, std::string *err)
 {
     Impl &m = *impl_;
     size_t produced = 0;
+    if (newlines) *newlines = 0;
     while (produced < cap) {
         if (m.cur_pos == m.cur_len) {
             if (m.drained) break;
@@ -797,7 +815,28 @@ long long ParallelGunzip::read(uint8_t *out, size_t cap, std::string *err)
             if (m.cur_len == 0) { if (m.drained) break; continue; }
         }
         const size_t n = std::min(cap - produced, m.cur_len - m.cur_pos);
-        memcpy(out + produced, m.cur + m.cur_pos, n);
+        if (!newlines) {
+            memcpy(out + produced, m.cur + m.cur_pos, n);
+        } else {
+            // split over the threads (the background decode of the next segment shares the cores: fine)
+            const size_t min_part = (size_t)2 << 20;
+            int parts = (int)std::min<size_t>((size_t)m.threads, n / min_part);
+            if (parts <= 1) {
+                *newlines += copy_count(out + produced, m.cur + m.cur_pos, n);
+            } else {
+                std::vector<size_t> cnt((size_t)parts, 0);
+                std::vector<std::thread> pool;
+                const size_t per = n / (size_t)parts;
+                auto run = [&](int t) {
+                    const size_t lo = (size_t)t * per, hi = t + 1 == parts ? n : lo + per;
+                    cnt[(size_t)t] = copy_count(out + produced + lo, m.cur + m.cur_pos + lo, hi - lo);
+                };
+                for (int t = 1; t < parts; ++t) pool.emplace_back(run, t);
+                run(0);
+                for (auto &th : pool) th.join();
+                for (size_t c : cnt) *newlines += c;
+            }
+        }
         m.cur_pos += n;
         produced += n;
     }
