@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ingest-reads", type=int, default=4_000_000,
                     help="reads in the block-gzip FASTQ file of the ingest leg (N=1 only; 0 = skip)")
+    ap.add_argument("--table-hint", type=int, default=40_000_000, help="expected distinct variants per GPU (table capacity hint)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -239,7 +240,7 @@ def main():
     torch.cuda.synchronize()
 
     stream = torch.cuda.Stream(device=dev)
-    ctx = api.Context(adapters, device=local, table_capacity_hint=min(R, 40_000_000), batch_reads=args.chunk_reads)
+    ctx = api.Context(adapters, device=local, table_capacity_hint=min(R, args.table_hint), batch_reads=args.chunk_reads)
     ctx.set_compute_stream(stream.cuda_stream)
 
     merge_events = []
