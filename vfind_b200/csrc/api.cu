@@ -773,7 +773,7 @@ static int process_batch(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_sp
     VFB_CUDA(cudaMemsetAsync(c->d_t64.as<unsigned long long>() + T_KEYBYTES, 0, 8, st));
     ScanJob sj;
     memset(&sj, 0, sizeof sj);
-    sj.text = d_text; sj.spans = d_spans; sj.n_reads = n;
+    sj.text = d_text; sj.spans = d_spans; sj.n_reads = n; sj.text_bytes = span_bytes_upper;
     sj.start = c->d_start.as<uint32_t>(); sj.end = c->d_end.as<uint32_t>();
     if (c->align_pre) { sj.list_pre = c->d_list_a.as<uint32_t>(); sj.n_pre = c->d_c32.as<uint32_t>() + C_NPRE; }
     if (c->align_suf) { sj.list_suf = c->d_list_b.as<uint32_t>(); sj.n_suf = c->d_c32.as<uint32_t>() + C_NSUF; }

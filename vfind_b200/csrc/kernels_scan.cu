@@ -16,6 +16,8 @@
 // ~1 instruction per byte per lane on the common (miss) path.
 #include "vfb_internal.cuh"
 
+#include <stdlib.h>
+
 namespace vfb {
 
 #define SCAN_THREADS 256
@@ -392,6 +394,241 @@ k1_scan_fast(const __grid_constant__ ScanArgs args)
 }
 
 // ---------------------------------------------------------------------------------------
+// Tile kernel (adapters of 15..64 nt whose sampled 8-byte keys are all distinct): the warp's 32
+// reads are staged in shared memory by ONE bulk copy (TMA, cp.async.bulk global -> shared,
+// completion on an mbarrier) of the contiguous text range that covers them, so HBM is read in
+// whole lines exactly once; then one lane owns one read and walks it in 16-byte chunks out of
+// shared memory.  Per sampled key: p = w0*m1 + w1*m2, slot p >> 23 of a 512-entry perfect hash
+// {p, adapter | offset << 8}; one compare.  A hit is only remembered (the leftmost candidate
+// per adapter); the candidates are verified byte-exactly once, after the walk, by all lanes
+// together.  A unit whose text range does not fit the tile (wildly scattered spans, giant
+// reads) is scanned byte-wise by the whole warp.
+#define TILE_WARPS_MAX 8
+#define TILE_SLACK 16            // bytes past a tile: the verify's unaligned word reads stay inside the allocation
+
+struct TileTables {
+    uint2 slot[SCAN_SLOTS];
+    uint32_t adw[2][16];         // adapters as little-endian words, zero padded
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// the table never changes after the block's set-up: a plain (schedulable) shared load by address
+__device__ __forceinline__ uint2 lds64(uint32_t addr)
+{
+    uint2 r;
+    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
+    return r;
+}
+
+__device__ __forceinline__ bool tile_verify(const uint32_t *tile32, uint32_t byte_off, const uint32_t *adw, uint32_t A)
+{
+    const uint32_t sh = (byte_off & 3u) * 8u;
+    const uint32_t *p = tile32 + (byte_off >> 2);
+    const uint32_t nw = (A + 3) >> 2;
+    uint32_t lo = p[0], diff = 0;
+    for (uint32_t k = 0; k < nw; ++k) {
+        const uint32_t hi = p[k + 1];
+        const uint32_t w = __funnelshift_r(lo, hi, sh);
+        const uint32_t left = A - 4 * k;
+        const uint32_t m = left >= 4 ? 0xFFFFFFFFu : (1u << (8 * left)) - 1u;
+        diff |= (w ^ adw[k]) & m;
+        lo = hi;
+    }
+    return diff == 0;
+}
+
+// candidate (start + 64) -> verified start or VFB_NONE
+__device__ __forceinline__ uint32_t tile_check(const uint32_t *tile32, uint32_t toff, uint32_t len, uint32_t pend,
+                                               const uint32_t *adw, uint32_t A)
+{
+    if (pend == VFB_NONE) return VFB_NONE;
+    const int s = (int)pend - 64;
+    if (s < 0 || (uint32_t)s + A > len) return VFB_NONE;
+    return tile_verify(tile32, toff + (uint32_t)s, adw, A) ? (uint32_t)s : VFB_NONE;
+}
+
+// A second candidate for an adapter while one is waiting (a repeated adapter or a false key hit):
+// candidates arrive left to right, so the waiting one wins if it verifies.
+__device__ __noinline__ uint32_t tile_second(const uint32_t *tile32, uint32_t toff, uint32_t len, uint32_t pend,
+                                             uint32_t cand, const uint32_t *adw, uint32_t A)
+{
+    return tile_check(tile32, toff, len, pend, adw, A) != VFB_NONE ? pend : cand;
+}
+
+template <bool STRIDE16>
+__global__ void __launch_bounds__(TILE_WARPS_MAX * 32)
+k1_scan_tile(const __grid_constant__ ScanArgs args, const uint32_t tile_bytes)
+{
+    extern __shared__ __align__(128) uint8_t tiles[];
+    __shared__ TileTables Ts;
+    __shared__ uint32_t stage_all[TILE_WARPS_MAX * 2 * WL_BUF];
+    __shared__ unsigned long long bars[TILE_WARPS_MAX];
+    TileTables *T = &Ts;
+    const int n_warps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t mult = args.mult, mult2 = hash8_mult2(args.mult);
+    const uint32_t AP = args.prefix.len, AS = args.suffix.len;
+
+    for (int i = threadIdx.x; i < SCAN_SLOTS; i += blockDim.x)
+        T->slot[i] = make_uint2(((uint32_t)i ^ 1u) << 23, 0u);       // a tag that hashes elsewhere: never equal
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) {
+        const AdapterBytes &ad = (i >> 4) ? args.suffix : args.prefix;
+        T->adw[i >> 4][i & 15] = load_word_le(ad.b, 4 * (i & 15), (int)ad.len);
+    }
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + warp)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int max_k = STRIDE16 ? 16 : 8;
+        for (int x = 0; x < 2; ++x) {
+            const AdapterBytes &ad = x ? args.suffix : args.prefix;
+            for (int k = 0; k < max_k && k + 8 <= (int)ad.len; ++k) {
+                const uint32_t p = load_word_le(ad.b, k, (int)ad.len) * mult + load_word_le(ad.b, k + 4, (int)ad.len) * mult2;
+                T->slot[p >> 23] = make_uint2(p, (uint32_t)x | ((uint32_t)k << 8));
+            }
+        }
+    }
+    __syncthreads();
+
+    const ScanJob &job = args.job;
+    uint32_t *stageP = stage_all + warp * 2 * WL_BUF, *stageS = stageP + WL_BUF;
+    uint8_t *tile = tiles + (size_t)warp * (tile_bytes + TILE_SLACK);
+    const uint32_t *tile32 = reinterpret_cast<const uint32_t *>(tile);
+    const uint32_t bar = smem_u32(bars + warp), tile_s = smem_u32(tile);
+    uint32_t slot_s;                                   // kept in a register (opaque: no re-derivation per chunk)
+    asm volatile("mov.u32 %0, %1;" : "=r"(slot_s) : "r"(smem_u32(Ts.slot)));
+    uint32_t cntP = 0, cntS = 0, parity = 0;
+    const uint32_t n_units = (job.n_reads + 31) / 32;
+    for (uint32_t unit = blockIdx.x * n_warps + warp; unit < n_units; unit += gridDim.x * n_warps) {
+        const uint32_t r = unit * 32 + lane;
+        const bool have = r < job.n_reads;
+        const vfb_span sp = have ? job.spans[r] : vfb_span{0u, 0u};
+        const bool live = have && sp.len > 0;
+        const uint32_t lo = __reduce_min_sync(0xffffffffu, live ? sp.off : 0xFFFFFFFFu);
+        const uint32_t last = __reduce_max_sync(0xffffffffu, live ? sp.off + (sp.len - 1) : 0u);
+        uint32_t bestP = VFB_NONE, bestS = VFB_NONE;
+        if (lo != 0xFFFFFFFFu) {
+            const uintptr_t g0 = reinterpret_cast<uintptr_t>(job.text + lo);
+            const uint32_t lead_tile = (uint32_t)(g0 & 15u);
+            const uint64_t n_bytes = ((uint64_t)(last - lo) + 1 + lead_tile + 15) & ~15ull;
+            if (n_bytes <= tile_bytes) {
+                __syncwarp();                      // every lane is done with the previous unit's tile
+                if (lane == 0) {
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)n_bytes) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(tile_s), "l"(g0 & ~(uintptr_t)15), "r"((uint32_t)n_bytes), "r"(bar) : "memory");
+                }
+                uint32_t ok;
+                do {
+                    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+                } while (!ok);
+                parity ^= 1u;
+                if (live) {
+                    const uint32_t toff = lead_tile + (sp.off - lo);       // the read inside the tile
+                    const uint32_t lead = toff & 15u;
+                    const uint4 *tp = reinterpret_cast<const uint4 *>(tile) + (toff >> 4);
+                    const uint32_t nch = (lead + sp.len + 15) >> 4;
+                    uint32_t pendP = VFB_NONE, pendS = VFB_NONE;
+                    int relq = 64 - (int)lead;                             // candidate starts are kept + 64
+                    auto hit = [&](uint32_t meta, int at) {
+                        const uint32_t cand = (uint32_t)(at - (int)(meta >> 8));
+                        if (meta & 1u)
+                            pendS = pendS == VFB_NONE ? cand : tile_second(tile32, toff, sp.len, pendS, cand, Ts.adw[1], AS);
+                        else
+                            pendP = pendP == VFB_NONE ? cand : tile_second(tile32, toff, sp.len, pendP, cand, Ts.adw[0], AP);
+                    };
+#pragma unroll 2
+                    for (uint32_t c = 0; c < nch; ++c, relq += 16) {
+                        const uint4 v = tp[c];
+                        const uint32_t p0 = v.x * mult + v.y * mult2;
+                        const uint2 e0 = lds64(slot_s + ((p0 >> 23) << 3));
+                        if (STRIDE16) {
+                            if (e0.x == p0) hit(e0.y, relq);
+                        } else {
+                            const uint32_t p1 = v.z * mult + v.w * mult2;
+                            const uint2 e1 = lds64(slot_s + ((p1 >> 23) << 3));
+                            if (e0.x == p0 || e1.x == p1) {                // one (rarely taken) branch per chunk
+                                if (e0.x == p0) hit(e0.y, relq);
+                                if (e1.x == p1) hit(e1.y, relq + 8);
+                            }
+                        }
+                    }
+                    bestP = tile_check(tile32, toff, sp.len, pendP, T->adw[0], AP);
+                    bestS = tile_check(tile32, toff, sp.len, pendS, T->adw[1], AS);
+                }
+            } else {
+                // the unit's reads are too far apart for a tile: byte-wise, the whole warp per read
+                unsigned todo = __ballot_sync(0xffffffffu, live);
+                while (todo) {
+                    const int q = __ffs((int)todo) - 1;
+                    todo &= todo - 1;
+                    const uint32_t off = __shfl_sync(0xffffffffu, sp.off, q);
+                    const uint32_t ln = __shfl_sync(0xffffffffu, sp.len, q);
+                    const uint2 b = scan_giant(job.text + off, ln, args, lane);
+                    if (lane == q) { bestP = b.x; bestS = b.y; }
+                }
+            }
+        }
+        const uint32_t start = bestP == VFB_NONE ? VFB_NONE : bestP + AP;
+        if (have) {
+            job.start[r] = start;
+            job.end[r] = bestS;
+        }
+        const bool needP = live && job.list_pre && start == VFB_NONE;
+        const bool needS = live && job.list_suf && bestS == VFB_NONE && (job.compute_all || start != VFB_NONE);
+        wl_push(stageP, cntP, needP, r, job.list_pre, job.n_pre, lane);
+        wl_push(stageS, cntS, needS, r, job.list_suf, job.n_suf, lane);
+    }
+    wl_flush(stageP, cntP, job.list_pre, job.n_pre, lane);
+    wl_flush(stageS, cntS, job.list_suf, job.n_suf, lane);
+}
+
+// Tile size for a batch whose reads sit `stride` bytes apart on average: 32 reads and a little slack.
+static uint32_t tile_bytes_for(uint64_t text_bytes, uint32_t n_reads)
+{
+    uint64_t stride = n_reads ? text_bytes / n_reads : 0;
+    if (stride < 32) stride = 32;
+    uint64_t t = 32 * stride + stride + 64;
+    t = (t + 127) & ~127ull;
+    if (t < 2048) t = 2048;
+    if (t > 96 * 1024) t = 96 * 1024;
+    return (uint32_t)t;
+}
+
+template <bool STRIDE16>
+static int launch_scan_tile(const ScanArgs &a, int sm_count, cudaStream_t st)
+{
+    const uint32_t tile = tile_bytes_for(a.job.text_bytes, a.job.n_reads);
+    const size_t smem_cap = 227 * 1024;
+    int warps = TILE_WARPS_MAX;
+    auto smem_for = [&](int w) {
+        return (size_t)w * (tile + TILE_SLACK);
+    };
+    // as many warps per SM as the tiles allow, in blocks of 8 / 4 / 2 / 1 warps
+    int best_w = 1, best_total = 0;
+    for (int w = TILE_WARPS_MAX; w >= 1; w >>= 1) {
+        const size_t per_block = smem_for(w) + sizeof(TileTables) + TILE_WARPS_MAX * (2 * WL_BUF * 4 + 8) + 1024;
+        int bps = (int)(smem_cap / per_block);
+        if (bps * w > 32) bps = 32 / w;            // 1024 resident threads are plenty
+        if (bps * w > best_total) { best_total = bps * w; best_w = w; }
+    }
+    warps = best_w;
+    const size_t smem = smem_for(warps);
+    if (best_total == 0) return -1;
+    const int bps = best_total / warps;
+    VFB_CUDA(cudaFuncSetAttribute(k1_scan_tile<STRIDE16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t units = (a.job.n_reads + 31) / 32;
+    uint32_t blocks = (units + warps - 1) / warps;
+    const uint32_t cap = (uint32_t)sm_count * (uint32_t)bps;
+    if (blocks > cap) blocks = cap;
+    k1_scan_tile<STRIDE16><<<blocks, warps * 32, smem, st>>>(a, tile);
+    return VFB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // General kernel: any adapter length (including 0 and > 64).  One warp per read; lanes test
 // consecutive start positions byte by byte and vote.
 __global__ void __launch_bounds__(SCAN_THREADS)
@@ -483,7 +720,15 @@ int launch_scan(const ScanJob &job, const AdapterBytes &prefix, const AdapterByt
         if (a.multi) k1_scan_fast<S, true, K8><<<blocks, SCAN_THREADS, 0, st>>>(a);         \
         else k1_scan_fast<S, false, K8><<<blocks, SCAN_THREADS, 0, st>>>(a);                \
     } while (0)
-    if (!fast) k1_scan_general<<<blocks, SCAN_THREADS, 0, st>>>(a);
+    static const bool old_scan = getenv("VFB_SCAN_TILE") && atoi(getenv("VFB_SCAN_TILE")) == 0;
+    bool tiled = false;
+    if (fast && key8 && !a.multi && !old_scan && job.text_bytes) {
+        const int rc = stride_words == 4 ? launch_scan_tile<true>(a, sm_count, st) : launch_scan_tile<false>(a, sm_count, st);
+        if (rc > 0) return rc;
+        tiled = rc == VFB_OK;
+    }
+    if (tiled) {}
+    else if (!fast) k1_scan_general<<<blocks, SCAN_THREADS, 0, st>>>(a);
     else if (key8 && stride_words == 4) VFB_SCAN_LAUNCH(4, true);
     else if (key8) VFB_SCAN_LAUNCH(2, true);
     else if (stride_words == 2) VFB_SCAN_LAUNCH(2, false);

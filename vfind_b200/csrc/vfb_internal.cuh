@@ -123,6 +123,7 @@ struct ScanJob {
     const uint8_t *text;
     const vfb_span *spans;
     uint32_t n_reads;
+    uint64_t text_bytes;   // bytes of text the spans address (sizes the scan tiles; 0 = unknown)
     uint32_t *start;   // prefix boundary: pos + A, or VFB_NONE
     uint32_t *end;     // suffix boundary: pos, or VFB_NONE
     // DP worklists built by the scan (null = that alignment is disabled)
