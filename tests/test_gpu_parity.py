@@ -229,6 +229,67 @@ def test_scan_repetitive_and_nested_adapters(pre, suf):
     assert fast[0] == slow[0] == otable
 
 
+def _scan_only(text, off, ln, adapters, **kw):
+    kw = dict(accept_prefix_alignment=1.0, accept_suffix_alignment=1.0, skip_translation=True, **kw)
+    with api.Context(adapters, diagnostics=True, **kw) as ctx:
+        ctx.submit_host(text, spans_of(off, ln))
+        diag = ctx.diag(len(off))
+        table = ctx.finish_dict()
+    return table, diag
+
+
+@pytest.mark.parametrize("pre,suf", [
+    (b"GGGCCCAGCCGGCCGGATTA", b"CCGGAGGCGGAGGTTCAGAC"),                      # 8-byte keys every 8 bytes
+    (b"GGGCCCAGCCGGCCGGATTACGATCGGA", b"CCGGAGGCGGAGGTTCAGACTTGACCATGCAAT"),    # 8-byte keys every 16 bytes
+])
+def test_scan_tile_candidates_and_scattered_spans(pre, suf):
+    """The tile scan (kernels_scan.cu, k1_scan_tile): decoy keys that fail verification before a real
+    occurrence, repeated adapters (leftmost wins, src/lib.rs:148), occurrences cut by a read end or
+    continued in the next read, empty / short / very long reads, and span orders that make a warp's
+    text range exceed its tile (byte-wise path) -- against the oracle and the byte-wise kernel."""
+    rng = random.Random(len(pre) * 7 + 3)
+    rnd = lambda n: bytes(rng.choice(b"ACGT") for _ in range(n))
+    seqs = []
+    for i in range(6000):
+        k = rng.randrange(12)
+        if k == 0:      # decoy (adapter head, then a mismatch) before the real thing
+            seqs.append(rnd(rng.randrange(0, 9)) + pre[:rng.randrange(8, len(pre))] + b"N" + rnd(rng.randrange(0, 20)) + pre +
+                        rnd(30) + suf[:rng.randrange(8, len(suf))] + rnd(3) + suf + rnd(rng.randrange(0, 9)))
+        elif k == 1:    # adapters twice
+            seqs.append(rnd(rng.randrange(0, 17)) + pre + rnd(rng.randrange(0, 40)) + pre + rnd(21) + suf + rnd(rng.randrange(0, 40)) + suf)
+        elif k == 2:    # occurrence cut by the read end; the rest opens the next read
+            cut = rng.randrange(1, len(pre))
+            seqs.append(rnd(rng.randrange(0, 60)) + pre[:cut])
+            seqs.append(pre[cut:] + rnd(rng.randrange(0, 60)) + suf[:rng.randrange(1, len(suf))])
+        elif k == 3:
+            seqs.append(b"" if rng.random() < 0.5 else rnd(rng.randrange(1, len(pre))))
+        elif k == 4 and i % 50 == 0:
+            seqs.append(rnd(rng.randrange(3000, 9000)) + pre + rnd(300) + suf + rnd(rng.randrange(0, 3000)))
+        elif k == 5:    # suffix before prefix, overlapping adapters
+            seqs.append(suf + pre[:5] + pre + rnd(12))
+        else:
+            seqs.append(rnd(rng.randrange(0, 13)) + pre + rnd(rng.choice((21, 24, 30, 198))) + suf + rnd(rng.randrange(0, 13)))
+    text, off, ln = oracle.pack_reads(seqs)
+    want, odiag, _ = oracle.process_reads(oracle.make_params((pre, suf), accept_prefix_alignment=1.0, accept_suffix_alignment=1.0,
+                                                             skip_translation=True), text, off, ln, want_diag=True)
+    got, diag = _scan_only(text, off, ln, (pre, suf))
+    assert_diag_equal(diag, odiag)
+    assert got == want
+    slow, sdiag = _scan_only(text, off, ln, (pre, suf), force_general_scan=True)
+    assert_diag_equal(sdiag, odiag)
+    # the same reads visited in a random order (a warp's 32 reads span the whole buffer), and in an
+    # order that is sorted except for every 7th read
+    n = len(off)
+    swapped = np.arange(n)
+    for i in range(0, n // 2, 7):
+        swapped[i], swapped[n - 1 - i] = n - 1 - i, i
+    for order in (np.array(rng.sample(range(n), n)), swapped):
+        got2, diag2 = _scan_only(text, off[order], ln[order], (pre, suf))
+        for f in ("exact_prefix", "exact_suffix", "start", "end"):
+            assert (diag2[f] == odiag[f][order]).all(), f
+        assert got2 == want
+
+
 def test_scan_unaligned_text_offsets():
     # reads at every byte alignment inside a larger text buffer (as FASTQ text delivers them)
     rng = random.Random(21)

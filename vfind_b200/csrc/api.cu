@@ -804,7 +804,7 @@ static int process_batch(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_sp
     KeyJob kj;
     kj.text = d_text; kj.spans = d_spans;
     kj.start = c->d_start.as<uint32_t>(); kj.end = c->d_end.as<uint32_t>();
-    kj.n_reads = n; kj.skip_translation = c->prm.skip_translation;
+    kj.n_reads = n; kj.text_bytes = span_bytes_upper; kj.skip_translation = c->prm.skip_translation;
     kj.keys = c->d_keys.as<uint8_t>(); kj.koff = c->d_koff.as<uint64_t>();
     kj.key_cursor = c->d_t64.as<unsigned long long>() + T_KEYBYTES;
     kj.klen = c->d_klen.as<uint32_t>(); kj.khash = c->d_khash.as<uint64_t>();

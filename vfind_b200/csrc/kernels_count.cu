@@ -8,6 +8,8 @@
 #include "hash.h"
 #include "vfb_internal.cuh"
 
+#include <stdlib.h>
+
 namespace vfb {
 
 // ------------------------------------------------------------------------------------ K3
@@ -230,8 +232,224 @@ k3_keys(const __grid_constant__ KeyJob job)
     }
 }
 
+// ---- tile version: the text range that covers the regions of a warp's 32 reads is staged in shared
+// memory by one bulk copy (TMA, completion on an mbarrier), as in k1_scan_tile; one lane owns one read
+// and walks its region out of shared memory (no global-load latency inside the translate loop); the
+// unit's keys are assembled in shared memory and leave with coalesced 16-byte stores; koff / klen /
+// khash are written one lane per read.  A unit whose regions do not fit the tile reads global memory
+// directly, a unit whose keys do not fit the key staging writes them directly.
+#define K3T_WARPS_MAX 8
+#define K3T_OUT_BYTES 4096
+#define K3T_SLACK 16
+
+struct Key3Tables {
+    uint8_t lut25[256], lut5[256], lut1[256];
+    uint8_t aa[128];
+    uint64_t mult[KEY_MULTS];
+};
+
+__device__ __forceinline__ uint32_t k3_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// aligned word `idx` of the region's source: shared-memory tile, or global memory never touching a word
+// at or beyond `limit`
+template <bool SMEM>
+__device__ __forceinline__ uint32_t k3_word(const uint32_t *w, uint32_t idx, const uint32_t *limit)
+{
+    if (SMEM) return w[idx];
+    return (w + idx) < limit ? __ldg(w + idx) : 0u;
+}
+
+// One lane translates (or copies) its region into key words; returns the hash accumulator.
+template <bool SMEM, bool TRANSLATE>
+__device__ __forceinline__ uint64_t k3_lane(const Key3Tables &T, const uint32_t *w, const uint32_t *limit, uint32_t sh,
+                                            uint32_t kl, uint32_t *out, uint32_t &high)
+{
+    const uint32_t nw = (kl + 3) >> 2, npad = ((kl + 15u) & ~15u) >> 2;
+    uint64_t acc = 0;
+    uint32_t t0 = k3_word<SMEM>(w, 0, limit), wp = 1;
+    for (uint32_t wi = 0; wi < nw; ++wi) {
+        uint32_t word;
+        if (TRANSLATE) {
+            const uint32_t t1 = k3_word<SMEM>(w, wp, limit), t2 = k3_word<SMEM>(w, wp + 1, limit), t3 = k3_word<SMEM>(w, wp + 2, limit);
+            wp += 3;
+            const uint32_t x0 = __funnelshift_r(t0, t1, sh), x1 = __funnelshift_r(t1, t2, sh), x2 = __funnelshift_r(t2, t3, sh);
+            t0 = t3;
+            // codon a = bytes 3a .. 3a+2 of the 12 (translate, src/lib.rs:16-44)
+            const uint32_t i0 = T.lut25[x0 & 0xFFu] + T.lut5[(x0 >> 8) & 0xFFu] + T.lut1[(x0 >> 16) & 0xFFu];
+            const uint32_t i1 = T.lut25[x0 >> 24] + T.lut5[x1 & 0xFFu] + T.lut1[(x1 >> 8) & 0xFFu];
+            const uint32_t i2 = T.lut25[(x1 >> 16) & 0xFFu] + T.lut5[x1 >> 24] + T.lut1[x2 & 0xFFu];
+            const uint32_t i3 = T.lut25[(x2 >> 8) & 0xFFu] + T.lut5[(x2 >> 16) & 0xFFu] + T.lut1[x2 >> 24];
+            word = (uint32_t)T.aa[i0] | ((uint32_t)T.aa[i1] << 8) | ((uint32_t)T.aa[i2] << 16) | ((uint32_t)T.aa[i3] << 24);
+        } else {
+            const uint32_t t1 = k3_word<SMEM>(w, wp, limit);
+            wp += 1;
+            word = __funnelshift_r(t0, t1, sh);
+            t0 = t1;
+        }
+        const uint32_t left = kl - 4 * wi;                 // key bytes from this word on, >= 1
+        if (left < 4) word &= (1u << (8 * left)) - 1u;
+        if (!TRANSLATE) high |= word & 0x80808080u;
+        acc += (uint64_t)(word ^ VFB_HASH_K) * (wi < KEY_MULTS ? T.mult[wi] : vfb_hash_mult(wi));
+        out[wi] = word;
+    }
+    for (uint32_t wi = nw; wi < npad; ++wi) out[wi] = 0u;
+    return acc;
+}
+
+template <bool TRANSLATE>
+__global__ void __launch_bounds__(K3T_WARPS_MAX * 32)
+k3_keys_tile(const __grid_constant__ KeyJob job, const uint32_t tile_bytes)
+{
+    extern __shared__ __align__(128) uint8_t dyn[];
+    __shared__ Key3Tables T;
+    __shared__ unsigned long long bars[K3T_WARPS_MAX];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const uint32_t c = i >= 128 ? 4u : tr_index((uint8_t)i);
+        T.lut25[i] = (uint8_t)(25u * c); T.lut5[i] = (uint8_t)(5u * c); T.lut1[i] = (uint8_t)c;
+    }
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+        const int c0 = i / 25, c1 = (i / 5) % 5, c2 = i % 5;
+        T.aa[i] = (i >= 125 || c0 == 4 || c1 == 4 || c2 == 4) ? (uint8_t)'X' : (uint8_t)c_aa[c0 * 16 + c1 * 4 + c2];
+    }
+    for (int i = threadIdx.x; i < KEY_MULTS; i += blockDim.x) T.mult[i] = vfb_hash_mult((uint32_t)i);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(k3_smem_u32(bars + warp)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const size_t per_warp = (size_t)tile_bytes + K3T_SLACK + K3T_OUT_BYTES;
+    uint8_t *tile = dyn + (size_t)warp * per_warp;
+    const uint32_t *tile32 = reinterpret_cast<const uint32_t *>(tile);
+    uint32_t *out32 = reinterpret_cast<uint32_t *>(tile + tile_bytes + K3T_SLACK);
+    const uint32_t bar = k3_smem_u32(bars + warp), tile_s = k3_smem_u32(tile);
+    uint32_t parity = 0;
+    const uint32_t n_units = (job.n_reads + 31) / 32;
+    for (uint32_t unit = blockIdx.x * n_warps + warp; unit < n_units; unit += gridDim.x * n_warps) {
+        // ---- one lane per read: key length, key space (one atomic per 32 reads)
+        const uint32_t r = unit * 32 + lane;
+        uint32_t klen = 0, V = 0, roff = 0;            // roff: byte offset of the region in the text
+        if (r < job.n_reads) {
+            const uint32_t s = job.start[r], e = job.end[r];
+            // src/lib.rs:288: both located and start < end (strict)
+            if (s != VFB_NONE && e != VFB_NONE && s < e) {
+                const vfb_span sp = job.spans[r];
+                if (e <= sp.len) {
+                    V = e - s;
+                    roff = sp.off + s;
+                    if (!TRANSLATE) klen = V;
+                    else if (V % 3 == 0) klen = V / 3;                 // :17-19 partial codon -> None
+                }
+            }
+        }
+        const unsigned owners = __ballot_sync(0xffffffffu, klen != 0);
+        if (owners == 0) {
+            if (r < job.n_reads) job.klen[r] = 0;
+            continue;
+        }
+        const uint32_t padded = (klen + 15u) & ~15u;
+        uint32_t incl = padded;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        unsigned long long base = 0;
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 31) base = atomicAdd(job.key_cursor, (unsigned long long)total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        const uint32_t local = incl - padded;              // this lane's key inside the unit's key block
+        // ---- stage the text that covers the owners' regions
+        const uint32_t lo = __reduce_min_sync(0xffffffffu, klen ? roff : 0xFFFFFFFFu);
+        const uint32_t last = __reduce_max_sync(0xffffffffu, klen ? roff + (V - 1) : 0u);
+        const uintptr_t g0 = reinterpret_cast<uintptr_t>(job.text + lo);
+        const uint32_t lead_tile = (uint32_t)(g0 & 15u);
+        const uint64_t n_bytes = ((uint64_t)(last - lo) + 1 + lead_tile + 15) & ~15ull;
+        const bool staged = n_bytes <= tile_bytes;
+        const bool out_staged = total <= K3T_OUT_BYTES;
+        __syncwarp();                                      // the previous unit's tile and key block are done with
+        if (staged) {
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)n_bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(tile_s), "l"(g0 & ~(uintptr_t)15), "r"((uint32_t)n_bytes), "r"(bar) : "memory");
+            }
+            uint32_t ok;
+            do {
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+            } while (!ok);
+            parity ^= 1u;
+        }
+        uint64_t acc = 0;
+        uint32_t high = 0;
+        if (klen) {
+            uint32_t *out = out_staged ? out32 + (local >> 2) : reinterpret_cast<uint32_t *>(job.keys + base + local);
+            if (staged) {
+                const uint32_t toff = lead_tile + (roff - lo);
+                acc = k3_lane<true, TRANSLATE>(T, tile32 + (toff >> 2), nullptr, (toff & 3u) * 8u, klen, out, high);
+            } else {
+                const uintptr_t va = reinterpret_cast<uintptr_t>(job.text + roff);
+                const uint32_t *limit = reinterpret_cast<const uint32_t *>((va + V + 3) & ~(uintptr_t)3);
+                acc = k3_lane<false, TRANSLATE>(T, reinterpret_cast<const uint32_t *>(va & ~(uintptr_t)3), limit,
+                                                (uint32_t)(va & 3u) * 8u, klen, out, high);
+            }
+        }
+        __syncwarp();
+        if (out_staged) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(out32);
+            uint4 *dst = reinterpret_cast<uint4 *>(job.keys + base);
+            for (uint32_t c = lane; c < total / 16; c += 32) dst[c] = src[c];
+        }
+        if (klen) {
+            job.koff[r] = base + local;
+            uint64_t h = vfb_hash_finish(acc, klen);
+            if (job.hash_bits > 0 && job.hash_bits < 64) h &= (1ull << job.hash_bits) - 1;
+            job.khash[r] = h;
+            // String::from_utf8 (:295): only regions holding a byte >= 0x80 need the validator
+            if (!TRANSLATE && high && !utf8_valid(job.text + roff, V)) klen = 0;
+        }
+        if (r < job.n_reads) job.klen[r] = klen;
+    }
+}
+
+template <bool TRANSLATE>
+static int launch_keys_tile(const KeyJob &job, cudaStream_t st)
+{
+    const uint32_t tile = vfb_tile_bytes_for(job.text_bytes, job.n_reads);
+    const size_t smem_cap = 227 * 1024;
+    const size_t per_warp = (size_t)tile + K3T_SLACK + K3T_OUT_BYTES;
+    int best_w = 0, best_total = 0;
+    for (int w = K3T_WARPS_MAX; w >= 1; w >>= 1) {
+        const size_t per_block = (size_t)w * per_warp + sizeof(Key3Tables) + 64 + 1024;
+        int bps = (int)(smem_cap / per_block);
+        if (bps * w > 32) bps = 32 / w;
+        if (bps * w > best_total) { best_total = bps * w; best_w = w; }
+    }
+    if (best_total == 0) return -1;
+    const size_t smem = (size_t)best_w * per_warp;
+    VFB_CUDA(cudaFuncSetAttribute(k3_keys_tile<TRANSLATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t units = (job.n_reads + 31) / 32;
+    uint32_t blocks = (units + best_w - 1) / best_w;
+    const uint32_t cap = 148u * (uint32_t)(best_total / best_w);
+    if (blocks > cap) blocks = cap;
+    k3_keys_tile<TRANSLATE><<<blocks, best_w * 32, smem, st>>>(job, tile);
+    return VFB_OK;
+}
+
 int launch_keys(const KeyJob &job, cudaStream_t st)
 {
+    static const bool old_keys = getenv("VFB_KEYS_TILE") && atoi(getenv("VFB_KEYS_TILE")) == 0;
+    if (job.n_reads && job.text_bytes && !old_keys) {
+        const int rc = job.skip_translation ? launch_keys_tile<false>(job, st) : launch_keys_tile<true>(job, st);
+        if (rc > 0) return rc;
+        if (rc == VFB_OK) {
+            ++g_launches;
+            VFB_CUDA(cudaGetLastError());
+            return VFB_OK;
+        }
+    }
     if (job.n_reads == 0) return VFB_OK;
     uint32_t blocks = (job.n_reads / 32 + (KEY_THREADS / 32)) / (KEY_THREADS / 32);
     if (blocks > 148 * 8) blocks = 148 * 8;
@@ -255,15 +473,27 @@ __device__ __forceinline__ const uint8_t *job_key(const InsertJob &j, uint32_t i
     return j.koff ? j.keys + j.koff[i] : j.keys + (size_t)i * j.key_stride;
 }
 
+// No early exit: a tag match is almost always a key match, so all chunks are needed anyway, and
+// without the exit the loads of both keys are in flight together (one memory round trip, not n).
 __device__ __forceinline__ bool keys_equal16(const uint8_t *a, const uint8_t *b, uint32_t len)
 {
     const uint4 *x = reinterpret_cast<const uint4 *>(a), *y = reinterpret_cast<const uint4 *>(b);
     const uint32_t n = (len + 15) / 16;
-    for (uint32_t i = 0; i < n; ++i) {
-        const uint4 u = x[i], v = y[i];
-        if (u.x != v.x || u.y != v.y || u.z != v.z || u.w != v.w) return false;
+    uint32_t diff = 0;
+    uint32_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        uint4 u[4], v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { u[k] = x[i + k]; v[k] = y[i + k]; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            diff |= (u[k].x ^ v[k].x) | (u[k].y ^ v[k].y) | (u[k].z ^ v[k].z) | (u[k].w ^ v[k].w);
     }
-    return true;
+    for (; i < n; ++i) {
+        const uint4 u = x[i], v = y[i];
+        diff |= (u.x ^ v.x) | (u.y ^ v.y) | (u.z ^ v.z) | (u.w ^ v.w);
+    }
+    return diff == 0;
 }
 
 // One thread per key: probe, claim or match (full key compare), count.  Counts are first
@@ -304,7 +534,12 @@ k4_insert(const __grid_constant__ InsertArgs a)
         const uint8_t *mykey = job_key(j, i);
         for (;;) {
             unsigned long long *ent = t.slots + slot * VFB_SLOT_WORDS;
-            unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(ent);
+            // the whole 32-byte slot in one go (two 16-byte loads of one sector, L1 bypassed): a row's
+            // arena offset and length are there when the tag matches, no second round trip
+            unsigned long long cur, cnt_unused, m_off, m_len;
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(cur), "=l"(cnt_unused) : "l"(ent) : "memory");
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(m_off), "=l"(m_len) : "l"(ent + 2) : "memory");
+            (void)cnt_unused;
             if (cur == 0ull) {
                 cur = atomicCAS(ent, 0ull, mine);
                 if (cur == 0ull) {
@@ -322,9 +557,8 @@ k4_insert(const __grid_constant__ InsertArgs a)
                     olen = j.klen[o];
                 } else {
                     // a row published by an earlier batch: its arena offset and length sit in the slot
-                    const ulonglong2 m = *reinterpret_cast<const ulonglong2 *>(ent + 2);
-                    okey = t.arena + m.x;
-                    olen = (uint32_t)m.y;
+                    okey = t.arena + m_off;
+                    olen = (uint32_t)m_len;
                 }
                 if (olen == klen && keys_equal16(okey, mykey, klen)) break;
             }
@@ -359,7 +593,6 @@ k4_publish(const __grid_constant__ InsertArgs a)
     const bool own = slot != VFB_NONE;
     if (own) klen = j.klen[i];
     const unsigned m = __ballot_sync(0xffffffffu, own);
-    if (!m) return;
     const uint32_t padded = own ? (klen + 15u) & ~15u : 0u;
     uint32_t incl = padded;
 #pragma unroll
@@ -367,14 +600,27 @@ k4_publish(const __grid_constant__ InsertArgs a)
         const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += v;
     }
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    unsigned long long row0 = 0, off0 = 0;
-    if (lane == 0) {
-        row0 = atomicAdd(&t.counters[0], (unsigned long long)__popc(m));
-        off0 = atomicAdd(&t.counters[1], (unsigned long long)total);
+    // row ids and arena space are claimed once per BLOCK: the two counters are single addresses, and
+    // a claim per warp made every warp of the grid queue up on them
+    __shared__ uint32_t s_rows[8], s_bytes[8];
+    __shared__ unsigned long long s_row0, s_off0;
+    const int warp = threadIdx.x >> 5;
+    if (lane == 31) { s_rows[warp] = (uint32_t)__popc(m); s_bytes[warp] = incl; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t rows = 0, bytes = 0;
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t rw = s_rows[w], bw = s_bytes[w];
+            s_rows[w] = rows; s_bytes[w] = bytes;          // exclusive over the block's warps
+            rows += rw; bytes += bw;
+        }
+        if (rows) {
+            s_row0 = atomicAdd(&t.counters[0], (unsigned long long)rows);
+            s_off0 = atomicAdd(&t.counters[1], (unsigned long long)bytes);
+        }
     }
-    row0 = __shfl_sync(0xffffffffu, row0, 0);
-    off0 = __shfl_sync(0xffffffffu, off0, 0);
+    __syncthreads();
+    const unsigned long long row0 = s_row0 + s_rows[warp], off0 = s_off0 + s_bytes[warp];
     if (!own) return;
     const unsigned long long row = row0 + __popc(m & ((1u << lane) - 1));
     const unsigned long long off = off0 + (incl - padded);

@@ -164,10 +164,11 @@ k2_filter(const __grid_constant__ DpwArgs a)
         int score = A;
         int first = 0, last = 0;          // current group of flagged columns (0 = none)
         bool overflow = false;
-        uint4 nx = __ldg(base16);
+        uint4 nx = __ldg(base16), nx2 = n_chunks > 1 ? __ldg(base16 + 1) : make_uint4(0, 0, 0, 0);
         for (int c = 0; c < n_chunks; ++c) {
-            const uint4 v = nx;
-            if (c + 1 < n_chunks) nx = __ldg(base16 + c + 1);
+            const uint4 v = nx;               // two chunks in flight
+            nx = nx2;
+            if (c + 2 < n_chunks) nx2 = __ldg(base16 + c + 2);
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
             const uint32_t Pv0 = Pv, Mv0 = Mv;
             const int score0 = score;
@@ -278,8 +279,12 @@ k2_dp_window(const __grid_constant__ DpwArgs a)
         for (int i = 0; i < AMAX; ++i) { H[i] = hinit; E[i] = lay.neg_e; }
         int best = INT_MIN / 2, bestcap = INT_MIN / 2, bestj = 0;
         cells += (unsigned long long)(j1 >= j0 ? j1 - j0 + 1 : 0) * (unsigned long long)A;
+        // the read's byte for column j+1 is fetched while column j is computed: the global load never
+        // sits at the head of a column's dependency chain
+        uint32_t bn = j1 >= j0 ? __ldg(seq + j0 - 1) : 0u;
         for (int j = j0; j <= j1; ++j) {
-            const int c16 = lut[__ldg(seq + j - 1)];
+            const int c16 = lut[bn];
+            if (j < j1) bn = __ldg(seq + j);
             const int4 *pc = reinterpret_cast<const int4 *>(profb + c16);
             int hup = 0, F = lay.neg_f;
             int4 W4 = pc[0];

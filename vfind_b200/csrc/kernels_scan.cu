@@ -587,7 +587,7 @@ k1_scan_tile(const __grid_constant__ ScanArgs args, const uint32_t tile_bytes)
 }
 
 // Tile size for a batch whose reads sit `stride` bytes apart on average: 32 reads and a little slack.
-static uint32_t tile_bytes_for(uint64_t text_bytes, uint32_t n_reads)
+uint32_t vfb_tile_bytes_for(uint64_t text_bytes, uint32_t n_reads)
 {
     uint64_t stride = n_reads ? text_bytes / n_reads : 0;
     if (stride < 32) stride = 32;
@@ -601,7 +601,7 @@ static uint32_t tile_bytes_for(uint64_t text_bytes, uint32_t n_reads)
 template <bool STRIDE16>
 static int launch_scan_tile(const ScanArgs &a, int sm_count, cudaStream_t st)
 {
-    const uint32_t tile = tile_bytes_for(a.job.text_bytes, a.job.n_reads);
+    const uint32_t tile = vfb_tile_bytes_for(a.job.text_bytes, a.job.n_reads);
     const size_t smem_cap = 227 * 1024;
     int warps = TILE_WARPS_MAX;
     auto smem_for = [&](int w) {

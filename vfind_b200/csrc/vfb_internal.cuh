@@ -132,6 +132,8 @@ struct ScanJob {
     int compute_all;              // 1: list every suffix miss (what the reference computes)
     int force_general;            // tests: use the byte-wise kernel
 };
+// Shared-memory tile for 32 reads that sit text_bytes / n_reads apart on average (scan and key kernels).
+uint32_t vfb_tile_bytes_for(uint64_t text_bytes, uint32_t n_reads);
 int launch_scan(const ScanJob &job, const AdapterBytes &prefix, const AdapterBytes &suffix,
                 int sm_count, cudaStream_t st);
 
@@ -141,6 +143,7 @@ struct KeyJob {
     const vfb_span *spans;
     const uint32_t *start, *end;
     uint32_t n_reads;
+    uint64_t text_bytes;      // bytes of text the spans address (sizes the tiles; 0 = unknown)
     int skip_translation;
     uint8_t *keys;            // key arena of the batch; keys are bump-allocated, 16-byte aligned
     uint64_t *koff;           // per read: offset of its key in `keys`
