@@ -15,10 +15,17 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libvfind_b200.so")
 OBJ = os.path.join(HERE, "_obj")
-SOURCES = ["api.cu", "ingest.cu", "pgunzip.cu", "kernels_parse.cu", "kernels_inflate.cu", "kernels_scan.cu", "kernels_dp.cu", "kernels_dpw.cu", "kernels_count.cu", "kernels_misc.cu"]
+SOURCES = ["api.cu", "hostpack.cu", "hostpack_cpu.cpp", "ingest.cu", "pgunzip.cu", "kernels_parse.cu", "kernels_inflate.cu", "kernels_scan.cu", "kernels_dp.cu", "kernels_dpw.cu", "kernels_count.cu", "kernels_misc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v"]
+
+
+CXX = os.environ.get("CXX", "g++")
+
+
+def _obj_name(src):
+    return os.path.splitext(src)[0] + ".o"
 
 
 def _deps():
@@ -40,13 +47,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
     jobs = []
     for s in SOURCES:
         src = os.path.join(CSRC, s)
-        obj = os.path.join(OBJ, s.replace(".cu", ".o"))
+        obj = os.path.join(OBJ, _obj_name(s))
         if force or _stale(obj, [src] + hdr):
             jobs.append((src, obj))
 
     def cc(job):
         src, obj = job
-        r = subprocess.run([NVCC] + FLAGS + ["-c", src, "-o", obj], capture_output=True, text=True)
+        if src.endswith(".cpp"):      # host-only code: g++ (the AVX2 packer picks its path at run time)
+            cmd = [CXX, "-O3", "-std=c++17", "-fPIC", "-Wall", "-c", src, "-o", obj]
+        else:
+            cmd = [NVCC] + FLAGS + ["-c", src, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
         log = r.stdout + r.stderr
         with open(obj + ".log", "w") as f:
             f.write(log)
@@ -60,7 +71,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose:
             for l in logs:
                 print(l)
-    objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
+    objs = [os.path.join(OBJ, _obj_name(s)) for s in SOURCES]
     if force or jobs or _stale(OUT, objs):
         r = subprocess.run([NVCC, "-shared", "-o", OUT] + objs + ["-lz", "-cudart", "static",
                                                                     "-gencode", "arch=compute_100a,code=sm_100a"],

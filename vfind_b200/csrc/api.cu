@@ -8,7 +8,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <sched.h>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "hash.h"
@@ -221,6 +223,9 @@ struct vfb_ctx {
     int device = 0, sm_count = 148;
     cudaStream_t st_compute = nullptr, st_copy = nullptr;
     Slot slots[2];
+    HostPacker *packer = nullptr;      // host threads that 2-bit-pack read text for the link (hostpack.cu)
+    bool packer_tried = false;
+    uint64_t packed_blocks = 0;
     uint64_t batch_seq = 0;
     uint64_t batch_reads = 0, batch_bytes = 0;
 
@@ -573,6 +578,8 @@ int vfb_destroy(vfb_ctx *c)
     cudaSetDevice(c->device);
     if (c->st_compute) cudaStreamSynchronize(c->st_compute);
     if (c->st_copy) cudaStreamSynchronize(c->st_copy);
+    hostpack_destroy(c->packer);
+    c->packer = nullptr;
     for (auto &s : c->slots) {
         s.d_text.release(); s.d_spans.release(); s.h_text.release(); s.h_spans.release();
         if (s.copied) cudaEventDestroy(s.copied);
@@ -730,6 +737,35 @@ static int run_dp(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_spans, bo
 }
 
 // The hot loop over one device-resident batch (all work queued on the compute stream).
+// The host packer is created on the first batch big enough to use it.  VFB_HOST_PACK = number of
+// packing threads; "auto" = the CPUs this process may run on, divided by the visible GPUs (one
+// process per GPU shares the host), minus two, at most 16.  Unset or 0 = off: on the B200 boxes
+// this was measured on, reading the caller's text out of host DRAM is what bounds the transfer
+// (~48 GB/s whether the copy engine or the cores read it), so packing moves fewer bytes over PCIe
+// without finishing sooner (profiles/README.md); it pays on hosts whose DRAM is well ahead of the link.
+static bool packer_for(vfb_ctx *c)
+{
+    if (c->packer_tried) return c->packer != nullptr;
+    c->packer_tried = true;
+    int threads = 0;
+    const char *e = getenv("VFB_HOST_PACK");
+    if (e && !strcmp(e, "auto")) {
+        int ncpu = (int)std::thread::hardware_concurrency();
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0) ncpu = CPU_COUNT(&set);
+        int ndev = 1;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); ndev = 1; }
+        threads = ncpu / ndev - 2;
+        if (threads > 16) threads = 16;
+        if (threads < 2) threads = 0;
+    } else if (e) {
+        threads = atoi(e);
+    }
+    if (threads > 0) c->packer = hostpack_create(threads);
+    trace("host packer: %d threads", c->packer ? hostpack_threads(c->packer) : 0);
+    return c->packer != nullptr;
+}
+
 static int process_batch(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_spans, uint32_t n,
                          uint64_t span_bytes_upper)
 {
@@ -898,11 +934,19 @@ int vfb_submit_host(vfb_ctx *c, const uint8_t *text, uint64_t text_bytes, const 
             memcpy(s.h_spans.p, src_spans, n * sizeof(vfb_span));
             src_spans = (const vfb_span *)s.h_spans.p;
         }
-        if (bytes) VFB_CUDA(cudaMemcpyAsync(s.d_text.p, src_text, bytes, cudaMemcpyHostToDevice, c->st_copy));
+        uint64_t link_bytes = bytes;
         VFB_CUDA(cudaMemcpyAsync(s.d_spans.p, src_spans, n * sizeof(vfb_span), cudaMemcpyHostToDevice, c->st_copy));
+        if (bytes >= VFB_HOSTPACK_MIN_BYTES && pinned_text && packer_for(c)) {
+            // part of the text crosses the link as 2-bit codes packed by the context's host threads
+            uint64_t nb = 0;
+            if ((rc = hostpack_copy(c->packer, src_text, bytes, s.d_text.as<uint8_t>(), c->st_copy, &link_bytes, &nb))) break;
+            c->packed_blocks += nb;
+        } else if (bytes) {
+            VFB_CUDA(cudaMemcpyAsync(s.d_text.p, src_text, bytes, cudaMemcpyHostToDevice, c->st_copy));
+        }
         VFB_CUDA(cudaEventRecord(s.copied, c->st_copy));
         VFB_CUDA(cudaStreamWaitEvent(c->st_compute, s.copied, 0));
-        c->stats.h2d_bytes += bytes + n * sizeof(vfb_span);
+        c->stats.h2d_bytes += link_bytes + n * sizeof(vfb_span);
         // span offsets stay relative to the caller's buffer: bias the device base by -lo
         const uint8_t *d_base = s.d_text.as<uint8_t>() - lo;
         rc = process_batch(c, d_base, s.d_spans.as<vfb_span>(), (uint32_t)n, bytes);

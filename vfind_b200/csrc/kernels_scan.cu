@@ -501,10 +501,22 @@ k1_scan_tile(const __grid_constant__ ScanArgs args, const uint32_t tile_bytes)
     asm volatile("mov.u32 %0, %1;" : "=r"(slot_s) : "r"(smem_u32(Ts.slot)));
     uint32_t cntP = 0, cntS = 0, parity = 0;
     const uint32_t n_units = (job.n_reads + 31) / 32;
-    for (uint32_t unit = blockIdx.x * n_warps + warp; unit < n_units; unit += gridDim.x * n_warps) {
+    // the next unit's spans are fetched while the current unit is staged and scanned
+    const uint32_t unit_stride = gridDim.x * n_warps;
+    vfb_span nsp = vfb_span{0u, 0u};
+    {
+        const uint32_t r0 = (blockIdx.x * n_warps + warp) * 32 + lane;
+        if (r0 < job.n_reads) nsp = job.spans[r0];
+    }
+    for (uint32_t unit = blockIdx.x * n_warps + warp; unit < n_units; unit += unit_stride) {
         const uint32_t r = unit * 32 + lane;
         const bool have = r < job.n_reads;
-        const vfb_span sp = have ? job.spans[r] : vfb_span{0u, 0u};
+        const vfb_span sp = nsp;
+        {
+            const uint32_t rn = (unit + unit_stride) * 32 + lane;
+            nsp = vfb_span{0u, 0u};
+            if (unit + unit_stride < n_units && rn < job.n_reads) nsp = job.spans[rn];
+        }
         const bool live = have && sp.len > 0;
         const uint32_t lo = __reduce_min_sync(0xffffffffu, live ? sp.off : 0xFFFFFFFFu);
         const uint32_t last = __reduce_max_sync(0xffffffffu, live ? sp.off + (sp.len - 1) : 0u);

@@ -243,6 +243,15 @@ int launch_synth(const vfb_synth_cfg &cfg, uint64_t first, uint64_t n, uint8_t *
                  vfb_span *d_spans, cudaStream_t st);
 int measure_int_peak(int device, double *alu_gops, double *dual_gops);
 
+// ---------------------------------------------------------------- packed host->device copies (hostpack.cu)
+struct HostPacker;
+HostPacker *hostpack_create(int threads);
+void hostpack_destroy(HostPacker *hp);
+int hostpack_threads(const HostPacker *hp);
+int hostpack_copy(HostPacker *hp, const uint8_t *text, uint64_t bytes, uint8_t *d_text, cudaStream_t st_copy,
+                  uint64_t *link_bytes, uint64_t *packed_blocks);
+#define VFB_HOSTPACK_MIN_BYTES (16u << 20)    // smaller batches are copied as they are
+
 extern thread_local uint64_t g_launches;   // kernels launched by this thread's calls
 }  // namespace vfb
 
