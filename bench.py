@@ -40,7 +40,8 @@ def c3_cfg(api):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock, power and throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML every
+    10 ms from a thread (the timed region of the resident leg is ~0.15 s), `nvidia-smi -lms` if NVML is not importable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -49,29 +50,63 @@ class ClockSampler:
         self.idx = gpu_index
         self.rows = []
         self.proc = None
+        self.nv = None
+        self.stop_flag = threading.Event()
+        self.t = None
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.nv = pynvml
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nv = None
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
             self.proc = None
+
+    def _poll(self):
+        nv = self.nv
+        bits = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append(["", sm, self.mx, pw, ""] + ["Active" if rs & b else "Not Active" for _, b in bits])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.01)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
-        if not self.proc:
+        if self.nv is not None:
+            self.stop_flag.set()
+            self.t.join(timeout=2)
+        elif not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
@@ -82,10 +117,11 @@ class ClockSampler:
             except ValueError:
                 continue
             for n, v in zip(names, r[5:9]):
-                if v.lower().startswith("active"):
+                if str(v).lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons),
+                "source": "nvml, 10 ms" if self.nv is not None else "nvidia-smi -lms 50"}
 
 
 FULL_AFFINITY = None
