@@ -445,6 +445,34 @@ __device__ int infw_build(const InfTables *T, InfWarp *W, int nlen, int ndist, i
         W->dtab[e] = sym < 0 ? 0u : dist_entry(T, sym, len);
     }
     __syncwarp();
+    // Literal runs: where the index bits behind a literal's code hold one or two more complete literal
+    // codes, the entry decodes them all at once -- bytes in bits 8-15 / 16-23 / 24-31, (count - 1) in bits
+    // 6-7, total code length in bits 0-3.  Read text is mostly literals with 2-3 bit codes (the bases), so
+    // most look-ups then yield three bytes.  Every lane first derives its entries from the single-symbol
+    // table, then all write.
+    uint32_t fused[(1 << INFW_LBITS) / 32];
+#pragma unroll
+    for (int k = 0; k < (1 << INFW_LBITS) / 32; ++k) {
+        const uint32_t e = (uint32_t)lane + 32u * (uint32_t)k;
+        uint32_t a = W->ltab[e];
+        if (a != 0 && ((a >> 4) & 3u) == 0) {
+            uint32_t used = a & 15u, cnt = 1, bytes = (a >> 8) & 0xFFu;
+            while (cnt < 3 && used < INFW_LBITS) {
+                const uint32_t nx = W->ltab[e >> used];             // the bits above `used`, zero-extended
+                const uint32_t nb = nx & 15u;
+                if (nx == 0 || ((nx >> 4) & 3u) != 0 || used + nb > INFW_LBITS) break;   // not a literal fully inside the index
+                bytes |= ((nx >> 8) & 0xFFu) << (8 * cnt);
+                used += nb;
+                ++cnt;
+            }
+            a = used | ((cnt - 1) << 6) | (bytes << 8);
+        }
+        fused[k] = a;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < (1 << INFW_LBITS) / 32; ++k) W->ltab[lane + 32 * k] = fused[k];
+    __syncwarp();
     return 0;
 }
 
@@ -568,9 +596,10 @@ __device__ int inflate_member_warp(const InfShared *S, InfWarp *W, const uint8_t
                 b.buf >>= nb; b.cnt -= nb;
                 const uint32_t kind = (e >> 4) & 3u;
                 if (kind == 0) {
-                    if (n_out >= isize) return -14;
-                    if (lane == 0) out[n_out] = (uint8_t)(e >> 8);
-                    ++n_out;
+                    const uint32_t cnt = 1u + ((e >> 6) & 3u);       // one to three literals per look-up
+                    if (n_out + cnt > isize) return -14;
+                    if ((uint32_t)lane < cnt) out[n_out + lane] = (uint8_t)(e >> (8 + 8 * lane));
+                    n_out += cnt;
                 } else if (kind == 2) {
                     break;
                 } else if (kind == 3) {
@@ -633,7 +662,7 @@ __device__ int inflate_member_warp(const InfShared *S, InfWarp *W, const uint8_t
     return 0;
 }
 
-__global__ void __launch_bounds__(INFW_WARPS * 32)
+__global__ void __launch_bounds__(INFW_WARPS * 32, 8)
 k_inflate_warp(const __grid_constant__ InflateArgs a)
 {
     __shared__ InfShared S;
