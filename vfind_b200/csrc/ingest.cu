@@ -391,6 +391,7 @@ struct ZSegment {
     size_t z_bytes = 0, text_bytes = 0;
     uint32_t n = 0;
     bool last = false;             // nothing more for the GPU phase after this segment
+    double read_ms = 0;            // what the reader thread spent filling it (trace)
 };
 
 // Consumes BGZF members from prod.f until the end of the file or the first member that is not
@@ -440,6 +441,7 @@ int run_bgzf_gpu(vfb_ctx *ctx, ChunkProducer &prod, size_t text_target, uint64_t
             }
             ZSegment &g = seg[k];
             g.z_bytes = g.text_bytes = 0; g.n = 0; g.last = false;
+            const auto r0 = std::chrono::steady_clock::now();
             std::string err;
             // pread straight into the pinned buffer — about as much as the last segment needed,
             // topped up while whole members are still missing — then walk the member headers
@@ -501,6 +503,7 @@ int run_bgzf_gpu(vfb_ctx *ctx, ChunkProducer &prod, size_t text_target, uint64_t
             if (off) z_estimate = off + off / 16 + 65536;
             vfb::trace("ingest reader: segment of %u members, %zu compressed bytes read", g.n, off);
             g.z_bytes = off;
+            g.read_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - r0).count();
             pos += off;
             if (err.empty() && !stop && eof && off == avail) { prod.at_end = true; g.last = true; }
             std::lock_guard<std::mutex> lk(pp.mu);
@@ -519,6 +522,7 @@ int run_bgzf_gpu(vfb_ctx *ctx, ChunkProducer &prod, size_t text_target, uint64_t
     uint64_t seg_bytes_done = pos;
     while (rc == VFB_OK) {
         int k = -1;
+        const auto w0 = std::chrono::steady_clock::now();
         {
             std::unique_lock<std::mutex> lk(pp.mu);
             pp.cv.wait(lk, [&] { return !pp.ready_q.empty() || pp.done; });
@@ -541,9 +545,10 @@ int run_bgzf_gpu(vfb_ctx *ctx, ChunkProducer &prod, size_t text_target, uint64_t
             *n_total += n_rec;
             seg_bytes_done += g.z_bytes;
             vfb_internal_progress(ctx, *n_total, seg_bytes_done, prod.file_size, false);
-            if (trace) fprintf(stderr, "[vfb ingest] gpu segment: %u members, %zu -> %zu bytes, %llu records, %.1f ms\n", g.n,
+            if (trace) fprintf(stderr, "[vfb ingest] gpu segment: %u members, %zu -> %zu bytes, %llu records, %.1f ms (waited %.1f ms for the reader, which took %.1f ms)\n", g.n,
                                g.z_bytes, g.text_bytes, (unsigned long long)n_rec,
-                               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+                               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(),
+                               std::chrono::duration<double, std::milli>(t0 - w0).count(), g.read_ms);
         }
         std::lock_guard<std::mutex> lk(pp.mu);
         pp.free_q.push_back(k);

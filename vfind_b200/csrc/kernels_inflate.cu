@@ -626,7 +626,12 @@ __device__ int inflate_member_warp(const InfShared *S, InfWarp *W, const uint8_t
                     __syncwarp();                                 // earlier stores of all lanes are visible
                     const uint8_t *from = out + n_out - dist;
                     if (dist >= len) {
-                        for (uint32_t i = lane; i < len; i += 32) out[n_out + i] = __ldcg(from + i);
+                        // (most matches in read text are a few bases long: one predicated load / store)
+                        if (len <= 32) {
+                            if ((uint32_t)lane < len) out[n_out + lane] = __ldcg(from + lane);
+                        } else {
+                            for (uint32_t i = lane; i < len; i += 32) out[n_out + i] = __ldcg(from + i);
+                        }
                     } else {
                         for (uint32_t i = lane; i < len; i += 32) out[n_out + i] = __ldcg(from + i % dist);
                     }
@@ -645,7 +650,20 @@ __device__ int inflate_member_warp(const InfShared *S, InfWarp *W, const uint8_t
     const uint32_t chunk = (isize + 31u) / 32u;
     const uint32_t lo = min(isize, (uint32_t)lane * chunk), hi = min(isize, lo + chunk);
     uint32_t crc = 0xFFFFFFFFu;
-    for (uint32_t i = lo; i < hi; ++i) crc = T->crc[(crc ^ __ldcg(out + i)) & 0xFFu] ^ (crc >> 8);
+    {
+        // bytes up to the first 16-byte boundary, then 16 bytes per load (two loads in flight), then the rest
+        uint32_t i = lo;
+        while (i < hi && ((reinterpret_cast<uintptr_t>(out) + i) & 15u)) { crc = T->crc[(crc ^ __ldcg(out + i)) & 0xFFu] ^ (crc >> 8); ++i; }
+        auto word = [&](uint32_t w) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { crc = T->crc[(crc ^ w) & 0xFFu] ^ (crc >> 8); w >>= 8; }
+        };
+        for (; i + 32 <= hi; i += 32) {
+            const uint4 a = __ldcg(reinterpret_cast<const uint4 *>(out + i)), c = __ldcg(reinterpret_cast<const uint4 *>(out + i + 16));
+            word(a.x); word(a.y); word(a.z); word(a.w); word(c.x); word(c.y); word(c.z); word(c.w);
+        }
+        for (; i < hi; ++i) crc = T->crc[(crc ^ __ldcg(out + i)) & 0xFFu] ^ (crc >> 8);
+    }
     crc ^= 0xFFFFFFFFu;
     uint32_t total = __shfl_sync(0xffffffffu, crc, 0);
     if (chunk) {
