@@ -198,7 +198,11 @@ struct Slot {
 };
 
 // device counters of one batch
-enum { C_NPRE = 0, C_NSUF, C_FBPRE, C_FBSUF, C_FB2PRE, C_FB2SUF, C_NWINPRE, C_NWINSUF, C_COUNT32 };
+enum { C_NPRE = 0, C_NSUF, C_FBPRE, C_FBSUF, C_FB2PRE, C_FB2SUF, C_NWINPRE, C_NWINSUF,
+       // work cursors of the filter / window kernels (dynamic distribution), each in a 128-byte line of its own: the
+       // counters above take millions of atomics per launch, a cursor in their line would queue behind them
+       C_WORKPRE = 32, C_WORKPRE2 = 64, C_WORKSUF = 96, C_WORKSUF2 = 128,
+       C_COUNT32 = 160 };
 // 64-bit device counters
 enum { T_CELLS = 0, T_DPPRE, T_DPSUF, T_KEYBYTES, T_CELLSCOMP, T_WINDOWS, T_COUNT64 };
 
@@ -701,7 +705,8 @@ static int run_dp(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_spans, bo
         const uint32_t lcap = is_prefix ? c->lcap_pre : c->lcap_suf;
         if ((rc = launch_dp_windowed(job, lay, K, lcap, n_batch, c->d_wins.p, c32 + (is_prefix ? C_NWINPRE : C_NWINSUF),
                                      c->win_cap, c->d_bestkey.as<unsigned long long>(), c->d_cbval.as<unsigned long long>(),
-                                     fb, nfb, c->d_t64.as<unsigned long long>() + T_CELLSCOMP, c->sm_count, c->st_compute,
+                                     fb, nfb, c->d_t64.as<unsigned long long>() + T_CELLSCOMP, c32 + (is_prefix ? C_WORKPRE : C_WORKSUF) /* the window cursor sits 32 words on */,
+                                     c->sm_count, c->st_compute,
                                      pev ? pev[is_prefix ? 8 : 10] : nullptr, pev ? pev[is_prefix ? 9 : 11] : nullptr)))
             return rc;
         DpJob fj = job;

@@ -34,6 +34,8 @@
 
 #include "vfb_internal.cuh"
 
+#include <stdlib.h>
+
 namespace vfb {
 
 // ------------------------------------------------------------------------------------ host: K
@@ -83,6 +85,7 @@ struct DpwArgs {
     unsigned long long *cb_val;       // per worklist item: (score+BIAS)<<32 | len, 0 = window did not reach column L
     uint32_t *fallback, *n_fallback;  // reads handed to the full kernel
     unsigned long long *cells_computed;
+    uint32_t *work;                   // [32]: the window kernel's cursor (next unclaimed window; warps claim 32 at a time)
 };
 
 __device__ __forceinline__ void win_emit(const DpwArgs &a, uint32_t r, uint32_t item, int first, int last, int span, int L,
@@ -141,10 +144,13 @@ k2_filter(const __grid_constant__ DpwArgs a)
     const unsigned char *lutb = reinterpret_cast<const unsigned char *>(lutEq);
     const int lane = threadIdx.x & 31;
     const uint32_t n_items = *job.n_items;
-    const uint32_t stride = gridDim.x * blockDim.x;
     const int span = A + a.K;
     const int K = a.K;
     unsigned long long cells = 0;
+    // (a static grid-stride share per block, but many more blocks than fit at once: the block scheduler evens
+    // out the differences in cost between items; claiming work from a global cursor, as k2_dp_window does, made
+    // this kernel 3.5x slower)
+    const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_items; base += stride) {
         const uint32_t item = base + lane;
         if (item >= n_items) continue;
@@ -258,14 +264,17 @@ k2_dp_window(const __grid_constant__ DpwArgs a)
     const int lane = threadIdx.x & 31;
     uint32_t n_wins = *a.n_wins;
     if (n_wins > a.win_cap) n_wins = a.win_cap;
-    const uint32_t stride = gridDim.x * blockDim.x;
     const int c_eopen = lay.c_eopen, c_eext = lay.c_eext, c_fopen = lay.c_fopen, c_fext = lay.c_fext;
     const int hmask = lay.hmask, lowmask = lay.lowmask, one = lay.one;
     const int S0 = lay.S0;
     const unsigned char *profb = reinterpret_cast<const unsigned char *>(prof);
     unsigned long long cells = 0;
 
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_wins; base += stride) {
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(a.work + 32, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n_wins) break;
         const uint32_t w = base + lane;
         const bool have = w < n_wins;
         WinItem it = have ? a.wins[w] : WinItem{0u, 0u, 1u, 0u};
@@ -404,7 +413,7 @@ static int launch_window(const DpwArgs &args, int sm_count, cudaStream_t st)
 int launch_dp_windowed(const DpJob &job, const DpLayout &lay, int K, uint32_t lcap, uint32_t max_items,
                        void *wins, uint32_t *n_wins, uint32_t win_cap, unsigned long long *best_key,
                        unsigned long long *cb_val, uint32_t *fallback, uint32_t *n_fallback,
-                       unsigned long long *cells_computed, int sm_count, cudaStream_t st,
+                       unsigned long long *cells_computed, uint32_t *work_cursors, int sm_count, cudaStream_t st,
                        cudaEvent_t ev_filter_done, cudaEvent_t ev_windows_done)
 {
     DpwArgs a;
@@ -412,9 +421,10 @@ int launch_dp_windowed(const DpJob &job, const DpLayout &lay, int K, uint32_t lc
     a.wins = static_cast<WinItem *>(wins); a.n_wins = n_wins; a.win_cap = win_cap;
     a.best_key = best_key; a.cb_val = cb_val; a.fallback = fallback; a.n_fallback = n_fallback;
     a.cells_computed = cells_computed;
+    a.work = work_cursors;
     VFB_CUDA(cudaMemsetAsync(best_key, 0, (size_t)max_items * 8, st));
     VFB_CUDA(cudaMemsetAsync(cb_val, 0, (size_t)max_items * 8, st));
-    k2_filter<<<sm_count * 12, DPW_THREADS, 0, st>>>(a);
+    k2_filter<<<sm_count * 48, DPW_THREADS, 0, st>>>(a);     // six waves of blocks: see the kernel
     ++g_launches;
     if (ev_filter_done) VFB_CUDA(cudaEventRecord(ev_filter_done, st));
     int rc;

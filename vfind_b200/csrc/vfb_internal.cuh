@@ -105,7 +105,7 @@ uint32_t dpw_item_bytes();
 int launch_dp_windowed(const DpJob &job, const DpLayout &lay, int K, uint32_t lcap, uint32_t max_items,
                        void *wins, uint32_t *n_wins, uint32_t win_cap, unsigned long long *best_key,
                        unsigned long long *cb_val, uint32_t *fallback, uint32_t *n_fallback,
-                       unsigned long long *cells_computed, int sm_count, cudaStream_t st,
+                       unsigned long long *cells_computed, uint32_t *work_cursors /* [0] and [32], zeroed */, int sm_count, cudaStream_t st,
                        cudaEvent_t ev_filter_done = nullptr, cudaEvent_t ev_windows_done = nullptr);
 
 struct DpGenericJob {
