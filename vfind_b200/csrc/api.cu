@@ -116,7 +116,9 @@ void *pinned_acquire(size_t want, size_t *cap_out)
         std::lock_guard<std::mutex> lk(pp.mu);
         int best = -1;
         for (size_t i = 0; i < pp.idle.size(); ++i)
-            if (pp.idle[i].second >= want && pp.idle[i].second <= 2 * want + (1u << 20) &&
+            // (a close fit only: a result column of 60 MB must not walk off with an 81 MB staging buffer that the
+            // next call will want back -- page-locking a fresh one costs more than the call's kernels)
+            if (pp.idle[i].second >= want && pp.idle[i].second <= want + want / 8 + (64u << 10) &&
                 (best < 0 || pp.idle[i].second < pp.idle[(size_t)best].second)) best = (int)i;
         if (best >= 0) {
             void *p = pp.idle[(size_t)best].first;
@@ -145,15 +147,26 @@ void pinned_release(void *p, size_t cap)
         limit = ((size_t)(e ? strtoull(e, nullptr, 10) : 1024ull) << 20) + 1;
     }
     PinnedPool &pp = pinned_pool();
+    std::vector<void *> evict;
+    bool keep = false;
     {
         std::lock_guard<std::mutex> lk(pp.mu);
-        if (pp.bytes + cap < limit) {
+        if (cap < limit) {
+            // the buffer just used is the one the next call will ask for: make room for it by letting the
+            // longest-idle buffers go (a finished 100 M-read context leaves ~1 GB of result columns behind,
+            // which used to crowd out the ingest's staging buffers and made every later call page-lock anew)
+            while (pp.bytes + cap >= limit && !pp.idle.empty()) {
+                evict.push_back(pp.idle.front().first);
+                pp.bytes -= pp.idle.front().second;
+                pp.idle.erase(pp.idle.begin());
+            }
             pp.idle.emplace_back(p, cap);
             pp.bytes += cap;
-            return;
+            keep = true;
         }
     }
-    cudaFreeHost(p);
+    for (void *q : evict) cudaFreeHost(q);
+    if (!keep) cudaFreeHost(p);
 }
 void pinned_pool_trim()
 {
