@@ -290,6 +290,21 @@ def test_scan_tile_candidates_and_scattered_spans(pre, suf):
         assert got2 == want
 
 
+@pytest.mark.parametrize("skip_translation,region", [(True, 198), (False, 600), (False, 198)])
+def test_key_blocks_larger_than_the_staging(skip_translation, region):
+    """k3_keys_tile assembles a warp's keys in 4 KB of shared memory; 32 keys of 198 raw bytes (skip_translation)
+    or 200 amino acids do not fit and are written to the arena directly -- same table either way."""
+    rng = random.Random(region + int(skip_translation))
+    rnd = lambda n: bytes(rng.choice(b"ACGT") for _ in range(n))
+    lib = [rnd(region) for _ in range(40)]
+    seqs = [rnd(rng.randrange(0, 5)) + PREFIX + rng.choice(lib) + SUFFIX + rnd(rng.randrange(0, 5)) for _ in range(3000)]
+    kw = dict(skip_translation=skip_translation)
+    got, diag, _ = gpu_run(seqs, (PREFIX, SUFFIX), **kw)
+    want, odiag, _ = oracle_run(seqs, (PREFIX, SUFFIX), **kw)
+    assert_diag_equal(diag, odiag)
+    assert got == want and sum(want.values()) == 3000
+
+
 def test_scan_unaligned_text_offsets():
     # reads at every byte alignment inside a larger text buffer (as FASTQ text delivers them)
     rng = random.Random(21)
