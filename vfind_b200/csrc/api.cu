@@ -784,9 +784,12 @@ static bool packer_for(vfb_ctx *c)
     return c->packer != nullptr;
 }
 
+// span_bytes_upper bounds the bytes the batch's spans cover (key space); text_bytes_hint is the text this batch's reads
+// are spread over (it sizes the shared-memory tiles of the scan and key kernels; 0 = span_bytes_upper).
 static int process_batch(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_spans, uint32_t n,
-                         uint64_t span_bytes_upper)
+                         uint64_t span_bytes_upper, uint64_t text_bytes_hint = 0)
 {
+    if (!text_bytes_hint) text_bytes_hint = span_bytes_upper;
     int rc;
     if (n == 0) return VFB_OK;
     cudaStream_t st = c->st_compute;
@@ -827,7 +830,7 @@ static int process_batch(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_sp
     VFB_CUDA(cudaMemsetAsync(c->d_t64.as<unsigned long long>() + T_KEYBYTES, 0, 8, st));
     ScanJob sj;
     memset(&sj, 0, sizeof sj);
-    sj.text = d_text; sj.spans = d_spans; sj.n_reads = n; sj.text_bytes = span_bytes_upper;
+    sj.text = d_text; sj.spans = d_spans; sj.n_reads = n; sj.text_bytes = text_bytes_hint;
     sj.start = c->d_start.as<uint32_t>(); sj.end = c->d_end.as<uint32_t>();
     if (c->align_pre) { sj.list_pre = c->d_list_a.as<uint32_t>(); sj.n_pre = c->d_c32.as<uint32_t>() + C_NPRE; }
     if (c->align_suf) { sj.list_suf = c->d_list_b.as<uint32_t>(); sj.n_suf = c->d_c32.as<uint32_t>() + C_NSUF; }
@@ -858,7 +861,7 @@ static int process_batch(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_sp
     KeyJob kj;
     kj.text = d_text; kj.spans = d_spans;
     kj.start = c->d_start.as<uint32_t>(); kj.end = c->d_end.as<uint32_t>();
-    kj.n_reads = n; kj.text_bytes = span_bytes_upper; kj.skip_translation = c->prm.skip_translation;
+    kj.n_reads = n; kj.text_bytes = text_bytes_hint; kj.skip_translation = c->prm.skip_translation;
     kj.keys = c->d_keys.as<uint8_t>(); kj.koff = c->d_koff.as<uint64_t>();
     kj.key_cursor = c->d_t64.as<unsigned long long>() + T_KEYBYTES;
     kj.klen = c->d_klen.as<uint32_t>(); kj.khash = c->d_khash.as<uint64_t>();
@@ -902,8 +905,9 @@ int vfb_submit_device(vfb_ctx *c, const uint8_t *d_text, uint64_t text_bytes, co
     }
     while (done < n_reads) {
         const uint64_t n = n_reads - done < c->batch_reads ? n_reads - done : c->batch_reads;
-        // key space bound: conservatively the whole buffer
-        if ((rc = process_batch(c, d_text, d_spans + done, (uint32_t)n, text_bytes))) break;
+        // key space bound: conservatively the whole buffer; tile size: this batch's share of it
+        if ((rc = process_batch(c, d_text, d_spans + done, (uint32_t)n, text_bytes,
+                                (uint64_t)((double)text_bytes * (double)n / (double)n_reads) + 1))) break;
         done += n;
     }
     bump_launches(c, before);
@@ -1021,7 +1025,8 @@ int vfb_internal_submit_fastq(vfb_ctx *c, const uint8_t *pinned_text, uint64_t n
         uint32_t done = 0;
         while (done < n_rec) {
             const uint32_t n = n_rec - done < c->batch_reads ? n_rec - done : (uint32_t)c->batch_reads;
-            if ((rc = process_batch(c, s.d_text.as<uint8_t>(), s.d_spans.as<vfb_span>() + done, n, n_bytes))) return rc;
+            if ((rc = process_batch(c, s.d_text.as<uint8_t>(), s.d_spans.as<vfb_span>() + done, n, n_bytes,
+                                    (uint64_t)((double)n_bytes * (double)n / (double)n_rec) + 1))) return rc;
             done += n;
         }
     }
@@ -1114,7 +1119,8 @@ int vfb_internal_submit_bgzf(vfb_ctx *c, const uint8_t *pinned_z, uint64_t z_byt
         uint32_t done = 0;
         while (done < n_rec) {
             const uint32_t n = n_rec - done < c->batch_reads ? n_rec - done : (uint32_t)c->batch_reads;
-            if ((rc = process_batch(c, txt.as<uint8_t>(), s.d_spans.as<vfb_span>() + done, n, used))) return rc;
+            if ((rc = process_batch(c, txt.as<uint8_t>(), s.d_spans.as<vfb_span>() + done, n, used,
+                                    (uint64_t)((double)used * (double)n / (double)n_rec) + 1))) return rc;
             done += n;
         }
     }

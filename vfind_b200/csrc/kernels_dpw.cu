@@ -424,7 +424,13 @@ int launch_dp_windowed(const DpJob &job, const DpLayout &lay, int K, uint32_t lc
     a.work = work_cursors;
     VFB_CUDA(cudaMemsetAsync(best_key, 0, (size_t)max_items * 8, st));
     VFB_CUDA(cudaMemsetAsync(cb_val, 0, (size_t)max_items * 8, st));
-    k2_filter<<<sm_count * 48, DPW_THREADS, 0, st>>>(a);     // six waves of blocks: see the kernel
+    static int filter_bps = 0;       // blocks per SM: several waves, see the kernel (VFB_FILTER_BPS overrides, for measurements)
+    if (!filter_bps) {
+        const char *e = getenv("VFB_FILTER_BPS");
+        filter_bps = e ? atoi(e) : 48;
+        if (filter_bps < 1) filter_bps = 48;
+    }
+    k2_filter<<<sm_count * filter_bps, DPW_THREADS, 0, st>>>(a);
     ++g_launches;
     if (ev_filter_done) VFB_CUDA(cudaEventRecord(ev_filter_done, st));
     int rc;
