@@ -499,6 +499,16 @@ def main():
     ingest = None
     if world == 1 and args.ingest_reads > 0:
         bind_to_gpu_cpus(local)
+        # A user's process does not sit on the resident legs' 30 GB of inputs and tables: let them go before timing whole
+        # find_variants calls (with them in place every call's cudaMalloc / cudaFree takes several times longer and the
+        # leg measures the driver's allocator, see profiles/README.md).  Nothing below uses ctx or chunks.
+        try:
+            del t, s
+        except NameError:
+            pass
+        chunks.clear()
+        ctx.close()
+        torch.cuda.empty_cache()
         try:
             import tempfile
             sys.path.insert(0, os.path.join(ROOT, "tools"))
