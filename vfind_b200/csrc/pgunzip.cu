@@ -684,6 +684,16 @@ bool ParallelGunzip::Impl::segment()
             // cache-sized pieces: narrow 64 symbols at a time (vectorises; a block that held a marker is gone
             // over again symbol by symbol), then CRC the piece while it is still in cache
             const size_t n = w.outp->n;
+            // In read text markers do not die out (a quality line copied from the previous record's keeps them
+            // alive for the whole stream), so most blocks take the second pass: it goes through one table --
+            // symbol -> byte, literals and the 32 KiB window behind each other -- without a branch per symbol;
+            // a marker that points in front of the member's first byte is caught by one compare (none can once
+            // the member has produced a full window).
+            std::vector<uint8_t> lut(256 + WSIZE);
+            for (int b = 0; b < 256; ++b) lut[(size_t)b] = (uint8_t)b;
+            memcpy(lut.data() + 256, win, WSIZE);
+            const uint8_t *tab = lut.data();
+            const uint16_t n_invalid = (uint16_t)(WSIZE - avail);       // markers 256 .. 256 + n_invalid - 1 are out of range
             uLong c32 = crc32(0L, Z_NULL, 0);
             for (size_t p0 = 0; p0 < n; p0 += (size_t)1 << 16) {
                 const size_t p1 = std::min(n, p0 + ((size_t)1 << 16));
@@ -692,24 +702,19 @@ bool ParallelGunzip::Impl::segment()
                     uint16_t any = 0;
                     for (int k = 0; k < 64; ++k) { any |= src[i + k]; dst[i + k] = (uint8_t)src[i + k]; }
                     if (any >= 256) {
+                        uint16_t inval = 0;
                         for (int k = 0; k < 64; ++k) {
                             const uint16_t s = src[i + k];
-                            if (s >= 256) {
-                                const uint32_t p = s - 256u;
-                                if ((uint64_t)(WSIZE - p) > avail) { bad = true; return; }
-                                dst[i + k] = win[p];
-                            }
+                            dst[i + k] = tab[s];
+                            inval |= (uint16_t)((uint16_t)(s - 256u) < n_invalid);
                         }
+                        if (inval) { bad = true; return; }
                     }
                 }
                 for (; i < p1; ++i) {
                     const uint16_t s = src[i];
-                    if (s < 256) dst[i] = (uint8_t)s;
-                    else {
-                        const uint32_t p = s - 256u;
-                        if ((uint64_t)(WSIZE - p) > avail) { bad = true; return; }
-                        dst[i] = win[p];
-                    }
+                    if ((uint16_t)(s - 256u) < n_invalid) { bad = true; return; }
+                    dst[i] = tab[s];
                 }
                 c32 = crc32(c32, dst + p0, (uInt)(p1 - p0));
             }
