@@ -698,18 +698,30 @@ bool ParallelGunzip::Impl::segment()
             for (size_t p0 = 0; p0 < n; p0 += (size_t)1 << 16) {
                 const size_t p1 = std::min(n, p0 + ((size_t)1 << 16));
                 size_t i = p0;
+                bool markers = true;            // the previous block held one: skip the narrowing attempt
                 for (; i + 64 <= p1; i += 64) {
-                    uint16_t any = 0;
-                    for (int k = 0; k < 64; ++k) { any |= src[i + k]; dst[i + k] = (uint8_t)src[i + k]; }
-                    if (any >= 256) {
-                        uint16_t inval = 0;
+                    if (!markers) {
+                        uint16_t any = 0;
+                        for (int k = 0; k < 64; ++k) { any |= src[i + k]; dst[i + k] = (uint8_t)src[i + k]; }
+                        if (any < 256) continue;
+                    }
+                    uint16_t inval = 0, any = 0;
+                    if (n_invalid) {
                         for (int k = 0; k < 64; ++k) {
                             const uint16_t s = src[i + k];
                             dst[i + k] = tab[s];
+                            any |= s;
                             inval |= (uint16_t)((uint16_t)(s - 256u) < n_invalid);
                         }
-                        if (inval) { bad = true; return; }
+                    } else {
+                        for (int k = 0; k < 64; ++k) {
+                            const uint16_t s = src[i + k];
+                            dst[i + k] = tab[s];
+                            any |= s;
+                        }
                     }
+                    if (inval) { bad = true; return; }
+                    markers = any >= 256;
                 }
                 for (; i < p1; ++i) {
                     const uint16_t s = src[i];
