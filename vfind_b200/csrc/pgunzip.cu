@@ -311,11 +311,17 @@ int huffman_block_t(Bits &bb, const Tables &T, OutBuf *out, uint64_t *n_virtual,
             }
         }
         if (WRITE) {
-            if (n + len > cap) { out->n = n; out->need(len); base = out->p; cap = out->cap; }
+            if (n + len + 16 > cap) { out->n = n; out->need(len + 16); base = out->p; cap = out->cap; }
             uint16_t *o = base + n;
             if (dist <= n) {
                 const uint16_t *f = o - dist;
-                if (dist >= len) memcpy(o, f, (size_t)len * 2);
+                if (dist >= 16) {
+                    // fixed 16-symbol pieces (two vector moves each, no call): a piece never overlaps its own source,
+                    // pieces are written in order, and the up to 15 symbols written past the match are overwritten by
+                    // what follows (the buffer keeps 16 symbols of slack).  Most matches in read text are a few bases.
+                    uint32_t done = 0;
+                    do { memcpy(o + done, f + done, 32); done += 16; } while (done < len);
+                } else if (dist >= len) memcpy(o, f, (size_t)len * 2);
                 else for (uint32_t i = 0; i < len; ++i) o[i] = f[i];
             } else {
                 for (uint32_t i = 0; i < len; ++i) {
