@@ -7,13 +7,18 @@
 // when there is no exact hit (the DP kernel may fill it in later).  Reads that still need an
 // alignment (`aligner?.align`, :155) are appended to the prefix / suffix worklists here.
 //
-// Fast kernel (7 <= A <= 64): HBM-bound by design.  A half-warp owns a read; each lane pulls
-// 16-byte aligned chunks of the text with one LDG.128 and tests only every s-th aligned
-// 32-bit word (s = 4, 2 or 1 words, chosen so that every occurrence of the shorter adapter
-// fully contains a sampled word).  A sampled word is looked up in a 256-slot shared-memory
-// hash of the adapters' 4-mers; a hit names the adapter offsets it can sit at, and each
-// candidate start is verified against the adapter pre-shifted to the text's word alignment.
-// ~1 instruction per byte per lane on the common (miss) path.
+// Three kernels, chosen by launch_scan():
+//  * k1_scan_tile (adapters of 15..64 nt whose sampled 8-byte keys are distinct -- the usual case): the text
+//    range of a warp's 32 reads is staged in shared memory by one TMA bulk copy, one lane walks one read and
+//    looks up an 8-byte key every 8 (16) bytes in a 512-slot perfect hash; candidates are verified after the
+//    walk.  HBM-bound by design: every line of the text is read once.  See the comment above the kernel.
+//  * k1_scan_fast (7 <= A <= 64 otherwise: short or repetitive adapters): eight lanes own a read; each lane
+//    pulls 16-byte aligned chunks of the text with one LDG.128 and tests only every s-th aligned 32-bit word
+//    (s = 4, 2 or 1 words, chosen so that every occurrence of the shorter adapter fully contains a sampled
+//    word) -- or 8-byte keys -- in a shared-memory hash of the adapters' k-mers; a hit names the adapter
+//    offsets it can sit at, and each candidate start is verified against the adapter pre-shifted to the
+//    text's word alignment.
+//  * k1_scan_general (any adapter length, including 0 and > 64): one warp per read, byte-wise, ballot.
 #include "vfb_internal.cuh"
 
 #include <stdlib.h>
