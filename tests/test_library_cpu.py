@@ -162,3 +162,38 @@ def test_host_packer_round_trip(lib):
     # too many verbatim groups for the caller's budget: the block is to travel as it is
     rawmap[:] = 0
     assert lib.vfb_pack_groups(text.ctypes.data, n_groups, codes.ctypes.data, rawmap.ctypes.data, raw.ctypes.data, 10) == ctypes.c_size_t(-1).value
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_host_packer_arbitrary_bytes(lib, seed):
+    """Any byte string survives pack -> unpack: runs of random bytes (nothing packable), runs of bases, group
+    boundaries inside runs, and a budget of verbatim groups that is hit exactly."""
+    rng = np.random.default_rng(seed)
+    parts = []
+    for _ in range(60):
+        n = int(rng.integers(1, 400))
+        if rng.random() < 0.5:
+            parts.append(rng.integers(0, 256, size=n, dtype=np.uint8))
+        else:
+            parts.append(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=n))
+    text = np.concatenate(parts)
+    n_groups = len(text) // 32
+    text = np.ascontiguousarray(text[:32 * n_groups])
+    lib.vfb_pack_groups.restype = ctypes.c_size_t
+    lib.vfb_pack_groups.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+    lib.vfb_unpack_groups.restype = None
+    lib.vfb_unpack_groups.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    codes = np.zeros(n_groups, dtype=np.uint64)
+    rawmap = np.zeros((n_groups + 31) // 32, dtype=np.uint32)
+    raw = np.zeros(32 * n_groups, dtype=np.uint8)
+    n_raw = lib.vfb_pack_groups(text.ctypes.data, n_groups, codes.ctypes.data, rawmap.ctypes.data, raw.ctypes.data, n_groups)
+    is_acgt = np.isin(text, np.frombuffer(b"ACGT", dtype=np.uint8)).reshape(n_groups, 32).all(axis=1)
+    assert n_raw == int((~is_acgt).sum()) and 0 < n_raw < n_groups
+    back = np.zeros_like(text)
+    lib.vfb_unpack_groups(codes.ctypes.data, rawmap.ctypes.data, raw.ctypes.data, n_groups, back.ctypes.data)
+    assert (back == text).all()
+    # a budget of exactly n_raw verbatim groups is enough, one fewer is not
+    rawmap[:] = 0
+    assert lib.vfb_pack_groups(text.ctypes.data, n_groups, codes.ctypes.data, rawmap.ctypes.data, raw.ctypes.data, n_raw) == n_raw
+    rawmap[:] = 0
+    assert lib.vfb_pack_groups(text.ctypes.data, n_groups, codes.ctypes.data, rawmap.ctypes.data, raw.ctypes.data, n_raw - 1) == ctypes.c_size_t(-1).value
