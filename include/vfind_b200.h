@@ -55,7 +55,8 @@ typedef struct vfb_params {
     uint32_t n_threads;               /* :228 host ingest threads (inflate/parse)           */
     uint64_t queue_len;               /* :229 batches in flight                             */
     int32_t skip_translation;         /* :230 */
-    int32_t show_progress;            /* :231 accepted, ignored (the reference's spinner is never ticked) */
+    int32_t show_progress;            /* :231 stored; the reference's spinner is never ticked — progress is
+                                         reported through vfb_set_progress                                */
     /* ---- additions ---- */
     int32_t device;                   /* CUDA ordinal; -1 = current device                  */
     int32_t diagnostics;              /* keep per-read diagnostics of the last batch        */
@@ -171,12 +172,16 @@ int vfb_set_progress(vfb_ctx *ctx, vfb_progress_fn fn, void *user);
 
 /* The per-read hot loop (worker + reducer closures, src/lib.rs:275-306) over a batch of
  * reads held in HOST memory: host->device copies happen inside.  `text`/`spans` may be
- * pageable or pinned (pinned is copied directly).  Asynchronous: returns once the batch
- * is staged; vfb_sync / vfb_finish wait. */
+ * pageable or pinned.  Asynchronous: pageable input is staged before the call returns; PINNED input is
+ * copied straight from the caller's buffer by the copy engine, so it must stay unmodified until vfb_sync /
+ * vfb_finish (or until two further submits have returned: two batches are in flight at most).
+ * A span is text[off .. off+len) and must lie inside the buffer (VFB_ERR_ARG otherwise); spans may overlap or
+ * repeat. */
 int vfb_submit_host(vfb_ctx *ctx, const uint8_t *text, uint64_t text_bytes,
                     const vfb_span *spans, uint64_t n_reads);
 
-/* Same, reads already resident in device memory (any size: split internally). */
+/* Same, reads already resident in device memory (any size: split internally).  The spans are validated on the
+ * device (one small kernel and an 16-byte read-back per batch). */
 int vfb_submit_device(vfb_ctx *ctx, const uint8_t *d_text, uint64_t text_bytes,
                       const vfb_span *d_spans, uint64_t n_reads);
 
@@ -224,10 +229,44 @@ int vfb_get_stats(vfb_ctx *ctx, vfb_stats *out);
  * last submit was a single batch).  Parity tests compare these with the oracle. */
 int vfb_get_diag(vfb_ctx *ctx, vfb_read_diag *out, uint64_t n_reads);
 
-/* ---- multi-GPU merge (no reference equivalent) ----
- * Keys are owned by rank = owner(hash(key)) in [0, n_parts).  Export the local table as
- * n_parts self-describing chunks in device memory, exchange them with any transport
- * (NCCL all-to-all in vfind_b200/distributed.py), then absorb the received chunks. */
+/* ---- multi-GPU (no reference equivalent) ----
+ * Reads shard across devices with no data-path collective; the only exchange is the final merge of the per-device
+ * tables.  Keys are owned by part = owner(hash(key)) in [0, n_parts).
+ *
+ * (1) One process, several devices: a vfb_multi is one context per device behind one handle.  vfb_multi_run_file
+ * deals the file's block-gzip segments (or inflated chunks) round robin to the devices; vfb_multi_finish merges
+ * the tables over peer copies (NVLink) — every device keeps the keys it owns and receives the others' counts for
+ * them — and returns ONE table, each device writing its partition into its piece of the host columns.  This is what
+ * find_variants(path, ..., devices=[...]) calls.  devices = NULL / n_devices = 0 means all visible devices.
+ * vfb_multi_ctx gives the per-device contexts for vfb_submit_host / vfb_submit_device. */
+typedef struct vfb_multi vfb_multi;
+int vfb_device_count(void);            /* visible CUDA devices (0 without a driver) */
+int vfb_multi_create(const vfb_params *p, const int32_t *devices, uint32_t n_devices, vfb_multi **out);
+int vfb_multi_destroy(vfb_multi *m);
+uint32_t vfb_multi_devices(const vfb_multi *m);
+vfb_ctx *vfb_multi_ctx(vfb_multi *m, uint32_t i);
+int vfb_multi_run_file(vfb_multi *m, const char *path, uint32_t flags, uint64_t *n_reads);
+int vfb_multi_set_progress(vfb_multi *m, vfb_progress_fn fn, void *user);
+int vfb_multi_sync(vfb_multi *m);
+int vfb_multi_reset(vfb_multi *m);
+int vfb_multi_merge(vfb_multi *m);      /* afterwards context i holds exactly the keys it owns, with global counts */
+int vfb_multi_finish(vfb_multi *m, vfb_table *out);          /* merge + export; columns owned by m            */
+int vfb_multi_finish_arrow(vfb_multi *m, vfb_arrow_array *out_array, vfb_arrow_schema *out_schema);
+int vfb_multi_get_stats(vfb_multi *m, vfb_stats *out);       /* summed over the devices                       */
+
+/* (2) One process per device (torchrun, MPI): the same keep-your-own-keys merge over NCCL send/recv, queued on the
+ * context's compute stream, one host synchronisation.  libnccl.so.2 is loaded at run time (VFB_NCCL_LIB names
+ * another path); the communicator comes from a 128-byte id made on one rank and carried to the others by the
+ * caller's control plane.  `comm` is an ncclComm_t (vfb_nccl_comm_init, or the caller's own). */
+int vfb_nccl_available(void);
+int vfb_nccl_unique_id(uint8_t *id128);
+int vfb_nccl_comm_init(const uint8_t *id128, uint32_t n_ranks, uint32_t rank, int device, void **comm_out);
+int vfb_nccl_comm_destroy(void *comm);
+int vfb_merge_nccl(vfb_ctx *ctx, void *comm, uint32_t rank, uint32_t n_ranks);
+
+/* (3) Any other transport: export the local table as n_parts self-describing chunks in device memory (every row,
+ * the rank's own included), exchange them, clear, absorb the received chunks (the round-1 interface; the gloo
+ * tests drive it). */
 int vfb_table_partition_sizes(vfb_ctx *ctx, uint32_t n_parts, uint64_t *chunk_bytes /* n_parts */);
 int vfb_table_partition_fill(vfb_ctx *ctx, uint32_t n_parts, uint8_t *d_buf,
                              const uint64_t *chunk_offsets /* n_parts */);
@@ -283,6 +322,9 @@ int vfb_host_free(void *p);
  * because page-locking costs more than a small run; this frees the cache (VFB_PINNED_POOL_MB caps it,
  * default 1024). */
 int vfb_pinned_pool_trim(void);
+/* Device buffers are cached the same way (cudaMalloc / cudaFree cost milliseconds apiece; VFB_DEVICE_POOL_MB caps
+ * the cache per device, default 8192). */
+int vfb_device_pool_trim(void);
 
 #ifdef __cplusplus
 }

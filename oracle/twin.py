@@ -72,11 +72,15 @@ def sg_stats(adapter: bytes, read: bytes, match=3, mismatch=-2, gap_open=5, gap_
             else:
                 H[i][j] = E[i][j] if e >= f else F[i][j]
     score, length, ei, ej = NEG, 0, A, 0
+    if end_rule == 3:               # last-column cells of rows 1..A-1 are candidates before the last row
+        for i in range(1, A):
+            if H[i][L][0] > score:
+                score, length, ei, ej = H[i][L][0], H[i][L][1], i, L
     for j in range(1, L + 1):
         s = H[A][j][0]
         if s > score or (end_rule == 1 and s >= score):
             score, length, ei, ej = s, H[A][j][1], A, j
-    if end_rule != 2:
+    if end_rule not in (2, 3):
         cb, ci = NEG, 0
         for i in range(1, A + 1):
             if H[i][L][0] > cb:

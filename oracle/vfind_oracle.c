@@ -152,11 +152,18 @@ int vfo_sg_stats(const uint8_t *adapter, int A, const uint8_t *read, int L,
 
     /* end-cell choice (sg: both s1 end and s2 end free) */
     int score = NEG_INF, length = 0, ei = A, ej = 0;
+    if (rules->end_rule == 3) {
+        /* candidate order "column inside the row loop": the last-column cells of rows 1..A-1 are seen first
+           (strict >), the last row afterwards (strict >, the corner included), so a last-column cell that ties
+           the best last-row cell wins */
+        for (int i = 1; i < A; ++i)
+            if (colH[i] > score) { score = colH[i]; length = colHL[i]; ei = i; ej = L; }
+    }
     for (int j = 1; j <= L; ++j) {
         int better = rules->end_rule == 1 ? (H[j] >= score) : (H[j] > score);
         if (better) { score = H[j]; length = HL[j]; ei = A; ej = j; }
     }
-    if (rules->end_rule != 2) {
+    if (rules->end_rule != 2 && rules->end_rule != 3) {
         int cbest = NEG_INF, ci = 0;
         for (int i = 1; i <= A; ++i)
             if (colH[i] > cbest) { cbest = colH[i]; ci = i; }

@@ -68,7 +68,8 @@ def mutate(rng, ad, max_edits=3, alphabet=b"ACGT"):
 
 
 def make_reads(rng, pre, suf, n, var_lens=(21, 21, 24, 22, 30), lead=(0, 6), alphabet=b"ACGT", lib=24):
-    variants = [bytes(rng.choice(b"ACGT") for _ in range(rng.choice(var_lens))) for _ in range(lib)]
+    # (regions are drawn from `alphabet` too: lower case, U, N and other bytes reach the translate kernel's tables)
+    variants = [bytes(rng.choice(alphabet) for _ in range(rng.choice(var_lens))) for _ in range(lib)]
     seqs = []
     for _ in range(n):
         a = pre if rng.random() < 0.5 else mutate(rng, pre, alphabet=alphabet)
@@ -184,6 +185,44 @@ def test_wildcards_case_and_u():
         otable, odiag, _ = oracle_run(seqs, (PREFIX, SUFFIX), skip_translation=skip)
         assert_diag_equal(diag, odiag)
         assert table == otable
+
+
+TRIPLET_ALPHABET = b"ACGTUacgtuN-"
+
+
+@pytest.mark.parametrize("skip", [False, True])
+@pytest.mark.parametrize("windowed", [False, True])
+def test_translate_all_triplets(skip, windowed):
+    """Every triplet over the 10 accepted letters x 3 positions of ASCII_TO_INDEX (src/lib.rs:86-95) plus 'N', '-'
+    and a non-ASCII byte reaches k3_keys_tile's three premultiplied LUTs and the codon table (src/lib.rs:16-44,
+    :52-77): once as a one-codon region, and in 7-codon regions at every codon position; with skip_translation
+    the raw regions (valid and invalid UTF-8) are the keys (src/lib.rs:294-297)."""
+    letters = list(TRIPLET_ALPHABET) + [0xC3]
+    triplets = [bytes((a, b, c)) for a in letters for b in letters for c in letters]
+    assert len(triplets) == 13 ** 3
+    rng = random.Random(17)
+    seqs = [PREFIX + t + SUFFIX for t in triplets]
+    order = triplets[:]
+    for rot in range(7):                       # every triplet at each of the 7 codon positions of a region
+        rng.shuffle(order)
+        for i in range(0, len(order) - 6, 7):
+            grp = order[i:i + 7]
+            seqs.append(PREFIX + b"".join(grp[rot:] + grp[:rot]) + SUFFIX)
+    seqs += [PREFIX + t + b"\xa9" + b"ACG" + SUFFIX for t in triplets[:300]]     # 7-byte regions: partial codon / UTF-8 pairs
+    if windowed:
+        text, off, ln = oracle.pack_reads(seqs)
+        with api.Context((PREFIX, SUFFIX), skip_translation=skip) as ctx:
+            ctx.submit_host(text, spans_of(off, ln))
+            table = ctx.finish_dict()
+            assert ctx.stats()["dp_kernel_kind"] == 3
+    else:
+        table, _, _ = gpu_run(seqs, (PREFIX, SUFFIX), skip_translation=skip)
+    otable, _, _ = oracle_run(seqs, (PREFIX, SUFFIX), skip_translation=skip)
+    assert table == otable
+    if not skip:
+        # the oracle's own table is the reference's AA_TABLE_CANONICAL (pinned by tests/golden): spot checks
+        assert otable[b"M"] >= 1 and otable[b"*"] >= 3 and b"X" in otable
+        assert sum(otable.values()) >= 13 ** 3
 
 
 def test_adapter_with_wildcard_bases():

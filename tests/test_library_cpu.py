@@ -126,74 +126,3 @@ def test_hash_reference_properties(lib):
     rows = ctypes.c_uint64(0)
     buf = np.zeros(64, dtype=np.uint8)
     assert lib.vfb_chunk_rows(buf.ctypes.data, 64, ctypes.byref(rows)) == api.VFB_ERR_FORMAT
-
-
-def test_host_packer_round_trip(lib):
-    """The host half of the packed host->device path (hostpack_cpu.cpp): 32-byte groups of upper-case
-    ACGT become 2-bit codes, every other group stays verbatim, and the expansion restores the bytes."""
-    rng = np.random.default_rng(5)
-    n_groups = 5000
-    text = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=32 * n_groups)
-    odd = np.frombuffer(b"NacgtU\n@+F#0\x00\xff", dtype=np.uint8)
-    for g in rng.choice(n_groups, size=400, replace=False):          # one odd byte in 400 groups
-        text[32 * g + rng.integers(32)] = rng.choice(odd)
-    text[32 * 100:32 * 140] = ord("N")                                # a run of verbatim groups
-    text = np.ascontiguousarray(text)
-    words = (n_groups + 31) // 32
-    codes = np.zeros(n_groups, dtype=np.uint64)
-    rawmap = np.zeros(words, dtype=np.uint32)
-    raw = np.zeros(32 * n_groups, dtype=np.uint8)
-    lib.vfb_pack_groups.restype = ctypes.c_size_t
-    lib.vfb_pack_groups.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
-    lib.vfb_unpack_groups.restype = None
-    lib.vfb_unpack_groups.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
-    n_raw = lib.vfb_pack_groups(text.ctypes.data, n_groups, codes.ctypes.data, rawmap.ctypes.data, raw.ctypes.data, n_groups)
-    is_acgt = np.isin(text, np.frombuffer(b"ACGT", dtype=np.uint8)).reshape(n_groups, 32).all(axis=1)
-    assert n_raw == int((~is_acgt).sum())
-    bits = np.unpackbits(rawmap.view(np.uint8), bitorder="little")[:n_groups].astype(bool)
-    assert (bits == ~is_acgt).all()
-    # code of base k of a packed group sits in bits 2k..2k+1: A 0, C 1, T 2, G 3
-    g0 = int(np.nonzero(is_acgt)[0][0])
-    want = sum(int(b"ACTG".index(bytes([c]))) << (2 * k) for k, c in enumerate(text[32 * g0:32 * g0 + 32]))
-    assert int(codes[g0]) == want
-    back = np.zeros_like(text)
-    lib.vfb_unpack_groups(codes.ctypes.data, rawmap.ctypes.data, raw.ctypes.data, n_groups, back.ctypes.data)
-    assert (back == text).all()
-    # too many verbatim groups for the caller's budget: the block is to travel as it is
-    rawmap[:] = 0
-    assert lib.vfb_pack_groups(text.ctypes.data, n_groups, codes.ctypes.data, rawmap.ctypes.data, raw.ctypes.data, 10) == ctypes.c_size_t(-1).value
-
-
-@pytest.mark.parametrize("seed", [0, 1, 2])
-def test_host_packer_arbitrary_bytes(lib, seed):
-    """Any byte string survives pack -> unpack: runs of random bytes (nothing packable), runs of bases, group
-    boundaries inside runs, and a budget of verbatim groups that is hit exactly."""
-    rng = np.random.default_rng(seed)
-    parts = []
-    for _ in range(60):
-        n = int(rng.integers(1, 400))
-        if rng.random() < 0.5:
-            parts.append(rng.integers(0, 256, size=n, dtype=np.uint8))
-        else:
-            parts.append(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=n))
-    text = np.concatenate(parts)
-    n_groups = len(text) // 32
-    text = np.ascontiguousarray(text[:32 * n_groups])
-    lib.vfb_pack_groups.restype = ctypes.c_size_t
-    lib.vfb_pack_groups.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
-    lib.vfb_unpack_groups.restype = None
-    lib.vfb_unpack_groups.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
-    codes = np.zeros(n_groups, dtype=np.uint64)
-    rawmap = np.zeros((n_groups + 31) // 32, dtype=np.uint32)
-    raw = np.zeros(32 * n_groups, dtype=np.uint8)
-    n_raw = lib.vfb_pack_groups(text.ctypes.data, n_groups, codes.ctypes.data, rawmap.ctypes.data, raw.ctypes.data, n_groups)
-    is_acgt = np.isin(text, np.frombuffer(b"ACGT", dtype=np.uint8)).reshape(n_groups, 32).all(axis=1)
-    assert n_raw == int((~is_acgt).sum()) and 0 < n_raw < n_groups
-    back = np.zeros_like(text)
-    lib.vfb_unpack_groups(codes.ctypes.data, rawmap.ctypes.data, raw.ctypes.data, n_groups, back.ctypes.data)
-    assert (back == text).all()
-    # a budget of exactly n_raw verbatim groups is enough, one fewer is not
-    rawmap[:] = 0
-    assert lib.vfb_pack_groups(text.ctypes.data, n_groups, codes.ctypes.data, rawmap.ctypes.data, raw.ctypes.data, n_raw) == n_raw
-    rawmap[:] = 0
-    assert lib.vfb_pack_groups(text.ctypes.data, n_groups, codes.ctypes.data, rawmap.ctypes.data, raw.ctypes.data, n_raw - 1) == ctypes.c_size_t(-1).value

@@ -184,6 +184,50 @@ def test_kat_end_cell_tie():
     assert oracle.sg_stats(a, r, rules=oracle.DpRules(end_rule=1))[:2] == (31, 13)  # rightmost
 
 
+def test_kat_end_rule_column_first():
+    # end_rule 3: a last-column cell of a row < A that TIES the best last-row cell wins.
+    # Here the last row's best cell (12, 10) and the last-column cell (11, 11) both score 15 with lengths 10 / 11.
+    a, r = b"CGACTAACGGGG", b"ACTAGCACGGT"
+    assert oracle.sg_stats(a, r) == (15, 10, 12, 10)                                     # row first (assumed)
+    assert oracle.sg_stats(a, r, rules=oracle.DpRules(end_rule=3)) == (15, 11, 11, 11)   # column first
+    assert twin.sg_stats(a, r, end_rule=3) == (15, 11, 11, 11)
+
+
+def test_end_rule_sensitivity_count():
+    """How often would the two candidate end-cell orders (0 = row first, column only if strictly better or the corner;
+    3 = column rows 1..A-1 first) give find_variants a different boundary?  Counted over accepted alignments of
+    C3-like reads at the default scoring and at threshold 0.6 (parity unpinned without parasail)."""
+    rng = random.Random(2024)
+    diff = {0.75: 0, 0.6: 0}
+    accepted = {0.75: 0, 0.6: 0}
+    for it in range(3000):
+        inst = bytearray(PREFIX)
+        for _ in range(rng.randrange(1, 4)):
+            k = rng.randrange(len(inst))
+            op = rng.randrange(3)
+            if op == 0:
+                inst[k] = rng.choice(b"ACGT")
+            elif op == 1:
+                del inst[k]
+            else:
+                inst.insert(k, rng.choice(b"ACGT"))
+        # suffix-side geometry too: the adapter instance at the very end of the read, possibly cut short
+        tail_cut = rng.randrange(0, 4)
+        body = bytes(rng.choice(b"ACGT") for _ in range(rng.randrange(20, 60)))
+        read = body + bytes(inst)[:len(inst) - tail_cut] if rng.random() < 0.5 else bytes(inst) + body
+        s0, l0 = oracle.sg_stats(PREFIX, read)[:2]
+        s3, l3 = oracle.sg_stats(PREFIX, read, rules=oracle.DpRules(end_rule=3))[:2]
+        assert s0 == s3
+        for thr in (0.75, 0.6):
+            if s0 > thr * 3 * len(PREFIX):
+                accepted[thr] += 1
+                diff[thr] += l0 != l3
+    # the switch exists so that one run against real parasail can settle it; the counts document the exposure
+    print("end_rule 0 vs 3: boundary differs in %d / %d accepted alignments at 0.75, %d / %d at 0.6"
+          % (diff[0.75], accepted[0.75], diff[0.6], accepted[0.6]))
+    assert accepted[0.75] > 500 and diff[0.75] <= accepted[0.75]
+
+
 def test_kat_h_priority():
     a, r = b"CTTATATGCGAG", b"CTATATTGCGAGGCAACAGCAAGGAGA"
     assert oracle.sg_stats(a, r)[:2] == (23, 13)                                    # diag > F > E (assumed)
@@ -237,7 +281,7 @@ def test_c_oracle_vs_python_twin_random():
     pool = [(3, -2, 5, 2), (1, -1, 0, 0), (2, -3, 4, 1), (5, -4, 10, 1), (1, -1, 1, 1), (2, -1, 3, 0)]
     for it in range(1500):
         a, r, (m, x, o, e) = _rand_case(rng, pool)
-        for rules in ({}, {"gap_tie_open": 1}, {"h_priority": 1}, {"end_rule": 1}, {"end_rule": 2},
+        for rules in ({}, {"gap_tie_open": 1}, {"h_priority": 1}, {"end_rule": 1}, {"end_rule": 2}, {"end_rule": 3},
                       {"wildcard_zero": 0}):
             base = dict(gap_tie_open=0, h_priority=0, end_rule=0, wildcard_zero=1)
             base.update(rules)

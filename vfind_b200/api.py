@@ -142,6 +142,26 @@ def load_library():
     L.vfb_run_file_ex.argtypes = [vp, C.c_char_p, u32, C.POINTER(u64)]
     L.vfb_set_progress.argtypes = [vp, vp, vp]
     L.vfb_pinned_pool_trim.argtypes = []
+    L.vfb_device_pool_trim.argtypes = []
+    L.vfb_multi_create.argtypes = [C.POINTER(Params), C.POINTER(C.c_int32), u32, C.POINTER(vp)]
+    L.vfb_multi_destroy.argtypes = [vp]
+    L.vfb_multi_devices.argtypes = [vp]
+    L.vfb_multi_devices.restype = u32
+    L.vfb_multi_ctx.argtypes = [vp, u32]
+    L.vfb_multi_ctx.restype = vp
+    L.vfb_multi_run_file.argtypes = [vp, C.c_char_p, u32, C.POINTER(u64)]
+    L.vfb_multi_set_progress.argtypes = [vp, vp, vp]
+    L.vfb_multi_sync.argtypes = [vp]
+    L.vfb_multi_reset.argtypes = [vp]
+    L.vfb_multi_merge.argtypes = [vp]
+    L.vfb_multi_finish.argtypes = [vp, C.POINTER(Table)]
+    L.vfb_multi_finish_arrow.argtypes = [vp, vp, vp]
+    L.vfb_multi_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.vfb_nccl_available.restype = i32
+    L.vfb_nccl_unique_id.argtypes = [vp]
+    L.vfb_nccl_comm_init.argtypes = [vp, u32, u32, i32, C.POINTER(vp)]
+    L.vfb_nccl_comm_destroy.argtypes = [vp]
+    L.vfb_merge_nccl.argtypes = [vp, vp, u32, u32]
     _lib = L
     return L
 
@@ -176,6 +196,36 @@ def _as_bytes(s, what):
     raise TypeError("%s must be str" % what)
 
 
+def _make_params(L, adapters, match_score, mismatch_score, gap_open_penalty, gap_extend_penalty,
+                 accept_prefix_alignment, accept_suffix_alignment, n_threads, queue_len, skip_translation,
+                 show_progress, device, diagnostics, batch_reads, batch_bytes, table_capacity_hint,
+                 debug_hash_bits, force_generic_dp, dp_compute_all, force_general_scan, dp_mode, debug_win_cap):
+    p = Params()
+    L.vfb_default_params(C.byref(p))
+    pre = _as_bytes(adapters[0], "adapters[0]")
+    suf = _as_bytes(adapters[1], "adapters[1]")
+    p.prefix, p.prefix_len = pre, len(pre)
+    p.suffix, p.suffix_len = suf, len(suf)
+    p.match_score, p.mismatch_score = match_score, mismatch_score
+    p.gap_open_penalty, p.gap_extend_penalty = gap_open_penalty, gap_extend_penalty
+    p.accept_prefix_alignment = accept_prefix_alignment
+    p.accept_suffix_alignment = accept_suffix_alignment
+    p.n_threads, p.queue_len = n_threads, queue_len
+    p.skip_translation = 1 if skip_translation else 0
+    p.show_progress = 1 if show_progress else 0
+    p.device = -1 if device is None else int(device)
+    p.diagnostics = 1 if diagnostics else 0
+    p.batch_reads, p.batch_bytes = int(batch_reads), int(batch_bytes)
+    p.table_capacity_hint = int(table_capacity_hint)
+    p.debug_hash_bits = int(debug_hash_bits)
+    p.force_generic_dp = 1 if force_generic_dp else 0
+    p.dp_compute_all = 1 if dp_compute_all else 0
+    p.force_general_scan = 1 if force_general_scan else 0
+    p.dp_mode = int(dp_mode)
+    p.debug_win_cap = int(debug_win_cap)
+    return p, pre, suf          # the byte strings must outlive the call that reads p
+
+
 class Context:
     """One configured variant-recovery pipeline on one GPU (vfb_ctx)."""
 
@@ -188,35 +238,27 @@ class Context:
         L = load_library()
         self._lib = L
         self._h = C.c_void_p()
-        p = Params()
-        L.vfb_default_params(C.byref(p))
-        self._pre = _as_bytes(adapters[0], "adapters[0]")
-        self._suf = _as_bytes(adapters[1], "adapters[1]")
-        p.prefix, p.prefix_len = self._pre, len(self._pre)
-        p.suffix, p.suffix_len = self._suf, len(self._suf)
-        p.match_score, p.mismatch_score = match_score, mismatch_score
-        p.gap_open_penalty, p.gap_extend_penalty = gap_open_penalty, gap_extend_penalty
-        p.accept_prefix_alignment = accept_prefix_alignment
-        p.accept_suffix_alignment = accept_suffix_alignment
-        p.n_threads, p.queue_len = n_threads, queue_len
-        p.skip_translation = 1 if skip_translation else 0
-        p.show_progress = 1 if show_progress else 0
-        p.device = -1 if device is None else int(device)
-        p.diagnostics = 1 if diagnostics else 0
-        p.batch_reads, p.batch_bytes = int(batch_reads), int(batch_bytes)
-        p.table_capacity_hint = int(table_capacity_hint)
-        p.debug_hash_bits = int(debug_hash_bits)
-        p.force_generic_dp = 1 if force_generic_dp else 0
-        p.dp_compute_all = 1 if dp_compute_all else 0
-        p.force_general_scan = 1 if force_general_scan else 0
-        p.dp_mode = int(dp_mode)
-        p.debug_win_cap = int(debug_win_cap)
+        self._owned = True
+        p, self._pre, self._suf = _make_params(L, adapters, match_score, mismatch_score, gap_open_penalty,
+                                               gap_extend_penalty, accept_prefix_alignment, accept_suffix_alignment,
+                                               n_threads, queue_len, skip_translation, show_progress, device,
+                                               diagnostics, batch_reads, batch_bytes, table_capacity_hint,
+                                               debug_hash_bits, force_generic_dp, dp_compute_all, force_general_scan,
+                                               dp_mode, debug_win_cap)
         _check(L.vfb_create(C.byref(p), C.byref(self._h)))
+
+    @classmethod
+    def _borrowed(cls, lib, handle):
+        """A view of a context owned by a MultiContext (not destroyed on close)."""
+        self = cls.__new__(cls)
+        self._lib, self._h, self._owned = lib, C.c_void_p(handle), False
+        return self
 
     # -- lifetime
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
-            self._lib.vfb_destroy(self._h)
+            if self._owned:
+                self._lib.vfb_destroy(self._h)
             self._h = C.c_void_p()
 
     def __enter__(self):
@@ -295,16 +337,7 @@ class Context:
         finish on this context or its close()."""
         t = Table()
         _check(self._lib.vfb_finish(self._h, C.byref(t)))
-        try:
-            rows, kb = int(t.rows), int(t.key_bytes)
-            offsets = np.ctypeslib.as_array(t.offsets, shape=(rows + 1,))
-            data = np.ctypeslib.as_array(t.data, shape=(kb,)) if kb else np.zeros(0, np.uint8)
-            counts = np.ctypeslib.as_array(t.counts, shape=(rows,)) if rows else np.zeros(0, np.uint64)
-            if copy:
-                offsets, data, counts = offsets.copy(), data.copy(), counts.copy()
-        finally:
-            self._lib.vfb_table_free(C.byref(t))
-        return offsets, data, counts
+        return _table_views(self._lib, t, copy)
 
     def finish_arrow(self):
         """The table as a pyarrow.RecordBatch {sequence: large_string, count: uint64} imported through the
@@ -336,6 +369,131 @@ class Context:
 
     def absorb(self, chunk_ptr: int, chunk_bytes: int):
         _check(self._lib.vfb_table_absorb(self._h, chunk_ptr, chunk_bytes))
+
+    def merge_nccl(self, comm, rank: int, n_ranks: int):
+        """Keep-own-keys merge over NCCL send/recv inside the library (one process per GPU); `comm` from
+        nccl_comm_init.  Afterwards this context holds exactly the keys it owns, with global counts."""
+        _check(self._lib.vfb_merge_nccl(self._h, comm, rank, n_ranks))
+
+
+def _table_views(lib, t, copy):
+    try:
+        rows, kb = int(t.rows), int(t.key_bytes)
+        offsets = np.ctypeslib.as_array(t.offsets, shape=(rows + 1,))
+        data = np.ctypeslib.as_array(t.data, shape=(kb,)) if kb else np.zeros(0, np.uint8)
+        counts = np.ctypeslib.as_array(t.counts, shape=(rows,)) if rows else np.zeros(0, np.uint64)
+        if copy:
+            offsets, data, counts = offsets.copy(), data.copy(), counts.copy()
+    finally:
+        lib.vfb_table_free(C.byref(t))
+    return offsets, data, counts
+
+
+class MultiContext:
+    """One pipeline per GPU behind one handle (vfb_multi): one process drives `devices` (None = all visible).
+    run_file deals the file's segments round robin; finish_* merge the per-device tables over peer copies
+    (NVLink) and return ONE table.  `contexts` are the per-device Context views (submit_host / submit_device)."""
+
+    def __init__(self, adapters, match_score=3, mismatch_score=-2, gap_open_penalty=5,
+                 gap_extend_penalty=2, accept_prefix_alignment=0.75, accept_suffix_alignment=0.75,
+                 n_threads=3, queue_len=2, skip_translation=False, show_progress=True, *,
+                 devices=None, batch_reads=0, batch_bytes=0, table_capacity_hint=0, debug_hash_bits=0, dp_mode=0):
+        L = load_library()
+        self._lib = L
+        self._h = C.c_void_p()
+        p, self._pre, self._suf = _make_params(L, adapters, match_score, mismatch_score, gap_open_penalty,
+                                               gap_extend_penalty, accept_prefix_alignment, accept_suffix_alignment,
+                                               n_threads, queue_len, skip_translation, show_progress, None, False,
+                                               batch_reads, batch_bytes, table_capacity_hint, debug_hash_bits,
+                                               False, False, False, dp_mode, 0)
+        if devices is None:
+            _check(L.vfb_multi_create(C.byref(p), None, 0, C.byref(self._h)))
+        else:
+            devs = [int(d) for d in devices]
+            arr = (C.c_int32 * len(devs))(*devs)
+            if not devs:
+                raise ValueError("devices must not be empty")
+            _check(L.vfb_multi_create(C.byref(p), arr, len(devs), C.byref(self._h)))
+        self.n_devices = int(L.vfb_multi_devices(self._h))
+        self.contexts = [Context._borrowed(L, L.vfb_multi_ctx(self._h, i)) for i in range(self.n_devices)]
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            for c in self.contexts:
+                c.close()
+            self._lib.vfb_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run_file(self, path, allow_text=False) -> int:
+        n = C.c_uint64(0)
+        _check(self._lib.vfb_multi_run_file(self._h, os.fsencode(path), 1 if allow_text else 0, C.byref(n)))
+        return int(n.value)
+
+    def set_progress(self, fn):
+        if fn is None:
+            self._progress_cb = None
+            _check(self._lib.vfb_multi_set_progress(self._h, None, None))
+            return
+        self._progress_cb = PROGRESS_FN(lambda r, d, t, _u: fn(int(r), int(d), int(t)))
+        _check(self._lib.vfb_multi_set_progress(self._h, C.cast(self._progress_cb, C.c_void_p), None))
+
+    def sync(self):
+        _check(self._lib.vfb_multi_sync(self._h))
+
+    def reset(self):
+        _check(self._lib.vfb_multi_reset(self._h))
+
+    def merge(self):
+        _check(self._lib.vfb_multi_merge(self._h))
+
+    def stats(self) -> dict:
+        s = Stats()
+        _check(self._lib.vfb_multi_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def finish_arrays(self, copy=True):
+        t = Table()
+        _check(self._lib.vfb_multi_finish(self._h, C.byref(t)))
+        return _table_views(self._lib, t, copy)
+
+    def finish_dict(self) -> dict:
+        offsets, data, counts = self.finish_arrays()
+        raw = data.tobytes()
+        return {raw[int(offsets[i]):int(offsets[i + 1])]: int(counts[i]) for i in range(len(counts))}
+
+    def finish_arrow(self):
+        import pyarrow as pa
+        arr, sch = ArrowArray(), ArrowSchema()
+        _check(self._lib.vfb_multi_finish_arrow(self._h, C.byref(arr), C.byref(sch)))
+        return pa.RecordBatch._import_from_c(C.addressof(arr), C.addressof(sch))
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _check(load_library().vfb_nccl_unique_id(buf))
+    return buf.raw
+
+
+def nccl_comm_init(unique_id: bytes, n_ranks: int, rank: int, device: int = -1):
+    comm = C.c_void_p()
+    _check(load_library().vfb_nccl_comm_init(unique_id, n_ranks, rank, device, C.byref(comm)))
+    return comm
+
+
+def nccl_comm_destroy(comm):
+    _check(load_library().vfb_nccl_comm_destroy(comm))
 
 
 def batch_to_frame(batch):
@@ -400,7 +558,7 @@ def _bool_arg(v, name):
 def find_variants(fq_path, adapters, match_score=3, mismatch_score=-2, gap_open_penalty=5,
                   gap_extend_penalty=2, accept_prefix_alignment=0.75, accept_suffix_alignment=0.75,
                   n_threads=3, queue_len=2, skip_translation=False, show_progress=True, *,
-                  device=None, batch_reads=0, table_capacity_hint=0, progress=None, allow_text=False):
+                  device=None, devices=None, batch_reads=0, table_capacity_hint=0, progress=None, allow_text=False):
     """Find variable regions flanked by adapters in a gzipped FASTQ dataset.
 
     Drop-in for `vfind.find_variants` (/root/reference/src/lib.rs:168-232): same positional
@@ -410,7 +568,10 @@ def find_variants(fq_path, adapters, match_score=3, mismatch_score=-2, gap_open_
     polars.DataFrame when polars is installed, else a pyarrow.Table.  Row order is
     unspecified (as in the reference, src/lib.rs:312).
 
-    Extra keyword-only arguments: device (CUDA ordinal), batch_reads, table_capacity_hint,
+    Extra keyword-only arguments: device (one CUDA ordinal) or devices (a list of ordinals, or "all": one
+    process drives them all, the file's segments are dealt round robin and the per-GPU tables are merged over
+    NVLink inside the library; default: every visible GPU that gets at least 64 MB of the compressed input —
+    VFB_DEVICES=n caps it), batch_reads, table_capacity_hint,
     progress (callable(records, bytes_done, bytes_total), called about ten times per second),
     allow_text (read a file without the gzip magic as uncompressed FASTQ; the reference panics on it).
     With show_progress (the default) and a terminal on stderr a one-line progress display is shown
@@ -423,13 +584,13 @@ def find_variants(fq_path, adapters, match_score=3, mismatch_score=-2, gap_open_
                         % type(fq_path).__name__)
     return _find_variants([fq_path], adapters, match_score, mismatch_score, gap_open_penalty, gap_extend_penalty,
                           accept_prefix_alignment, accept_suffix_alignment, n_threads, queue_len, skip_translation,
-                          show_progress, device, batch_reads, table_capacity_hint, progress, allow_text)
+                          show_progress, device, devices, batch_reads, table_capacity_hint, progress, allow_text)
 
 
 def find_variants_multi(fq_paths, adapters, match_score=3, mismatch_score=-2, gap_open_penalty=5,
                         gap_extend_penalty=2, accept_prefix_alignment=0.75, accept_suffix_alignment=0.75,
                         n_threads=3, queue_len=2, skip_translation=False, show_progress=True, *,
-                        device=None, batch_reads=0, table_capacity_hint=0, progress=None, allow_text=False):
+                        device=None, devices=None, batch_reads=0, table_capacity_hint=0, progress=None, allow_text=False):
     """find_variants over several FASTQ files (lanes, split runs) counted into ONE table, on one context
     (SURVEY §8(f) next-4).  Same arguments as find_variants; fq_paths is a non-empty sequence of paths."""
     if isinstance(fq_paths, (str, bytes, os.PathLike)) or not hasattr(fq_paths, "__iter__"):
@@ -439,12 +600,12 @@ def find_variants_multi(fq_paths, adapters, match_score=3, mismatch_score=-2, ga
         raise TypeError("argument 'fq_paths': expected a non-empty sequence of str / os.PathLike")
     return _find_variants(paths, adapters, match_score, mismatch_score, gap_open_penalty, gap_extend_penalty,
                           accept_prefix_alignment, accept_suffix_alignment, n_threads, queue_len, skip_translation,
-                          show_progress, device, batch_reads, table_capacity_hint, progress, allow_text)
+                          show_progress, device, devices, batch_reads, table_capacity_hint, progress, allow_text)
 
 
 def _find_variants(paths, adapters, match_score, mismatch_score, gap_open_penalty, gap_extend_penalty,
                    accept_prefix_alignment, accept_suffix_alignment, n_threads, queue_len, skip_translation,
-                   show_progress, device, batch_reads, table_capacity_hint, progress, allow_text):
+                   show_progress, device, devices, batch_reads, table_capacity_hint, progress, allow_text):
     if not isinstance(adapters, (tuple, list)):
         raise TypeError("argument 'adapters': '%s' object cannot be converted to 'PyTuple'"
                         % type(adapters).__name__)
@@ -471,10 +632,18 @@ def _find_variants(paths, adapters, match_score, mismatch_score, gap_open_penalt
     for p in paths:
         with open(p, "rb"):
             pass
-    with Context(adapters, match_score, mismatch_score, gap_open_penalty, gap_extend_penalty,
-                 accept_prefix_alignment, accept_suffix_alignment, n_threads, queue_len,
-                 skip_translation, show_progress, device=device, batch_reads=batch_reads,
-                 table_capacity_hint=table_capacity_hint) as ctx:
+    devs = _pick_devices(device, devices, paths)
+    if len(devs) == 1:
+        ctx = Context(adapters, match_score, mismatch_score, gap_open_penalty, gap_extend_penalty,
+                      accept_prefix_alignment, accept_suffix_alignment, n_threads, queue_len,
+                      skip_translation, show_progress, device=devs[0], batch_reads=batch_reads,
+                      table_capacity_hint=table_capacity_hint)
+    else:
+        ctx = MultiContext(adapters, match_score, mismatch_score, gap_open_penalty, gap_extend_penalty,
+                           accept_prefix_alignment, accept_suffix_alignment, n_threads, queue_len,
+                           skip_translation, show_progress, devices=devs, batch_reads=batch_reads,
+                           table_capacity_hint=table_capacity_hint)
+    with ctx:
         shown = show_progress and progress is None and sys.stderr.isatty()
         if progress is not None:
             ctx.set_progress(progress)
@@ -493,6 +662,36 @@ def _find_variants(paths, adapters, match_score, mismatch_score, gap_open_penalt
                 sys.stderr.write("\r" + " " * 60 + "\r")       # finish_and_clear
                 sys.stderr.flush()
         return batch_to_frame(ctx.finish_arrow())
+
+
+def _visible_devices() -> int:
+    L = load_library()
+    L.vfb_device_count.restype = C.c_int
+    return int(L.vfb_device_count())
+
+
+def _pick_devices(device, devices, paths):
+    """[ordinal or None] for one context, or the list a MultiContext gets."""
+    if device is not None and devices is not None:
+        raise ValueError("give either device or devices, not both")
+    if device is not None:
+        return [int(device)]
+    if devices is not None and not (isinstance(devices, str) and devices == "all"):
+        devs = [int(d) for d in devices]
+        if not devs:
+            raise ValueError("devices must not be empty")
+        return devs
+    n = _visible_devices()
+    if devices is None:
+        # a GPU is worth starting for about 64 MB of compressed input (context creation costs more than that)
+        size = sum(os.path.getsize(p) for p in paths)
+        n = min(n, max(1, size >> 26))
+        cap = os.environ.get("VFB_DEVICES")
+        if cap:
+            n = max(1, min(n, int(cap)))
+    if n <= 1:
+        return [None]
+    return list(range(n))
 
 
 def read_diagnostics(reads, adapters, match_score=3, mismatch_score=-2, gap_open_penalty=5, gap_extend_penalty=2,

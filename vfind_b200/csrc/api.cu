@@ -15,7 +15,7 @@
 
 #include "hash.h"
 #include "synth.h"
-#include "vfb_internal.cuh"
+#include "ctx.cuh"
 
 namespace vfb {
 
@@ -60,41 +60,6 @@ void trace(const char *fmt, ...)
     va_end(ap);
     fputc('\n', stderr);
 }
-
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    int ensure(size_t bytes, bool keep = false, cudaStream_t st = 0)
-    {
-        if (bytes <= cap) return VFB_OK;
-        size_t ncap = bytes + bytes / 4 + 256;
-        void *np = nullptr;
-        if (ncap >= (8u << 20)) trace("cudaMalloc %zu MB (was %zu MB)", ncap >> 20, cap >> 20);
-        cudaError_t e = cudaMalloc(&np, ncap);
-        if (e != cudaSuccess) {
-            set_error("out of device memory allocating " + std::to_string(ncap) + " bytes");
-            cudaGetLastError();
-            return VFB_ERR_NOMEM;
-        }
-        if (p) {
-            if (keep && cap) {
-                VFB_CUDA(cudaMemcpyAsync(np, p, cap, cudaMemcpyDeviceToDevice, st));
-                VFB_CUDA(cudaStreamSynchronize(st));
-            }
-            VFB_CUDA(cudaFree(p));
-        }
-        p = np;
-        cap = ncap;
-        return VFB_OK;
-    }
-    void release()
-    {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
-};
 
 // Process-wide cache of pinned host buffers: page-locking costs about 1 ms per MB, more than a
 // whole small run.  Buffers released by a context / an ingest are kept (up to VFB_PINNED_POOL_MB,
@@ -180,114 +145,110 @@ void pinned_pool_trim()
     for (auto &b : all) cudaFreeHost(b.first);
 }
 
-struct PinBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    int ensure(size_t bytes)
+// Device buffers: one idle list per device.  A buffer fits a request when it is at least as large and at most
+// twice as large (+1 MB): device memory is plentiful, a fresh cudaMalloc is what costs.
+struct DevicePool {
+    std::mutex mu;
+    std::vector<std::vector<std::pair<void *, size_t>>> idle;   // per device
+    std::vector<size_t> bytes;
+};
+static DevicePool &device_pool()
+{
+    static DevicePool *p = new DevicePool;       // never destroyed: the driver may be gone at exit
+    return *p;
+}
+static size_t device_pool_limit()
+{
+    static size_t limit = 0;
+    if (!limit) {
+        const char *e = getenv("VFB_DEVICE_POOL_MB");
+        limit = ((size_t)(e ? strtoull(e, nullptr, 10) : 8192ull) << 20) + 1;
+    }
+    return limit;
+}
+void *device_acquire(int device, size_t want, size_t *cap_out)
+{
+    DevicePool &dp = device_pool();
     {
-        if (bytes <= cap) return VFB_OK;
-        release();
-        p = pinned_acquire(bytes + bytes / 8 + 4096, &cap);
-        if (!p) {
-            cap = 0;
-            set_error("cannot allocate pinned host memory");
-            return VFB_ERR_NOMEM;
+        std::lock_guard<std::mutex> lk(dp.mu);
+        if ((size_t)device < dp.idle.size()) {
+            auto &v = dp.idle[(size_t)device];
+            int best = -1;
+            for (size_t i = 0; i < v.size(); ++i)
+                if (v[i].second >= want && v[i].second <= 2 * want + (1u << 20) &&
+                    (best < 0 || v[i].second < v[(size_t)best].second)) best = (int)i;
+            if (best >= 0) {
+                void *p = v[(size_t)best].first;
+                *cap_out = v[(size_t)best].second;
+                dp.bytes[(size_t)device] -= *cap_out;
+                v.erase(v.begin() + best);
+                return p;
+            }
         }
-        return VFB_OK;
     }
-    void release()
+    void *p = nullptr;
+    if (want >= (8u << 20)) trace("cudaMalloc %zu MB on device %d", want >> 20, device);
+    if (cudaMalloc(&p, want) != cudaSuccess) {
+        cudaGetLastError();
+        device_pool_trim();                     // give the cache back and try once more
+        if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    *cap_out = want;
+    return p;
+}
+void device_release(int device, void *p, size_t cap)
+{
+    if (!p) return;
+    DevicePool &dp = device_pool();
+    const size_t limit = device_pool_limit();
+    std::vector<void *> evict;
+    bool keep = false;
     {
-        pinned_release(p, cap);
-        p = nullptr;
-        cap = 0;
+        std::lock_guard<std::mutex> lk(dp.mu);
+        if (device >= 0 && cap < limit) {
+            if ((size_t)device >= dp.idle.size()) { dp.idle.resize((size_t)device + 1); dp.bytes.resize((size_t)device + 1, 0); }
+            auto &v = dp.idle[(size_t)device];
+            while (dp.bytes[(size_t)device] + cap >= limit && !v.empty()) {     // longest idle first
+                evict.push_back(v.front().first);
+                dp.bytes[(size_t)device] -= v.front().second;
+                v.erase(v.begin());
+            }
+            v.emplace_back(p, cap);
+            dp.bytes[(size_t)device] += cap;
+            keep = true;
+        }
     }
-};
-
-struct Slot {
-    DevBuf d_text, d_spans;
-    PinBuf h_text, h_spans;
-    cudaEvent_t copied = nullptr, computed = nullptr;
-    bool busy = false;
-};
-
-// device counters of one batch
-enum { C_NPRE = 0, C_NSUF, C_FBPRE, C_FBSUF, C_FB2PRE, C_FB2SUF, C_NWINPRE, C_NWINSUF,
-       // work cursors of the filter / window kernels (dynamic distribution), each in a 128-byte line of its own: the
-       // counters above take millions of atomics per launch, a cursor in their line would queue behind them
-       C_WORKPRE = 32, C_WORKPRE2 = 64, C_WORKSUF = 96, C_WORKSUF2 = 128,
-       C_COUNT32 = 160 };
-// 64-bit device counters
-enum { T_CELLS = 0, T_DPPRE, T_DPSUF, T_KEYBYTES, T_CELLSCOMP, T_WINDOWS, T_COUNT64 };
+    if (!evict.empty() || !keep) {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (cur != device && device >= 0) cudaSetDevice(device);
+        for (void *q : evict) cudaFree(q);
+        if (!keep) cudaFree(p);
+        if (cur != device && cur >= 0) cudaSetDevice(cur);
+    }
+}
+void device_pool_trim()
+{
+    DevicePool &dp = device_pool();
+    std::vector<std::vector<std::pair<void *, size_t>>> all;
+    {
+        std::lock_guard<std::mutex> lk(dp.mu);
+        all.swap(dp.idle);
+        dp.bytes.clear();
+    }
+    int cur = -1;
+    cudaGetDevice(&cur);
+    for (size_t d = 0; d < all.size(); ++d) {
+        if (all[d].empty()) continue;
+        cudaSetDevice((int)d);
+        for (auto &b : all[d]) cudaFree(b.first);
+    }
+    if (cur >= 0) cudaSetDevice(cur);
+}
 
 }  // namespace vfb
 
 using namespace vfb;
-
-struct vfb_ctx {
-    vfb_params prm;
-    std::string prefix, suffix;
-    AdapterBytes ad_pre, ad_suf;
-    DpScoring sc;
-    bool align_pre = false, align_suf = false;
-    int min_accept_pre = 0, min_accept_suf = 0;
-    bool packed_pre = false, packed_suf = false;
-    DpLayout lay_pre, lay_suf;
-    uint32_t lcap_pre = 0, lcap_suf = 0;
-    DevBuf d_code_pre, d_code_suf;   // adapter codes for the fallback kernel
-    DevBuf d_generic_scratch;
-    uint32_t generic_threads = 0;
-
-    int device = 0, sm_count = 148;
-    cudaStream_t st_compute = nullptr, st_copy = nullptr;
-    Slot slots[2];
-    HostPacker *packer = nullptr;      // host threads that 2-bit-pack read text for the link (hostpack.cu)
-    bool packer_tried = false;
-    uint64_t packed_blocks = 0;
-    uint64_t batch_seq = 0;
-    uint64_t batch_reads = 0, batch_bytes = 0;
-
-    // per-batch scratch
-    DevBuf d_start, d_end, d_list_a, d_list_b, d_fb_a, d_fb_b, d_c32, d_t64;
-    DevBuf d_keys, d_koff, d_klen, d_khash, d_owner;
-    DevBuf d_wins, d_bestkey, d_cbval, d_fb2;   // windowed DP: window items, per-item results, second fallback list
-    uint32_t win_cap = 0;
-    int win_k_pre = -1, win_k_suf = -1;         // Myers thresholds (-1: the windowed DP does not apply)
-    DevBuf d_aligned_text;     // aligned copy of an unaligned caller buffer (vfb_submit_device)
-    DevBuf d_diag_exact_pre, d_diag_exact_suf, d_diag_score_pre, d_diag_len_pre, d_diag_score_suf, d_diag_len_suf;
-    uint64_t diag_n = 0;
-    bool diag_valid = false;
-
-    // table
-    DevTable tab{};
-    DevBuf t_slots, t_row_hash, t_row_off, t_row_len, t_arena, t_counters, t_row_count;
-    uint64_t ub_rows = 0, ub_arena = 0;   // host-side upper bounds of rows / arena bytes
-
-    // ingest, GPU inflate path: compressed members, member table, text (double buffered), tail
-    DevBuf g_z, g_members, g_text[2], g_tail, g_info;
-    PinBuf g_pin;               // carry staging + tail/info landing zone
-    uint64_t g_seq = 0;
-
-    // ingest: GPU FASTQ parse scratch and the first-malformed-record word
-    DevBuf p_tiles, p_line_end, p_err;      // p_err: u32 chunk-relative + u64 global (at +8)
-    bool p_err_init = false;
-
-    // export: device-side Arrow compaction and pinned host columns
-    DevBuf x_block_sums, x_offsets, x_data;
-    PinBuf h_offsets, h_counts, h_data;
-
-    // merge scratch
-    DevBuf m_part_rows, m_part_keys, m_cursors, m_chunk_off;
-    std::vector<uint64_t> h_part_rows, h_part_keys;
-
-    bool profiling = false;
-    vfb_progress_fn progress_fn = nullptr;
-    void *progress_user = nullptr;
-    std::chrono::steady_clock::time_point progress_last{};
-    bool own_compute_stream = true;
-    std::vector<cudaEvent_t> evpool;   // 12 events per profiled batch, resolved at sync time
-    size_t ev_used = 0;
-    vfb_stats stats{};
-};
 
 // Profiling: events are recorded on the compute stream without blocking; the per-stage
 // times are accumulated when the stream is next synchronised.
@@ -337,6 +298,7 @@ static int bump_launches(vfb_ctx *c, uint64_t before)
     c->stats.kernel_launches += g_launches - before;
     return VFB_OK;
 }
+void bump_launches_for(vfb_ctx *c, uint64_t before) { bump_launches(c, before); }
 
 // ------------------------------------------------------------------------------------ helpers
 static int table_alloc(vfb_ctx *c, uint64_t capacity, uint64_t rows_cap, uint64_t arena_cap)
@@ -538,14 +500,26 @@ int vfb_create(const vfb_params *p, vfb_ctx **out)
     if ((e = cudaGetDeviceProperties(&prop, c->device)) != cudaSuccess)
         return fail(cuda_fail(e, "cudaGetDeviceProperties", __FILE__, __LINE__));
     c->sm_count = prop.multiProcessorCount;
+    // the ingest stream (H2D of compressed members, inflate, parse) outranks the compute stream: the short parse
+    // kernels of the next segment sit on the critical path of the segment chain and must not queue behind K1..K4
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if ((e = cudaStreamCreateWithFlags(&c->st_compute, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking)) != cudaSuccess)
+        (e = cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithPriority(&c->st_ingest, cudaStreamNonBlocking, prio_hi)) != cudaSuccess)
         return fail(cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__));
     for (auto &s : c->slots) {
         if ((e = cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming)) != cudaSuccess ||
             (e = cudaEventCreateWithFlags(&s.computed, cudaEventDisableTiming)) != cudaSuccess)
             return fail(cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__));
     }
+    for (auto &g : c->seg) {
+        if ((e = cudaEventCreateWithFlags(&g.parsed, cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&g.computed, cudaEventDisableTiming)) != cudaSuccess)
+            return fail(cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__));
+    }
+    if ((e = cudaEventCreateWithFlags(&c->m_filled, cudaEventDisableTiming)) != cudaSuccess)
+        return fail(cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__));
 
     // DP setup: packed layout when the scores fit, else the fallback kernel
     const bool force_generic = p->force_generic_dp != 0;
@@ -595,30 +569,34 @@ int vfb_destroy(vfb_ctx *c)
     cudaSetDevice(c->device);
     if (c->st_compute) cudaStreamSynchronize(c->st_compute);
     if (c->st_copy) cudaStreamSynchronize(c->st_copy);
-    hostpack_destroy(c->packer);
-    c->packer = nullptr;
+    if (c->st_ingest) cudaStreamSynchronize(c->st_ingest);
     for (auto &s : c->slots) {
         s.d_text.release(); s.d_spans.release(); s.h_text.release(); s.h_spans.release();
         if (s.copied) cudaEventDestroy(s.copied);
         if (s.computed) cudaEventDestroy(s.computed);
+    }
+    for (auto &g : c->seg) {
+        g.text.release(); g.z.release(); g.members.release(); g.spans.release();
+        if (g.parsed) cudaEventDestroy(g.parsed);
+        if (g.computed) cudaEventDestroy(g.computed);
     }
     DevBuf *bufs[] = {&c->d_code_pre, &c->d_code_suf, &c->d_generic_scratch, &c->d_start, &c->d_end, &c->d_list_a,
                       &c->d_list_b, &c->d_fb_a, &c->d_fb_b, &c->d_c32, &c->d_t64, &c->d_keys, &c->d_koff, &c->d_klen,
                       &c->d_khash, &c->d_owner, &c->d_diag_exact_pre, &c->d_diag_exact_suf, &c->d_diag_score_pre,
                       &c->d_diag_len_pre, &c->d_diag_score_suf, &c->d_diag_len_suf, &c->t_slots,
                       &c->t_row_hash, &c->t_row_off, &c->t_row_len, &c->t_arena, &c->t_counters, &c->t_row_count,
-                      &c->m_part_rows, &c->m_part_keys, &c->m_cursors, &c->m_chunk_off,
-                      &c->d_wins, &c->d_bestkey, &c->d_cbval, &c->d_fb2};
+                      &c->m_part_rows, &c->m_part_keys, &c->m_cursors, &c->m_chunk_off, &c->m_send, &c->m_recv,
+                      &c->d_wins, &c->d_bestkey, &c->d_cbval, &c->d_fb2, &c->d_aligned_text, &c->d_span_sum,
+                      &c->x_block_bytes, &c->x_block_rows, &c->x_offsets, &c->x_counts, &c->x_data,
+                      &c->p_tiles, &c->p_line_end, &c->p_err, &c->g_tail, &c->g_info};
     for (auto *b : bufs) b->release();
-    c->x_block_sums.release(); c->x_offsets.release(); c->x_data.release();
-    c->d_aligned_text.release();
-    c->p_tiles.release(); c->p_line_end.release(); c->p_err.release();
-    c->g_z.release(); c->g_members.release(); c->g_text[0].release(); c->g_text[1].release();
-    c->g_tail.release(); c->g_info.release(); c->g_pin.release();
+    c->g_pin.release(); c->m_pin.release();
     c->h_offsets.release(); c->h_counts.release(); c->h_data.release();
     for (auto &ev : c->evpool) if (ev) cudaEventDestroy(ev);
+    if (c->m_filled) cudaEventDestroy(c->m_filled);
     if (c->st_compute && c->own_compute_stream) cudaStreamDestroy(c->st_compute);
     if (c->st_copy) cudaStreamDestroy(c->st_copy);
+    if (c->st_ingest) cudaStreamDestroy(c->st_ingest);
     delete c;
     return VFB_OK;
 }
@@ -755,40 +733,13 @@ static int run_dp(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_spans, bo
 }
 
 // The hot loop over one device-resident batch (all work queued on the compute stream).
-// The host packer is created on the first batch big enough to use it.  VFB_HOST_PACK = number of
-// packing threads; "auto" = the CPUs this process may run on, divided by the visible GPUs (one
-// process per GPU shares the host), minus two, at most 16.  Unset or 0 = off: on the B200 boxes
-// this was measured on, reading the caller's text out of host DRAM is what bounds the transfer
-// (~48 GB/s whether the copy engine or the cores read it), so packing moves fewer bytes over PCIe
-// without finishing sooner (profiles/README.md); it pays on hosts whose DRAM is well ahead of the link.
-static bool packer_for(vfb_ctx *c)
-{
-    if (c->packer_tried) return c->packer != nullptr;
-    c->packer_tried = true;
-    int threads = 0;
-    const char *e = getenv("VFB_HOST_PACK");
-    if (e && !strcmp(e, "auto")) {
-        int ncpu = (int)std::thread::hardware_concurrency();
-        cpu_set_t set;
-        if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0) ncpu = CPU_COUNT(&set);
-        int ndev = 1;
-        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); ndev = 1; }
-        threads = ncpu / ndev - 2;
-        if (threads > 16) threads = 16;
-        if (threads < 2) threads = 0;
-    } else if (e) {
-        threads = atoi(e);
-    }
-    if (threads > 0) c->packer = hostpack_create(threads);
-    trace("host packer: %d threads", c->packer ? hostpack_threads(c->packer) : 0);
-    return c->packer != nullptr;
-}
-
-// span_bytes_upper bounds the bytes the batch's spans cover (key space); text_bytes_hint is the text this batch's reads
-// are spread over (it sizes the shared-memory tiles of the scan and key kernels; 0 = span_bytes_upper).
+// span_len_ub bounds the SUM of the batch's span lengths (it sizes the key space: spans may overlap or repeat, so
+// the text range they address is not a bound); text_bytes_hint is the text this batch's reads are spread over (it
+// sizes the shared-memory tiles of the scan and key kernels; 0 = span_len_ub).
 static int process_batch(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_spans, uint32_t n,
-                         uint64_t span_bytes_upper, uint64_t text_bytes_hint = 0)
+                         uint64_t span_len_ub, uint64_t text_bytes_hint = 0)
 {
+    const uint64_t span_bytes_upper = span_len_ub;
     if (!text_bytes_hint) text_bytes_hint = span_bytes_upper;
     int rc;
     if (n == 0) return VFB_OK;
@@ -903,10 +854,19 @@ int vfb_submit_device(vfb_ctx *c, const uint8_t *d_text, uint64_t text_bytes, co
         VFB_CUDA(cudaMemcpyAsync(dst, d_text, text_bytes, cudaMemcpyDeviceToDevice, c->st_compute));
         d_text = dst;
     }
+    if ((rc = c->d_span_sum.ensure(16))) return rc;
     while (done < n_reads) {
         const uint64_t n = n_reads - done < c->batch_reads ? n_reads - done : c->batch_reads;
-        // key space bound: conservatively the whole buffer; tile size: this batch's share of it
-        if ((rc = process_batch(c, d_text, d_spans + done, (uint32_t)n, text_bytes,
+        // the spans are the caller's: every one must lie inside the buffer, and the key space of the batch is
+        // bounded by the sum of their lengths (overlapping and repeated spans are legal)
+        unsigned long long chk[2] = {0, 0};
+        VFB_CUDA(cudaMemsetAsync(c->d_span_sum.p, 0, 16, c->st_compute));
+        if ((rc = launch_span_check(d_spans + done, n, text_bytes, c->d_span_sum.as<unsigned long long>(), c->st_compute))) break;
+        VFB_CUDA(cudaMemcpyAsync(chk, c->d_span_sum.p, 16, cudaMemcpyDeviceToHost, c->st_compute));
+        VFB_CUDA(cudaStreamSynchronize(c->st_compute));
+        c->stats.d2h_bytes += 16;
+        if (chk[1]) { set_error("span outside the text buffer"); rc = VFB_ERR_ARG; break; }
+        if ((rc = process_batch(c, d_text, d_spans + done, (uint32_t)n, chk[0],
                                 (uint64_t)((double)text_bytes * (double)n / (double)n_reads) + 1))) break;
         done += n;
     }
@@ -928,13 +888,13 @@ int vfb_submit_host(vfb_ctx *c, const uint8_t *text, uint64_t text_bytes, const 
     uint64_t done = 0;
     while (done < n_reads && rc == VFB_OK) {
         // cut a batch: up to batch_reads reads whose text range fits batch_bytes
-        uint64_t n = 0, lo = UINT64_MAX, hi = 0;
+        uint64_t n = 0, lo = UINT64_MAX, hi = 0, len_sum = 0;
         while (done + n < n_reads && n < c->batch_reads) {
             const vfb_span s = spans[done + n];
             if ((uint64_t)s.off + s.len > text_bytes) { set_error("span outside the text buffer"); rc = VFB_ERR_ARG; break; }
             const uint64_t nlo = s.off < lo ? s.off : lo, nhi = (uint64_t)s.off + s.len > hi ? (uint64_t)s.off + s.len : hi;
             if (n > 0 && nhi - nlo > c->batch_bytes) break;
-            lo = nlo; hi = nhi; ++n;
+            lo = nlo; hi = nhi; len_sum += s.len; ++n;
         }
         if (rc) break;
         if (n == 0) { set_error("a read is larger than batch_bytes"); rc = VFB_ERR_ARG; break; }
@@ -956,22 +916,14 @@ int vfb_submit_host(vfb_ctx *c, const uint8_t *text, uint64_t text_bytes, const 
             memcpy(s.h_spans.p, src_spans, n * sizeof(vfb_span));
             src_spans = (const vfb_span *)s.h_spans.p;
         }
-        uint64_t link_bytes = bytes;
         VFB_CUDA(cudaMemcpyAsync(s.d_spans.p, src_spans, n * sizeof(vfb_span), cudaMemcpyHostToDevice, c->st_copy));
-        if (bytes >= VFB_HOSTPACK_MIN_BYTES && pinned_text && packer_for(c)) {
-            // part of the text crosses the link as 2-bit codes packed by the context's host threads
-            uint64_t nb = 0;
-            if ((rc = hostpack_copy(c->packer, src_text, bytes, s.d_text.as<uint8_t>(), c->st_copy, &link_bytes, &nb))) break;
-            c->packed_blocks += nb;
-        } else if (bytes) {
-            VFB_CUDA(cudaMemcpyAsync(s.d_text.p, src_text, bytes, cudaMemcpyHostToDevice, c->st_copy));
-        }
+        if (bytes) VFB_CUDA(cudaMemcpyAsync(s.d_text.p, src_text, bytes, cudaMemcpyHostToDevice, c->st_copy));
         VFB_CUDA(cudaEventRecord(s.copied, c->st_copy));
         VFB_CUDA(cudaStreamWaitEvent(c->st_compute, s.copied, 0));
-        c->stats.h2d_bytes += link_bytes + n * sizeof(vfb_span);
+        c->stats.h2d_bytes += bytes + n * sizeof(vfb_span);
         // span offsets stay relative to the caller's buffer: bias the device base by -lo
         const uint8_t *d_base = s.d_text.as<uint8_t>() - lo;
-        rc = process_batch(c, d_base, s.d_spans.as<vfb_span>(), (uint32_t)n, bytes);
+        rc = process_batch(c, d_base, s.d_spans.as<vfb_span>(), (uint32_t)n, len_sum, bytes);
         if (rc) break;
         VFB_CUDA(cudaEventRecord(s.computed, c->st_compute));
         s.busy = true;
@@ -1037,96 +989,128 @@ int vfb_internal_submit_fastq(vfb_ctx *c, const uint8_t *pinned_text, uint64_t n
     return VFB_OK;
 }
 
-int vfb_internal_submit_bgzf(vfb_ctx *c, const uint8_t *pinned_z, uint64_t z_bytes, vfb_member *members,
-                             uint32_t n_members, uint64_t text_bytes, const uint8_t *carry, uint64_t carry_len,
-                             uint64_t record_base, uint64_t *n_records, uint8_t *tail, uint64_t *tail_len,
-                             uint32_t *bad_member)
+// ---- block-gzip segments, in two phases so that several segments (on one device or on several) overlap:
+// begin  = H2D of the compressed members + inflate, independent of every other segment;
+// finish = what needs the text carried over from the previous segment (the bytes after its last complete record):
+//          carry in front of the inflated text, newline count, record framing, tail out, then the hot loop.
+// The inflated text sits VFB_TAIL_CAP bytes into its buffer, so that the carry fits in front of it whatever its
+// length; the parse kernels want a 16-byte aligned base and skip the (< 16) bytes between it and the carry.
+int vfb_internal_bgzf_begin(vfb_ctx *c, const vfb_zpiece *pieces, uint32_t n_pieces, const vfb_member *members,
+                            uint32_t n_members, uint64_t text_bytes, void (*release)(void *), void *release_arg, int *slot_out)
 {
-    *n_records = 0; *tail_len = 0; *bad_member = 0xFFFFFFFFu;
-    const uint64_t used = carry_len + text_bytes;
-    if (used > 0xFFFFFF00ull || z_bytes > 0xFFFFFF00ull) { set_error("ingest segment too large"); return VFB_ERR_ARG; }
+    uint64_t z_bytes = 0;
+    for (uint32_t i = 0; i < n_pieces; ++i) z_bytes += pieces[i].len;
+    if (text_bytes + VFB_TAIL_CAP > 0xFFFFFF00ull || z_bytes > 0xFFFFFF00ull) { set_error("ingest segment too large"); return VFB_ERR_ARG; }
     VFB_CUDA(cudaSetDevice(c->device));
     const uint64_t before = g_launches;
     int rc;
     if (!c->p_err_init) {
         if ((rc = c->p_err.ensure(16))) return rc;
-        VFB_CUDA(cudaMemsetAsync(c->p_err.p, 0xFF, 16, c->st_compute));
+        VFB_CUDA(cudaMemsetAsync(c->p_err.p, 0xFF, 16, c->st_ingest));
         c->p_err_init = true;
     }
-    DevBuf &txt = c->g_text[c->g_seq & 1];
+    const int slot = (int)(c->g_seq % VFB_SEG_SLOTS);
     ++c->g_seq;
-    if ((rc = txt.ensure(used + 64))) return rc;
-    if ((rc = c->g_z.ensure(z_bytes + 64))) return rc;
-    if ((rc = c->g_members.ensure((size_t)(n_members ? n_members : 1) * sizeof(vfb_member)))) return rc;
+    SegSlot &g = c->seg[slot];
+    if ((rc = g.text.ensure(VFB_TAIL_CAP + text_bytes + 64))) return rc;
+    if ((rc = g.z.ensure(z_bytes + 64))) return rc;
+    if ((rc = g.members.ensure((size_t)(n_members ? n_members : 1) * sizeof(vfb_member) + 16))) return rc;
+    if ((rc = c->g_info.ensure(64 * VFB_SEG_SLOTS))) return rc;
+    // the hot loop that last read this slot's text must be done before the inflate overwrites it
+    if (g.busy) VFB_CUDA(cudaStreamWaitEvent(c->st_ingest, g.computed, 0));
+    uint64_t zo = 0;
+    for (uint32_t i = 0; i < n_pieces; ++i) {
+        if (pieces[i].len) VFB_CUDA(cudaMemcpyAsync(g.z.as<uint8_t>() + zo, pieces[i].p, pieces[i].len, cudaMemcpyHostToDevice, c->st_ingest));
+        zo += pieces[i].len;
+    }
+    if (release) VFB_CUDA(cudaLaunchHostFunc(c->st_ingest, release, release_arg));
+    if (n_members) VFB_CUDA(cudaMemcpyAsync(g.members.p, members, (size_t)n_members * sizeof(vfb_member), cudaMemcpyHostToDevice, c->st_ingest));
+    c->stats.h2d_bytes += z_bytes + (uint64_t)n_members * sizeof(vfb_member);
+    uint32_t *d_bad = c->g_info.as<uint32_t>() + 16 * slot + 8;
+    VFB_CUDA(cudaMemsetAsync(d_bad, 0xFF, 4, c->st_ingest));
+    if ((rc = launch_inflate(g.z.as<uint8_t>(), g.members.as<vfb_member>(), n_members, g.text.as<uint8_t>() + VFB_TAIL_CAP, d_bad, c->st_ingest))) return rc;
+    g.text_bytes = text_bytes; g.z_bytes = z_bytes; g.n_members = n_members;
+    *slot_out = slot;
+    bump_launches(c, before);
+    return VFB_OK;
+}
+
+int vfb_internal_bgzf_finish(vfb_ctx *c, int slot, const uint8_t *carry, uint64_t carry_len, uint64_t record_base,
+                             uint64_t *n_records, uint8_t *tail, uint64_t *tail_len, uint32_t *bad_member)
+{
+    *n_records = 0; *tail_len = 0; *bad_member = 0xFFFFFFFFu;
+    if (carry_len > VFB_TAIL_CAP) { set_error("a FASTQ record is larger than 16 MiB"); return VFB_ERR_FORMAT; }
+    VFB_CUDA(cudaSetDevice(c->device));
+    const uint64_t before = g_launches;
+    SegSlot &g = c->seg[slot];
+    cudaStream_t si = c->st_ingest;
+    int rc;
+    const uint64_t front = VFB_TAIL_CAP - carry_len;           // where the carried bytes start in the buffer
+    const uint32_t skip = (uint32_t)(front & 15u);
+    const uint8_t *base = g.text.as<uint8_t>() + (front & ~(uint64_t)15);
+    const uint64_t used = skip + carry_len + g.text_bytes;      // bytes from `base`
     if ((rc = c->g_tail.ensure(VFB_TAIL_CAP))) return rc;
-    if ((rc = c->g_info.ensure(64))) return rc;
     if ((rc = c->g_pin.ensure(VFB_TAIL_CAP + 64))) return rc;
     if ((rc = c->p_tiles.ensure(parse_tile_words((uint32_t)used) * 8 + 8))) return rc;
     uint8_t *pin = (uint8_t *)c->g_pin.p;
-    // the text of this segment starts behind the carried bytes
-    for (uint32_t i = 0; i < n_members; ++i) members[i].out_off += (uint32_t)carry_len;
     if (carry_len) {
         memcpy(pin, carry, carry_len);
-        VFB_CUDA(cudaMemcpyAsync(txt.p, pin, carry_len, cudaMemcpyHostToDevice, c->st_compute));
+        VFB_CUDA(cudaMemcpyAsync(g.text.as<uint8_t>() + front, pin, carry_len, cudaMemcpyHostToDevice, si));
+        c->stats.h2d_bytes += carry_len;
     }
-    if (z_bytes) VFB_CUDA(cudaMemcpyAsync(c->g_z.p, pinned_z, z_bytes, cudaMemcpyHostToDevice, c->st_compute));
-    if (n_members) VFB_CUDA(cudaMemcpyAsync(c->g_members.p, members, (size_t)n_members * sizeof(vfb_member), cudaMemcpyHostToDevice, c->st_compute));
-    c->stats.h2d_bytes += carry_len + z_bytes + (uint64_t)n_members * sizeof(vfb_member);
-    uint32_t *d_bad = c->g_info.as<uint32_t>() + 8;
-    VFB_CUDA(cudaMemsetAsync(d_bad, 0xFF, 4, c->st_compute));
-    if ((rc = launch_inflate(c->g_z.as<uint8_t>(), c->g_members.as<vfb_member>(), n_members, txt.as<uint8_t>(), d_bad, c->st_compute))) return rc;
     unsigned long long lines = 0;
     uint32_t bad = 0xFFFFFFFFu;
-    if (used) {
-        if ((rc = launch_parse_count(txt.as<uint8_t>(), (uint32_t)used, c->p_tiles.as<unsigned long long>(), c->st_compute))) return rc;
+    uint32_t *d_info = c->g_info.as<uint32_t>() + 16 * slot;
+    if (used > skip) {
+        if ((rc = launch_parse_count(base, (uint32_t)used, skip, c->p_tiles.as<unsigned long long>(), si))) return rc;
         const uint64_t n_tiles = parse_tile_words((uint32_t)used) - 1;
-        VFB_CUDA(cudaMemcpyAsync(&lines, c->p_tiles.as<unsigned long long>() + n_tiles, 8, cudaMemcpyDeviceToHost, c->st_compute));
+        VFB_CUDA(cudaMemcpyAsync(&lines, c->p_tiles.as<unsigned long long>() + n_tiles, 8, cudaMemcpyDeviceToHost, si));
     }
-    VFB_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, c->st_compute));
-    trace("submit_bgzf: H2D + inflate + line count queued");
-    VFB_CUDA(cudaStreamSynchronize(c->st_compute));
-    trace("submit_bgzf: inflated, %llu lines", lines);
+    VFB_CUDA(cudaMemcpyAsync(&bad, d_info + 8, 4, cudaMemcpyDeviceToHost, si));
+    VFB_CUDA(cudaStreamSynchronize(si));
     c->stats.d2h_bytes += 12;
     *bad_member = bad;
-    if (bad != 0xFFFFFFFFu || used == 0) { bump_launches(c, before); return VFB_OK; }
+    if (bad != 0xFFFFFFFFu || used <= skip) { bump_launches(c, before); return VFB_OK; }
     const uint32_t n_rec = (uint32_t)(lines / 4);
     if ((rc = c->p_line_end.ensure((lines ? lines : 1) * 4))) return rc;
-    Slot &s = c->slots[0];      // spans live in the host-path slot buffers (not in use by this path)
-    if ((rc = s.d_spans.ensure((size_t)(n_rec ? n_rec : 1) * sizeof(vfb_span)))) return rc;
-    if ((rc = launch_parse_index(txt.as<uint8_t>(), (uint32_t)used, (uint32_t)lines, n_rec,
-                                 c->p_tiles.as<unsigned long long>(), c->p_line_end.as<uint32_t>(), s.d_spans.as<vfb_span>(),
-                                 c->p_err.as<uint32_t>(), c->g_tail.as<uint8_t>(), VFB_TAIL_CAP, c->g_info.as<uint32_t>(),
-                                 c->st_compute))) return rc;
+    if ((rc = g.spans.ensure((size_t)(n_rec ? n_rec : 1) * sizeof(vfb_span)))) return rc;
+    if ((rc = launch_parse_index(base, (uint32_t)used, skip, (uint32_t)lines, n_rec, c->p_tiles.as<unsigned long long>(),
+                                 c->p_line_end.as<uint32_t>(), g.spans.as<vfb_span>(), c->p_err.as<uint32_t>(),
+                                 c->g_tail.as<uint8_t>(), VFB_TAIL_CAP, d_info, si))) return rc;
+    if (n_rec) {
+        k_parse_err_fold<<<1, 1, 0, si>>>(c->p_err.as<uint32_t>(), record_base,
+                                          reinterpret_cast<unsigned long long *>(c->p_err.as<uint8_t>() + 8));
+        ++g_launches;
+    }
     uint32_t *h_info = reinterpret_cast<uint32_t *>(pin + VFB_TAIL_CAP);
-    VFB_CUDA(cudaMemcpyAsync(h_info, c->g_info.p, 8, cudaMemcpyDeviceToHost, c->st_compute));
+    VFB_CUDA(cudaMemcpyAsync(h_info, d_info, 8, cudaMemcpyDeviceToHost, si));
     // the tail is normally a fraction of one record: fetch a first page with the info, the rest if needed
-    VFB_CUDA(cudaMemcpyAsync(pin, c->g_tail.p, 65536, cudaMemcpyDeviceToHost, c->st_compute));
-    VFB_CUDA(cudaStreamSynchronize(c->st_compute));
+    VFB_CUDA(cudaMemcpyAsync(pin, c->g_tail.p, 65536, cudaMemcpyDeviceToHost, si));
+    VFB_CUDA(cudaEventRecord(g.parsed, si));
+    VFB_CUDA(cudaStreamSynchronize(si));
     const uint32_t tl = h_info[1];
     if (tl > VFB_TAIL_CAP) { set_error("a FASTQ record is larger than 16 MiB"); return VFB_ERR_FORMAT; }
     if (tl > 65536) {
-        VFB_CUDA(cudaMemcpyAsync(pin, c->g_tail.p, tl, cudaMemcpyDeviceToHost, c->st_compute));
-        VFB_CUDA(cudaStreamSynchronize(c->st_compute));
+        VFB_CUDA(cudaMemcpyAsync(pin, c->g_tail.p, tl, cudaMemcpyDeviceToHost, si));
+        VFB_CUDA(cudaStreamSynchronize(si));
     }
     memcpy(tail, pin, tl);
     *tail_len = tl;
-    trace("submit_bgzf: parsed, tail %u bytes", tl);
     c->stats.d2h_bytes += 8 + tl;
     if (n_rec) {
-        k_parse_err_fold<<<1, 1, 0, c->st_compute>>>(c->p_err.as<uint32_t>(), record_base,
-                                                     reinterpret_cast<unsigned long long *>(c->p_err.as<uint8_t>() + 8));
-        ++g_launches;
+        VFB_CUDA(cudaStreamWaitEvent(c->st_compute, g.parsed, 0));
         uint32_t done = 0;
         while (done < n_rec) {
             const uint32_t n = n_rec - done < c->batch_reads ? n_rec - done : (uint32_t)c->batch_reads;
-            if ((rc = process_batch(c, txt.as<uint8_t>(), s.d_spans.as<vfb_span>() + done, n, used,
+            if ((rc = process_batch(c, base, g.spans.as<vfb_span>() + done, n, used,
                                     (uint64_t)((double)used * (double)n / (double)n_rec) + 1))) return rc;
             done += n;
         }
+        VFB_CUDA(cudaEventRecord(g.computed, c->st_compute));
+        g.busy = true;
     }
     *n_records = n_rec;
     bump_launches(c, before);
-    trace("submit_bgzf: hot loop queued (%u records)", n_rec);
     return VFB_OK;
 }
 
@@ -1158,6 +1142,7 @@ int vfb_internal_parse_error(vfb_ctx *c, uint64_t *first_bad)
 {
     *first_bad = UINT64_MAX;
     if (!c->p_err_init) return VFB_OK;
+    VFB_CUDA(cudaSetDevice(c->device));
     unsigned long long v = 0;
     VFB_CUDA(cudaMemcpy(&v, c->p_err.as<uint8_t>() + 8, 8, cudaMemcpyDeviceToHost));
     *first_bad = v;
@@ -1173,8 +1158,10 @@ int vfb_sync(vfb_ctx *c)
     if (!c) { set_error("null context"); return VFB_ERR_ARG; }
     VFB_CUDA(cudaSetDevice(c->device));
     VFB_CUDA(cudaStreamSynchronize(c->st_copy));
+    VFB_CUDA(cudaStreamSynchronize(c->st_ingest));
     VFB_CUDA(cudaStreamSynchronize(c->st_compute));
     for (auto &s : c->slots) s.busy = false;
+    for (auto &g : c->seg) g.busy = false;
     return prof_resolve(c);
 }
 
@@ -1243,51 +1230,86 @@ int vfb_get_diag(vfb_ctx *c, vfb_read_diag *out, uint64_t n_reads)
     return VFB_OK;
 }
 
-int vfb_finish(vfb_ctx *c, vfb_table *out)
+}  // extern "C"
+
+// Export, pass 1: slot counts -> row counts, sizes of what will be exported (rows with a non-zero count).
+int vfb_internal_export_sizes(vfb_ctx *c, uint64_t *rows_out, uint64_t *bytes_out)
 {
-    if (!c || !out) { set_error("null argument"); return VFB_ERR_ARG; }
-    memset(out, 0, sizeof *out);
+    *rows_out = 0; *bytes_out = 0;
     int rc = vfb_sync(c);
     if (rc) return rc;
     const uint64_t before = g_launches;
     unsigned long long ctr[3];
     VFB_CUDA(cudaMemcpy(ctr, c->tab.counters, sizeof ctr, cudaMemcpyDeviceToHost));
-    const uint64_t rows = ctr[0], arena = ctr[1];
+    const uint64_t rows = ctr[0];
+    c->x_table_rows = rows; c->x_rows = 0; c->x_bytes = 0;
+    if (rows == 0) return VFB_OK;
+    const uint64_t nb = (rows + 1023) / 1024;
+    if ((rc = c->t_row_count.ensure(rows * 8))) return rc;
+    if ((rc = c->x_block_bytes.ensure((nb + 2) * 8))) return rc;
+    if ((rc = c->x_block_rows.ensure(nb * 8))) return rc;
+    unsigned long long *d_totals = c->x_block_bytes.as<unsigned long long>() + nb;
+    // rows published without a slot count cannot exist, but the buffer may be a recycled one: zero first
+    VFB_CUDA(cudaMemsetAsync(c->t_row_count.p, 0, rows * 8, c->st_compute));
+    if ((rc = launch_export_counts(c->tab, rows, c->t_row_count.as<unsigned long long>(), c->st_compute))) return rc;
+    if ((rc = launch_export_sizes(c->tab, rows, c->t_row_count.as<unsigned long long>(), c->x_block_bytes.as<unsigned long long>(),
+                                  c->x_block_rows.as<unsigned long long>(), d_totals, c->st_compute))) return rc;
+    unsigned long long totals[2] = {0, 0};
+    VFB_CUDA(cudaMemcpyAsync(totals, d_totals, 16, cudaMemcpyDeviceToHost, c->st_compute));
+    VFB_CUDA(cudaStreamSynchronize(c->st_compute));
+    c->stats.d2h_bytes += 16 + sizeof ctr;
+    c->x_bytes = totals[0]; c->x_rows = totals[1];
+    *rows_out = c->x_rows; *bytes_out = c->x_bytes;
+    bump_launches(c, before);
+    return VFB_OK;
+}
+
+// Export, pass 2 (asynchronous on the compute stream): h_offsets receives x_rows offsets (byte_base + ...; the
+// closing offset is the caller's), h_counts x_rows counts, h_data x_bytes key bytes.  Pinned destinations.
+int vfb_internal_export_write(vfb_ctx *c, uint64_t byte_base, uint64_t *h_offsets, uint64_t *h_counts, uint8_t *h_data)
+{
+    VFB_CUDA(cudaSetDevice(c->device));
+    if (c->x_rows == 0) return VFB_OK;
+    const uint64_t before = g_launches;
+    int rc;
+    if ((rc = c->x_offsets.ensure(c->x_rows * 8))) return rc;
+    if ((rc = c->x_counts.ensure(c->x_rows * 8))) return rc;
+    if ((rc = c->x_data.ensure(c->x_bytes ? c->x_bytes : 16))) return rc;
+    if ((rc = launch_export_gather(c->tab, c->x_table_rows, c->t_row_count.as<unsigned long long>(),
+                                   c->x_block_bytes.as<unsigned long long>(), c->x_block_rows.as<unsigned long long>(), byte_base,
+                                   c->x_offsets.as<unsigned long long>(), c->x_counts.as<unsigned long long>(),
+                                   c->x_data.as<uint8_t>(), c->st_compute))) return rc;
+    VFB_CUDA(cudaMemcpyAsync(h_offsets, c->x_offsets.p, c->x_rows * 8, cudaMemcpyDeviceToHost, c->st_compute));
+    VFB_CUDA(cudaMemcpyAsync(h_counts, c->x_counts.p, c->x_rows * 8, cudaMemcpyDeviceToHost, c->st_compute));
+    if (c->x_bytes) VFB_CUDA(cudaMemcpyAsync(h_data, c->x_data.p, c->x_bytes, cudaMemcpyDeviceToHost, c->st_compute));
+    c->stats.d2h_bytes += c->x_rows * 16 + c->x_bytes;
+    bump_launches(c, before);
+    return VFB_OK;
+}
+
+extern "C" {
+
+int vfb_finish(vfb_ctx *c, vfb_table *out)
+{
+    if (!c || !out) { set_error("null argument"); return VFB_ERR_ARG; }
+    memset(out, 0, sizeof *out);
+    uint64_t rows = 0, bytes = 0;
+    int rc = vfb_internal_export_sizes(c, &rows, &bytes);
+    if (rc) return rc;
     // The columns are compacted on the device and land in pinned host buffers owned by the
     // context (valid until the next vfb_finish / vfb_destroy on it).
     if ((rc = c->h_offsets.ensure((rows + 1) * 8))) return rc;
     if ((rc = c->h_counts.ensure((rows ? rows : 1) * 8))) return rc;
+    if ((rc = c->h_data.ensure(bytes ? bytes : 16))) return rc;
     out->rows = rows;
+    out->key_bytes = bytes;
     out->offsets = (uint64_t *)c->h_offsets.p;
     out->counts = (uint64_t *)c->h_counts.p;
-    out->offsets[0] = 0;
-    out->owner = c;
-    if (rows == 0) {
-        if ((rc = c->h_data.ensure(16))) return rc;
-        out->data = (uint8_t *)c->h_data.p;
-        return VFB_OK;
-    }
-    const uint64_t nb = (rows + 1023) / 1024;
-    if ((rc = c->t_row_count.ensure(rows * 8))) return rc;
-    if ((rc = c->x_block_sums.ensure((nb + 1) * 8))) return rc;
-    if ((rc = c->x_offsets.ensure((rows + 1) * 8))) return rc;
-    if ((rc = c->x_data.ensure(arena ? arena : 16))) return rc;
-    unsigned long long *d_total = c->x_block_sums.as<unsigned long long>() + nb;
-    if ((rc = launch_export_counts(c->tab, rows, c->t_row_count.as<unsigned long long>(), c->st_compute))) return rc;
-    if ((rc = launch_export_arrow(c->tab, rows, c->x_block_sums.as<unsigned long long>(), d_total,
-                                  c->x_offsets.as<unsigned long long>(), c->x_data.as<uint8_t>(), c->st_compute))) return rc;
-    unsigned long long total = 0;
-    VFB_CUDA(cudaMemcpyAsync(out->counts, c->t_row_count.p, rows * 8, cudaMemcpyDeviceToHost, c->st_compute));
-    VFB_CUDA(cudaMemcpyAsync(out->offsets, c->x_offsets.p, (rows + 1) * 8, cudaMemcpyDeviceToHost, c->st_compute));
-    VFB_CUDA(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, c->st_compute));
-    VFB_CUDA(cudaStreamSynchronize(c->st_compute));
-    if ((rc = c->h_data.ensure(total ? total : 16))) return rc;
     out->data = (uint8_t *)c->h_data.p;
-    out->key_bytes = total;
-    if (total) VFB_CUDA(cudaMemcpyAsync(out->data, c->x_data.p, total, cudaMemcpyDeviceToHost, c->st_compute));
+    out->owner = c;
+    if ((rc = vfb_internal_export_write(c, 0, out->offsets, out->counts, out->data))) return rc;
     VFB_CUDA(cudaStreamSynchronize(c->st_compute));
-    c->stats.d2h_bytes += rows * 16 + 8 + total;
-    bump_launches(c, before);
+    out->offsets[rows] = bytes;
     return VFB_OK;
 }
 
@@ -1342,29 +1364,27 @@ void schema_top_release(vfb_arrow_schema *s)
 }
 }  // namespace
 
-int vfb_finish_arrow(vfb_ctx *c, vfb_arrow_array *out_array, vfb_arrow_schema *out_schema)
+}  // extern "C"
+
+// Wraps three pinned columns (ownership moves into the array) as the Arrow struct array of vfb_finish_arrow.
+int vfb_internal_arrow_wrap(PinBuf offsets, PinBuf data, PinBuf counts, uint64_t rows, vfb_arrow_array *out_array,
+                            vfb_arrow_schema *out_schema)
 {
-    if (!c || !out_array || !out_schema) { set_error("null argument"); return VFB_ERR_ARG; }
-    vfb_table t;
-    int rc = vfb_finish(c, &t);
-    if (rc) return rc;
     ArrowHolder *h = new ArrowHolder;
-    // the context gives its pinned columns away; its next vfb_finish takes fresh ones from the pool
-    h->offsets = c->h_offsets; h->data = c->h_data; h->counts = c->h_counts;
-    c->h_offsets = PinBuf(); c->h_data = PinBuf(); c->h_counts = PinBuf();
+    h->offsets = offsets; h->data = data; h->counts = counts;
     h->refs = 3;
-    h->seq_bufs[0] = nullptr; h->seq_bufs[1] = t.offsets; h->seq_bufs[2] = t.data;
-    h->cnt_bufs[0] = nullptr; h->cnt_bufs[1] = t.counts;
+    h->seq_bufs[0] = nullptr; h->seq_bufs[1] = offsets.p; h->seq_bufs[2] = data.p;
+    h->cnt_bufs[0] = nullptr; h->cnt_bufs[1] = counts.p;
     h->top_bufs[0] = nullptr;
     vfb_arrow_array &seq = h->children[0], &cnt = h->children[1];
     memset(&seq, 0, sizeof seq); memset(&cnt, 0, sizeof cnt);
-    seq.length = (int64_t)t.rows; seq.n_buffers = 3; seq.buffers = h->seq_bufs;
+    seq.length = (int64_t)rows; seq.n_buffers = 3; seq.buffers = h->seq_bufs;
     seq.release = arrow_child_release; seq.private_data = h;
-    cnt.length = (int64_t)t.rows; cnt.n_buffers = 2; cnt.buffers = h->cnt_bufs;
+    cnt.length = (int64_t)rows; cnt.n_buffers = 2; cnt.buffers = h->cnt_bufs;
     cnt.release = arrow_child_release; cnt.private_data = h;
     h->child_ptrs[0] = &seq; h->child_ptrs[1] = &cnt;
     memset(out_array, 0, sizeof *out_array);
-    out_array->length = (int64_t)t.rows; out_array->n_buffers = 1; out_array->buffers = h->top_bufs;
+    out_array->length = (int64_t)rows; out_array->n_buffers = 1; out_array->buffers = h->top_bufs;
     out_array->n_children = 2; out_array->children = h->child_ptrs;
     out_array->release = arrow_top_release; out_array->private_data = h;
 
@@ -1379,6 +1399,20 @@ int vfb_finish_arrow(vfb_ctx *c, vfb_arrow_array *out_array, vfb_arrow_schema *o
     return VFB_OK;
 }
 
+extern "C" {
+
+int vfb_finish_arrow(vfb_ctx *c, vfb_arrow_array *out_array, vfb_arrow_schema *out_schema)
+{
+    if (!c || !out_array || !out_schema) { set_error("null argument"); return VFB_ERR_ARG; }
+    vfb_table t;
+    int rc = vfb_finish(c, &t);
+    if (rc) return rc;
+    // the context gives its pinned columns away; its next vfb_finish takes fresh ones from the pool
+    PinBuf o = c->h_offsets, d = c->h_data, n = c->h_counts;
+    c->h_offsets = PinBuf(); c->h_data = PinBuf(); c->h_counts = PinBuf();
+    return vfb_internal_arrow_wrap(o, d, n, t.rows, out_array, out_schema);
+}
+
 void vfb_table_free(vfb_table *t)
 {
     if (!t) return;
@@ -1391,59 +1425,140 @@ void vfb_table_free(vfb_table *t)
 }
 
 // ------------------------------------------------------------------------------------ merge
-int vfb_table_partition_sizes(vfb_ctx *c, uint32_t n_parts, uint64_t *chunk_bytes)
+}  // extern "C"
+
+// Pass 1 of a partition (asynchronous): slot counts -> row counts, rows and padded key bytes per part; the
+// results stay on the device, m_part_rows = [rows per part (n_parts) | key bytes per part (n_parts)].
+int vfb_internal_partition_count(vfb_ctx *c, uint32_t n_parts, uint32_t self, uint64_t *table_rows)
 {
-    if (!c || !chunk_bytes || n_parts == 0 || n_parts > 1024) { set_error("bad argument"); return VFB_ERR_ARG; }
     int rc = vfb_sync(c);
     if (rc) return rc;
     const uint64_t before = g_launches;
     unsigned long long ctr[3];
     VFB_CUDA(cudaMemcpy(ctr, c->tab.counters, sizeof ctr, cudaMemcpyDeviceToHost));
     const uint64_t rows = ctr[0];
-    if ((rc = c->m_part_rows.ensure(n_parts * 8))) return rc;
-    if ((rc = c->m_part_keys.ensure(n_parts * 8))) return rc;
-    VFB_CUDA(cudaMemsetAsync(c->m_part_rows.p, 0, n_parts * 8, c->st_compute));
-    VFB_CUDA(cudaMemsetAsync(c->m_part_keys.p, 0, n_parts * 8, c->st_compute));
-    if ((rc = launch_partition_count(c->tab, rows, n_parts, c->m_part_rows.as<unsigned long long>(),
-                                     c->m_part_keys.as<unsigned long long>(), c->st_compute))) return rc;
+    c->x_table_rows = rows;
+    c->m_self = self;
+    if ((rc = c->m_part_rows.ensure((size_t)n_parts * 16))) return rc;
+    if ((rc = c->t_row_count.ensure((rows ? rows : 1) * 8))) return rc;
+    VFB_CUDA(cudaMemsetAsync(c->m_part_rows.p, 0, (size_t)n_parts * 16, c->st_compute));
+    if (rows) {
+        VFB_CUDA(cudaMemsetAsync(c->t_row_count.p, 0, rows * 8, c->st_compute));
+        if ((rc = launch_export_counts(c->tab, rows, c->t_row_count.as<unsigned long long>(), c->st_compute))) return rc;
+        if ((rc = launch_partition_count(c->tab, rows, c->t_row_count.as<unsigned long long>(), n_parts, self,
+                                         c->m_part_rows.as<unsigned long long>(),
+                                         c->m_part_rows.as<unsigned long long>() + n_parts, c->st_compute))) return rc;
+    }
+    if (table_rows) *table_rows = rows;
+    bump_launches(c, before);
+    return VFB_OK;
+}
+
+// Pass 2 (asynchronous): one chunk per part (not for `self`) at d_buf + chunk_offsets[p]; part sizes as counted.
+int vfb_internal_partition_fill(vfb_ctx *c, uint32_t n_parts, uint32_t self, uint8_t *d_buf, const uint64_t *chunk_offsets)
+{
+    VFB_CUDA(cudaSetDevice(c->device));
+    const uint64_t before = g_launches;
+    int rc;
+    if ((rc = c->m_cursors.ensure((size_t)n_parts * 16))) return rc;
+    if ((rc = c->m_chunk_off.ensure((size_t)n_parts * 8))) return rc;
+    VFB_CUDA(cudaMemsetAsync(c->m_cursors.p, 0, (size_t)n_parts * 16, c->st_compute));
+    // (pageable source: staged by the driver before the call returns)
+    VFB_CUDA(cudaMemcpyAsync(c->m_chunk_off.p, chunk_offsets, (size_t)n_parts * 8, cudaMemcpyHostToDevice, c->st_compute));
+    if ((rc = launch_partition_fill(c->tab, c->x_table_rows, n_parts, self, c->t_row_count.as<unsigned long long>(), d_buf,
+                                    c->m_chunk_off.as<uint64_t>(), c->m_part_rows.as<uint64_t>(),
+                                    c->m_part_rows.as<uint64_t>() + n_parts, c->m_cursors.as<unsigned long long>(), c->st_compute)))
+        return rc;
+    bump_launches(c, before);
+    return VFB_OK;
+}
+
+static int partition_fetch(vfb_ctx *c, uint32_t n_parts)
+{
     c->h_part_rows.assign(n_parts, 0);
     c->h_part_keys.assign(n_parts, 0);
-    VFB_CUDA(cudaMemcpyAsync(c->h_part_rows.data(), c->m_part_rows.p, n_parts * 8, cudaMemcpyDeviceToHost, c->st_compute));
-    VFB_CUDA(cudaMemcpyAsync(c->h_part_keys.data(), c->m_part_keys.p, n_parts * 8, cudaMemcpyDeviceToHost, c->st_compute));
+    std::vector<uint64_t> tmp((size_t)n_parts * 2);
+    VFB_CUDA(cudaMemcpyAsync(tmp.data(), c->m_part_rows.p, (size_t)n_parts * 16, cudaMemcpyDeviceToHost, c->st_compute));
     VFB_CUDA(cudaStreamSynchronize(c->st_compute));
-    for (uint32_t p = 0; p < n_parts; ++p) chunk_bytes[p] = chunk_bytes_for(c->h_part_rows[p], c->h_part_keys[p]);
+    c->stats.d2h_bytes += (uint64_t)n_parts * 16;
+    for (uint32_t p = 0; p < n_parts; ++p) { c->h_part_rows[p] = tmp[p]; c->h_part_keys[p] = tmp[n_parts + p]; }
+    return VFB_OK;
+}
+
+int vfb_internal_merge_export(vfb_ctx *c, uint32_t n_parts, uint32_t self, bool release, uint64_t *chunk_bytes,
+                              uint64_t *chunk_offsets, uint64_t *part_rows, uint64_t *part_keys)
+{
+    int rc;
+    if ((rc = vfb_internal_partition_count(c, n_parts, self, nullptr))) return rc;
+    if ((rc = partition_fetch(c, n_parts))) return rc;
+    uint64_t total = 0;
+    for (uint32_t p = 0; p < n_parts; ++p) {
+        const uint64_t r = c->h_part_rows[p], k = c->h_part_keys[p];
+        chunk_bytes[p] = (p == self || r == 0) ? 0 : chunk_bytes_for(r, k);
+        chunk_offsets[p] = total;
+        total += chunk_bytes[p];
+        if (part_rows) part_rows[p] = p == self ? 0 : r;
+        if (part_keys) part_keys[p] = p == self ? 0 : k;
+    }
+    if ((rc = c->m_send.ensure(total ? total : 16))) return rc;
+    if (total) {
+        if ((rc = vfb_internal_partition_fill(c, n_parts, self, c->m_send.as<uint8_t>(), chunk_offsets))) return rc;
+        if (release) {
+            const uint64_t before = g_launches;
+            if ((rc = launch_release_foreign(c->tab, n_parts, self, c->st_compute))) return rc;
+            bump_launches(c, before);
+        }
+    }
+    VFB_CUDA(cudaEventRecord(c->m_filled, c->st_compute));
+    return VFB_OK;
+}
+
+int vfb_internal_absorb_known(vfb_ctx *c, const uint8_t *d_chunk, uint64_t rows, uint64_t key_bytes)
+{
+    if (rows == 0) return VFB_OK;
+    if (rows > 0x7FFFFFFFull) { set_error("chunk too large"); return VFB_ERR_ARG; }
+    VFB_CUDA(cudaSetDevice(c->device));
+    const uint64_t before = g_launches;
+    int rc;
+    if ((rc = table_reserve(c, rows, key_bytes))) return rc;
+    if ((rc = c->d_owner.ensure(rows * 4))) return rc;
+    const uint64_t n = rows;
+    const uint8_t *base = d_chunk + sizeof(ChunkHeader);
+    InsertJob ij;
+    ij.khash = reinterpret_cast<const uint64_t *>(base);
+    ij.kcount = reinterpret_cast<const unsigned long long *>(base + vfb_align16(n * 8));
+    ij.koff = reinterpret_cast<const uint64_t *>(base + vfb_align16(n * 8) * 2);
+    ij.klen = reinterpret_cast<const uint32_t *>(base + vfb_align16(n * 8) * 3);
+    ij.keys = base + vfb_align16(n * 8) * 3 + vfb_align16(n * 4);
+    ij.key_stride = 0;
+    ij.n_keys = (uint32_t)n;
+    ij.owner_slot = c->d_owner.as<uint32_t>();
+    if ((rc = launch_insert(c->tab, ij, c->st_compute))) return rc;
     bump_launches(c, before);
+    return VFB_OK;
+}
+
+extern "C" {
+
+int vfb_table_partition_sizes(vfb_ctx *c, uint32_t n_parts, uint64_t *chunk_bytes)
+{
+    if (!c || !chunk_bytes || n_parts == 0 || n_parts > 1024) { set_error("bad argument"); return VFB_ERR_ARG; }
+    int rc;
+    if ((rc = vfb_internal_partition_count(c, n_parts, 0xFFFFFFFFu, nullptr))) return rc;
+    if ((rc = partition_fetch(c, n_parts))) return rc;
+    for (uint32_t p = 0; p < n_parts; ++p) chunk_bytes[p] = chunk_bytes_for(c->h_part_rows[p], c->h_part_keys[p]);
     return VFB_OK;
 }
 
 int vfb_table_partition_fill(vfb_ctx *c, uint32_t n_parts, uint8_t *d_buf, const uint64_t *chunk_offsets)
 {
-    if (!c || !d_buf || !chunk_offsets || n_parts == 0 || c->h_part_rows.size() != n_parts) {
+    if (!c || !d_buf || !chunk_offsets || n_parts == 0 || c->h_part_rows.size() != n_parts || c->m_self != 0xFFFFFFFFu) {
         set_error("call vfb_table_partition_sizes with the same n_parts first");
         return VFB_ERR_ARG;
     }
-    VFB_CUDA(cudaSetDevice(c->device));
-    const uint64_t before = g_launches;
-    int rc;
-    uint64_t rows = 0;
-    for (auto r : c->h_part_rows) rows += r;
-    if ((rc = c->m_cursors.ensure(n_parts * 16))) return rc;
-    if ((rc = c->m_chunk_off.ensure(n_parts * 8))) return rc;
-    if ((rc = c->t_row_count.ensure((rows ? rows : 1) * 8))) return rc;
-    VFB_CUDA(cudaMemsetAsync(c->m_cursors.p, 0, n_parts * 16, c->st_compute));
-    VFB_CUDA(cudaMemcpyAsync(c->m_chunk_off.p, chunk_offsets, n_parts * 8, cudaMemcpyHostToDevice, c->st_compute));
-    for (uint32_t p = 0; p < n_parts; ++p) {
-        ChunkHeader h{VFB_CHUNK_MAGIC, c->h_part_rows[p], c->h_part_keys[p], 0};
-        VFB_CUDA(cudaMemcpyAsync(d_buf + chunk_offsets[p], &h, sizeof h, cudaMemcpyHostToDevice, c->st_compute));
-        VFB_CUDA(cudaStreamSynchronize(c->st_compute));   // h is a stack temporary
-    }
-    if ((rc = launch_export_counts(c->tab, rows, c->t_row_count.as<unsigned long long>(), c->st_compute))) return rc;
-    if ((rc = launch_partition_fill(c->tab, rows, n_parts, c->t_row_count.as<unsigned long long>(), d_buf,
-                                    c->m_chunk_off.as<uint64_t>(), c->m_part_rows.as<uint64_t>(),
-                                    c->m_part_keys.as<uint64_t>(), c->m_cursors.as<unsigned long long>(), c->st_compute)))
-        return rc;
+    int rc = vfb_internal_partition_fill(c, n_parts, 0xFFFFFFFFu, d_buf, chunk_offsets);
+    if (rc) return rc;
     VFB_CUDA(cudaStreamSynchronize(c->st_compute));
-    bump_launches(c, before);
     return VFB_OK;
 }
 
@@ -1464,30 +1579,11 @@ int vfb_table_absorb(vfb_ctx *c, const uint8_t *d_chunk, uint64_t chunk_bytes)
 {
     if (!c || !d_chunk || chunk_bytes < sizeof(ChunkHeader)) { set_error("bad argument"); return VFB_ERR_ARG; }
     VFB_CUDA(cudaSetDevice(c->device));
-    const uint64_t before = g_launches;
     ChunkHeader h;
     VFB_CUDA(cudaMemcpyAsync(&h, d_chunk, sizeof h, cudaMemcpyDeviceToHost, c->st_compute));
     VFB_CUDA(cudaStreamSynchronize(c->st_compute));
     if (h.magic != VFB_CHUNK_MAGIC || chunk_bytes_for(h.rows, h.key_bytes) > chunk_bytes) { set_error("bad chunk header"); return VFB_ERR_FORMAT; }
-    if (h.rows == 0) return VFB_OK;
-    if (h.rows > 0x7FFFFFFFull) { set_error("chunk too large"); return VFB_ERR_ARG; }
-    int rc;
-    if ((rc = table_reserve(c, h.rows, h.key_bytes))) return rc;
-    if ((rc = c->d_owner.ensure(h.rows * 4))) return rc;
-    const uint64_t n = h.rows;
-    const uint8_t *base = d_chunk + sizeof(ChunkHeader);
-    InsertJob ij;
-    ij.khash = reinterpret_cast<const uint64_t *>(base);
-    ij.kcount = reinterpret_cast<const unsigned long long *>(base + vfb_align16(n * 8));
-    ij.koff = reinterpret_cast<const uint64_t *>(base + vfb_align16(n * 8) * 2);
-    ij.klen = reinterpret_cast<const uint32_t *>(base + vfb_align16(n * 8) * 3);
-    ij.keys = base + vfb_align16(n * 8) * 3 + vfb_align16(n * 4);
-    ij.key_stride = 0;
-    ij.n_keys = (uint32_t)n;
-    ij.owner_slot = c->d_owner.as<uint32_t>();
-    if ((rc = launch_insert(c->tab, ij, c->st_compute))) return rc;
-    bump_launches(c, before);
-    return VFB_OK;
+    return vfb_internal_absorb_known(c, d_chunk, h.rows, h.key_bytes);
 }
 
 // ------------------------------------------------------------------------------------ synth + misc
@@ -1581,6 +1677,12 @@ int vfb_host_free(void *p)
 int vfb_pinned_pool_trim(void)
 {
     pinned_pool_trim();
+    return VFB_OK;
+}
+
+int vfb_device_pool_trim(void)
+{
+    device_pool_trim();
     return VFB_OK;
 }
 

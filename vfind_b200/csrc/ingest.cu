@@ -35,8 +35,8 @@
 #include <thread>
 #include <vector>
 
+#include "ctx.cuh"
 #include "pgunzip.h"
-#include "vfb_internal.cuh"
 
 using namespace vfb;
 
@@ -383,193 +383,464 @@ struct Pipe {
     int err_code = VFB_OK;
 };
 
-// ---- GPU inflate phase: block-gzip members are shipped compressed and inflated on the device.
-struct ZSegment {
-    uint8_t *z = nullptr;          // pinned: whole members back to back
-    vfb_member *members = nullptr; // pinned
-    size_t z_cap = 0, m_cap = 0;   // pinned capacities (for the pool)
-    size_t z_bytes = 0, text_bytes = 0;
-    uint32_t n = 0;
-    bool last = false;             // nothing more for the GPU phase after this segment
-    double read_ms = 0;            // what the reader thread spent filling it (trace)
+// ---- GPU inflate phase: block-gzip members are shipped compressed and inflated on the device(s).
+//
+//   reader threads   pread fixed-size raw blocks of the file into a ring of pinned buffers, in parallel and
+//                    without looking at the bytes (a block boundary falls anywhere);
+//   indexer thread   walks the member headers across the raw blocks in file order and cuts segments of about
+//                    `text_target` bytes of text: a list of members plus the pieces of raw blocks that hold them;
+//   one worker per   takes every n-th segment: phase 1 (vfb_internal_bgzf_begin: H2D of the pieces + inflate) for up
+//   device           to two segments ahead, then phase 2 (vfb_internal_bgzf_finish) in segment order;
+//   the chain        a record may straddle two segments, so phase 2 of segment s needs the text after the last
+//                    complete record of segment s-1 (and the number of records before it, for error messages):
+//                    each worker publishes that when its phase 2 has framed the records, about half a
+//                    millisecond of small kernels per segment — the only serial part of the pipeline.
+// The calling thread waits, reports progress and collects errors.
+struct RawRing {
+    struct Block {
+        uint8_t *p = nullptr;
+        size_t cap = 0, len = 0;
+        uint64_t idx = UINT64_MAX;
+        int state = 0;                 // 0 free, 1 being read, 2 ready
+        int refs = 0;                  // the indexer while it walks the block + one per segment with a piece in it
+    };
+    int fd = -1;
+    uint64_t base = 0, end = 0;        // file range [base, end)
+    size_t block = 0;
+    uint64_t n_blocks = 0, next_idx = 0;
+    std::vector<Block> ring;
+    std::vector<std::thread> threads;
+    std::mutex mu;
+    std::condition_variable cv;
+    bool abort = false;
+    std::string err;
+
+    bool start(int fd_, uint64_t base_, uint64_t end_, size_t block_, int n_ring, int n_threads)
+    {
+        fd = fd_; base = base_; end = end_; block = block_;
+        n_blocks = (end - base + block - 1) / block;
+        if ((uint64_t)n_ring > n_blocks) n_ring = (int)n_blocks;
+        if (n_ring < 1) n_ring = 1;
+        ring.resize((size_t)n_ring);
+        for (auto &b : ring) {
+            b.p = (uint8_t *)pinned_acquire(block, &b.cap);
+            if (!b.p) return false;
+        }
+        if ((uint64_t)n_threads > n_blocks) n_threads = (int)n_blocks;
+        for (int t = 0; t < n_threads; ++t) threads.emplace_back([this] { run(); });
+        return true;
+    }
+    void run()
+    {
+        for (;;) {
+            uint64_t idx;
+            Block *b;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return abort || next_idx >= n_blocks || ring[next_idx % ring.size()].state == 0; });
+                if (abort || next_idx >= n_blocks) return;
+                idx = next_idx++;
+                b = &ring[idx % ring.size()];
+                b->state = 1; b->idx = idx; b->refs = 0;
+            }
+            const uint64_t lo = base + idx * block;
+            const size_t want = (size_t)std::min<uint64_t>(block, end - lo);
+            size_t done = 0;
+            bool bad = false;
+            while (done < want) {
+                const ssize_t got = pread(fd, b->p + done, want - done, (off_t)(lo + done));
+                if (got < 0) { if (errno == EINTR) continue; bad = true; break; }
+                if (got == 0) break;                       // the file shrank: the indexer reports the truncation
+                done += (size_t)got;
+            }
+            std::lock_guard<std::mutex> lk(mu);
+            if (bad) { abort = true; err = std::string("read error: ") + strerror(errno); }
+            b->len = done;
+            b->state = 2;
+            cv.notify_all();
+        }
+    }
+    // Block idx, ready, with one more reference (nullptr after an abort).
+    Block *acquire(uint64_t idx)
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        Block *b = &ring[idx % ring.size()];
+        cv.wait(lk, [&] { return abort || (b->state == 2 && b->idx == idx); });
+        if (abort) return nullptr;
+        ++b->refs;
+        return b;
+    }
+    void ref(uint64_t idx)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        ++ring[idx % ring.size()].refs;
+    }
+    void unref(uint64_t idx)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        Block &b = ring[idx % ring.size()];
+        if (--b.refs == 0) { b.state = 0; cv.notify_all(); }
+    }
+    void stop()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            abort = true;
+            cv.notify_all();
+        }
+        for (auto &t : threads) t.join();
+        threads.clear();
+        for (auto &b : ring) pinned_release(b.p, b.cap);
+        ring.clear();
+    }
 };
 
-// Consumes BGZF members from prod.f until the end of the file or the first member that is not
-// BGZF.  On return prod.carry holds the text after the last complete record, prod.at_end /
-// prod.bgzf say what is left for the host path (which also applies the end-of-input rules).
-int run_bgzf_gpu(vfb_ctx *ctx, ChunkProducer &prod, size_t text_target, uint64_t *n_total, bool trace)
+struct Segment {
+    uint64_t seq = 0;
+    std::vector<vfb_zpiece> pieces;
+    std::vector<uint64_t> blocks;      // raw blocks the pieces live in (one reference each)
+    std::vector<vfb_member> members;
+    uint64_t text_bytes = 0, z_bytes = 0;
+    RawRing *ring = nullptr;
+    int slot = -1;
+};
+
+void segment_release_blocks(void *arg)        // runs on a driver thread once the pieces are on the device
 {
-    // pinned staging for the compressed members of one segment: sized for a 3.2x ratio (a segment
-    // closes early when the buffer fills first) and never beyond what is left of the file
-    size_t zcap = text_target / 16 * 5 + (1u << 20);
-    {
-        const long here = ftell(prod.f);
-        fseek(prod.f, 0, SEEK_END);
-        const long fsz = ftell(prod.f);
-        fseek(prod.f, here, SEEK_SET);
-        if (fsz > here && (size_t)(fsz - here) + 65536 < zcap) zcap = (size_t)(fsz - here) + 65536;
-    }
-    const size_t mcap = text_target / 512 + 4096;
-    constexpr int NSEG = 2;
-    ZSegment seg[NSEG];
+    Segment *g = static_cast<Segment *>(arg);
+    for (uint64_t b : g->blocks) g->ring->unref(b);
+}
+
+struct GpuPhase {
+    std::mutex mu;
+    std::condition_variable cv;
+    bool abort = false, indexed = false;       // indexed: the indexer has queued its last segment
     int rc = VFB_OK;
-    for (auto &g : seg) {
-        void *a = pinned_acquire(zcap, &g.z_cap), *b = pinned_acquire(mcap * sizeof(vfb_member), &g.m_cap);
-        if (!a || !b) {
-            set_error("cannot allocate pinned ingest buffers");
-            rc = VFB_ERR_NOMEM;
-        }
-        g.z = (uint8_t *)a;
-        g.members = (vfb_member *)b;
+    std::string err;
+    uint64_t n_segments = 0;                   // valid once indexed
+    std::vector<std::deque<Segment *>> queues; // per device
+    // the chain: link s = text carried into segment s + records before it
+    struct Link { bool ready = false; std::vector<uint8_t> carry; uint64_t records = 0; };
+    std::deque<Link> links;                    // links[s - link_base]
+    uint64_t link_base = 0;
+    uint64_t records_done = 0, z_done = 0, segments_done = 0;
+    uint64_t stop_off = 0;                     // file offset where the GPU phase ended (valid once indexed)
+    bool hit_plain = false;                    // ... because a member that is not block gzip follows
+
+    void fail(int code, const std::string &msg)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (rc == VFB_OK) { rc = code; err = msg; }
+        abort = true;
+        cv.notify_all();
     }
-    vfb::trace("ingest: pinned segment buffers ready (2 x %zu MB)", zcap >> 20);
-    Pipe pp;
-    for (int i = 0; i < NSEG; ++i) pp.free_q.push_back(i);
-    const int fd = fileno(prod.f);
-    size_t pos = (size_t)ftell(prod.f);
-    size_t z_estimate = std::min(zcap, text_target / 4 + (1u << 20));     // compressed bytes a segment is expected to need
-    std::thread reader;
-    if (rc == VFB_OK) reader = std::thread([&]() {
-        for (;;) {
-            int k;
-            {
-                std::unique_lock<std::mutex> lk(pp.mu);
-                pp.cv.wait(lk, [&] { return !pp.free_q.empty() || pp.abort; });
-                if (pp.abort) return;
-                k = pp.free_q.front();
-                pp.free_q.pop_front();
+    Link &link(uint64_t s)                     // mu held
+    {
+        while (links.size() <= s - link_base) links.emplace_back();
+        return links[s - link_base];
+    }
+};
+
+// Walks member headers over the raw blocks and deals segments to the device queues.
+void index_members(RawRing &ring, GpuPhase &gp, size_t text_target, size_t mcap, size_t max_blocks, int n_dev, size_t queue_depth)
+{
+    uint64_t bi = 0;                           // current raw block
+    size_t bo = 0;                             // offset inside it
+    RawRing::Block *cur = ring.n_blocks ? ring.acquire(0) : nullptr;
+    RawRing::Block *nxt = nullptr;             // block bi + 1 when a header / trailer straddles the boundary
+    if (ring.n_blocks && !cur) { gp.fail(VFB_ERR_IO, ring.err.empty() ? "read aborted" : ring.err); return; }
+    uint64_t seq = 0;
+    Segment *g = nullptr;
+    std::string err;
+    bool plain = false, at_end = false;
+    auto file_off = [&] { return ring.base + bi * ring.block + bo; };
+    // bytes [bo + at, bo + at + n) of the stream that starts at block bi, copied out (they may straddle a block end)
+    auto peek = [&](size_t at, size_t n, uint8_t *out) -> int {          // 1 ok, 0 end of file inside, -1 abort
+        size_t pos = bo + at, got = 0;
+        uint64_t b = bi;
+        while (got < n) {
+            RawRing::Block *blk;
+            if (b == bi) blk = cur;
+            else if (b == bi + 1) {
+                if (!nxt) { if (b >= ring.n_blocks) return 0; nxt = ring.acquire(b); if (!nxt) return -1; }
+                blk = nxt;
+            } else return 0;                   // members are at most 64 KiB: never more than two blocks
+            if (pos >= blk->len) {
+                if (blk->len < ring.block) return 0;                     // short block = end of file
+                pos -= blk->len; ++b;
+                continue;
             }
-            ZSegment &g = seg[k];
-            g.z_bytes = g.text_bytes = 0; g.n = 0; g.last = false;
-            const auto r0 = std::chrono::steady_clock::now();
-            std::string err;
-            // pread straight into the pinned buffer — about as much as the last segment needed,
-            // topped up while whole members are still missing — then walk the member headers
-            size_t avail = 0, off = 0;
-            bool eof = false, stop = false, full = false;
-            size_t step = z_estimate;
-            while (err.empty() && !stop && !full) {
-                if (!eof && avail < zcap) {
-                    const size_t want = std::min(zcap - avail, step);
-                    const ssize_t got = pread_parallel(fd, g.z + avail, want, (off_t)(pos + avail), prod.threads);
-                    if (got < 0) { err = std::string("read error: ") + strerror(errno); break; }
-                    if ((size_t)got < want) eof = true;
-                    avail += (size_t)got;
-                    step = std::max<size_t>((size_t)4 << 20, z_estimate / 4);
-                }
-                bool need_more = false;
-                while (off < avail && g.n < mcap) {
-                    const uint8_t *h = g.z + off;
-                    size_t msize = 0;
-                    bool is_bgzf = false, cut = false;
-                    if (avail - off >= 18 && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4)) {
-                        const uint32_t xlen = h[10] | (h[11] << 8);
-                        if (avail - off >= 12 + (size_t)xlen) {
-                            for (uint32_t x = 0; x + 4 <= xlen;) {
-                                const uint8_t *sf = h + 12 + x;
-                                const uint32_t slen = sf[2] | (sf[3] << 8);
-                                if (sf[0] == 'B' && sf[1] == 'C' && slen == 2 && x + 6 <= xlen) { msize = (size_t)(sf[4] | (sf[5] << 8)) + 1; is_bgzf = true; break; }
-                                x += 4 + slen;
-                            }
-                        } else cut = true;                          // header cut by what has been read so far
-                    } else if (avail - off < 18) cut = true;
-                    if (cut && !eof) { need_more = true; break; }
-                    if (!is_bgzf) {
-                        if (cut) { err = "truncated gzip stream"; break; }     // end of file inside a header
-                        prod.bgzf = false; g.last = true; stop = true;       // plain gzip from here: host path
-                        break;
-                    }
-                    if (msize < 26) { err = "invalid BGZF member"; break; }
-                    if (off + msize > avail) {
-                        if (eof) err = "truncated gzip stream";              // end of file inside a member
-                        else need_more = true;
-                        break;
-                    }
-                    const uint8_t *t = h + msize - 4;
-                    const uint32_t isize = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
-                    if (g.n && g.text_bytes + isize > text_target) { full = true; break; }
-                    g.members[g.n++] = vfb_member{(uint32_t)off, (uint32_t)msize, (uint32_t)g.text_bytes, isize};
-                    off += msize;
-                    g.text_bytes += isize;
-                }
-                if (!err.empty() || stop || full) break;
-                if (g.n >= mcap) break;
-                if (avail >= zcap) {
-                    if (need_more && off == 0) err = "a gzip member does not fit the ingest buffer";
-                    break;                                           // the buffer is full: next segment
-                }
-                if (eof) break;                                      // everything read and consumed
-            }
-            if (off) z_estimate = off + off / 16 + 65536;
-            vfb::trace("ingest reader: segment of %u members, %zu compressed bytes read", g.n, off);
-            g.z_bytes = off;
-            g.read_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - r0).count();
-            pos += off;
-            if (err.empty() && !stop && eof && off == avail) { prod.at_end = true; g.last = true; }
-            std::lock_guard<std::mutex> lk(pp.mu);
-            if (!err.empty()) {
-                pp.failed = true; pp.err = err; pp.err_code = VFB_ERR_FORMAT; pp.done = true;
-                pp.cv.notify_all();
-                return;
-            }
-            pp.ready_q.push_back(k);
-            if (g.last) pp.done = true;
-            pp.cv.notify_all();
-            if (g.last) return;
+            const size_t take = std::min(n - got, blk->len - pos);
+            memcpy(out + got, blk->p + pos, take);
+            got += take; pos += take;
         }
-    });
-    std::vector<uint8_t> tail(VFB_TAIL_CAP);
-    uint64_t seg_bytes_done = pos;
-    while (rc == VFB_OK) {
-        int k = -1;
-        const auto w0 = std::chrono::steady_clock::now();
+        return 1;
+    };
+    auto discard = [&](Segment *seg) {
+        for (uint64_t b : seg->blocks) ring.unref(b);
+        delete seg;
+    };
+    auto push = [&](Segment *seg) -> bool {            // takes the segment either way
         {
-            std::unique_lock<std::mutex> lk(pp.mu);
-            pp.cv.wait(lk, [&] { return !pp.ready_q.empty() || pp.done; });
-            if (!pp.ready_q.empty()) { k = pp.ready_q.front(); pp.ready_q.pop_front(); }
-            else if (pp.failed) { set_error(pp.err); rc = pp.err_code; break; }
-            else break;
+            std::unique_lock<std::mutex> lk(gp.mu);
+            auto &q = gp.queues[seg->seq % (uint64_t)n_dev];
+            gp.cv.wait(lk, [&] { return gp.abort || q.size() < queue_depth; });
+            if (!gp.abort) {
+                q.push_back(seg);
+                gp.cv.notify_all();
+                return true;
+            }
         }
-        ZSegment &g = seg[k];
-        const auto t0 = std::chrono::steady_clock::now();
+        discard(seg);
+        return false;
+    };
+    while (cur) {
+        if (bo >= cur->len) {
+            // next block (or the end of the file)
+            const bool short_block = cur->len < ring.block;
+            if (short_block || bi + 1 >= ring.n_blocks) { at_end = true; break; }
+            RawRing::Block *n2 = nxt ? nxt : ring.acquire(bi + 1);
+            if (!n2) { err = ring.err.empty() ? "read aborted" : ring.err; break; }
+            bo -= cur->len;
+            ring.unref(bi);
+            cur = n2; nxt = nullptr; ++bi;
+            continue;
+        }
+        uint8_t h[18];
+        int k = peek(0, 18, h);
+        if (k < 0) { err = ring.err.empty() ? "read aborted" : ring.err; break; }
+        size_t msize = 0;
+        bool is_bgzf = false;
+        if (k == 1 && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4)) {
+            const uint32_t xlen = h[10] | (h[11] << 8);
+            std::vector<uint8_t> x(xlen);
+            const int kx = xlen >= 6 ? peek(12, xlen, x.data()) : 0;
+            if (kx < 0) { err = "read aborted"; break; }
+            if (kx == 1)
+                for (uint32_t p = 0; p + 4 <= xlen;) {
+                    const uint32_t slen = x[p + 2] | (x[p + 3] << 8);
+                    if (x[p] == 'B' && x[p + 1] == 'C' && slen == 2 && p + 6 <= xlen) { msize = (size_t)(x[p + 4] | (x[p + 5] << 8)) + 1; is_bgzf = true; break; }
+                    p += 4 + slen;
+                }
+            else if (xlen >= 6) { err = "truncated gzip stream"; break; }
+        }
+        if (k == 0) { err = "truncated gzip stream"; break; }      // fewer than 18 bytes left: no gzip member is that short
+        if (!is_bgzf) { plain = true; break; }     // some other gzip member (or garbage): the host path decides
+        if (msize < 26) { err = "invalid BGZF member"; break; }
+        uint8_t t[4];
+        k = peek(msize - 4, 4, t);
+        if (k < 0) { err = "read aborted"; break; }
+        if (k == 0) { err = "truncated gzip stream"; break; }
+        const uint32_t isize = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
+        if (g && (g->text_bytes + isize > text_target || g->members.size() >= mcap || g->blocks.size() >= max_blocks)) {
+            Segment *full = g;
+            g = nullptr;
+            if (!push(full)) break;
+        }
+        if (!g) {
+            g = new Segment;
+            g->seq = seq++;
+            g->ring = &ring;
+        }
+        g->members.push_back(vfb_member{(uint32_t)g->z_bytes, (uint32_t)msize, (uint32_t)g->text_bytes, isize});
+        // the member's bytes: in this block, and the next one if it straddles the boundary
+        size_t left = msize, pos = bo;
+        uint64_t b = bi;
+        while (left) {
+            RawRing::Block *blk = b == bi ? cur : nxt;
+            const size_t take = std::min(left, blk->len - pos);
+            if (g->blocks.empty() || g->blocks.back() != b) { g->blocks.push_back(b); ring.ref(b); }
+            if (!g->pieces.empty() && g->pieces.back().p + g->pieces.back().len == blk->p + pos) g->pieces.back().len += take;
+            else g->pieces.push_back(vfb_zpiece{blk->p + pos, take});
+            left -= take; pos = 0; ++b;
+        }
+        g->z_bytes += msize;
+        g->text_bytes += isize;
+        bo += msize;                           // may run past the block: the loop head moves on
+    }
+    if (nxt) ring.unref(bi + 1);
+    const uint64_t stop = cur ? file_off() : ring.base;
+    if (cur) ring.unref(bi);
+    if (g && err.empty() && !g->members.empty()) { push(g); g = nullptr; }
+    if (g) { discard(g); --seq; }
+    if (!err.empty()) { gp.fail(VFB_ERR_FORMAT, err); return; }
+    std::lock_guard<std::mutex> lk(gp.mu);
+    gp.indexed = true;
+    gp.n_segments = seq;
+    gp.stop_off = stop;
+    gp.hit_plain = plain && !at_end;
+    gp.cv.notify_all();
+}
+
+// One device: phase 1 up to two segments ahead, phase 2 in segment order.
+void device_worker(vfb_ctx *ctx, int dev_index, GpuPhase &gp)
+{
+    std::deque<Segment *> pending;
+    std::vector<uint8_t> tail(VFB_TAIL_CAP);
+    auto drop = [&](Segment *g) { delete g; };
+    for (;;) {
+        // phase 1 for what is queued (wait only when nothing is pending)
+        bool finished = false;
+        while (pending.size() < VFB_SEG_SLOTS - 1) {
+            Segment *g = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(gp.mu);
+                auto &q = gp.queues[(size_t)dev_index];
+                if (pending.empty()) gp.cv.wait(lk, [&] { return gp.abort || !q.empty() || gp.indexed; });
+                if (gp.abort) break;
+                if (!q.empty()) { g = q.front(); q.pop_front(); gp.cv.notify_all(); }
+                else { finished = gp.indexed; }
+            }
+            if (!g) break;
+            const int rc = vfb_internal_bgzf_begin(ctx, g->pieces.data(), (uint32_t)g->pieces.size(), g->members.data(),
+                                                   (uint32_t)g->members.size(), g->text_bytes, segment_release_blocks, g, &g->slot);
+            if (rc) {
+                for (uint64_t b : g->blocks) g->ring->unref(b);
+                gp.fail(rc, vfb_last_error());
+                drop(g);
+                break;
+            }
+            pending.push_back(g);
+        }
+        {
+            std::lock_guard<std::mutex> lk(gp.mu);
+            if (gp.abort) break;
+        }
+        if (pending.empty()) { if (finished) break; else continue; }
+        Segment *g = pending.front();
+        pending.pop_front();
+        std::vector<uint8_t> carry;
+        uint64_t record_base = 0;
+        {
+            std::unique_lock<std::mutex> lk(gp.mu);
+            gp.cv.wait(lk, [&] { return gp.abort || gp.link(g->seq).ready; });
+            if (gp.abort) { drop(g); break; }
+            GpuPhase::Link &l = gp.link(g->seq);
+            carry.swap(l.carry);
+            record_base = l.records;
+            while (gp.link_base < g->seq && !gp.links.empty()) { gp.links.pop_front(); ++gp.link_base; }
+        }
         uint64_t n_rec = 0, tail_len = 0;
         uint32_t bad = 0xFFFFFFFFu;
-        rc = vfb_internal_submit_bgzf(ctx, g.z, g.z_bytes, g.members, g.n, g.text_bytes, prod.carry.data(),
-                                      prod.carry.size(), *n_total, &n_rec, tail.data(), &tail_len, &bad);
+        int rc = vfb_internal_bgzf_finish(ctx, g->slot, carry.data(), carry.size(), record_base, &n_rec, tail.data(), &tail_len, &bad);
         if (rc == VFB_OK && bad != 0xFFFFFFFFu) {
             set_error("invalid gzip data in a BGZF member (deflate stream, CRC-32 or size mismatch)");
             rc = VFB_ERR_FORMAT;
         }
-        if (rc == VFB_OK) {
-            prod.carry.assign(tail.data(), tail.data() + tail_len);
-            *n_total += n_rec;
-            seg_bytes_done += g.z_bytes;
-            vfb_internal_progress(ctx, *n_total, seg_bytes_done, prod.file_size, false);
-            if (trace) fprintf(stderr, "[vfb ingest] gpu segment: %u members, %zu -> %zu bytes, %llu records, %.1f ms (waited %.1f ms for the reader, which took %.1f ms)\n", g.n,
-                               g.z_bytes, g.text_bytes, (unsigned long long)n_rec,
-                               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(),
-                               std::chrono::duration<double, std::milli>(t0 - w0).count(), g.read_ms);
+        if (rc) { gp.fail(rc, vfb_last_error()); drop(g); break; }
+        {
+            std::lock_guard<std::mutex> lk(gp.mu);
+            GpuPhase::Link &l = gp.link(g->seq + 1);
+            l.carry.assign(tail.data(), tail.data() + tail_len);
+            l.records = record_base + n_rec;
+            l.ready = true;
+            gp.records_done += n_rec;
+            gp.z_done += g->z_bytes;
+            ++gp.segments_done;
+            gp.cv.notify_all();
         }
-        std::lock_guard<std::mutex> lk(pp.mu);
-        pp.free_q.push_back(k);
-        pp.cv.notify_all();
+        drop(g);
+    }
+    // an abort may leave segments behind whose release callback is still queued: wait for the stream, then free
+    if (!pending.empty()) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->st_ingest);
+        for (Segment *g : pending) delete g;
+    }
+}
+
+// Consumes BGZF members from prod.f until the end of the file or the first member that is not
+// BGZF.  On return prod.carry holds the text after the last complete record, prod.at_end /
+// prod.bgzf say what is left for the host path (which also applies the end-of-input rules).
+int run_bgzf_gpu(vfb_ctx **ctxs, int n_dev, ChunkProducer &prod, size_t text_target, uint64_t *n_total, bool trace)
+{
+    const int fd = fileno(prod.f);
+    const uint64_t here = (uint64_t)ftell(prod.f);
+    fseek(prod.f, 0, SEEK_END);
+    const uint64_t fsz = (uint64_t)ftell(prod.f);
+    fseek(prod.f, (long)here, SEEK_SET);
+    if (fsz <= here) { prod.at_end = true; return VFB_OK; }
+    // segments: about text_target bytes of text, smaller when the file would not give every device a few of them
+    if (!getenv("VFB_INGEST_CHUNK")) {
+        const uint64_t est_text = (fsz - here) * 4;
+        uint64_t per = est_text / ((uint64_t)n_dev * 4);
+        if (per < ((uint64_t)16 << 20)) per = (uint64_t)16 << 20;
+        if (per < text_target) text_target = (size_t)per;
+    }
+    // raw blocks of 8 MB; the ring holds 128 MB for one device, up to 512 MB for eight (page-locked once per process:
+    // the buffers come from the pinned pool); a segment may hold a third of the ring
+    size_t block = (size_t)8 << 20;
+    if (const char *e = getenv("VFB_RAW_BLOCK")) block = (size_t)strtoull(e, nullptr, 10);
+    if (block < 131072) block = 131072;                     // a member (<= 64 KiB) spans at most two blocks
+    if (block > fsz - here) block = (size_t)((fsz - here + 4095) & ~(uint64_t)4095);
+    if (block < 131072) block = 131072;
+    size_t ring_bytes = (size_t)96 << 20;
+    ring_bytes *= (size_t)n_dev;
+    if (ring_bytes < ((size_t)128 << 20)) ring_bytes = (size_t)128 << 20;
+    if (ring_bytes > ((size_t)512 << 20)) ring_bytes = (size_t)512 << 20;
+    int n_ring = (int)(ring_bytes / block);
+    if (n_ring < 6) n_ring = 6;
+    int n_threads = prod.threads < 1 ? 1 : prod.threads;
+    if (n_threads > n_ring / 2) n_threads = n_ring / 2;
+    const size_t max_blocks = (size_t)(n_ring / 3);
+    RawRing ring;
+    GpuPhase gp;
+    gp.queues.resize((size_t)n_dev);
+    gp.link(0).ready = true;
+    gp.link(0).carry = prod.carry;
+    gp.link(0).records = *n_total;
+    if (!ring.start(fd, here, fsz, block, n_ring, n_threads)) {
+        ring.stop();
+        set_error("cannot allocate pinned ingest buffers");
+        return VFB_ERR_NOMEM;
+    }
+    vfb::trace("ingest: %d raw blocks of %zu MB, %d reader threads, %d device(s), segments of %zu MB of text", (int)ring.ring.size(),
+               block >> 20, n_threads, n_dev, text_target >> 20);
+    const size_t mcap = text_target / 512 + 4096;
+    std::thread indexer([&] { index_members(ring, gp, text_target, mcap, max_blocks, n_dev, 2); });
+    std::vector<std::thread> workers;
+    for (int d = 0; d < n_dev; ++d) workers.emplace_back([&, d] { device_worker(ctxs[d], d, gp); });
+    // the calling thread: progress and the end
+    const uint64_t base_records = *n_total;
+    {
+        std::unique_lock<std::mutex> lk(gp.mu);
+        for (;;) {
+            gp.cv.wait_for(lk, std::chrono::milliseconds(100), [&] { return gp.abort || (gp.indexed && gp.segments_done == gp.n_segments); });
+            if (gp.abort || (gp.indexed && gp.segments_done == gp.n_segments)) break;
+            const uint64_t r = base_records + gp.records_done, z = here + gp.z_done;
+            lk.unlock();
+            vfb_internal_progress(ctxs[0], r, z, prod.file_size, false);
+            lk.lock();
+        }
     }
     {
-        std::lock_guard<std::mutex> lk(pp.mu);
-        pp.abort = true;
-        pp.cv.notify_all();
+        // an abort must reach the threads that wait on the ring, too
+        std::lock_guard<std::mutex> lk(gp.mu);
+        if (gp.abort) { std::lock_guard<std::mutex> l2(ring.mu); ring.abort = true; ring.cv.notify_all(); }
     }
-    if (reader.joinable()) reader.join();
-    fseek(prod.f, (long)pos, SEEK_SET);      // the host path continues where the GPU phase stopped
-    if (rc == VFB_OK && pp.failed) { set_error(pp.err); rc = pp.err_code; }
-    const std::string keep = rc ? std::string(vfb_last_error()) : std::string();
-    vfb_sync(ctx);                 // the pinned buffers are about to go away
-    if (rc) set_error(keep);
-    for (auto &g : seg) {
-        pinned_release(g.z, g.z_cap);
-        pinned_release(g.members, g.m_cap);
+    indexer.join();
+    for (auto &t : workers) t.join();
+    int rc = gp.rc;
+    std::string keep = gp.err;
+    for (int d = 0; d < n_dev; ++d) {
+        const int src = vfb_sync(ctxs[d]);     // the raw blocks are about to go away
+        if (src && rc == VFB_OK) { rc = src; keep = vfb_last_error(); }
     }
-    return rc;
+    for (auto &q : gp.queues) for (Segment *g : q) { for (uint64_t b : g->blocks) ring.unref(b); delete g; }
+    ring.stop();
+    if (rc) { set_error(keep); return rc; }
+    GpuPhase::Link &last = gp.link(gp.n_segments);
+    prod.carry = last.carry;
+    *n_total = last.records;
+    if (trace) fprintf(stderr, "[vfb ingest] gpu phase: %llu segments, %llu records, stopped at offset %llu of %llu%s\n",
+                       (unsigned long long)gp.n_segments, (unsigned long long)(*n_total - base_records),
+                       (unsigned long long)gp.stop_off, (unsigned long long)fsz, gp.hit_plain ? " (a plain gzip member follows)" : "");
+    fseek(prod.f, (long)gp.stop_off, SEEK_SET);      // the host path continues where the GPU phase stopped
+    if (gp.hit_plain) prod.bgzf = false;
+    else prod.at_end = true;
+    prod.consumed = gp.stop_off;
+    vfb_internal_progress(ctxs[0], *n_total, gp.stop_off, prod.file_size, false);
+    return VFB_OK;
 }
 
 }  // namespace
@@ -615,6 +886,14 @@ extern "C" int vfb_run_file(vfb_ctx *ctx, const char *path, uint64_t *n_reads_ou
 extern "C" int vfb_run_file_ex(vfb_ctx *ctx, const char *path, uint32_t flags, uint64_t *n_reads_out)
 {
     if (!ctx || !path) { set_error("null argument"); return VFB_ERR_ARG; }
+    return vfb_internal_run_file(&ctx, 1, path, flags, n_reads_out);
+}
+
+// One file over n_ctx contexts (one per device; vfb_multi_run_file): block-gzip segments and host-inflated
+// chunks are dealt round robin, every context counts what it is given into its own table.
+int vfb_internal_run_file(vfb_ctx **ctxs, uint32_t n_ctx, const char *path, uint32_t flags, uint64_t *n_reads_out)
+{
+    vfb_ctx *ctx = ctxs[0];
     ChunkProducer prod;
     {
         std::string e;
@@ -630,7 +909,7 @@ extern "C" int vfb_run_file_ex(vfb_ctx *ctx, const char *path, uint32_t flags, u
     const char *gi = getenv("VFB_GPU_INFLATE");
     if (prod.bgzf && !(gi && gi[0] == '0')) {
         if (trace) fprintf(stderr, "[vfb ingest] %s: block gzip, inflating on the GPU\n", path);
-        rc = run_bgzf_gpu(ctx, prod, getenv("VFB_INGEST_CHUNK") ? cap : ((size_t)256 << 20), &n_total, trace);
+        rc = run_bgzf_gpu(ctxs, (int)n_ctx, prod, getenv("VFB_INGEST_CHUNK") ? cap : ((size_t)256 << 20), &n_total, trace);
         if (rc) return rc;
         // only the text after the last complete record may be left: no need for big chunks
         if (prod.at_end) cap = prod.carry.size() * 2 + 65536;
@@ -638,16 +917,21 @@ extern "C" int vfb_run_file_ex(vfb_ctx *ctx, const char *path, uint32_t flags, u
 
     constexpr int NCH = 3;
     Chunk ch[NCH];
+    std::vector<cudaEvent_t> ch_events((size_t)NCH * n_ctx, nullptr);     // [chunk][context]: an event belongs to a device
+    int ch_ctx[NCH] = {0, 0, 0};
     Pipe pp;
     for (int i = 0; i < NCH; ++i) {
         void *p = pinned_acquire(cap + 64, &ch[i].buf_cap);
-        if (!p || cudaEventCreateWithFlags(&ch[i].copied, cudaEventDisableTiming) != cudaSuccess) {
-            cudaGetLastError();
-            set_error("cannot allocate pinned ingest buffers");
-            rc = VFB_ERR_NOMEM;
-        }
+        if (!p) { set_error("cannot allocate pinned ingest buffers"); rc = VFB_ERR_NOMEM; }
         ch[i].buf = (uint8_t *)p;
         pp.free_q.push_back(i);
+        for (uint32_t d = 0; d < n_ctx && rc == VFB_OK; ++d)
+            if (cudaSetDevice(ctxs[d]->device) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ch_events[(size_t)i * n_ctx + d], cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError();
+                set_error("cannot create ingest events");
+                rc = VFB_ERR_CUDA;
+            }
     }
 
     auto ms_since = [&](std::chrono::steady_clock::time_point t) {
@@ -685,6 +969,7 @@ extern "C" int vfb_run_file_ex(vfb_ctx *ctx, const char *path, uint32_t flags, u
     });
 
     std::deque<int> in_flight;
+    uint64_t n_chunks = 0;
     while (rc == VFB_OK) {
         int k = -1;
         {
@@ -695,13 +980,16 @@ extern "C" int vfb_run_file_ex(vfb_ctx *ctx, const char *path, uint32_t flags, u
             else break;     // done and drained
         }
         Chunk &c = ch[k];
+        const uint32_t d = (uint32_t)(n_chunks++ % n_ctx);
+        ch_ctx[k] = (int)d;
+        c.copied = ch_events[(size_t)k * n_ctx + d];
         if (c.lines) {
             const auto t0 = std::chrono::steady_clock::now();
-            rc = vfb_internal_submit_fastq(ctx, c.buf, c.cut, c.lines, n_total, c.copied);
+            rc = vfb_internal_submit_fastq(ctxs[d], c.buf, c.cut, c.lines, n_total, c.copied);
             if (trace) fprintf(stderr, "[vfb ingest] submit at %.1f ms took %.1f ms\n", ms_since(t_start), ms_since(t0));
             n_total += c.lines / 4;
             vfb_internal_progress(ctx, n_total, prod.consumed.load(), prod.file_size, false);
-        } else if (cudaEventRecord(c.copied, 0) != cudaSuccess) {
+        } else if (cudaSetDevice(ctxs[d]->device) != cudaSuccess || cudaEventRecord(c.copied, ctxs[d]->st_copy) != cudaSuccess) {
             cudaGetLastError();
         }
         in_flight.push_back(k);
@@ -709,6 +997,7 @@ extern "C" int vfb_run_file_ex(vfb_ctx *ctx, const char *path, uint32_t flags, u
         // stays outstanding so that inflating the next chunk overlaps it
         while (rc == VFB_OK && in_flight.size() > 1) {
             const int o = in_flight.front();
+            cudaSetDevice(ctxs[ch_ctx[o]]->device);
             if (cudaEventSynchronize(ch[o].copied) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "ingest event", __FILE__, __LINE__); break; }
             in_flight.pop_front();
             std::lock_guard<std::mutex> lk(pp.mu);
@@ -724,24 +1013,30 @@ extern "C" int vfb_run_file_ex(vfb_ctx *ctx, const char *path, uint32_t flags, u
     if (producer.joinable()) producer.join();
     if (rc == VFB_OK && pp.failed) { set_error(pp.err); rc = pp.err_code; }
     // the malformed-record flag comes back from the device
-    const std::string keep = rc ? std::string(vfb_last_error()) : std::string();
+    std::string keep = rc ? std::string(vfb_last_error()) : std::string();
     if (trace) fprintf(stderr, "[vfb ingest] all chunks queued at %.1f ms\n", ms_since(t_start));
-    const int src = vfb_sync(ctx);
+    for (uint32_t d = 0; d < n_ctx; ++d) {
+        const int src = vfb_sync(ctxs[d]);
+        if (src && rc == VFB_OK) { rc = src; keep = vfb_last_error(); }
+    }
     if (trace) fprintf(stderr, "[vfb ingest] device drained at %.1f ms\n", ms_since(t_start));
-    if (rc == VFB_OK) rc = src; else set_error(keep);
+    if (rc) set_error(keep);
     if (rc == VFB_OK) {
         uint64_t bad = UINT64_MAX;
-        rc = vfb_internal_parse_error(ctx, &bad);
+        for (uint32_t d = 0; d < n_ctx && rc == VFB_OK; ++d) {
+            uint64_t b = UINT64_MAX;
+            rc = vfb_internal_parse_error(ctxs[d], &b);
+            if (b < bad) bad = b;
+        }
         if (rc == VFB_OK && bad != UINT64_MAX) {
             set_error("FASTQ record " + std::to_string(bad) +
                       ": malformed (expected '@' header, '+' separator, sequence and quality of equal length)");
             rc = VFB_ERR_FORMAT;
         }
     }
-    for (int i = 0; i < NCH; ++i) {
-        pinned_release(ch[i].buf, ch[i].buf_cap);
-        if (ch[i].copied) cudaEventDestroy(ch[i].copied);
-    }
+    for (int i = 0; i < NCH; ++i) pinned_release(ch[i].buf, ch[i].buf_cap);
+    for (size_t i = 0; i < ch_events.size(); ++i)
+        if (ch_events[i]) { cudaSetDevice(ctxs[i % n_ctx]->device); cudaEventDestroy(ch_events[i]); }
     if (n_reads_out) *n_reads_out = n_total;
     if (rc == VFB_OK) vfb_internal_progress(ctx, n_total, prod.file_size, prod.file_size, true);
     if (trace) fprintf(stderr, "[vfb ingest] %llu records in %.1f ms\n", (unsigned long long)n_total,

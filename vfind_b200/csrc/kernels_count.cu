@@ -705,26 +705,33 @@ int launch_export_counts(const DevTable &t, uint64_t rows, unsigned long long *r
 }
 
 // ------------------------------------------------------------------------------------ export
-// Arrow-style compaction of the table on the device: offsets = exclusive scan of the row
-// lengths, data = the keys back to back (the arena pads every key to 16 bytes).
+// Arrow-style compaction of the table on the device: the rows whose count is not zero (a merge leaves the
+// rows it handed to another rank behind with count 0), offsets = exclusive scan of their lengths (plus
+// `byte_base`, so that several devices can write consecutive pieces of one column), counts, and the keys
+// back to back (the arena pads every key to 16 bytes).
 #define EXP_ROWS 1024   // rows per block
 
 __global__ void __launch_bounds__(256)
-k_export_sums(const uint32_t *__restrict__ row_len, uint64_t rows, unsigned long long *__restrict__ block_sums)
+k_export_sums(const uint32_t *__restrict__ row_len, const unsigned long long *__restrict__ row_count, uint64_t rows,
+              unsigned long long *__restrict__ block_bytes, unsigned long long *__restrict__ block_rows)
 {
-    __shared__ unsigned long long s_part[8];
+    __shared__ unsigned long long s_part[8], s_rows[8];
     const uint64_t r0 = (uint64_t)blockIdx.x * EXP_ROWS;
-    unsigned long long acc = 0;
+    unsigned long long acc = 0, kept = 0;
     for (uint32_t k = threadIdx.x; k < EXP_ROWS; k += 256)
-        if (r0 + k < rows) acc += row_len[r0 + k];
+        if (r0 + k < rows && row_count[r0 + k]) { acc += row_len[r0 + k]; ++kept; }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        kept += __shfl_xor_sync(0xffffffffu, kept, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_part[threadIdx.x >> 5] = acc; s_rows[threadIdx.x >> 5] = kept; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned long long t = 0;
-        for (int w = 0; w < 8; ++w) t += s_part[w];
-        block_sums[blockIdx.x] = t;
+        unsigned long long t = 0, n = 0;
+        for (int w = 0; w < 8; ++w) { t += s_part[w]; n += s_rows[w]; }
+        block_bytes[blockIdx.x] = t;
+        block_rows[blockIdx.x] = n;
     }
 }
 
@@ -768,46 +775,60 @@ k_export_scan(unsigned long long *block_sums, uint64_t n_blocks, unsigned long l
 }
 
 __global__ void __launch_bounds__(256)
-k_export_gather(const DevTable t, uint64_t rows, const unsigned long long *__restrict__ block_off,
-                unsigned long long *__restrict__ offsets, uint8_t *__restrict__ data)
+k_export_gather(const DevTable t, uint64_t rows, const unsigned long long *__restrict__ row_count,
+                const unsigned long long *__restrict__ block_off, const unsigned long long *__restrict__ block_row,
+                unsigned long long byte_base, unsigned long long *__restrict__ offsets,
+                unsigned long long *__restrict__ counts, uint8_t *__restrict__ data)
 {
-    __shared__ unsigned long long s_off[EXP_ROWS];
+    __shared__ unsigned long long s_off[EXP_ROWS];       // ~0 = row not exported
     __shared__ unsigned long long s_warp[8];
+    __shared__ uint32_t s_wrows[8];
     const uint64_t r0 = (uint64_t)blockIdx.x * EXP_ROWS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // each thread owns 4 consecutive rows of the block
     uint32_t len[4];
+    unsigned long long cnt[4];
     unsigned long long mine = 0;
+    uint32_t mine_rows = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const uint64_t r = r0 + threadIdx.x * 4 + k;
-        len[k] = r < rows ? t.row_len[r] : 0u;
+        cnt[k] = r < rows ? row_count[r] : 0ull;
+        len[k] = cnt[k] ? t.row_len[r] : 0u;
         mine += len[k];
+        mine_rows += cnt[k] ? 1u : 0u;
     }
     unsigned long long incl = mine;
+    uint32_t incl_rows = mine_rows;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += u;
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl_rows, o);
+        if (lane >= o) { incl += u; incl_rows += v; }
     }
-    if (lane == 31) s_warp[warp] = incl;
+    if (lane == 31) { s_warp[warp] = incl; s_wrows[warp] = incl_rows; }
     __syncthreads();
     unsigned long long wbase = 0;
-    for (int w = 0; w < warp; ++w) wbase += s_warp[w];
+    uint32_t wrows = 0;
+    for (int w = 0; w < warp; ++w) { wbase += s_warp[w]; wrows += s_wrows[w]; }
     unsigned long long o = block_off[blockIdx.x] + wbase + (incl - mine);
+    unsigned long long ri = block_row[blockIdx.x] + wrows + (incl_rows - mine_rows);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const uint64_t r = r0 + threadIdx.x * 4 + k;
-        s_off[threadIdx.x * 4 + k] = o;
-        if (r < rows) offsets[r] = o;
+        s_off[threadIdx.x * 4 + k] = cnt[k] ? o : ~0ull;
+        if (cnt[k]) {
+            offsets[ri] = byte_base + o;
+            counts[ri] = cnt[k];
+            ++ri;
+        }
         o += len[k];
-        if (r + 1 == rows) offsets[rows] = o;
     }
     __syncthreads();
     // copy: one warp per row, lanes over bytes
     for (uint32_t k = warp; k < EXP_ROWS; k += 8) {
         const uint64_t r = r0 + k;
         if (r >= rows) break;
+        if (s_off[k] == ~0ull) continue;
         const uint32_t n = t.row_len[r];
         const uint8_t *src = t.arena + t.row_off[r];
         uint8_t *dst = data + s_off[k];
@@ -815,15 +836,31 @@ k_export_gather(const DevTable t, uint64_t rows, const unsigned long long *__res
     }
 }
 
-int launch_export_arrow(const DevTable &t, uint64_t rows, unsigned long long *block_sums,
-                        unsigned long long *total, unsigned long long *offsets, uint8_t *data, cudaStream_t st)
+// Pass 1: block sums and their scans; totals[0] = key bytes, totals[1] = rows that will be exported.
+int launch_export_sizes(const DevTable &t, uint64_t rows, const unsigned long long *row_count,
+                        unsigned long long *block_bytes, unsigned long long *block_rows, unsigned long long *totals,
+                        cudaStream_t st)
 {
     if (rows == 0) return VFB_OK;
     const uint64_t nb = (rows + EXP_ROWS - 1) / EXP_ROWS;
-    k_export_sums<<<(uint32_t)nb, 256, 0, st>>>(t.row_len, rows, block_sums);
-    k_export_scan<<<1, 1024, 0, st>>>(block_sums, nb, total);
-    k_export_gather<<<(uint32_t)nb, 256, 0, st>>>(t, rows, block_sums, offsets, data);
+    k_export_sums<<<(uint32_t)nb, 256, 0, st>>>(t.row_len, row_count, rows, block_bytes, block_rows);
+    k_export_scan<<<1, 1024, 0, st>>>(block_bytes, nb, totals);
+    k_export_scan<<<1, 1024, 0, st>>>(block_rows, nb, totals + 1);
     g_launches += 3;
+    VFB_CUDA(cudaGetLastError());
+    return VFB_OK;
+}
+
+// Pass 2: offsets[i] = byte_base + start of exported row i, counts[i], keys back to back in data.
+int launch_export_gather(const DevTable &t, uint64_t rows, const unsigned long long *row_count,
+                         const unsigned long long *block_bytes, const unsigned long long *block_rows,
+                         unsigned long long byte_base, unsigned long long *offsets, unsigned long long *counts,
+                         uint8_t *data, cudaStream_t st)
+{
+    if (rows == 0) return VFB_OK;
+    const uint64_t nb = (rows + EXP_ROWS - 1) / EXP_ROWS;
+    k_export_gather<<<(uint32_t)nb, 256, 0, st>>>(t, rows, row_count, block_bytes, block_rows, byte_base, offsets, counts, data);
+    ++g_launches;
     VFB_CUDA(cudaGetLastError());
     return VFB_OK;
 }
@@ -850,16 +887,29 @@ __device__ __forceinline__ void part_group(uint32_t p, bool valid, uint32_t padd
     }
 }
 
+// Rows take part in a merge when their count is not zero and, if `self` names a part (self < n_parts), when
+// they are owned by another part: a rank keeps the rows it owns where they are.
+__device__ __forceinline__ bool part_of(const DevTable &t, uint64_t r, const unsigned long long *row_count,
+                                        uint32_t n_parts, uint32_t self, uint64_t *h_out, uint32_t *p_out)
+{
+    const uint64_t h = t.row_hash[r];
+    const uint32_t p = vfb_hash_owner(h, n_parts);
+    *h_out = h;
+    *p_out = p;
+    return row_count[r] != 0ull && p != self;
+}
+
 __global__ void __launch_bounds__(256)
-k5_partition_count(const DevTable t, uint64_t rows, uint32_t n_parts,
-                   unsigned long long *part_rows, unsigned long long *part_keybytes)
+k5_partition_count(const DevTable t, uint64_t rows, const unsigned long long *__restrict__ row_count, uint32_t n_parts,
+                   uint32_t self, unsigned long long *part_rows, unsigned long long *part_keybytes)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
     for (uint64_t r0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); r0 < rows; r0 += stride) {
         const uint64_t r = r0 + lane;
-        const bool valid = r < rows;
-        const uint32_t p = valid ? vfb_hash_owner(t.row_hash[r], n_parts) : 0u;
+        uint64_t h = 0;
+        uint32_t p = 0;
+        const bool valid = r < rows && part_of(t, r, row_count, n_parts, self, &h, &p);
         const uint32_t padded = valid ? (t.row_len[r] + 15u) & ~15u : 0u;
         unsigned peers;
         uint32_t rank, brank, gbytes;
@@ -871,32 +921,39 @@ k5_partition_count(const DevTable t, uint64_t rows, uint32_t n_parts,
     }
 }
 
-int launch_partition_count(const DevTable &t, uint64_t rows, uint32_t n_parts,
-                           unsigned long long *part_rows, unsigned long long *part_keybytes,
+int launch_partition_count(const DevTable &t, uint64_t rows, const unsigned long long *row_count, uint32_t n_parts,
+                           uint32_t self, unsigned long long *part_rows, unsigned long long *part_keybytes,
                            cudaStream_t st)
 {
     if (rows == 0) return VFB_OK;
     uint64_t blocks = (rows + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    k5_partition_count<<<(uint32_t)blocks, 256, 0, st>>>(t, rows, n_parts, part_rows, part_keybytes);
+    k5_partition_count<<<(uint32_t)blocks, 256, 0, st>>>(t, rows, row_count, n_parts, self, part_rows, part_keybytes);
     ++g_launches;
     VFB_CUDA(cudaGetLastError());
     return VFB_OK;
 }
 
+// Chunk headers are written by the kernel too (block 0), from the part sizes the count pass left on the device.
 __global__ void __launch_bounds__(256)
-k5_partition_fill(const DevTable t, uint64_t rows, uint32_t n_parts,
+k5_partition_fill(const DevTable t, uint64_t rows, uint32_t n_parts, uint32_t self,
                   const unsigned long long *row_count, uint8_t *buf, const uint64_t *chunk_off,
-                  const uint64_t *part_rows, const uint64_t * /*part_keybytes*/,
+                  const uint64_t *part_rows, const uint64_t *part_keybytes,
                   unsigned long long *cursors)
 {
+    if (blockIdx.x == 0)
+        for (uint32_t p = threadIdx.x; p < n_parts; p += blockDim.x)
+            if (p != self) {
+                ChunkHeader *hd = reinterpret_cast<ChunkHeader *>(buf + chunk_off[p]);
+                hd->magic = VFB_CHUNK_MAGIC; hd->rows = part_rows[p]; hd->key_bytes = part_keybytes[p]; hd->reserved = 0;
+            }
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
     for (uint64_t r0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); r0 < rows; r0 += stride) {
         const uint64_t r = r0 + lane;
-        const bool valid = r < rows;
-        const uint64_t h = valid ? t.row_hash[r] : 0ull;
-        const uint32_t p = valid ? vfb_hash_owner(h, n_parts) : 0u;
+        uint64_t h = 0;
+        uint32_t p = 0;
+        const bool valid = r < rows && part_of(t, r, row_count, n_parts, self, &h, &p);
         const uint32_t len = valid ? t.row_len[r] : 0u;
         const uint32_t padded = (len + 15u) & ~15u;
         unsigned peers;
@@ -929,17 +986,41 @@ k5_partition_fill(const DevTable t, uint64_t rows, uint32_t n_parts,
     }
 }
 
-int launch_partition_fill(const DevTable &t, uint64_t rows, uint32_t n_parts,
+int launch_partition_fill(const DevTable &t, uint64_t rows, uint32_t n_parts, uint32_t self,
                           const unsigned long long *row_count, uint8_t *buf,
                           const uint64_t *d_chunk_off, const uint64_t *d_part_rows,
                           const uint64_t *d_part_keybytes, unsigned long long *cursors,
                           cudaStream_t st)
 {
-    if (rows == 0) return VFB_OK;
     uint64_t blocks = (rows + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    k5_partition_fill<<<(uint32_t)blocks, 256, 0, st>>>(t, rows, n_parts, row_count, buf, d_chunk_off,
+    if (blocks < 1) blocks = 1;
+    k5_partition_fill<<<(uint32_t)blocks, 256, 0, st>>>(t, rows, n_parts, self, row_count, buf, d_chunk_off,
                                                         d_part_rows, d_part_keybytes, cursors);
+    ++g_launches;
+    VFB_CUDA(cudaGetLastError());
+    return VFB_OK;
+}
+
+// After the chunks have been filled: the rows that went to another part keep their slot (a later read with the
+// same key finds it again) but give up their count, so that neither the export nor a later merge sees them.
+__global__ void __launch_bounds__(256)
+k5_release_foreign(const DevTable t, uint32_t n_parts, uint32_t self)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < t.capacity; s += stride) {
+        unsigned long long *e = t.slots + s * VFB_SLOT_WORDS;
+        const unsigned long long w = e[0];
+        if (!w || !e[1]) continue;
+        if (vfb_hash_owner(t.row_hash[(uint32_t)w - 1], n_parts) != self) e[1] = 0ull;
+    }
+}
+
+int launch_release_foreign(const DevTable &t, uint32_t n_parts, uint32_t self, cudaStream_t st)
+{
+    uint64_t blocks = (t.capacity + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k5_release_foreign<<<(uint32_t)blocks, 256, 0, st>>>(t, n_parts, self);
     ++g_launches;
     VFB_CUDA(cudaGetLastError());
     return VFB_OK;

@@ -54,12 +54,46 @@ int launch_synth(const vfb_synth_cfg &cfg, uint64_t first, uint64_t n, uint8_t *
     uint64_t blocks = (n + SYNTH_THREADS - 1) / SYNTH_THREADS;
     if (blocks > 148 * 16) blocks = 148 * 16;
     size_t smem = (size_t)SYNTH_THREADS * cfg.read_len;
-    static bool attr = false;
-    if (!attr) {
+    {
+        // (per device: set every time, it costs nothing)
         VFB_CUDA(cudaFuncSetAttribute(k_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr = true;
     }
     k_synth<<<(uint32_t)blocks, SYNTH_THREADS, smem, st>>>(a);
+    ++g_launches;
+    VFB_CUDA(cudaGetLastError());
+    return VFB_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// vfb_submit_device: the caller's spans are validated and measured on the device.
+//   out[0] += sum of the span lengths (bounds the key bytes of the batch: spans may overlap or repeat)
+//   out[1] += spans that do not lie inside the text buffer
+__global__ void __launch_bounds__(256)
+k_span_check(const vfb_span *__restrict__ spans, uint64_t n, uint64_t text_bytes, unsigned long long *out)
+{
+    unsigned long long sum = 0, bad = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const vfb_span s = spans[i];
+        sum += s.len;
+        bad += ((uint64_t)s.off + s.len > text_bytes) ? 1ull : 0ull;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (sum) atomicAdd(out, sum);
+        if (bad) atomicAdd(out + 1, bad);
+    }
+}
+
+int launch_span_check(const vfb_span *d_spans, uint64_t n, uint64_t text_bytes, unsigned long long *d_out, cudaStream_t st)
+{
+    if (n == 0) return VFB_OK;
+    uint64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_span_check<<<(uint32_t)blocks, 256, 0, st>>>(d_spans, n, text_bytes, d_out);
     ++g_launches;
     VFB_CUDA(cudaGetLastError());
     return VFB_OK;

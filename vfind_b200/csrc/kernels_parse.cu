@@ -30,14 +30,18 @@ __device__ __forceinline__ uint32_t nl_mask16(const uint4 v, uint32_t valid)
 }
 
 __global__ void __launch_bounds__(PARSE_THREADS)
-k_parse_count(const uint8_t *__restrict__ text, uint32_t n, unsigned long long *__restrict__ tile_counts)
+k_parse_count(const uint8_t *__restrict__ text, uint32_t n, uint32_t skip, unsigned long long *__restrict__ tile_counts)
 {
     __shared__ uint32_t s_part[PARSE_THREADS / 32];
     const uint32_t n_tiles = (n + PARSE_TILE - 1) / PARSE_TILE;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t p = tile * PARSE_TILE + threadIdx.x * 16;
         uint32_t c = 0;
-        if (p < n) c = __popc(nl_mask16(__ldg(reinterpret_cast<const uint4 *>(text + p)), n - p));
+        if (p < n) {
+            uint32_t m = nl_mask16(__ldg(reinterpret_cast<const uint4 *>(text + p)), n - p);
+            if (p == 0) m &= ~((1u << skip) - 1u);          // the first `skip` (< 16) bytes are not text
+            c = __popc(m);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
         if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = c;
@@ -90,7 +94,7 @@ k_parse_scan(unsigned long long *v, uint32_t n, unsigned long long *total)
 }
 
 __global__ void __launch_bounds__(PARSE_THREADS)
-k_parse_index(const uint8_t *__restrict__ text, uint32_t n, const unsigned long long *__restrict__ tile_off,
+k_parse_index(const uint8_t *__restrict__ text, uint32_t n, uint32_t skip, const unsigned long long *__restrict__ tile_off,
               uint32_t *__restrict__ line_end, uint32_t max_lines)
 {
     __shared__ uint32_t s_warp[PARSE_THREADS / 32];
@@ -100,6 +104,7 @@ k_parse_index(const uint8_t *__restrict__ text, uint32_t n, const unsigned long 
         const uint32_t p = tile * PARSE_TILE + threadIdx.x * 16;
         uint32_t m = 0;
         if (p < n) m = nl_mask16(__ldg(reinterpret_cast<const uint4 *>(text + p)), n - p);
+        if (p == 0) m &= ~((1u << skip) - 1u);
         const uint32_t c = __popc(m);
         uint32_t incl = c;
 #pragma unroll
@@ -124,13 +129,13 @@ k_parse_index(const uint8_t *__restrict__ text, uint32_t n, const unsigned long 
 
 // err[0] = smallest bad record index in this chunk (0xFFFFFFFF = none)
 __global__ void __launch_bounds__(256)
-k_parse_spans(const uint8_t *__restrict__ text, const uint32_t *__restrict__ line_end, uint32_t n_records,
+k_parse_spans(const uint8_t *__restrict__ text, uint32_t skip, const uint32_t *__restrict__ line_end, uint32_t n_records,
               vfb_span *__restrict__ spans, uint32_t *__restrict__ err)
 {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_records) return;
     uint32_t s[4], e[4];
-    uint32_t prev = r ? line_end[4 * r - 1] + 1 : 0u;
+    uint32_t prev = r ? line_end[4 * r - 1] + 1 : skip;
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
         const uint32_t nl = line_end[4 * r + l];
@@ -152,10 +157,10 @@ int launch_parse(const uint8_t *d_text, uint32_t n_bytes, uint32_t n_lines, uint
     if (n_records == 0) return VFB_OK;
     const uint32_t n_tiles = (n_bytes + PARSE_TILE - 1) / PARSE_TILE;
     uint32_t blocks = n_tiles < 148u * 8u ? n_tiles : 148u * 8u;
-    k_parse_count<<<blocks, PARSE_THREADS, 0, st>>>(d_text, n_bytes, tile_scratch);
+    k_parse_count<<<blocks, PARSE_THREADS, 0, st>>>(d_text, n_bytes, 0u, tile_scratch);
     k_parse_scan<<<1, 1024, 0, st>>>(tile_scratch, n_tiles, tile_scratch + n_tiles);
-    k_parse_index<<<blocks, PARSE_THREADS, 0, st>>>(d_text, n_bytes, tile_scratch, line_end, n_lines);
-    k_parse_spans<<<(n_records + 255) / 256, 256, 0, st>>>(d_text, line_end, n_records, spans, err);
+    k_parse_index<<<blocks, PARSE_THREADS, 0, st>>>(d_text, n_bytes, 0u, tile_scratch, line_end, n_lines);
+    k_parse_spans<<<(n_records + 255) / 256, 256, 0, st>>>(d_text, 0u, line_end, n_records, spans, err);
     g_launches += 4;
     VFB_CUDA(cudaGetLastError());
     return VFB_OK;
@@ -165,12 +170,12 @@ uint64_t parse_tile_words(uint32_t n_bytes) { return (uint64_t)(n_bytes + PARSE_
 
 // ---- the same passes, split for text that was inflated on the device: the host does not know
 // ---- the line count (it never sees the text), so it reads it back between the passes.
-int launch_parse_count(const uint8_t *d_text, uint32_t n_bytes, unsigned long long *tile_scratch, cudaStream_t st)
+int launch_parse_count(const uint8_t *d_text, uint32_t n_bytes, uint32_t skip, unsigned long long *tile_scratch, cudaStream_t st)
 {
     if (n_bytes == 0) return VFB_OK;
     const uint32_t n_tiles = (n_bytes + PARSE_TILE - 1) / PARSE_TILE;
     uint32_t blocks = n_tiles < 148u * 8u ? n_tiles : 148u * 8u;
-    k_parse_count<<<blocks, PARSE_THREADS, 0, st>>>(d_text, n_bytes, tile_scratch);
+    k_parse_count<<<blocks, PARSE_THREADS, 0, st>>>(d_text, n_bytes, skip, tile_scratch);
     k_parse_scan<<<1, 1024, 0, st>>>(tile_scratch, n_tiles, tile_scratch + n_tiles);   // total at [n_tiles]
     g_launches += 2;
     VFB_CUDA(cudaGetLastError());
@@ -180,31 +185,31 @@ int launch_parse_count(const uint8_t *d_text, uint32_t n_bytes, unsigned long lo
 // info[0] = cut (bytes of complete records), info[1] = tail length; tail receives up to tail_cap
 // bytes of the text after the last complete record.
 __global__ void __launch_bounds__(256)
-k_parse_tail(const uint8_t *__restrict__ text, uint32_t n_bytes, const uint32_t *__restrict__ line_end,
+k_parse_tail(const uint8_t *__restrict__ text, uint32_t n_bytes, uint32_t skip, const uint32_t *__restrict__ line_end,
              uint32_t n_records, uint8_t *__restrict__ tail, uint32_t tail_cap, uint32_t *__restrict__ info)
 {
-    const uint32_t cut = n_records ? line_end[4 * n_records - 1] + 1 : 0u;
+    const uint32_t cut = n_records ? line_end[4 * n_records - 1] + 1 : skip;
     const uint32_t tl = n_bytes - cut;
     if (threadIdx.x == 0) { info[0] = cut; info[1] = tl; }
     const uint32_t n = tl < tail_cap ? tl : tail_cap;
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) tail[i] = text[cut + i];
 }
 
-int launch_parse_index(const uint8_t *d_text, uint32_t n_bytes, uint32_t n_lines, uint32_t n_records,
+int launch_parse_index(const uint8_t *d_text, uint32_t n_bytes, uint32_t skip, uint32_t n_lines, uint32_t n_records,
                        const unsigned long long *tile_scratch, uint32_t *line_end, vfb_span *spans, uint32_t *err,
                        uint8_t *tail, uint32_t tail_cap, uint32_t *info, cudaStream_t st)
 {
     const uint32_t n_tiles = (n_bytes + PARSE_TILE - 1) / PARSE_TILE;
     uint32_t blocks = n_tiles < 148u * 8u ? n_tiles : 148u * 8u;
     if (n_lines) {
-        k_parse_index<<<blocks, PARSE_THREADS, 0, st>>>(d_text, n_bytes, tile_scratch, line_end, n_lines);
+        k_parse_index<<<blocks, PARSE_THREADS, 0, st>>>(d_text, n_bytes, skip, tile_scratch, line_end, n_lines);
         ++g_launches;
     }
     if (n_records) {
-        k_parse_spans<<<(n_records + 255) / 256, 256, 0, st>>>(d_text, line_end, n_records, spans, err);
+        k_parse_spans<<<(n_records + 255) / 256, 256, 0, st>>>(d_text, skip, line_end, n_records, spans, err);
         ++g_launches;
     }
-    k_parse_tail<<<1, 256, 0, st>>>(d_text, n_bytes, line_end, n_records, tail, tail_cap, info);
+    k_parse_tail<<<1, 256, 0, st>>>(d_text, n_bytes, skip, line_end, n_records, tail, tail_cap, info);
     ++g_launches;
     VFB_CUDA(cudaGetLastError());
     return VFB_OK;

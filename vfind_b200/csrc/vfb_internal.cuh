@@ -189,10 +189,16 @@ struct InsertJob {
 int launch_insert(const DevTable &t, const InsertJob &job, cudaStream_t st);
 int launch_rehash(const DevTable &old_t, const DevTable &new_t, cudaStream_t st);
 int launch_export_counts(const DevTable &t, uint64_t rows, unsigned long long *row_count, cudaStream_t st);
-// offsets[rows+1] (exclusive scan of row lengths) and the keys back to back; block_sums holds
-// ceil(rows/1024) words of scratch, *total receives the number of key bytes.
-int launch_export_arrow(const DevTable &t, uint64_t rows, unsigned long long *block_sums,
-                        unsigned long long *total, unsigned long long *offsets, uint8_t *data, cudaStream_t st);
+// Export of the rows with a non-zero count, in two passes: sizes (block_bytes / block_rows hold ceil(rows/1024)
+// words of scratch each; totals[0] = key bytes, totals[1] = exported rows), then offsets (+ byte_base), counts and
+// the keys back to back.
+int launch_export_sizes(const DevTable &t, uint64_t rows, const unsigned long long *row_count,
+                        unsigned long long *block_bytes, unsigned long long *block_rows, unsigned long long *totals,
+                        cudaStream_t st);
+int launch_export_gather(const DevTable &t, uint64_t rows, const unsigned long long *row_count,
+                         const unsigned long long *block_bytes, const unsigned long long *block_rows,
+                         unsigned long long byte_base, unsigned long long *offsets, unsigned long long *counts,
+                         uint8_t *data, cudaStream_t st);
 
 // ---------------------------------------------------------------- merge chunks
 // Chunk layout (all sections 16-byte aligned):
@@ -207,14 +213,17 @@ __host__ __device__ __forceinline__ uint64_t chunk_bytes_for(uint64_t rows, uint
 {
     return sizeof(ChunkHeader) + vfb_align16(rows * 8) * 3 + vfb_align16(rows * 4) + vfb_align16(key_bytes);
 }
-int launch_partition_count(const DevTable &t, uint64_t rows, uint32_t n_parts,
-                           unsigned long long *part_rows, unsigned long long *part_keybytes,
+// `self` < n_parts: rows owned by that part stay where they are (keep-own merge); self >= n_parts: every row
+// with a non-zero count is exported.
+int launch_partition_count(const DevTable &t, uint64_t rows, const unsigned long long *row_count, uint32_t n_parts,
+                           uint32_t self, unsigned long long *part_rows, unsigned long long *part_keybytes,
                            cudaStream_t st);
-int launch_partition_fill(const DevTable &t, uint64_t rows, uint32_t n_parts,
+int launch_partition_fill(const DevTable &t, uint64_t rows, uint32_t n_parts, uint32_t self,
                           const unsigned long long *row_count, uint8_t *buf,
                           const uint64_t *d_chunk_off, const uint64_t *d_part_rows,
                           const uint64_t *d_part_keybytes, unsigned long long *cursors,
                           cudaStream_t st);
+int launch_release_foreign(const DevTable &t, uint32_t n_parts, uint32_t self, cudaStream_t st);
 
 // ---------------------------------------------------------------- FASTQ parse (ingest)
 // d_text holds n_lines complete lines (n_records = n_lines / 4 records, text starts at a record
@@ -223,9 +232,10 @@ int launch_parse(const uint8_t *d_text, uint32_t n_bytes, uint32_t n_lines, uint
                  unsigned long long *tile_scratch, uint32_t *line_end, vfb_span *spans, uint32_t *err,
                  cudaStream_t st);
 uint64_t parse_tile_words(uint32_t n_bytes);
-// Split form for text inflated on the device (the host learns the line count in between).
-int launch_parse_count(const uint8_t *d_text, uint32_t n_bytes, unsigned long long *tile_scratch, cudaStream_t st);
-int launch_parse_index(const uint8_t *d_text, uint32_t n_bytes, uint32_t n_lines, uint32_t n_records,
+// Split form for text inflated on the device (the host learns the line count in between).  d_text is 16-byte
+// aligned; its first `skip` (< 16) bytes are not part of the text (they are neither counted nor framed).
+int launch_parse_count(const uint8_t *d_text, uint32_t n_bytes, uint32_t skip, unsigned long long *tile_scratch, cudaStream_t st);
+int launch_parse_index(const uint8_t *d_text, uint32_t n_bytes, uint32_t skip, uint32_t n_lines, uint32_t n_records,
                        const unsigned long long *tile_scratch, uint32_t *line_end, vfb_span *spans, uint32_t *err,
                        uint8_t *tail, uint32_t tail_cap, uint32_t *info, cudaStream_t st);
 
@@ -242,15 +252,8 @@ int launch_inflate(const uint8_t *d_z, const vfb_member *d_members, uint32_t n_m
 int launch_synth(const vfb_synth_cfg &cfg, uint64_t first, uint64_t n, uint8_t *d_text,
                  vfb_span *d_spans, cudaStream_t st);
 int measure_int_peak(int device, double *alu_gops, double *dual_gops);
-
-// ---------------------------------------------------------------- packed host->device copies (hostpack.cu)
-struct HostPacker;
-HostPacker *hostpack_create(int threads);
-void hostpack_destroy(HostPacker *hp);
-int hostpack_threads(const HostPacker *hp);
-int hostpack_copy(HostPacker *hp, const uint8_t *text, uint64_t bytes, uint8_t *d_text, cudaStream_t st_copy,
-                  uint64_t *link_bytes, uint64_t *packed_blocks);
-#define VFB_HOSTPACK_MIN_BYTES (16u << 20)    // smaller batches are copied as they are
+// d_out[0] += sum of span lengths, d_out[1] += spans outside [0, text_bytes)
+int launch_span_check(const vfb_span *d_spans, uint64_t n, uint64_t text_bytes, unsigned long long *d_out, cudaStream_t st);
 
 extern thread_local uint64_t g_launches;   // kernels launched by this thread's calls
 }  // namespace vfb
@@ -260,16 +263,22 @@ extern thread_local uint64_t g_launches;   // kernels launched by this thread's 
 // hot loop.  `copied` is recorded on the copy stream once the host buffer may be reused.
 int vfb_internal_submit_fastq(vfb_ctx *ctx, const uint8_t *pinned_text, uint64_t n_bytes, uint64_t n_lines,
                               uint64_t record_base, cudaEvent_t copied);
-// One segment of block-gzip members held in PINNED host memory: H2D of the compressed bytes,
-// GPU inflate behind `carry` (text left over from the previous segment), GPU parse, the hot
-// loop over the complete records.  Synchronous for the values it returns: records processed,
-// the text after the last complete record (tail, at most tail_cap bytes), and the first member
-// that failed to inflate (UINT32_MAX = none).
+// One segment of block-gzip members, in two phases (api.cu).  begin: the compressed members (pieces of PINNED host
+// memory, back to back on the device; members[].z_off counts from the first piece) are copied and inflated on the
+// ingest stream — asynchronous; `release(arg)` runs on a driver thread once the pieces have been copied (it must
+// not call CUDA).  finish: `carry` (the text after the previous segment's last complete record) goes in front,
+// records are framed, the hot loop is queued; synchronous for the values it returns: records processed, the text
+// after the last complete record (tail, at most VFB_TAIL_CAP bytes), the first member that failed to inflate
+// (UINT32_MAX = none).  Segments of one context finish in the order they began.
 #define VFB_TAIL_CAP (16u << 20)
-int vfb_internal_submit_bgzf(vfb_ctx *ctx, const uint8_t *pinned_z, uint64_t z_bytes, vfb::vfb_member *pinned_members,
-                             uint32_t n_members, uint64_t text_bytes, const uint8_t *carry, uint64_t carry_len,
-                             uint64_t record_base, uint64_t *n_records, uint8_t *tail, uint64_t *tail_len,
-                             uint32_t *bad_member);
+struct vfb_zpiece {
+    const uint8_t *p;
+    uint64_t len;
+};
+int vfb_internal_bgzf_begin(vfb_ctx *ctx, const vfb_zpiece *pieces, uint32_t n_pieces, const vfb::vfb_member *members,
+                            uint32_t n_members, uint64_t text_bytes, void (*release)(void *), void *release_arg, int *slot);
+int vfb_internal_bgzf_finish(vfb_ctx *ctx, int slot, const uint8_t *carry, uint64_t carry_len, uint64_t record_base,
+                             uint64_t *n_records, uint8_t *tail, uint64_t *tail_len, uint32_t *bad_member);
 // Host threads the ingest may use to inflate block-gzip members in parallel (params.n_threads).
 int vfb_internal_ingest_threads(vfb_ctx *ctx);
 void vfb_internal_progress(vfb_ctx *ctx, uint64_t records, uint64_t bytes_done, uint64_t bytes_total, bool final);
