@@ -45,10 +45,66 @@ DIAG_DTYPE = np.dtype([("exact_prefix", "<i4"), ("exact_suffix", "<i4"),
                        ("start", "<i4"), ("end", "<i4")])
 
 
+class SynthCfg(C.Structure):
+    """vfb_synth_cfg (include/vfind_b200.h), restated here so that the reference arm never loads the product."""
+    _fields_ = [("seed", C.c_uint64), ("read_len", C.c_uint32), ("adapter_len", C.c_uint32),
+                ("region_len", C.c_uint32), ("n_variants", C.c_uint32), ("zipf", C.c_uint32),
+                ("p_err_ppm", C.c_uint32), ("indel_ppm", C.c_uint32), ("force_indel", C.c_uint32),
+                ("frameshift_ppm", C.c_uint32), ("noise_ppm", C.c_uint32), ("n_ppm", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+def synth_cfg(seed=1003, read_len=250, adapter_len=20, region_len=198, n_variants=1000000, zipf=1,
+              p_err=0.30, indel=0.5, force_indel=1, frameshift=0.05, noise=0.001, n_rate=1e-4) -> SynthCfg:
+    ppm = lambda x: int(round(x * 1e6))
+    return SynthCfg(seed, read_len, adapter_len, region_len, n_variants, zipf, ppm(p_err), ppm(indel),
+                    force_indel, ppm(frameshift), ppm(noise), ppm(n_rate), 0)
+
+
+def _cfg(cfg) -> SynthCfg:
+    """Accepts this module's SynthCfg or any ctypes struct with the same fields (vfind_b200.api.SynthCfg)."""
+    if isinstance(cfg, SynthCfg):
+        return cfg
+    return SynthCfg(*[getattr(cfg, f) for f, _ in SynthCfg._fields_])
+
+
+def synth_adapters(cfg):
+    c = _cfg(cfg)
+    a, b = C.create_string_buffer(64), C.create_string_buffer(64)
+    if lib().vfo_synth_adapters(C.byref(c), a, b) != 0:
+        raise ValueError("bad synth cfg")
+    return a.raw[:c.adapter_len], b.raw[:c.adapter_len]
+
+
+def synth_reads(cfg, first: int, n: int, threads: int = 0):
+    """(text uint8[n*L], off uint32[n], len uint32[n]) of reads [first, first+n): the same bytes as vfb_synth_host."""
+    c = _cfg(cfg)
+    text = np.zeros(n * c.read_len, dtype=np.uint8)
+    off = np.zeros(n, dtype=np.uint32)
+    ln = np.zeros(n, dtype=np.uint32)
+    if lib().vfo_synth_reads(C.byref(c), first, n, text.ctypes.data, off.ctypes.data, ln.ctypes.data,
+                             threads or (os.cpu_count() or 1)) != 0:
+        raise ValueError("bad synth cfg / size")
+    return text, off, ln
+
+
+def write_fastq(cfg, first: int, n: int, path: str, bgzf: bool = True, level: int = 1, threads: int = 0, append: bool = False):
+    """The stream as a FASTQ file ('@r<index>' headers, quality 'F'); bgzf: block-gzip members of 65280 text bytes.
+    Returns (text_bytes, file_bytes)."""
+    c = _cfg(cfg)
+    fb = C.c_uint64(0)
+    tb = lib().vfo_write_fastq(C.byref(c), first, n, os.fsencode(path), 1 if bgzf else 0, level,
+                               threads or (os.cpu_count() or 1), 1 if append else 0, C.byref(fb))
+    if tb == 0 and n:
+        raise OSError("cannot write %s" % path)
+    return int(tb), int(fb.value)
+
+
 def build(force: bool = False) -> str:
     """Compile the oracle with oracle/Makefile (gcc).  Building the checker is not using it."""
-    src = os.path.join(_HERE, "vfind_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, "vfind_oracle.c"), os.path.join(_HERE, "synth_host.c"), os.path.join(_HERE, "vfind_oracle.h"),
+            os.path.join(os.path.dirname(_HERE), "vfind_b200", "csrc", "synth.h")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "libvfind_oracle.so"])
     return _SO
 
@@ -61,6 +117,11 @@ def lib():
     if _lib is None:
         build()
         L = C.CDLL(_SO)
+        L.vfo_synth_adapters.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.vfo_synth_reads.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.vfo_write_fastq.restype = C.c_uint64
+        L.vfo_write_fastq.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.POINTER(C.c_uint64)]
         L.vfo_memmem.restype = C.c_int64
         L.vfo_memmem.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
         L.vfo_threshold_preflight.argtypes = [C.c_double, C.POINTER(C.c_int)]

@@ -126,3 +126,30 @@ def test_hash_reference_properties(lib):
     rows = ctypes.c_uint64(0)
     buf = np.zeros(64, dtype=np.uint8)
     assert lib.vfb_chunk_rows(buf.ctypes.data, 64, ctypes.byref(rows)) == api.VFB_ERR_FORMAT
+
+
+def test_oracle_side_generator_matches_the_library(lib, tmp_path):
+    """bench.py --impl reference takes its inputs from oracle/synth_host.c (it must not load the product): the two
+    generators compile the same header and must produce the same bytes; the FASTQ writer frames them as records."""
+    import gzip
+    import oracle
+    from vfind_b200 import api
+    for kw in (dict(), dict(seed=5, read_len=300, adapter_len=40, region_len=210, p_err=0.15, force_indel=0),
+               dict(seed=9, read_len=150, adapter_len=20, region_len=99, n_variants=1000, zipf=0, noise=0.0)):
+        cfg = api.synth_cfg(**kw)
+        ocfg = oracle.synth_cfg(**kw)
+        assert bytes(cfg) == bytes(ocfg)
+        t1, s1 = api.synth_host(cfg, 12345, 3000)
+        t2, off, ln = oracle.synth_reads(ocfg, 12345, 3000, 3)
+        assert (t1 == t2).all() and (off == s1["off"]).all() and (ln == s1["len"]).all()
+        assert oracle.synth_adapters(ocfg) == api.synth_adapters(cfg)
+    cfg = oracle.synth_cfg()
+    p = str(tmp_path / "s.fq.gz")
+    tb, fb = oracle.write_fastq(cfg, 7, 2000, p, bgzf=True, threads=3)
+    raw = gzip.open(p).read()
+    text, _, _ = oracle.synth_reads(cfg, 7, 2000)
+    L = cfg.read_len
+    assert tb == len(raw) == 2000 * (2 * L + 17) and fb == os.path.getsize(p)
+    for i in (0, 1, 1999):
+        rec = raw[i * (2 * L + 17):(i + 1) * (2 * L + 17)].split(b"\n")
+        assert rec[0] == b"@r%010d" % (7 + i) and rec[1] == text[i * L:(i + 1) * L].tobytes() and rec[2] == b"+" and rec[3] == b"F" * L

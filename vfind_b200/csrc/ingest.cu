@@ -649,8 +649,11 @@ void index_members(RawRing &ring, GpuPhase &gp, size_t text_target, size_t mcap,
         while (left) {
             RawRing::Block *blk = b == bi ? cur : nxt;
             const size_t take = std::min(left, blk->len - pos);
-            if (g->blocks.empty() || g->blocks.back() != b) { g->blocks.push_back(b); ring.ref(b); }
-            if (!g->pieces.empty() && g->pieces.back().p + g->pieces.back().len == blk->p + pos) g->pieces.back().len += take;
+            // (a piece never crosses from one raw block into another: two pinned allocations may be neighbours in the
+            // address space, but one copy must not span them)
+            const bool same_block = !g->blocks.empty() && g->blocks.back() == b;
+            if (!same_block) { g->blocks.push_back(b); ring.ref(b); }
+            if (same_block && !g->pieces.empty() && g->pieces.back().p + g->pieces.back().len == blk->p + pos) g->pieces.back().len += take;
             else g->pieces.push_back(vfb_zpiece{blk->p + pos, take});
             left -= take; pos = 0; ++b;
         }
