@@ -379,6 +379,7 @@ def main():
             ctx.submit_device(t.data_ptr(), t.numel(), s.data_ptr(), n)
         if world > 1:
             m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ctx.fence()
             m0.record(stream)
             ctx.merge_nccl(comm, rank, world)
             m1.record(stream)
@@ -423,7 +424,6 @@ def main():
                                "rows_per_rank": [p[1] for p in parts], "ok": tuple(one) == merged}
             barrier()
         ctx.reset()
-        ctx.set_profiling(True)
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
@@ -433,13 +433,29 @@ def main():
         e0.record(stream)
         for _ in range(args.steps):
             step_device()
+        ctx.fence()                      # the library's lane streams join the compute stream before the end event
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
         merge_ms = sum(a.elapsed_time(b) for a, b in merge_events) / max(1, len(merge_events)) if merge_events else 0.0
         clocks = sampler.stop() if rank == 0 else None
+        st_timed = ctx.stats()
+        # per-kernel times for the rooflines: the same steps once more with the batches back to back on ONE stream
+        # (in the timed region above consecutive batches overlap on two lanes, so a kernel's duration there includes
+        # whatever shared the SMs with it)
+        ctx.set_lanes(1)
+        ctx.reset()
+        ctx.set_profiling(True)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+        p1.record(stream)
+        barrier()
+        serial_ms = p0.elapsed_time(p1) / args.steps
         st = ctx.stats()
         ctx.set_profiling(False)
+        ctx.set_lanes(2)
         tms = torch.tensor([ms, merge_ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -725,7 +741,10 @@ def main():
                    "scoring": [3, -2, 5, 2], "l2": "inputs (%.1f GB per GPU) are larger than L2" % (R * L / 1e9),
                    "parallelism": "reads sharded over %d GPU(s), keep-own-keys table merge over NCCL send/recv inside the library" % world,
                    "cpu_affinity": affinity},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(st["kernel_launches"]),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(st_timed["kernel_launches"]),
+        "lanes": {"timed_region": "consecutive batches overlap on 2 lane streams (only the table insert is serialised)",
+                  "ms_per_step_one_lane": serial_ms,
+                  "stages_and_rooflines": "from %d extra steps with the batches back to back on one stream" % args.steps},
         "roofline": roofline, "roofline_filter": roofline_filter, "roofline_hbm": roofline_hbm,
         "stages_ms_per_step": stages,
         "dp": {"effective_gcups": gcups, "mode": "windowed (filter + windows)" if windowed else "full matrices",

@@ -206,10 +206,20 @@ int vfb_debug_inflate_file(const char *path, uint32_t n_threads, uint8_t *out, u
 
 int vfb_sync(vfb_ctx *ctx);
 
-/* Queue all kernels on the caller's CUDA stream (a cudaStream_t) instead of the context's
- * own, so that the caller's events and collectives order with them.  The caller keeps
- * ownership of the stream. */
+/* Use the caller's CUDA stream (a cudaStream_t) as the context's compute stream, so that the caller's events and
+ * collectives order with the library's work.  The caller keeps ownership of the stream.
+ *
+ * Streams: the hot loop of consecutive batches runs on two internal LANE streams (the ALU-bound alignment kernels of
+ * one batch share the SMs with the memory-bound scan / key / count kernels of its neighbours).  A lane forks from
+ * the compute stream when its batch is submitted — whatever the caller queued there before (a kernel that
+ * produces the reads, say) is seen — and is joined back by vfb_sync, vfb_finish, the merge calls, vfb_table_clear
+ * and vfb_fence.  A caller that records its own events or queues its own consumers on the compute stream calls
+ * vfb_fence first: it makes the compute stream wait (on the device, not the host) for everything submitted so
+ * far.  vfb_set_lanes(ctx, 1) runs every batch on the compute stream itself (the round-1 behaviour; per-stage
+ * profiling times are only meaningful then). */
 int vfb_set_compute_stream(vfb_ctx *ctx, void *stream);
+int vfb_fence(vfb_ctx *ctx);
+int vfb_set_lanes(vfb_ctx *ctx, int n_lanes);
 
 /* `variants.into_iter().unzip()` (src/lib.rs:312): waits for all batches, compacts the
  * table into Arrow-style columns on the device and copies them into pinned host buffers

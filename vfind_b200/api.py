@@ -118,6 +118,8 @@ def load_library():
     L.vfb_run_file.argtypes = [vp, C.c_char_p, C.POINTER(u64)]
     L.vfb_sync.argtypes = [vp]
     L.vfb_set_compute_stream.argtypes = [vp, vp]
+    L.vfb_fence.argtypes = [vp]
+    L.vfb_set_lanes.argtypes = [vp, i32]
     L.vfb_finish.argtypes = [vp, C.POINTER(Table)]
     L.vfb_table_free.argtypes = [C.POINTER(Table)]
     L.vfb_table_free.restype = None
@@ -305,6 +307,15 @@ class Context:
 
     def set_compute_stream(self, stream_ptr: int):
         _check(self._lib.vfb_set_compute_stream(self._h, stream_ptr))
+
+    def fence(self):
+        """The compute stream waits (on the device) for everything submitted so far: call before recording your own
+        events or queueing your own consumers on it."""
+        _check(self._lib.vfb_fence(self._h))
+
+    def set_lanes(self, n: int):
+        """1 = every batch on the compute stream itself (per-stage profiling), 2 = two overlapping lanes (default)."""
+        _check(self._lib.vfb_set_lanes(self._h, n))
 
     def set_progress(self, fn):
         """fn(records, bytes_done, bytes_total) is called from run_file about ten times per second and once at

@@ -301,6 +301,18 @@ static int bump_launches(vfb_ctx *c, uint64_t before)
 void bump_launches_for(vfb_ctx *c, uint64_t before) { bump_launches(c, before); }
 
 // ------------------------------------------------------------------------------------ helpers
+// Everything the lanes have been given so far is ordered before whatever is queued next on the compute stream.
+static int lanes_join(vfb_ctx *c)
+{
+    for (auto &ln : c->lanes)
+        if (ln.pending) {
+            VFB_CUDA(cudaStreamWaitEvent(c->st_compute, ln.done, 0));
+            ln.pending = false;
+        }
+    c->k4_pending = false;
+    return VFB_OK;
+}
+
 static int table_alloc(vfb_ctx *c, uint64_t capacity, uint64_t rows_cap, uint64_t arena_cap)
 {
     int rc;
@@ -358,6 +370,7 @@ static int table_reserve(vfb_ctx *c, uint64_t new_keys, uint64_t new_bytes)
     trace("table_reserve: bounds exceeded (rows %llu + %llu, capacity %llu): sync", (unsigned long long)c->ub_rows,
           (unsigned long long)new_keys, (unsigned long long)c->tab.capacity);
     unsigned long long ctr[2];
+    { const int jrc = lanes_join(c); if (jrc) return jrc; }
     VFB_CUDA(cudaMemcpyAsync(ctr, c->tab.counters, sizeof ctr, cudaMemcpyDeviceToHost, c->st_compute));
     VFB_CUDA(cudaStreamSynchronize(c->st_compute));
     c->stats.d2h_bytes += sizeof ctr;
@@ -500,26 +513,26 @@ int vfb_create(const vfb_params *p, vfb_ctx **out)
     if ((e = cudaGetDeviceProperties(&prop, c->device)) != cudaSuccess)
         return fail(cuda_fail(e, "cudaGetDeviceProperties", __FILE__, __LINE__));
     c->sm_count = prop.multiProcessorCount;
-    // the ingest stream (H2D of compressed members, inflate, parse) outranks the compute stream: the short parse
-    // kernels of the next segment sit on the critical path of the segment chain and must not queue behind K1..K4
+    // the parse stream outranks everything: the short record-framing kernels of a segment sit on the critical path
+    // of the segment chain and must queue neither behind K1..K4 nor behind the next segment's inflate
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if ((e = cudaStreamCreateWithFlags(&c->st_compute, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithPriority(&c->st_ingest, cudaStreamNonBlocking, prio_hi)) != cudaSuccess)
+        (e = cudaStreamCreateWithPriority(&c->st_ingest, cudaStreamNonBlocking, prio_lo)) != cudaSuccess ||
+        (e = cudaStreamCreateWithPriority(&c->st_parse, cudaStreamNonBlocking, prio_hi)) != cudaSuccess)
         return fail(cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__));
-    for (auto &s : c->slots) {
-        if ((e = cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming)) != cudaSuccess ||
-            (e = cudaEventCreateWithFlags(&s.computed, cudaEventDisableTiming)) != cudaSuccess)
-            return fail(cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__));
-    }
-    for (auto &g : c->seg) {
-        if ((e = cudaEventCreateWithFlags(&g.parsed, cudaEventDisableTiming)) != cudaSuccess ||
-            (e = cudaEventCreateWithFlags(&g.computed, cudaEventDisableTiming)) != cudaSuccess)
-            return fail(cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__));
-    }
-    if ((e = cudaEventCreateWithFlags(&c->m_filled, cudaEventDisableTiming)) != cudaSuccess)
-        return fail(cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__));
+    auto new_event = [&](cudaEvent_t *ev) { return (e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) == cudaSuccess; };
+    bool ev_ok = new_event(&c->m_filled) && new_event(&c->ev_fork) && new_event(&c->ev_k4);
+    for (auto &s : c->slots) ev_ok = ev_ok && new_event(&s.copied) && new_event(&s.computed[0]) && new_event(&s.computed[1]);
+    for (auto &g : c->seg) ev_ok = ev_ok && new_event(&g.inflated) && new_event(&g.parsed) && new_event(&g.computed[0]) && new_event(&g.computed[1]);
+    for (auto &ln : c->lanes)
+        ev_ok = ev_ok && new_event(&ln.done) && (e = cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking)) == cudaSuccess;
+    if (!ev_ok) return fail(cuda_fail(e, "cudaEventCreate / cudaStreamCreate", __FILE__, __LINE__));
+    // two lanes unless the per-read diagnostics of "the last batch" are wanted (or VFB_LANES=1 says so)
+    c->n_lanes = VFB_LANES;
+    if (p->diagnostics) c->n_lanes = 1;
+    if (const char *le = getenv("VFB_LANES")) if (atoi(le) == 1) c->n_lanes = 1;
 
     // DP setup: packed layout when the scores fit, else the fallback kernel
     const bool force_generic = p->force_generic_dp != 0;
@@ -552,10 +565,12 @@ int vfb_create(const vfb_params *p, vfb_ctx **out)
         size_t amax = c->prefix.size() > c->suffix.size() ? c->prefix.size() : c->suffix.size();
         if ((rc = c->d_generic_scratch.ensure(4 * amax * (size_t)c->generic_threads * sizeof(int32_t)))) return fail(rc);
     }
-    if ((rc = c->d_c32.ensure(C_COUNT32 * 4))) return fail(rc);
-    if ((rc = c->d_t64.ensure(T_COUNT64 * 8))) return fail(rc);
-    if ((e = cudaMemsetAsync(c->d_t64.p, 0, T_COUNT64 * 8, c->st_compute)) != cudaSuccess)
-        return fail(cuda_fail(e, "cudaMemsetAsync", __FILE__, __LINE__));
+    for (auto &ln : c->lanes) {
+        if ((rc = ln.d_c32.ensure(C_COUNT32 * 4))) return fail(rc);
+        if ((rc = ln.d_t64.ensure(T_COUNT64 * 8))) return fail(rc);
+        if ((e = cudaMemset(ln.d_t64.p, 0, T_COUNT64 * 8)) != cudaSuccess)
+            return fail(cuda_fail(e, "cudaMemset", __FILE__, __LINE__));
+    }
     if ((rc = table_init(c))) return fail(rc);
     c->stats.dp_kernel_kind = (c->packed_pre || c->packed_suf) ? 1 : ((c->align_pre || c->align_suf) ? 2 : 0);
     if ((c->win_k_pre >= 0 || c->win_k_suf >= 0) && (!p->diagnostics || p->dp_mode == 2)) c->stats.dp_kernel_kind = 3;
@@ -570,23 +585,33 @@ int vfb_destroy(vfb_ctx *c)
     if (c->st_compute) cudaStreamSynchronize(c->st_compute);
     if (c->st_copy) cudaStreamSynchronize(c->st_copy);
     if (c->st_ingest) cudaStreamSynchronize(c->st_ingest);
+    if (c->st_parse) cudaStreamSynchronize(c->st_parse);
+    for (auto &ln : c->lanes) if (ln.st) cudaStreamSynchronize(ln.st);
     for (auto &s : c->slots) {
         s.d_text.release(); s.d_spans.release(); s.h_text.release(); s.h_spans.release();
         if (s.copied) cudaEventDestroy(s.copied);
-        if (s.computed) cudaEventDestroy(s.computed);
+        for (auto &ev : s.computed) if (ev) cudaEventDestroy(ev);
     }
     for (auto &g : c->seg) {
         g.text.release(); g.z.release(); g.members.release(); g.spans.release();
         if (g.parsed) cudaEventDestroy(g.parsed);
-        if (g.computed) cudaEventDestroy(g.computed);
+        if (g.inflated) cudaEventDestroy(g.inflated);
+        for (auto &ev : g.computed) if (ev) cudaEventDestroy(ev);
     }
-    DevBuf *bufs[] = {&c->d_code_pre, &c->d_code_suf, &c->d_generic_scratch, &c->d_start, &c->d_end, &c->d_list_a,
-                      &c->d_list_b, &c->d_fb_a, &c->d_fb_b, &c->d_c32, &c->d_t64, &c->d_keys, &c->d_koff, &c->d_klen,
-                      &c->d_khash, &c->d_owner, &c->d_diag_exact_pre, &c->d_diag_exact_suf, &c->d_diag_score_pre,
+    for (auto &ln : c->lanes) {
+        DevBuf *lb[] = {&ln.d_start, &ln.d_end, &ln.d_list_a, &ln.d_list_b, &ln.d_fb_a, &ln.d_fb_b, &ln.d_c32, &ln.d_t64, &ln.d_keys,
+                        &ln.d_koff, &ln.d_klen, &ln.d_khash, &ln.d_owner, &ln.d_wins, &ln.d_bestkey, &ln.d_cbval, &ln.d_fb2};
+        for (auto *b : lb) b->release();
+        if (ln.done) cudaEventDestroy(ln.done);
+        if (ln.st) cudaStreamDestroy(ln.st);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_k4) cudaEventDestroy(c->ev_k4);
+    DevBuf *bufs[] = {&c->d_code_pre, &c->d_code_suf, &c->d_generic_scratch, &c->d_diag_exact_pre, &c->d_diag_exact_suf, &c->d_diag_score_pre,
                       &c->d_diag_len_pre, &c->d_diag_score_suf, &c->d_diag_len_suf, &c->t_slots,
                       &c->t_row_hash, &c->t_row_off, &c->t_row_len, &c->t_arena, &c->t_counters, &c->t_row_count,
                       &c->m_part_rows, &c->m_part_keys, &c->m_cursors, &c->m_chunk_off, &c->m_send, &c->m_recv,
-                      &c->d_wins, &c->d_bestkey, &c->d_cbval, &c->d_fb2, &c->d_aligned_text, &c->d_span_sum,
+                      &c->d_aligned_text, &c->d_span_sum,
                       &c->x_block_bytes, &c->x_block_rows, &c->x_offsets, &c->x_counts, &c->x_data,
                       &c->p_tiles, &c->p_line_end, &c->p_err, &c->g_tail, &c->g_info};
     for (auto *b : bufs) b->release();
@@ -597,6 +622,7 @@ int vfb_destroy(vfb_ctx *c)
     if (c->st_compute && c->own_compute_stream) cudaStreamDestroy(c->st_compute);
     if (c->st_copy) cudaStreamDestroy(c->st_copy);
     if (c->st_ingest) cudaStreamDestroy(c->st_ingest);
+    if (c->st_parse) cudaStreamDestroy(c->st_parse);
     delete c;
     return VFB_OK;
 }
@@ -621,6 +647,7 @@ int vfb_table_clear(vfb_ctx *c)
 {
     if (!c) { set_error("null context"); return VFB_ERR_ARG; }
     VFB_CUDA(cudaSetDevice(c->device));
+    { const int jrc = lanes_join(c); if (jrc) return jrc; }
     VFB_CUDA(cudaMemsetAsync(c->tab.slots, 0, c->tab.capacity * 8 * VFB_SLOT_WORDS, c->st_compute));
     VFB_CUDA(cudaMemsetAsync(c->tab.counters, 0, 8 * 8, c->st_compute));
     c->ub_rows = 0;
@@ -632,7 +659,7 @@ int vfb_reset(vfb_ctx *c)
 {
     int rc = vfb_table_clear(c);
     if (rc) return rc;
-    VFB_CUDA(cudaMemsetAsync(c->d_t64.p, 0, T_COUNT64 * 8, c->st_compute));
+    for (auto &ln : c->lanes) VFB_CUDA(cudaMemsetAsync(ln.d_t64.p, 0, T_COUNT64 * 8, c->st_compute));
     int kind = c->stats.dp_kernel_kind;
     memset(&c->stats, 0, sizeof c->stats);
     c->stats.dp_kernel_kind = kind;
@@ -650,26 +677,26 @@ __global__ void k_accumulate(unsigned long long *t64, const uint32_t *c32, uint3
     t64[T_WINDOWS] += (c32[C_NWINPRE] < win_cap ? c32[C_NWINPRE] : win_cap) + (c32[C_NWINSUF] < win_cap ? c32[C_NWINSUF] : win_cap);
 }
 
-static int run_dp(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_spans, bool is_prefix, uint32_t n_batch,
-                  cudaEvent_t *pev)
+static int run_dp(vfb_ctx *c, Lane &ln, cudaStream_t st, const uint8_t *d_text, const vfb_span *d_spans, bool is_prefix,
+                  uint32_t n_batch, cudaEvent_t *pev)
 {
     int rc;
     DpJob job;
     memset(&job, 0, sizeof job);
     job.text = d_text;
     job.spans = d_spans;
-    job.worklist = is_prefix ? c->d_list_a.as<uint32_t>() : c->d_list_b.as<uint32_t>();
-    job.n_items = c->d_c32.as<uint32_t>() + (is_prefix ? C_NPRE : C_NSUF);
-    job.bound = is_prefix ? c->d_start.as<uint32_t>() : c->d_end.as<uint32_t>();
+    job.worklist = is_prefix ? ln.d_list_a.as<uint32_t>() : ln.d_list_b.as<uint32_t>();
+    job.n_items = ln.d_c32.as<uint32_t>() + (is_prefix ? C_NPRE : C_NSUF);
+    job.bound = is_prefix ? ln.d_start.as<uint32_t>() : ln.d_end.as<uint32_t>();
     if (c->prm.diagnostics) {
         job.diag_score = is_prefix ? c->d_diag_score_pre.as<int32_t>() : c->d_diag_score_suf.as<int32_t>();
         job.diag_len = is_prefix ? c->d_diag_len_pre.as<int32_t>() : c->d_diag_len_suf.as<int32_t>();
     }
-    job.cells = c->d_t64.as<unsigned long long>() + T_CELLS;
+    job.cells = ln.d_t64.as<unsigned long long>() + T_CELLS;
     if (is_prefix && c->align_suf && !(c->prm.dp_compute_all || c->prm.diagnostics)) {
-        job.next_list = c->d_list_b.as<uint32_t>();
-        job.n_next = c->d_c32.as<uint32_t>() + C_NSUF;
-        job.other_bound = c->d_end.as<uint32_t>();
+        job.next_list = ln.d_list_b.as<uint32_t>();
+        job.n_next = ln.d_c32.as<uint32_t>() + C_NSUF;
+        job.other_bound = ln.d_end.as<uint32_t>();
     }
     job.is_prefix = is_prefix ? 1 : 0;
     job.min_accept = is_prefix ? c->min_accept_pre : c->min_accept_suf;
@@ -687,34 +714,34 @@ static int run_dp(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_spans, bo
         // filter -> DP on the flagged windows -> resolve; reads the windowed path cannot take go
         // to the full kernel, and from there (too long for the packed word) to the unpacked one
         for (size_t i = 0; i < ad.size(); ++i) job.adapter_code[i] = (uint8_t)dp_code((uint8_t)ad[i]);
-        uint32_t *c32 = c->d_c32.as<uint32_t>();
-        uint32_t *fb = is_prefix ? c->d_fb_a.as<uint32_t>() : c->d_fb_b.as<uint32_t>();
+        uint32_t *c32 = ln.d_c32.as<uint32_t>();
+        uint32_t *fb = is_prefix ? ln.d_fb_a.as<uint32_t>() : ln.d_fb_b.as<uint32_t>();
         uint32_t *nfb = c32 + (is_prefix ? C_FBPRE : C_FBSUF);
-        uint32_t *fb2 = c->d_fb2.as<uint32_t>();
+        uint32_t *fb2 = ln.d_fb2.as<uint32_t>();
         uint32_t *nfb2 = c32 + (is_prefix ? C_FB2PRE : C_FB2SUF);
         const DpLayout &lay = is_prefix ? c->lay_pre : c->lay_suf;
         const uint32_t lcap = is_prefix ? c->lcap_pre : c->lcap_suf;
-        if ((rc = launch_dp_windowed(job, lay, K, lcap, n_batch, c->d_wins.p, c32 + (is_prefix ? C_NWINPRE : C_NWINSUF),
-                                     c->win_cap, c->d_bestkey.as<unsigned long long>(), c->d_cbval.as<unsigned long long>(),
-                                     fb, nfb, c->d_t64.as<unsigned long long>() + T_CELLSCOMP, c32 + (is_prefix ? C_WORKPRE : C_WORKSUF) /* the window cursor sits 32 words on */,
-                                     c->sm_count, c->st_compute,
+        if ((rc = launch_dp_windowed(job, lay, K, lcap, n_batch, ln.d_wins.p, c32 + (is_prefix ? C_NWINPRE : C_NWINSUF),
+                                     ln.win_cap, ln.d_bestkey.as<unsigned long long>(), ln.d_cbval.as<unsigned long long>(),
+                                     fb, nfb, ln.d_t64.as<unsigned long long>() + T_CELLSCOMP, c32 + (is_prefix ? C_WORKPRE : C_WORKSUF) /* the window cursor sits 32 words on */,
+                                     c->sm_count, st,
                                      pev ? pev[is_prefix ? 8 : 10] : nullptr, pev ? pev[is_prefix ? 9 : 11] : nullptr)))
             return rc;
         DpJob fj = job;
         fj.worklist = fb;
         fj.n_items = nfb;
-        if ((rc = launch_dp_packed_ex(fj, lay, lcap, fb2, nfb2, c->sm_count, c->st_compute))) return rc;
+        if ((rc = launch_dp_packed_ex(fj, lay, lcap, fb2, nfb2, c->sm_count, st))) return rc;
         gj.base = fj;
         gj.base.worklist = fb2;
         gj.base.n_items = nfb2;
-        if ((rc = launch_dp_generic(gj, c->sm_count, c->st_compute))) return rc;
+        if ((rc = launch_dp_generic(gj, c->sm_count, st))) return rc;
         c->stats.dp_kernel_launches += 5;
     } else if (packed) {
         for (size_t i = 0; i < ad.size(); ++i) job.adapter_code[i] = (uint8_t)dp_code((uint8_t)ad[i]);
-        uint32_t *fb = is_prefix ? c->d_fb_a.as<uint32_t>() : c->d_fb_b.as<uint32_t>();
-        uint32_t *nfb = c->d_c32.as<uint32_t>() + (is_prefix ? C_FBPRE : C_FBSUF);
+        uint32_t *fb = is_prefix ? ln.d_fb_a.as<uint32_t>() : ln.d_fb_b.as<uint32_t>();
+        uint32_t *nfb = ln.d_c32.as<uint32_t>() + (is_prefix ? C_FBPRE : C_FBSUF);
         if ((rc = launch_dp_packed_ex(job, is_prefix ? c->lay_pre : c->lay_suf,
-                                      is_prefix ? c->lcap_pre : c->lcap_suf, fb, nfb, c->sm_count, c->st_compute)))
+                                      is_prefix ? c->lcap_pre : c->lcap_suf, fb, nfb, c->sm_count, st)))
             return rc;
         // reads too long for the packed word (normally none): same rule set, unpacked
         gj.base = job;
@@ -722,11 +749,11 @@ static int run_dp(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_spans, bo
         gj.base.n_items = nfb;
         gj.base.cells = nullptr;     // already counted by the packed kernel? no: it skipped them
         gj.base.cells = job.cells;
-        if ((rc = launch_dp_generic(gj, c->sm_count, c->st_compute))) return rc;
+        if ((rc = launch_dp_generic(gj, c->sm_count, st))) return rc;
         c->stats.dp_kernel_launches += 2;
     } else {
         gj.base = job;
-        if ((rc = launch_dp_generic(gj, c->sm_count, c->st_compute))) return rc;
+        if ((rc = launch_dp_generic(gj, c->sm_count, st))) return rc;
         c->stats.dp_kernel_launches += 1;
     }
     return VFB_OK;
@@ -737,34 +764,39 @@ static int run_dp(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_spans, bo
 // the text range they address is not a bound); text_bytes_hint is the text this batch's reads are spread over (it
 // sizes the shared-memory tiles of the scan and key kernels; 0 = span_len_ub).
 static int process_batch(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_spans, uint32_t n,
-                         uint64_t span_len_ub, uint64_t text_bytes_hint = 0)
+                         uint64_t span_len_ub, uint64_t text_bytes_hint = 0, unsigned *lanes_used = nullptr)
 {
     const uint64_t span_bytes_upper = span_len_ub;
     if (!text_bytes_hint) text_bytes_hint = span_bytes_upper;
     int rc;
     if (n == 0) return VFB_OK;
-    cudaStream_t st = c->st_compute;
+    // the lane: with two lanes consecutive batches alternate, each on its own stream, forked from the compute stream
+    // (whatever produced the batch's inputs was ordered into that stream by the caller)
+    const int li = c->n_lanes > 1 ? (int)(c->lane_seq++ & 1u) : 0;
+    Lane &ln = c->lanes[li];
+    cudaStream_t st = c->n_lanes > 1 ? ln.st : c->st_compute;
+    if (lanes_used) *lanes_used |= 1u << li;
     const bool prof = c->profiling;
     // scratch
-    if ((rc = c->d_start.ensure((size_t)n * 4))) return rc;
-    if ((rc = c->d_end.ensure((size_t)n * 4))) return rc;
-    if (c->align_pre) { if ((rc = c->d_list_a.ensure((size_t)n * 4))) return rc; if ((rc = c->d_fb_a.ensure((size_t)n * 4))) return rc; }
-    if (c->align_suf) { if ((rc = c->d_list_b.ensure((size_t)n * 4))) return rc; if ((rc = c->d_fb_b.ensure((size_t)n * 4))) return rc; }
+    if ((rc = ln.d_start.ensure((size_t)n * 4))) return rc;
+    if ((rc = ln.d_end.ensure((size_t)n * 4))) return rc;
+    if (c->align_pre) { if ((rc = ln.d_list_a.ensure((size_t)n * 4))) return rc; if ((rc = ln.d_fb_a.ensure((size_t)n * 4))) return rc; }
+    if (c->align_suf) { if ((rc = ln.d_list_b.ensure((size_t)n * 4))) return rc; if ((rc = ln.d_fb_b.ensure((size_t)n * 4))) return rc; }
     // keys: sum of padded key lengths <= bytes/(3|1) + 16 per read
     const uint64_t key_bytes_ub = (c->prm.skip_translation ? span_bytes_upper : span_bytes_upper / 3) + 16ull * n;
-    if ((rc = c->d_keys.ensure(key_bytes_ub))) return rc;
-    if ((rc = c->d_koff.ensure((size_t)n * 8))) return rc;
-    if ((rc = c->d_klen.ensure((size_t)n * 4))) return rc;
-    if ((rc = c->d_khash.ensure((size_t)n * 8))) return rc;
-    if ((rc = c->d_owner.ensure((size_t)n * 4))) return rc;
+    if ((rc = ln.d_keys.ensure(key_bytes_ub))) return rc;
+    if ((rc = ln.d_koff.ensure((size_t)n * 8))) return rc;
+    if ((rc = ln.d_klen.ensure((size_t)n * 4))) return rc;
+    if ((rc = ln.d_khash.ensure((size_t)n * 8))) return rc;
+    if ((rc = ln.d_owner.ensure((size_t)n * 4))) return rc;
     if (c->win_k_pre >= 0 || c->win_k_suf >= 0) {
         const uint32_t cap = n < 0x3FFFFFFFu ? n * 2u + 1024u : 0x7FFFFFFFu;
-        if ((rc = c->d_wins.ensure((size_t)cap * dpw_item_bytes()))) return rc;
-        c->win_cap = (uint32_t)(c->d_wins.cap / dpw_item_bytes());
-        if (c->prm.debug_win_cap > 0 && (uint32_t)c->prm.debug_win_cap < c->win_cap) c->win_cap = (uint32_t)c->prm.debug_win_cap;
-        if ((rc = c->d_bestkey.ensure((size_t)n * 8))) return rc;
-        if ((rc = c->d_cbval.ensure((size_t)n * 8))) return rc;
-        if ((rc = c->d_fb2.ensure((size_t)n * 4))) return rc;
+        if ((rc = ln.d_wins.ensure((size_t)cap * dpw_item_bytes()))) return rc;
+        ln.win_cap = (uint32_t)(ln.d_wins.cap / dpw_item_bytes());
+        if (c->prm.debug_win_cap > 0 && (uint32_t)c->prm.debug_win_cap < ln.win_cap) ln.win_cap = (uint32_t)c->prm.debug_win_cap;
+        if ((rc = ln.d_bestkey.ensure((size_t)n * 8))) return rc;
+        if ((rc = ln.d_cbval.ensure((size_t)n * 8))) return rc;
+        if ((rc = ln.d_fb2.ensure((size_t)n * 4))) return rc;
     }
     const bool diag = c->prm.diagnostics != 0;
     if (diag) {
@@ -775,23 +807,27 @@ static int process_batch(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_sp
     if ((rc = table_reserve(c, n, key_bytes_ub))) return rc;
     cudaEvent_t *pev = nullptr;
     if (prof && (rc = prof_events(c, &pev))) return rc;
+    if (c->n_lanes > 1) {
+        VFB_CUDA(cudaEventRecord(c->ev_fork, c->st_compute));
+        VFB_CUDA(cudaStreamWaitEvent(st, c->ev_fork, 0));
+    }
 
     if (prof) VFB_CUDA(cudaEventRecord(pev[0], st));
-    VFB_CUDA(cudaMemsetAsync(c->d_c32.p, 0, C_COUNT32 * 4, st));
-    VFB_CUDA(cudaMemsetAsync(c->d_t64.as<unsigned long long>() + T_KEYBYTES, 0, 8, st));
+    VFB_CUDA(cudaMemsetAsync(ln.d_c32.p, 0, C_COUNT32 * 4, st));
+    VFB_CUDA(cudaMemsetAsync(ln.d_t64.as<unsigned long long>() + T_KEYBYTES, 0, 8, st));
     ScanJob sj;
     memset(&sj, 0, sizeof sj);
     sj.text = d_text; sj.spans = d_spans; sj.n_reads = n; sj.text_bytes = text_bytes_hint;
-    sj.start = c->d_start.as<uint32_t>(); sj.end = c->d_end.as<uint32_t>();
-    if (c->align_pre) { sj.list_pre = c->d_list_a.as<uint32_t>(); sj.n_pre = c->d_c32.as<uint32_t>() + C_NPRE; }
-    if (c->align_suf) { sj.list_suf = c->d_list_b.as<uint32_t>(); sj.n_suf = c->d_c32.as<uint32_t>() + C_NSUF; }
+    sj.start = ln.d_start.as<uint32_t>(); sj.end = ln.d_end.as<uint32_t>();
+    if (c->align_pre) { sj.list_pre = ln.d_list_a.as<uint32_t>(); sj.n_pre = ln.d_c32.as<uint32_t>() + C_NPRE; }
+    if (c->align_suf) { sj.list_suf = ln.d_list_b.as<uint32_t>(); sj.n_suf = ln.d_c32.as<uint32_t>() + C_NSUF; }
     sj.compute_all = (c->prm.dp_compute_all || diag) ? 1 : 0;
     sj.force_general = c->prm.force_general_scan;
     if ((rc = launch_scan(sj, c->ad_pre, c->ad_suf, c->sm_count, st))) return rc;
     if (prof) VFB_CUDA(cudaEventRecord(pev[1], st));
     if (diag) {
-        VFB_CUDA(cudaMemcpyAsync(c->d_diag_exact_pre.p, c->d_start.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
-        VFB_CUDA(cudaMemcpyAsync(c->d_diag_exact_suf.p, c->d_end.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        VFB_CUDA(cudaMemcpyAsync(c->d_diag_exact_pre.p, ln.d_start.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        VFB_CUDA(cudaMemcpyAsync(c->d_diag_exact_suf.p, ln.d_end.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
         // "no DP ran" markers: score = INT32_MIN (0x80000000), len = -1
         VFB_CUDA(cudaMemsetAsync(c->d_diag_len_pre.p, 0xFF, (size_t)n * 4, st));
         VFB_CUDA(cudaMemsetAsync(c->d_diag_len_suf.p, 0xFF, (size_t)n * 4, st));
@@ -801,33 +837,66 @@ static int process_batch(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_sp
     // DP.  The prefix pass runs first: reads it rejects need no suffix alignment (no region
     // either way, src/lib.rs:288), reads it accepts join the suffix worklist if they need one.
     if (prof) VFB_CUDA(cudaEventRecord(pev[2], st));
-    if (c->align_pre) if ((rc = run_dp(c, d_text, d_spans, true, n, prof ? pev : nullptr))) return rc;
+    if (c->align_pre) if ((rc = run_dp(c, ln, st, d_text, d_spans, true, n, prof ? pev : nullptr))) return rc;
     if (prof) VFB_CUDA(cudaEventRecord(pev[3], st));
     if (prof) VFB_CUDA(cudaEventRecord(pev[4], st));
-    if (c->align_suf) if ((rc = run_dp(c, d_text, d_spans, false, n, prof ? pev : nullptr))) return rc;
+    if (c->align_suf) if ((rc = run_dp(c, ln, st, d_text, d_spans, false, n, prof ? pev : nullptr))) return rc;
     if (prof) VFB_CUDA(cudaEventRecord(pev[5], st));
-    k_accumulate<<<1, 1, 0, st>>>(c->d_t64.as<unsigned long long>(), c->d_c32.as<uint32_t>(), c->win_cap);
+    k_accumulate<<<1, 1, 0, st>>>(ln.d_t64.as<unsigned long long>(), ln.d_c32.as<uint32_t>(), ln.win_cap);
     ++g_launches;
 
     KeyJob kj;
     kj.text = d_text; kj.spans = d_spans;
-    kj.start = c->d_start.as<uint32_t>(); kj.end = c->d_end.as<uint32_t>();
+    kj.start = ln.d_start.as<uint32_t>(); kj.end = ln.d_end.as<uint32_t>();
     kj.n_reads = n; kj.text_bytes = text_bytes_hint; kj.skip_translation = c->prm.skip_translation;
-    kj.keys = c->d_keys.as<uint8_t>(); kj.koff = c->d_koff.as<uint64_t>();
-    kj.key_cursor = c->d_t64.as<unsigned long long>() + T_KEYBYTES;
-    kj.klen = c->d_klen.as<uint32_t>(); kj.khash = c->d_khash.as<uint64_t>();
+    kj.keys = ln.d_keys.as<uint8_t>(); kj.koff = ln.d_koff.as<uint64_t>();
+    kj.key_cursor = ln.d_t64.as<unsigned long long>() + T_KEYBYTES;
+    kj.klen = ln.d_klen.as<uint32_t>(); kj.khash = ln.d_khash.as<uint64_t>();
     kj.hash_bits = c->prm.debug_hash_bits;
     if ((rc = launch_keys(kj, st))) return rc;
     if (prof) VFB_CUDA(cudaEventRecord(pev[6], st));
 
     InsertJob ij;
     ij.keys = kj.keys; ij.klen = kj.klen; ij.khash = kj.khash; ij.kcount = nullptr; ij.koff = kj.koff;
-    ij.key_stride = 0; ij.n_keys = n; ij.owner_slot = c->d_owner.as<uint32_t>();
+    ij.key_stride = 0; ij.n_keys = n; ij.owner_slot = ln.d_owner.as<uint32_t>();
+    // the table insert of a batch claims slots by batch-relative read index: one batch at a time
+    if (c->n_lanes > 1 && c->k4_pending) VFB_CUDA(cudaStreamWaitEvent(st, c->ev_k4, 0));
     if ((rc = launch_insert(c->tab, ij, st))) return rc;
+    if (c->n_lanes > 1) {
+        VFB_CUDA(cudaEventRecord(c->ev_k4, st));
+        c->k4_pending = true;
+        VFB_CUDA(cudaEventRecord(ln.done, st));
+        ln.pending = true;
+    }
     if (prof) VFB_CUDA(cudaEventRecord(pev[7], st));
     c->stats.reads += n;
     c->diag_n = n;
     c->diag_valid = diag;
+    return VFB_OK;
+}
+
+// A staging slot may be refilled once the batches that read it are done: on whichever lanes they ran.
+static int slot_wait(Slot &s)
+{
+    for (int li = 0; li < VFB_LANES; ++li)
+        if (s.busy & (1u << li)) VFB_CUDA(cudaEventSynchronize(s.computed[li]));
+    s.busy = 0;
+    return VFB_OK;
+}
+
+static int mark_computed(vfb_ctx *c, cudaEvent_t *ev, unsigned *busy, unsigned lanes_used)
+{
+    if (c->n_lanes <= 1) {
+        VFB_CUDA(cudaEventRecord(ev[0], c->st_compute));
+        *busy = 1u;
+        return VFB_OK;
+    }
+    *busy = 0;
+    for (int li = 0; li < VFB_LANES; ++li)
+        if (lanes_used & (1u << li)) {
+            VFB_CUDA(cudaEventRecord(ev[li], c->lanes[li].st));
+            *busy |= 1u << li;
+        }
     return VFB_OK;
 }
 
@@ -887,9 +956,49 @@ int vfb_submit_host(vfb_ctx *c, const uint8_t *text, uint64_t text_bytes, const 
     int rc = VFB_OK;
     uint64_t done = 0;
     while (done < n_reads && rc == VFB_OK) {
-        // cut a batch: up to batch_reads reads whose text range fits batch_bytes
+        // cut a batch: up to batch_reads reads whose text range fits batch_bytes.  The common case — the next
+        // batch_reads spans fit — is checked on several threads (min / max / sum / bounds over 12.5 M spans take
+        // 37 ms on one core, and the copy cannot be queued before the range is known)
         uint64_t n = 0, lo = UINT64_MAX, hi = 0, len_sum = 0;
-        while (done + n < n_reads && n < c->batch_reads) {
+        bool cut = false;
+        {
+            const uint64_t cand = n_reads - done < c->batch_reads ? n_reads - done : c->batch_reads;
+            int nt = (int)std::thread::hardware_concurrency();
+            if (nt > 8) nt = 8;
+            if (cand >= (1u << 20) && nt > 1) {
+                struct Part { uint64_t lo = UINT64_MAX, hi = 0, sum = 0; bool bad = false; };
+                std::vector<Part> parts((size_t)nt);
+                auto scan = [&](int t) {
+                    const uint64_t a = done + cand * (uint64_t)t / (uint64_t)nt, b = done + cand * (uint64_t)(t + 1) / (uint64_t)nt;
+                    Part p;
+                    for (uint64_t i = a; i < b; ++i) {
+                        const vfb_span s = spans[i];
+                        const uint64_t e = (uint64_t)s.off + s.len;
+                        p.lo = s.off < p.lo ? s.off : p.lo;
+                        p.hi = e > p.hi ? e : p.hi;
+                        p.sum += s.len;
+                        p.bad |= e > text_bytes;
+                    }
+                    parts[(size_t)t] = p;
+                };
+                std::vector<std::thread> pool;
+                for (int t = 1; t < nt; ++t) pool.emplace_back(scan, t);
+                scan(0);
+                for (auto &t : pool) t.join();
+                Part all;
+                for (const Part &p : parts) {
+                    all.lo = p.lo < all.lo ? p.lo : all.lo;
+                    all.hi = p.hi > all.hi ? p.hi : all.hi;
+                    all.sum += p.sum;
+                    all.bad |= p.bad;
+                }
+                if (!all.bad && all.hi >= all.lo && all.hi - all.lo <= c->batch_bytes) {
+                    n = cand; lo = all.lo; hi = all.hi; len_sum = all.sum;
+                    cut = true;
+                }
+            }
+        }
+        while (!cut && done + n < n_reads && n < c->batch_reads) {
             const vfb_span s = spans[done + n];
             if ((uint64_t)s.off + s.len > text_bytes) { set_error("span outside the text buffer"); rc = VFB_ERR_ARG; break; }
             const uint64_t nlo = s.off < lo ? s.off : lo, nhi = (uint64_t)s.off + s.len > hi ? (uint64_t)s.off + s.len : hi;
@@ -901,7 +1010,7 @@ int vfb_submit_host(vfb_ctx *c, const uint8_t *text, uint64_t text_bytes, const 
         if (hi < lo) { lo = 0; hi = 0; }
         const uint64_t bytes = hi - lo;
         Slot &s = c->slots[c->batch_seq & 1];
-        if (s.busy) { VFB_CUDA(cudaEventSynchronize(s.computed)); s.busy = false; }
+        if ((rc = slot_wait(s))) break;
         if ((rc = s.d_text.ensure(bytes + 32))) break;     // aligned 16-byte loads may run past the last read
         if ((rc = s.d_spans.ensure(n * sizeof(vfb_span)))) break;
         const uint8_t *src_text = text + lo;
@@ -923,10 +1032,10 @@ int vfb_submit_host(vfb_ctx *c, const uint8_t *text, uint64_t text_bytes, const 
         c->stats.h2d_bytes += bytes + n * sizeof(vfb_span);
         // span offsets stay relative to the caller's buffer: bias the device base by -lo
         const uint8_t *d_base = s.d_text.as<uint8_t>() - lo;
-        rc = process_batch(c, d_base, s.d_spans.as<vfb_span>(), (uint32_t)n, len_sum, bytes);
+        unsigned used = 0;
+        rc = process_batch(c, d_base, s.d_spans.as<vfb_span>(), (uint32_t)n, len_sum, bytes, &used);
         if (rc) break;
-        VFB_CUDA(cudaEventRecord(s.computed, c->st_compute));
-        s.busy = true;
+        if ((rc = mark_computed(c, s.computed, &s.busy, used))) break;
         ++c->batch_seq;
         done += n;
     }
@@ -956,7 +1065,7 @@ int vfb_internal_submit_fastq(vfb_ctx *c, const uint8_t *pinned_text, uint64_t n
         c->p_err_init = true;
     }
     Slot &s = c->slots[c->batch_seq & 1];
-    if (s.busy) { VFB_CUDA(cudaEventSynchronize(s.computed)); s.busy = false; }
+    if ((rc = slot_wait(s))) return rc;
     if ((rc = s.d_text.ensure(n_bytes + 32))) return rc;
     if ((rc = s.d_spans.ensure((size_t)(n_rec ? n_rec : 1) * sizeof(vfb_span)))) return rc;
     if ((rc = c->p_tiles.ensure(parse_tile_words((uint32_t)n_bytes) * 8 + 8))) return rc;
@@ -966,6 +1075,7 @@ int vfb_internal_submit_fastq(vfb_ctx *c, const uint8_t *pinned_text, uint64_t n
     VFB_CUDA(cudaEventRecord(s.copied, c->st_copy));
     VFB_CUDA(cudaStreamWaitEvent(c->st_compute, s.copied, 0));
     c->stats.h2d_bytes += n_bytes;
+    unsigned used = 0;
     if (n_rec) {
         if ((rc = launch_parse(s.d_text.as<uint8_t>(), (uint32_t)n_bytes, (uint32_t)n_lines, n_rec,
                                c->p_tiles.as<unsigned long long>(), c->p_line_end.as<uint32_t>(),
@@ -978,12 +1088,11 @@ int vfb_internal_submit_fastq(vfb_ctx *c, const uint8_t *pinned_text, uint64_t n
         while (done < n_rec) {
             const uint32_t n = n_rec - done < c->batch_reads ? n_rec - done : (uint32_t)c->batch_reads;
             if ((rc = process_batch(c, s.d_text.as<uint8_t>(), s.d_spans.as<vfb_span>() + done, n, n_bytes,
-                                    (uint64_t)((double)n_bytes * (double)n / (double)n_rec) + 1))) return rc;
+                                    (uint64_t)((double)n_bytes * (double)n / (double)n_rec) + 1, &used))) return rc;
             done += n;
         }
     }
-    VFB_CUDA(cudaEventRecord(s.computed, c->st_compute));
-    s.busy = true;
+    if ((rc = mark_computed(c, s.computed, &s.busy, used))) return rc;
     ++c->batch_seq;
     bump_launches(c, before);
     return VFB_OK;
@@ -1017,7 +1126,8 @@ int vfb_internal_bgzf_begin(vfb_ctx *c, const vfb_zpiece *pieces, uint32_t n_pie
     if ((rc = g.members.ensure((size_t)(n_members ? n_members : 1) * sizeof(vfb_member) + 16))) return rc;
     if ((rc = c->g_info.ensure(64 * VFB_SEG_SLOTS))) return rc;
     // the hot loop that last read this slot's text must be done before the inflate overwrites it
-    if (g.busy) VFB_CUDA(cudaStreamWaitEvent(c->st_ingest, g.computed, 0));
+    for (int li = 0; li < VFB_LANES; ++li)
+        if (g.busy & (1u << li)) VFB_CUDA(cudaStreamWaitEvent(c->st_ingest, g.computed[li], 0));
     uint64_t zo = 0;
     for (uint32_t i = 0; i < n_pieces; ++i) {
         if (pieces[i].len) VFB_CUDA(cudaMemcpyAsync(g.z.as<uint8_t>() + zo, pieces[i].p, pieces[i].len, cudaMemcpyHostToDevice, c->st_ingest));
@@ -1029,6 +1139,7 @@ int vfb_internal_bgzf_begin(vfb_ctx *c, const vfb_zpiece *pieces, uint32_t n_pie
     uint32_t *d_bad = c->g_info.as<uint32_t>() + 16 * slot + 8;
     VFB_CUDA(cudaMemsetAsync(d_bad, 0xFF, 4, c->st_ingest));
     if ((rc = launch_inflate(g.z.as<uint8_t>(), g.members.as<vfb_member>(), n_members, g.text.as<uint8_t>() + VFB_TAIL_CAP, d_bad, c->st_ingest))) return rc;
+    VFB_CUDA(cudaEventRecord(g.inflated, c->st_ingest));
     g.text_bytes = text_bytes; g.z_bytes = z_bytes; g.n_members = n_members;
     *slot_out = slot;
     bump_launches(c, before);
@@ -1043,7 +1154,8 @@ int vfb_internal_bgzf_finish(vfb_ctx *c, int slot, const uint8_t *carry, uint64_
     VFB_CUDA(cudaSetDevice(c->device));
     const uint64_t before = g_launches;
     SegSlot &g = c->seg[slot];
-    cudaStream_t si = c->st_ingest;
+    cudaStream_t si = c->st_parse;
+    VFB_CUDA(cudaStreamWaitEvent(si, g.inflated, 0));
     int rc;
     const uint64_t front = VFB_TAIL_CAP - carry_len;           // where the carried bytes start in the buffer
     const uint32_t skip = (uint32_t)(front & 15u);
@@ -1100,14 +1212,15 @@ int vfb_internal_bgzf_finish(vfb_ctx *c, int slot, const uint8_t *carry, uint64_
     if (n_rec) {
         VFB_CUDA(cudaStreamWaitEvent(c->st_compute, g.parsed, 0));
         uint32_t done = 0;
+        unsigned lanes_used = 0;
+        g.busy = 0;
         while (done < n_rec) {
             const uint32_t n = n_rec - done < c->batch_reads ? n_rec - done : (uint32_t)c->batch_reads;
             if ((rc = process_batch(c, base, g.spans.as<vfb_span>() + done, n, used,
-                                    (uint64_t)((double)used * (double)n / (double)n_rec) + 1))) return rc;
+                                    (uint64_t)((double)used * (double)n / (double)n_rec) + 1, &lanes_used))) return rc;
             done += n;
         }
-        VFB_CUDA(cudaEventRecord(g.computed, c->st_compute));
-        g.busy = true;
+        if ((rc = mark_computed(c, g.computed, &g.busy, lanes_used))) return rc;
     }
     *n_records = n_rec;
     bump_launches(c, before);
@@ -1159,10 +1272,29 @@ int vfb_sync(vfb_ctx *c)
     VFB_CUDA(cudaSetDevice(c->device));
     VFB_CUDA(cudaStreamSynchronize(c->st_copy));
     VFB_CUDA(cudaStreamSynchronize(c->st_ingest));
+    VFB_CUDA(cudaStreamSynchronize(c->st_parse));
+    { const int jrc = lanes_join(c); if (jrc) return jrc; }
     VFB_CUDA(cudaStreamSynchronize(c->st_compute));
-    for (auto &s : c->slots) s.busy = false;
-    for (auto &g : c->seg) g.busy = false;
+    for (auto &s : c->slots) s.busy = 0;
+    for (auto &g : c->seg) g.busy = 0;
     return prof_resolve(c);
+}
+
+int vfb_fence(vfb_ctx *c)
+{
+    if (!c) { set_error("null context"); return VFB_ERR_ARG; }
+    VFB_CUDA(cudaSetDevice(c->device));
+    return lanes_join(c);
+}
+
+int vfb_set_lanes(vfb_ctx *c, int n)
+{
+    if (!c || n < 1 || n > VFB_LANES) { set_error("lanes: 1 or 2"); return VFB_ERR_ARG; }
+    int rc = vfb_sync(c);
+    if (rc) return rc;
+    if (c->prm.diagnostics) n = 1;
+    c->n_lanes = n;
+    return VFB_OK;
 }
 
 int vfb_set_compute_stream(vfb_ctx *c, void *stream)
@@ -1181,8 +1313,12 @@ int vfb_get_stats(vfb_ctx *c, vfb_stats *out)
     if (!c || !out) { set_error("null argument"); return VFB_ERR_ARG; }
     int rc = vfb_sync(c);
     if (rc) return rc;
-    unsigned long long t64[T_COUNT64], ctr[3];
-    VFB_CUDA(cudaMemcpy(t64, c->d_t64.p, sizeof t64, cudaMemcpyDeviceToHost));
+    unsigned long long t64[T_COUNT64] = {0}, ctr[3];
+    for (auto &ln : c->lanes) {
+        unsigned long long one[T_COUNT64];
+        VFB_CUDA(cudaMemcpy(one, ln.d_t64.p, sizeof one, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < T_COUNT64; ++k) t64[k] += one[k];
+    }
     VFB_CUDA(cudaMemcpy(ctr, c->tab.counters, sizeof ctr, cudaMemcpyDeviceToHost));
     c->stats.dp_cells = t64[T_CELLS];
     c->stats.dp_prefix = t64[T_DPPRE];
@@ -1207,8 +1343,8 @@ int vfb_get_diag(vfb_ctx *c, vfb_read_diag *out, uint64_t n_reads)
     std::vector<int32_t> sp(n), lp(n), ss(n), ls(n);
     VFB_CUDA(cudaMemcpy(ep.data(), c->d_diag_exact_pre.p, n * 4, cudaMemcpyDeviceToHost));
     VFB_CUDA(cudaMemcpy(es.data(), c->d_diag_exact_suf.p, n * 4, cudaMemcpyDeviceToHost));
-    VFB_CUDA(cudaMemcpy(st.data(), c->d_start.p, n * 4, cudaMemcpyDeviceToHost));
-    VFB_CUDA(cudaMemcpy(en.data(), c->d_end.p, n * 4, cudaMemcpyDeviceToHost));
+    VFB_CUDA(cudaMemcpy(st.data(), c->lanes[0].d_start.p, n * 4, cudaMemcpyDeviceToHost));
+    VFB_CUDA(cudaMemcpy(en.data(), c->lanes[0].d_end.p, n * 4, cudaMemcpyDeviceToHost));
     VFB_CUDA(cudaMemcpy(sp.data(), c->d_diag_score_pre.p, n * 4, cudaMemcpyDeviceToHost));
     VFB_CUDA(cudaMemcpy(lp.data(), c->d_diag_len_pre.p, n * 4, cudaMemcpyDeviceToHost));
     VFB_CUDA(cudaMemcpy(ss.data(), c->d_diag_score_suf.p, n * 4, cudaMemcpyDeviceToHost));
@@ -1520,8 +1656,9 @@ int vfb_internal_absorb_known(vfb_ctx *c, const uint8_t *d_chunk, uint64_t rows,
     VFB_CUDA(cudaSetDevice(c->device));
     const uint64_t before = g_launches;
     int rc;
+    if ((rc = lanes_join(c))) return rc;
     if ((rc = table_reserve(c, rows, key_bytes))) return rc;
-    if ((rc = c->d_owner.ensure(rows * 4))) return rc;
+    if ((rc = c->lanes[0].d_owner.ensure(rows * 4))) return rc;
     const uint64_t n = rows;
     const uint8_t *base = d_chunk + sizeof(ChunkHeader);
     InsertJob ij;
@@ -1532,7 +1669,7 @@ int vfb_internal_absorb_known(vfb_ctx *c, const uint8_t *d_chunk, uint64_t rows,
     ij.keys = base + vfb_align16(n * 8) * 3 + vfb_align16(n * 4);
     ij.key_stride = 0;
     ij.n_keys = (uint32_t)n;
-    ij.owner_slot = c->d_owner.as<uint32_t>();
+    ij.owner_slot = c->lanes[0].d_owner.as<uint32_t>();
     if ((rc = launch_insert(c->tab, ij, c->st_compute))) return rc;
     bump_launches(c, before);
     return VFB_OK;

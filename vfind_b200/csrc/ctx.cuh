@@ -76,11 +76,25 @@ struct PinBuf {
     }
 };
 
+// The hot loop of consecutive batches runs on two LANES (streams with their own per-batch scratch), so that the
+// ALU-bound DP kernels of one batch share the SMs with the memory-bound scan / key / count kernels of its
+// neighbours; only the table insert (K4) is serialised between the lanes.
+#define VFB_LANES 2
+struct Lane {
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;         // the lane's last batch has finished
+    bool pending = false;               // `done` has not been joined into the compute stream yet
+    DevBuf d_start, d_end, d_list_a, d_list_b, d_fb_a, d_fb_b, d_c32, d_t64;
+    DevBuf d_keys, d_koff, d_klen, d_khash, d_owner;
+    DevBuf d_wins, d_bestkey, d_cbval, d_fb2;   // windowed DP: window items, per-item results, second fallback list
+    uint32_t win_cap = 0;
+};
+
 struct Slot {
     DevBuf d_text, d_spans;
     PinBuf h_text, h_spans;
-    cudaEvent_t copied = nullptr, computed = nullptr;
-    bool busy = false;
+    cudaEvent_t copied = nullptr, computed[VFB_LANES] = {nullptr, nullptr};
+    unsigned busy = 0;                  // lanes whose `computed` event is pending
 };
 
 // One block-gzip segment in flight on the device (ingest): its text buffer, spans and the events that order the
@@ -88,8 +102,9 @@ struct Slot {
 #define VFB_SEG_SLOTS 3
 struct SegSlot {
     DevBuf text, z, members, spans;
-    cudaEvent_t parsed = nullptr, computed = nullptr;   // recorded on st_ingest / st_compute
-    bool busy = false;                                  // `computed` is pending
+    cudaEvent_t inflated = nullptr, parsed = nullptr;                         // recorded on st_ingest / st_parse
+    cudaEvent_t computed[VFB_LANES] = {nullptr, nullptr};                     // recorded on the lanes
+    unsigned busy = 0;                                  // lanes whose `computed` event is pending
     uint64_t text_bytes = 0, z_bytes = 0;
     uint32_t n_members = 0;
 };
@@ -121,16 +136,19 @@ struct vfb_ctx {
 
     int device = 0, sm_count = 148;
     cudaStream_t st_compute = nullptr, st_copy = nullptr;
-    cudaStream_t st_ingest = nullptr;     // H2D of compressed members, inflate, parse (high priority)
+    cudaStream_t st_ingest = nullptr;     // H2D of compressed members + inflate, segment after segment
+    cudaStream_t st_parse = nullptr;      // record framing of a segment (highest priority: it is the serial link
+                                          // between segments and must not queue behind the next segment's inflate)
     vfb::Slot slots[2];
     uint64_t batch_seq = 0;
     uint64_t batch_reads = 0, batch_bytes = 0;
 
-    // per-batch scratch
-    vfb::DevBuf d_start, d_end, d_list_a, d_list_b, d_fb_a, d_fb_b, d_c32, d_t64;
-    vfb::DevBuf d_keys, d_koff, d_klen, d_khash, d_owner;
-    vfb::DevBuf d_wins, d_bestkey, d_cbval, d_fb2;   // windowed DP: window items, per-item results, second fallback list
-    uint32_t win_cap = 0;
+    // per-batch scratch, one set per lane
+    vfb::Lane lanes[VFB_LANES];
+    int n_lanes = VFB_LANES;                    // 1: every batch on the compute stream itself (diagnostics, VFB_LANES=1)
+    uint64_t lane_seq = 0;
+    cudaEvent_t ev_fork = nullptr, ev_k4 = nullptr;   // compute stream -> lane; the previous batch's insert is done
+    bool k4_pending = false;
     int win_k_pre = -1, win_k_suf = -1;         // Myers thresholds (-1: the windowed DP does not apply)
     vfb::DevBuf d_aligned_text;     // aligned copy of an unaligned caller buffer (vfb_submit_device)
     vfb::DevBuf d_span_sum;         // vfb_submit_device: sum of the span lengths of a batch

@@ -511,7 +511,15 @@ void segment_release_blocks(void *arg)        // runs on a driver thread once th
     for (uint64_t b : g->blocks) g->ring->unref(b);
 }
 
+static inline double now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 struct GpuPhase {
+    // where the threads spent their time (ms; VFB_INGEST_TRACE prints them)
+    double ix_wait_block = 0, ix_wait_queue = 0, ix_total = 0;
+    std::vector<double> w_wait_seg, w_wait_chain, w_begin, w_finish;
     std::mutex mu;
     std::condition_variable cv;
     bool abort = false, indexed = false;       // indexed: the indexer has queued its last segment
@@ -580,11 +588,14 @@ void index_members(RawRing &ring, GpuPhase &gp, size_t text_target, size_t mcap,
         for (uint64_t b : seg->blocks) ring.unref(b);
         delete seg;
     };
+    const double ix_t0 = now_ms();
     auto push = [&](Segment *seg) -> bool {            // takes the segment either way
         {
+            const double w0 = now_ms();
             std::unique_lock<std::mutex> lk(gp.mu);
             auto &q = gp.queues[seg->seq % (uint64_t)n_dev];
             gp.cv.wait(lk, [&] { return gp.abort || q.size() < queue_depth; });
+            gp.ix_wait_queue += now_ms() - w0;
             if (!gp.abort) {
                 q.push_back(seg);
                 gp.cv.notify_all();
@@ -599,39 +610,53 @@ void index_members(RawRing &ring, GpuPhase &gp, size_t text_target, size_t mcap,
             // next block (or the end of the file)
             const bool short_block = cur->len < ring.block;
             if (short_block || bi + 1 >= ring.n_blocks) { at_end = true; break; }
+            const double w0 = now_ms();
             RawRing::Block *n2 = nxt ? nxt : ring.acquire(bi + 1);
+            gp.ix_wait_block += now_ms() - w0;
             if (!n2) { err = ring.err.empty() ? "read aborted" : ring.err; break; }
             bo -= cur->len;
             ring.unref(bi);
             cur = n2; nxt = nullptr; ++bi;
             continue;
         }
-        uint8_t h[18];
-        int k = peek(0, 18, h);
-        if (k < 0) { err = ring.err.empty() ? "read aborted" : ring.err; break; }
         size_t msize = 0;
+        uint32_t isize = 0;
         bool is_bgzf = false;
-        if (k == 1 && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4)) {
-            const uint32_t xlen = h[10] | (h[11] << 8);
-            std::vector<uint8_t> x(xlen);
-            const int kx = xlen >= 6 ? peek(12, xlen, x.data()) : 0;
-            if (kx < 0) { err = "read aborted"; break; }
-            if (kx == 1)
-                for (uint32_t p = 0; p + 4 <= xlen;) {
-                    const uint32_t slen = x[p + 2] | (x[p + 3] << 8);
-                    if (x[p] == 'B' && x[p + 1] == 'C' && slen == 2 && p + 6 <= xlen) { msize = (size_t)(x[p + 4] | (x[p + 5] << 8)) + 1; is_bgzf = true; break; }
-                    p += 4 + slen;
-                }
-            else if (xlen >= 6) { err = "truncated gzip stream"; break; }
+        const uint8_t *hp = cur->p + bo;
+        if (cur->len - bo >= 18 && hp[0] == 0x1f && hp[1] == 0x8b && hp[2] == 8 && hp[3] == 4 && hp[10] == 6 && hp[11] == 0 &&
+            hp[12] == 'B' && hp[13] == 'C' && hp[14] == 2 && hp[15] == 0 &&
+            bo + ((size_t)(hp[16] | (hp[17] << 8)) + 1) <= cur->len && (size_t)(hp[16] | (hp[17] << 8)) + 1 >= 26) {
+            // the usual member: the standard 18-byte header, all of it inside this block
+            msize = (size_t)(hp[16] | (hp[17] << 8)) + 1;
+            const uint8_t *t = hp + msize - 4;
+            isize = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
+            is_bgzf = true;
+        } else {
+            uint8_t h[18];
+            int k = peek(0, 18, h);
+            if (k < 0) { err = ring.err.empty() ? "read aborted" : ring.err; break; }
+            if (k == 1 && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4)) {
+                const uint32_t xlen = h[10] | (h[11] << 8);
+                std::vector<uint8_t> x(xlen);
+                const int kx = xlen >= 6 ? peek(12, xlen, x.data()) : 0;
+                if (kx < 0) { err = "read aborted"; break; }
+                if (kx == 1)
+                    for (uint32_t p = 0; p + 4 <= xlen;) {
+                        const uint32_t slen = x[p + 2] | (x[p + 3] << 8);
+                        if (x[p] == 'B' && x[p + 1] == 'C' && slen == 2 && p + 6 <= xlen) { msize = (size_t)(x[p + 4] | (x[p + 5] << 8)) + 1; is_bgzf = true; break; }
+                        p += 4 + slen;
+                    }
+                else if (xlen >= 6) { err = "truncated gzip stream"; break; }
+            }
+            if (k == 0) { err = "truncated gzip stream"; break; }      // fewer than 18 bytes left: no gzip member is that short
+            if (!is_bgzf) { plain = true; break; }     // some other gzip member (or garbage): the host path decides
+            if (msize < 26) { err = "invalid BGZF member"; break; }
+            uint8_t t[4];
+            k = peek(msize - 4, 4, t);
+            if (k < 0) { err = "read aborted"; break; }
+            if (k == 0) { err = "truncated gzip stream"; break; }
+            isize = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
         }
-        if (k == 0) { err = "truncated gzip stream"; break; }      // fewer than 18 bytes left: no gzip member is that short
-        if (!is_bgzf) { plain = true; break; }     // some other gzip member (or garbage): the host path decides
-        if (msize < 26) { err = "invalid BGZF member"; break; }
-        uint8_t t[4];
-        k = peek(msize - 4, 4, t);
-        if (k < 0) { err = "read aborted"; break; }
-        if (k == 0) { err = "truncated gzip stream"; break; }
-        const uint32_t isize = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
         if (g && (g->text_bytes + isize > text_target || g->members.size() >= mcap || g->blocks.size() >= max_blocks)) {
             Segment *full = g;
             g = nullptr;
@@ -668,6 +693,7 @@ void index_members(RawRing &ring, GpuPhase &gp, size_t text_target, size_t mcap,
     if (g) { discard(g); --seq; }
     if (!err.empty()) { gp.fail(VFB_ERR_FORMAT, err); return; }
     std::lock_guard<std::mutex> lk(gp.mu);
+    gp.ix_total = now_ms() - ix_t0;
     gp.indexed = true;
     gp.n_segments = seq;
     gp.stop_off = stop;
@@ -687,14 +713,17 @@ void device_worker(vfb_ctx *ctx, int dev_index, GpuPhase &gp)
         while (pending.size() < VFB_SEG_SLOTS - 1) {
             Segment *g = nullptr;
             {
+                const double w0 = now_ms();
                 std::unique_lock<std::mutex> lk(gp.mu);
                 auto &q = gp.queues[(size_t)dev_index];
                 if (pending.empty()) gp.cv.wait(lk, [&] { return gp.abort || !q.empty() || gp.indexed; });
+                gp.w_wait_seg[(size_t)dev_index] += now_ms() - w0;
                 if (gp.abort) break;
                 if (!q.empty()) { g = q.front(); q.pop_front(); gp.cv.notify_all(); }
                 else { finished = gp.indexed; }
             }
             if (!g) break;
+            const double b0 = now_ms();
             const int rc = vfb_internal_bgzf_begin(ctx, g->pieces.data(), (uint32_t)g->pieces.size(), g->members.data(),
                                                    (uint32_t)g->members.size(), g->text_bytes, segment_release_blocks, g, &g->slot);
             if (rc) {
@@ -704,6 +733,7 @@ void device_worker(vfb_ctx *ctx, int dev_index, GpuPhase &gp)
                 break;
             }
             pending.push_back(g);
+            gp.w_begin[(size_t)dev_index] += now_ms() - b0;
         }
         {
             std::lock_guard<std::mutex> lk(gp.mu);
@@ -715,8 +745,10 @@ void device_worker(vfb_ctx *ctx, int dev_index, GpuPhase &gp)
         std::vector<uint8_t> carry;
         uint64_t record_base = 0;
         {
+            const double w0 = now_ms();
             std::unique_lock<std::mutex> lk(gp.mu);
             gp.cv.wait(lk, [&] { return gp.abort || gp.link(g->seq).ready; });
+            gp.w_wait_chain[(size_t)dev_index] += now_ms() - w0;
             if (gp.abort) { drop(g); break; }
             GpuPhase::Link &l = gp.link(g->seq);
             carry.swap(l.carry);
@@ -725,12 +757,14 @@ void device_worker(vfb_ctx *ctx, int dev_index, GpuPhase &gp)
         }
         uint64_t n_rec = 0, tail_len = 0;
         uint32_t bad = 0xFFFFFFFFu;
+        const double f0 = now_ms();
         int rc = vfb_internal_bgzf_finish(ctx, g->slot, carry.data(), carry.size(), record_base, &n_rec, tail.data(), &tail_len, &bad);
         if (rc == VFB_OK && bad != 0xFFFFFFFFu) {
             set_error("invalid gzip data in a BGZF member (deflate stream, CRC-32 or size mismatch)");
             rc = VFB_ERR_FORMAT;
         }
         if (rc) { gp.fail(rc, vfb_last_error()); drop(g); break; }
+        gp.w_finish[(size_t)dev_index] += now_ms() - f0;
         {
             std::lock_guard<std::mutex> lk(gp.mu);
             GpuPhase::Link &l = gp.link(g->seq + 1);
@@ -789,6 +823,9 @@ int run_bgzf_gpu(vfb_ctx **ctxs, int n_dev, ChunkProducer &prod, size_t text_tar
     RawRing ring;
     GpuPhase gp;
     gp.queues.resize((size_t)n_dev);
+    gp.w_wait_seg.assign((size_t)n_dev, 0); gp.w_wait_chain.assign((size_t)n_dev, 0);
+    gp.w_begin.assign((size_t)n_dev, 0); gp.w_finish.assign((size_t)n_dev, 0);
+    const double phase_t0 = now_ms();
     gp.link(0).ready = true;
     gp.link(0).carry = prod.carry;
     gp.link(0).records = *n_total;
@@ -835,6 +872,13 @@ int run_bgzf_gpu(vfb_ctx **ctxs, int n_dev, ChunkProducer &prod, size_t text_tar
     GpuPhase::Link &last = gp.link(gp.n_segments);
     prod.carry = last.carry;
     *n_total = last.records;
+    if (trace) {
+        fprintf(stderr, "[vfb ingest] gpu phase %.1f ms; indexer %.1f ms (waited %.1f for blocks, %.1f for queue room)\n",
+                now_ms() - phase_t0, gp.ix_total, gp.ix_wait_block, gp.ix_wait_queue);
+        for (int d = 0; d < n_dev; ++d)
+            fprintf(stderr, "[vfb ingest]   device %d: waited %.1f ms for segments, %.1f ms for the chain; begin %.1f ms, finish %.1f ms\n",
+                    ctxs[d]->device, gp.w_wait_seg[(size_t)d], gp.w_wait_chain[(size_t)d], gp.w_begin[(size_t)d], gp.w_finish[(size_t)d]);
+    }
     if (trace) fprintf(stderr, "[vfb ingest] gpu phase: %llu segments, %llu records, stopped at offset %llu of %llu%s\n",
                        (unsigned long long)gp.n_segments, (unsigned long long)(*n_total - base_records),
                        (unsigned long long)gp.stop_off, (unsigned long long)fsz, gp.hit_plain ? " (a plain gzip member follows)" : "");
