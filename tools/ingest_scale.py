@@ -33,4 +33,21 @@ for n in (1, 2, 4, 8):
         dt = time.time() - t0
         os.environ.pop("VFB_INGEST_TRACE", None)
         print("n=%d rep %d: %.3f s  %.1f M reads/s  rows %d" % (n, rep, dt, n_reads / dt / 1e6, out.num_rows), flush=True)
+        del out
+    # the same call in pieces: where the time outside the ingest goes
+    t0 = time.time()
+    ctx = api.Context(ads, device=0) if n == 1 else api.MultiContext(ads, devices=list(range(n)))
+    t1 = time.time()
+    ctx.run_file(path)
+    t2 = time.time()
+    batch = ctx.finish_arrow()
+    t3 = time.time()
+    frame = api.batch_to_frame(batch)
+    t4 = time.time()
+    ctx.close()
+    t5 = time.time()
+    del batch, frame
+    t6 = time.time()
+    print("n=%d pieces: create %.1f ms, run_file %.1f ms, finish_arrow %.1f ms, to frame %.1f ms, close %.1f ms, release result %.1f ms"
+          % (n, 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2), 1e3 * (t4 - t3), 1e3 * (t5 - t4), 1e3 * (t6 - t5)), flush=True)
 os.remove(path)

@@ -320,12 +320,14 @@ static int table_alloc(vfb_ctx *c, uint64_t capacity, uint64_t rows_cap, uint64_
     if ((rc = c->t_row_hash.ensure(rows_cap * 8, true, c->st_compute))) return rc;
     if ((rc = c->t_row_off.ensure(rows_cap * 8, true, c->st_compute))) return rc;
     if ((rc = c->t_row_len.ensure(rows_cap * 4, true, c->st_compute))) return rc;
+    if ((rc = c->t_row_slot.ensure(rows_cap * 4, true, c->st_compute))) return rc;
     if ((rc = c->t_arena.ensure(arena_cap, true, c->st_compute))) return rc;
     c->tab.slots = c->t_slots.as<unsigned long long>();
     c->tab.capacity = capacity;
     c->tab.row_hash = c->t_row_hash.as<uint64_t>();
     c->tab.row_off = c->t_row_off.as<uint64_t>();
     c->tab.row_len = c->t_row_len.as<uint32_t>();
+    c->tab.row_slot = c->t_row_slot.as<uint32_t>();
     c->tab.row_capacity = rows_cap;
     c->tab.arena = c->t_arena.as<uint8_t>();
     c->tab.arena_capacity = arena_cap;
@@ -345,9 +347,11 @@ static int table_init(vfb_ctx *c)
     int rc;
     if ((rc = c->t_counters.ensure(8 * 8))) return rc;
     uint64_t hint = c->prm.table_capacity_hint;
-    uint64_t cap = pow2_at_least(hint ? hint * 2 : (1u << 16));
-    uint64_t rows = hint ? hint : (1u << 15);
-    if ((rc = table_alloc(c, cap, rows, rows * 32))) return rc;
+    // without a hint: room for 2 M distinct variants (about 250 MB in all) before the first rehash — a rehash stalls the
+    // pipeline, and the buffers come from the device pool after the first call
+    uint64_t cap = pow2_at_least(hint ? hint * 2 : (1u << 22));
+    uint64_t rows = hint ? hint : (1u << 21);
+    if ((rc = table_alloc(c, cap, rows, rows * 96))) return rc;
     VFB_CUDA(cudaMemsetAsync(c->tab.slots, 0, cap * 8 * VFB_SLOT_WORDS, c->st_compute));
     VFB_CUDA(cudaMemsetAsync(c->tab.counters, 0, 8 * 8, c->st_compute));
     c->ub_rows = 0;
@@ -355,40 +359,96 @@ static int table_init(vfb_ctx *c)
     return VFB_OK;
 }
 
-// Make room for `new_keys` more keys of `new_bytes` padded key bytes (upper bounds).
+// Counter snapshots: see vfb_ctx::snaps.
+static void snaps_poll(vfb_ctx *c, bool wait_oldest)
+{
+    while (c->snap_tail < c->snap_head) {
+        vfb_ctx::CtrSnap &sn = c->snaps[c->snap_tail % vfb_ctx::N_SNAP];
+        cudaError_t e = wait_oldest ? cudaEventSynchronize(sn.ev) : cudaEventQuery(sn.ev);
+        wait_oldest = false;
+        if (e != cudaSuccess) { cudaGetLastError(); break; }
+        const uint64_t *v = reinterpret_cast<const uint64_t *>(c->snap_pin.p) + 2 * (c->snap_tail % vfb_ctx::N_SNAP);
+        c->base_rows = v[0];
+        c->base_arena = v[1];
+        sn.pending = false;
+        ++c->snap_tail;
+    }
+    uint64_t r = c->base_rows, a = c->base_arena;
+    for (uint64_t k = c->snap_tail; k < c->snap_head; ++k) {
+        r += c->snaps[k % vfb_ctx::N_SNAP].add_rows;
+        a += c->snaps[k % vfb_ctx::N_SNAP].add_bytes;
+    }
+    c->ub_rows = r;
+    c->ub_arena = a;
+}
+
+// Called once the inserts of a batch that may add (new_keys, new_bytes) have been queued on `st`.
+static int snaps_push(vfb_ctx *c, uint64_t new_keys, uint64_t new_bytes, cudaStream_t st)
+{
+    if (!c->snap_pin.p) {
+        int rc = c->snap_pin.ensure(vfb_ctx::N_SNAP * 16);
+        if (rc) return rc;
+        for (auto &sn : c->snaps) VFB_CUDA(cudaEventCreateWithFlags(&sn.ev, cudaEventDisableTiming));
+    }
+    if (c->snap_head - c->snap_tail >= (uint64_t)vfb_ctx::N_SNAP) snaps_poll(c, true);
+    vfb_ctx::CtrSnap &sn = c->snaps[c->snap_head % vfb_ctx::N_SNAP];
+    sn.add_rows = new_keys; sn.add_bytes = new_bytes; sn.pending = true;
+    uint64_t *dst = reinterpret_cast<uint64_t *>(c->snap_pin.p) + 2 * (c->snap_head % vfb_ctx::N_SNAP);
+    VFB_CUDA(cudaMemcpyAsync(dst, c->tab.counters, 16, cudaMemcpyDeviceToHost, st));
+    VFB_CUDA(cudaEventRecord(sn.ev, st));
+    ++c->snap_head;
+    return VFB_OK;
+}
+
+static void snaps_reset(vfb_ctx *c)           // the table was cleared (after a join + on the compute stream)
+{
+    while (c->snap_tail < c->snap_head) {
+        cudaEventSynchronize(c->snaps[c->snap_tail % vfb_ctx::N_SNAP].ev);
+        c->snaps[c->snap_tail % vfb_ctx::N_SNAP].pending = false;
+        ++c->snap_tail;
+    }
+    c->base_rows = c->base_arena = 0;
+    c->ub_rows = c->ub_arena = 0;
+}
+
+// Make room for `new_keys` more keys of `new_bytes` padded key bytes (upper bounds).  The caller queues the inserts
+// and then calls snaps_push with the same numbers.
 static int table_reserve(vfb_ctx *c, uint64_t new_keys, uint64_t new_bytes)
 {
+    snaps_poll(c, false);
     uint64_t want_rows = c->ub_rows + new_keys, want_arena = c->ub_arena + new_bytes;
-    const bool fits = want_rows * 2 <= c->tab.capacity && want_rows <= c->tab.row_capacity &&
-                      want_arena <= c->tab.arena_capacity && want_rows < 0x7FFFFFF0ull;
-    if (fits) {
-        c->ub_rows = want_rows;
-        c->ub_arena = want_arena;
-        return VFB_OK;
-    }
-    // tighten the bounds with the true counters, then grow if still needed
-    trace("table_reserve: bounds exceeded (rows %llu + %llu, capacity %llu): sync", (unsigned long long)c->ub_rows,
-          (unsigned long long)new_keys, (unsigned long long)c->tab.capacity);
-    unsigned long long ctr[2];
+    auto fits = [&]() {
+        return want_rows * 2 <= c->tab.capacity && want_rows <= c->tab.row_capacity &&
+               want_arena <= c->tab.arena_capacity && want_rows < 0x7FFFFFF0ull;
+    };
+    if (fits()) return VFB_OK;
+    // the bounds say no: wait for the true counters (everything queued so far), then grow if it is still needed —
+    // geometrically, so that this happens O(log) times
+    trace("table_reserve: bounds exceeded (rows %llu + %llu of %llu, arena %llu + %llu of %llu MB): sync",
+          (unsigned long long)c->ub_rows, (unsigned long long)new_keys, (unsigned long long)c->tab.row_capacity,
+          (unsigned long long)(c->ub_arena >> 20), (unsigned long long)(new_bytes >> 20), (unsigned long long)(c->tab.arena_capacity >> 20));
     { const int jrc = lanes_join(c); if (jrc) return jrc; }
+    unsigned long long ctr[2];
     VFB_CUDA(cudaMemcpyAsync(ctr, c->tab.counters, sizeof ctr, cudaMemcpyDeviceToHost, c->st_compute));
     VFB_CUDA(cudaStreamSynchronize(c->st_compute));
     c->stats.d2h_bytes += sizeof ctr;
-    c->ub_rows = ctr[0];
-    c->ub_arena = ctr[1];
+    while (c->snap_tail < c->snap_head) { c->snaps[c->snap_tail % vfb_ctx::N_SNAP].pending = false; ++c->snap_tail; }
+    c->base_rows = c->ub_rows = ctr[0];
+    c->base_arena = c->ub_arena = ctr[1];
     want_rows = c->ub_rows + new_keys;
     want_arena = c->ub_arena + new_bytes;
+    if (fits()) return VFB_OK;
     if (want_rows >= 0x7FFFFFF0ull) {
         set_error("more than 2^31 distinct variants are not supported");
         return VFB_ERR_ARG;
     }
     int rc;
     uint64_t rows_cap = c->tab.row_capacity, arena_cap = c->tab.arena_capacity;
-    if (want_rows > rows_cap) rows_cap = want_rows + want_rows / 2;
-    if (want_arena > arena_cap) arena_cap = want_arena + want_arena / 2;
+    if (want_rows > rows_cap) rows_cap = 2 * want_rows;
+    if (want_arena > arena_cap) arena_cap = 2 * want_arena;
     if (want_rows * 2 > c->tab.capacity) {
         // rehash into a larger slot array
-        uint64_t ncap = pow2_at_least(want_rows * 3);
+        uint64_t ncap = pow2_at_least(want_rows * 4);
         trace("table rehash %llu -> %llu slots", (unsigned long long)c->tab.capacity, (unsigned long long)ncap);
         DevBuf nslots;
         if ((rc = nslots.ensure(ncap * 8 * VFB_SLOT_WORDS))) return rc;
@@ -403,8 +463,6 @@ static int table_reserve(vfb_ctx *c, uint64_t new_keys, uint64_t new_bytes)
         c->tab.capacity = ncap;
     }
     if ((rc = table_alloc(c, c->tab.capacity, rows_cap, arena_cap))) return rc;
-    c->ub_rows = want_rows;
-    c->ub_arena = want_arena;
     return VFB_OK;
 }
 
@@ -509,10 +567,10 @@ int vfb_create(const vfb_params *p, vfb_ctx **out)
     } else if ((e = cudaGetDevice(&c->device)) != cudaSuccess) {
         return fail(cuda_fail(e, "cudaGetDevice", __FILE__, __LINE__));
     }
-    cudaDeviceProp prop;
-    if ((e = cudaGetDeviceProperties(&prop, c->device)) != cudaSuccess)
-        return fail(cuda_fail(e, "cudaGetDeviceProperties", __FILE__, __LINE__));
-    c->sm_count = prop.multiProcessorCount;
+    // (cudaGetDeviceProperties takes milliseconds; one attribute does not)
+    if ((e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device)) != cudaSuccess)
+        return fail(cuda_fail(e, "cudaDeviceGetAttribute", __FILE__, __LINE__));
+    trace("vfb_create: device %d, %d SMs", c->device, c->sm_count);
     // the parse stream outranks everything: the short record-framing kernels of a segment sit on the critical path
     // of the segment chain and must queue neither behind K1..K4 nor behind the next segment's inflate
     int prio_lo = 0, prio_hi = 0;
@@ -571,7 +629,9 @@ int vfb_create(const vfb_params *p, vfb_ctx **out)
         if ((e = cudaMemset(ln.d_t64.p, 0, T_COUNT64 * 8)) != cudaSuccess)
             return fail(cuda_fail(e, "cudaMemset", __FILE__, __LINE__));
     }
+    trace("vfb_create: streams, events, DP setup done");
     if ((rc = table_init(c))) return fail(rc);
+    trace("vfb_create: table ready");
     c->stats.dp_kernel_kind = (c->packed_pre || c->packed_suf) ? 1 : ((c->align_pre || c->align_suf) ? 2 : 0);
     if ((c->win_k_pre >= 0 || c->win_k_suf >= 0) && (!p->diagnostics || p->dp_mode == 2)) c->stats.dp_kernel_kind = 3;
     *out = c;
@@ -609,13 +669,14 @@ int vfb_destroy(vfb_ctx *c)
     if (c->ev_k4) cudaEventDestroy(c->ev_k4);
     DevBuf *bufs[] = {&c->d_code_pre, &c->d_code_suf, &c->d_generic_scratch, &c->d_diag_exact_pre, &c->d_diag_exact_suf, &c->d_diag_score_pre,
                       &c->d_diag_len_pre, &c->d_diag_score_suf, &c->d_diag_len_suf, &c->t_slots,
-                      &c->t_row_hash, &c->t_row_off, &c->t_row_len, &c->t_arena, &c->t_counters, &c->t_row_count,
+                      &c->t_row_hash, &c->t_row_off, &c->t_row_len, &c->t_row_slot, &c->t_arena, &c->t_counters, &c->t_row_count,
                       &c->m_part_rows, &c->m_part_keys, &c->m_cursors, &c->m_chunk_off, &c->m_send, &c->m_recv,
                       &c->d_aligned_text, &c->d_span_sum,
                       &c->x_block_bytes, &c->x_block_rows, &c->x_offsets, &c->x_counts, &c->x_data,
                       &c->p_tiles, &c->p_line_end, &c->p_err, &c->g_tail, &c->g_info};
     for (auto *b : bufs) b->release();
-    c->g_pin.release(); c->m_pin.release();
+    c->g_pin.release(); c->m_pin.release(); c->snap_pin.release();
+    for (auto &sn : c->snaps) if (sn.ev) cudaEventDestroy(sn.ev);
     c->h_offsets.release(); c->h_counts.release(); c->h_data.release();
     for (auto &ev : c->evpool) if (ev) cudaEventDestroy(ev);
     if (c->m_filled) cudaEventDestroy(c->m_filled);
@@ -648,10 +709,9 @@ int vfb_table_clear(vfb_ctx *c)
     if (!c) { set_error("null context"); return VFB_ERR_ARG; }
     VFB_CUDA(cudaSetDevice(c->device));
     { const int jrc = lanes_join(c); if (jrc) return jrc; }
+    snaps_reset(c);
     VFB_CUDA(cudaMemsetAsync(c->tab.slots, 0, c->tab.capacity * 8 * VFB_SLOT_WORDS, c->st_compute));
     VFB_CUDA(cudaMemsetAsync(c->tab.counters, 0, 8 * 8, c->st_compute));
-    c->ub_rows = 0;
-    c->ub_arena = 0;
     return VFB_OK;
 }
 
@@ -862,6 +922,7 @@ static int process_batch(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_sp
     // the table insert of a batch claims slots by batch-relative read index: one batch at a time
     if (c->n_lanes > 1 && c->k4_pending) VFB_CUDA(cudaStreamWaitEvent(st, c->ev_k4, 0));
     if ((rc = launch_insert(c->tab, ij, st))) return rc;
+    if ((rc = snaps_push(c, n, key_bytes_ub, st))) return rc;
     if (c->n_lanes > 1) {
         VFB_CUDA(cudaEventRecord(c->ev_k4, st));
         c->k4_pending = true;
@@ -1385,8 +1446,6 @@ int vfb_internal_export_sizes(vfb_ctx *c, uint64_t *rows_out, uint64_t *bytes_ou
     if ((rc = c->x_block_bytes.ensure((nb + 2) * 8))) return rc;
     if ((rc = c->x_block_rows.ensure(nb * 8))) return rc;
     unsigned long long *d_totals = c->x_block_bytes.as<unsigned long long>() + nb;
-    // rows published without a slot count cannot exist, but the buffer may be a recycled one: zero first
-    VFB_CUDA(cudaMemsetAsync(c->t_row_count.p, 0, rows * 8, c->st_compute));
     if ((rc = launch_export_counts(c->tab, rows, c->t_row_count.as<unsigned long long>(), c->st_compute))) return rc;
     if ((rc = launch_export_sizes(c->tab, rows, c->t_row_count.as<unsigned long long>(), c->x_block_bytes.as<unsigned long long>(),
                                   c->x_block_rows.as<unsigned long long>(), d_totals, c->st_compute))) return rc;
@@ -1576,22 +1635,16 @@ int vfb_internal_partition_count(vfb_ctx *c, uint32_t n_parts, uint32_t self, ui
     c->x_table_rows = rows;
     c->m_self = self;
     if ((rc = c->m_part_rows.ensure((size_t)n_parts * 16))) return rc;
-    if ((rc = c->t_row_count.ensure((rows ? rows : 1) * 8))) return rc;
     VFB_CUDA(cudaMemsetAsync(c->m_part_rows.p, 0, (size_t)n_parts * 16, c->st_compute));
-    if (rows) {
-        VFB_CUDA(cudaMemsetAsync(c->t_row_count.p, 0, rows * 8, c->st_compute));
-        if ((rc = launch_export_counts(c->tab, rows, c->t_row_count.as<unsigned long long>(), c->st_compute))) return rc;
-        if ((rc = launch_partition_count(c->tab, rows, c->t_row_count.as<unsigned long long>(), n_parts, self,
-                                         c->m_part_rows.as<unsigned long long>(),
-                                         c->m_part_rows.as<unsigned long long>() + n_parts, c->st_compute))) return rc;
-    }
+    if (rows && (rc = launch_partition_count(c->tab, rows, n_parts, self, c->m_part_rows.as<unsigned long long>(),
+                                             c->m_part_rows.as<unsigned long long>() + n_parts, c->st_compute))) return rc;
     if (table_rows) *table_rows = rows;
     bump_launches(c, before);
     return VFB_OK;
 }
 
 // Pass 2 (asynchronous): one chunk per part (not for `self`) at d_buf + chunk_offsets[p]; part sizes as counted.
-int vfb_internal_partition_fill(vfb_ctx *c, uint32_t n_parts, uint32_t self, uint8_t *d_buf, const uint64_t *chunk_offsets)
+int vfb_internal_partition_fill(vfb_ctx *c, uint32_t n_parts, uint32_t self, bool release, uint8_t *d_buf, const uint64_t *chunk_offsets)
 {
     VFB_CUDA(cudaSetDevice(c->device));
     const uint64_t before = g_launches;
@@ -1601,7 +1654,7 @@ int vfb_internal_partition_fill(vfb_ctx *c, uint32_t n_parts, uint32_t self, uin
     VFB_CUDA(cudaMemsetAsync(c->m_cursors.p, 0, (size_t)n_parts * 16, c->st_compute));
     // (pageable source: staged by the driver before the call returns)
     VFB_CUDA(cudaMemcpyAsync(c->m_chunk_off.p, chunk_offsets, (size_t)n_parts * 8, cudaMemcpyHostToDevice, c->st_compute));
-    if ((rc = launch_partition_fill(c->tab, c->x_table_rows, n_parts, self, c->t_row_count.as<unsigned long long>(), d_buf,
+    if ((rc = launch_partition_fill(c->tab, c->x_table_rows, n_parts, self, release, d_buf,
                                     c->m_chunk_off.as<uint64_t>(), c->m_part_rows.as<uint64_t>(),
                                     c->m_part_rows.as<uint64_t>() + n_parts, c->m_cursors.as<unsigned long long>(), c->st_compute)))
         return rc;
@@ -1638,12 +1691,7 @@ int vfb_internal_merge_export(vfb_ctx *c, uint32_t n_parts, uint32_t self, bool 
     }
     if ((rc = c->m_send.ensure(total ? total : 16))) return rc;
     if (total) {
-        if ((rc = vfb_internal_partition_fill(c, n_parts, self, c->m_send.as<uint8_t>(), chunk_offsets))) return rc;
-        if (release) {
-            const uint64_t before = g_launches;
-            if ((rc = launch_release_foreign(c->tab, n_parts, self, c->st_compute))) return rc;
-            bump_launches(c, before);
-        }
+        if ((rc = vfb_internal_partition_fill(c, n_parts, self, release, c->m_send.as<uint8_t>(), chunk_offsets))) return rc;
     }
     VFB_CUDA(cudaEventRecord(c->m_filled, c->st_compute));
     return VFB_OK;
@@ -1671,6 +1719,7 @@ int vfb_internal_absorb_known(vfb_ctx *c, const uint8_t *d_chunk, uint64_t rows,
     ij.n_keys = (uint32_t)n;
     ij.owner_slot = c->lanes[0].d_owner.as<uint32_t>();
     if ((rc = launch_insert(c->tab, ij, c->st_compute))) return rc;
+    if ((rc = snaps_push(c, rows, key_bytes, c->st_compute))) return rc;
     bump_launches(c, before);
     return VFB_OK;
 }
@@ -1693,7 +1742,7 @@ int vfb_table_partition_fill(vfb_ctx *c, uint32_t n_parts, uint8_t *d_buf, const
         set_error("call vfb_table_partition_sizes with the same n_parts first");
         return VFB_ERR_ARG;
     }
-    int rc = vfb_internal_partition_fill(c, n_parts, 0xFFFFFFFFu, d_buf, chunk_offsets);
+    int rc = vfb_internal_partition_fill(c, n_parts, 0xFFFFFFFFu, false, d_buf, chunk_offsets);
     if (rc) return rc;
     VFB_CUDA(cudaStreamSynchronize(c->st_compute));
     return VFB_OK;

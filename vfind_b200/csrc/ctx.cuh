@@ -158,8 +158,17 @@ struct vfb_ctx {
 
     // table
     vfb::DevTable tab{};
-    vfb::DevBuf t_slots, t_row_hash, t_row_off, t_row_len, t_arena, t_counters, t_row_count;
-    uint64_t ub_rows = 0, ub_arena = 0;   // host-side upper bounds of rows / arena bytes
+    vfb::DevBuf t_slots, t_row_hash, t_row_off, t_row_len, t_row_slot, t_arena, t_counters, t_row_count;
+    // Host-side upper bounds of rows / arena bytes = the last counter snapshot that has come back + what the batches
+    // queued since may add.  A snapshot (rows, arena bytes) is copied to pinned memory behind every batch's insert
+    // and picked up without blocking: the bounds stay within a few batches of the truth and no batch waits for them.
+    uint64_t ub_rows = 0, ub_arena = 0;
+    struct CtrSnap { cudaEvent_t ev = nullptr; uint64_t add_rows = 0, add_bytes = 0; bool pending = false; };
+    static constexpr int N_SNAP = 16;
+    CtrSnap snaps[N_SNAP];
+    vfb::PinBuf snap_pin;                 // N_SNAP x 2 u64
+    uint64_t snap_head = 0, snap_tail = 0;   // [tail, head) are pending, in batch order
+    uint64_t base_rows = 0, base_arena = 0;  // the newest snapshot seen
 
     // ingest, GPU inflate path: segments in flight, tail / info landing zones
     vfb::SegSlot seg[VFB_SEG_SLOTS];
@@ -207,7 +216,7 @@ int vfb_internal_merge_export(vfb_ctx *ctx, uint32_t n_parts, uint32_t self, boo
                               uint64_t *chunk_offsets, uint64_t *part_rows, uint64_t *part_keys);
 int vfb_internal_absorb_known(vfb_ctx *ctx, const uint8_t *d_chunk, uint64_t rows, uint64_t key_bytes);
 int vfb_internal_partition_count(vfb_ctx *ctx, uint32_t n_parts, uint32_t self, uint64_t *table_rows);
-int vfb_internal_partition_fill(vfb_ctx *ctx, uint32_t n_parts, uint32_t self, uint8_t *d_buf, const uint64_t *chunk_offsets);
+int vfb_internal_partition_fill(vfb_ctx *ctx, uint32_t n_parts, uint32_t self, bool release, uint8_t *d_buf, const uint64_t *chunk_offsets);
 int vfb_internal_arrow_wrap(vfb::PinBuf offsets, vfb::PinBuf data, vfb::PinBuf counts, uint64_t rows,
                             vfb_arrow_array *out_array, vfb_arrow_schema *out_schema);
 // One file over n_ctx contexts, one per device (ingest.cu).

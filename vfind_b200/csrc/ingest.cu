@@ -396,6 +396,11 @@ struct Pipe {
 //                    each worker publishes that when its phase 2 has framed the records, about half a
 //                    millisecond of small kernels per segment — the only serial part of the pipeline.
 // The calling thread waits, reports progress and collects errors.
+static inline double now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 struct RawRing {
     struct Block {
         uint8_t *p = nullptr;
@@ -414,6 +419,7 @@ struct RawRing {
     std::condition_variable cv;
     bool abort = false;
     std::string err;
+    double t_read_ms = 0, t_wait_ms = 0;          // summed over the reader threads (trace)
 
     bool start(int fd_, uint64_t base_, uint64_t end_, size_t block_, int n_ring, int n_threads)
     {
@@ -436,8 +442,10 @@ struct RawRing {
             uint64_t idx;
             Block *b;
             {
+                const double w0 = now_ms();
                 std::unique_lock<std::mutex> lk(mu);
                 cv.wait(lk, [&] { return abort || next_idx >= n_blocks || ring[next_idx % ring.size()].state == 0; });
+                t_wait_ms += now_ms() - w0;
                 if (abort || next_idx >= n_blocks) return;
                 idx = next_idx++;
                 b = &ring[idx % ring.size()];
@@ -447,6 +455,7 @@ struct RawRing {
             const size_t want = (size_t)std::min<uint64_t>(block, end - lo);
             size_t done = 0;
             bool bad = false;
+            const double r0 = now_ms();
             while (done < want) {
                 const ssize_t got = pread(fd, b->p + done, want - done, (off_t)(lo + done));
                 if (got < 0) { if (errno == EINTR) continue; bad = true; break; }
@@ -454,6 +463,7 @@ struct RawRing {
                 done += (size_t)got;
             }
             std::lock_guard<std::mutex> lk(mu);
+            t_read_ms += now_ms() - r0;
             if (bad) { abort = true; err = std::string("read error: ") + strerror(errno); }
             b->len = done;
             b->state = 2;
@@ -503,6 +513,7 @@ struct Segment {
     uint64_t text_bytes = 0, z_bytes = 0;
     RawRing *ring = nullptr;
     int slot = -1;
+    double t_pushed = 0, t_begin = 0, t_fin0 = 0;     // trace
 };
 
 void segment_release_blocks(void *arg)        // runs on a driver thread once the pieces are on the device
@@ -511,14 +522,10 @@ void segment_release_blocks(void *arg)        // runs on a driver thread once th
     for (uint64_t b : g->blocks) g->ring->unref(b);
 }
 
-static inline double now_ms()
-{
-    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
-}
-
 struct GpuPhase {
     // where the threads spent their time (ms; VFB_INGEST_TRACE prints them)
     double ix_wait_block = 0, ix_wait_queue = 0, ix_total = 0;
+    double sum_queue_ms = 0, sum_begin_to_fin_ms = 0, sum_fin_ms = 0;     // per segment: queued -> begun -> finish starts -> ends
     std::vector<double> w_wait_seg, w_wait_chain, w_begin, w_finish;
     std::mutex mu;
     std::condition_variable cv;
@@ -570,7 +577,13 @@ void index_members(RawRing &ring, GpuPhase &gp, size_t text_target, size_t mcap,
             RawRing::Block *blk;
             if (b == bi) blk = cur;
             else if (b == bi + 1) {
-                if (!nxt) { if (b >= ring.n_blocks) return 0; nxt = ring.acquire(b); if (!nxt) return -1; }
+                if (!nxt) {
+                    if (b >= ring.n_blocks) return 0;
+                    const double w0 = now_ms();
+                    nxt = ring.acquire(b);
+                    gp.ix_wait_block += now_ms() - w0;
+                    if (!nxt) return -1;
+                }
                 blk = nxt;
             } else return 0;                   // members are at most 64 KiB: never more than two blocks
             if (pos >= blk->len) {
@@ -597,6 +610,7 @@ void index_members(RawRing &ring, GpuPhase &gp, size_t text_target, size_t mcap,
             gp.cv.wait(lk, [&] { return gp.abort || q.size() < queue_depth; });
             gp.ix_wait_queue += now_ms() - w0;
             if (!gp.abort) {
+                seg->t_pushed = now_ms();
                 q.push_back(seg);
                 gp.cv.notify_all();
                 return true;
@@ -724,6 +738,7 @@ void device_worker(vfb_ctx *ctx, int dev_index, GpuPhase &gp)
             }
             if (!g) break;
             const double b0 = now_ms();
+            g->t_begin = b0;
             const int rc = vfb_internal_bgzf_begin(ctx, g->pieces.data(), (uint32_t)g->pieces.size(), g->members.data(),
                                                    (uint32_t)g->members.size(), g->text_bytes, segment_release_blocks, g, &g->slot);
             if (rc) {
@@ -767,6 +782,9 @@ void device_worker(vfb_ctx *ctx, int dev_index, GpuPhase &gp)
         gp.w_finish[(size_t)dev_index] += now_ms() - f0;
         {
             std::lock_guard<std::mutex> lk(gp.mu);
+            gp.sum_queue_ms += g->t_begin - g->t_pushed;
+            gp.sum_begin_to_fin_ms += f0 - g->t_begin;
+            gp.sum_fin_ms += now_ms() - f0;
             GpuPhase::Link &l = gp.link(g->seq + 1);
             l.carry.assign(tail.data(), tail.data() + tail_len);
             l.records = record_base + n_rec;
@@ -804,17 +822,17 @@ int run_bgzf_gpu(vfb_ctx **ctxs, int n_dev, ChunkProducer &prod, size_t text_tar
         if (per < ((uint64_t)16 << 20)) per = (uint64_t)16 << 20;
         if (per < text_target) text_target = (size_t)per;
     }
-    // raw blocks of 8 MB; the ring holds 128 MB for one device, up to 512 MB for eight (page-locked once per process:
-    // the buffers come from the pinned pool); a segment may hold a third of the ring
+    // raw blocks of 8 MB; the ring holds 256 MB for one or two devices, up to 768 MB for eight (page-locked once per
+    // process: the buffers come from the pinned pool); a segment may hold a third of the ring
     size_t block = (size_t)8 << 20;
     if (const char *e = getenv("VFB_RAW_BLOCK")) block = (size_t)strtoull(e, nullptr, 10);
     if (block < 131072) block = 131072;                     // a member (<= 64 KiB) spans at most two blocks
     if (block > fsz - here) block = (size_t)((fsz - here + 4095) & ~(uint64_t)4095);
     if (block < 131072) block = 131072;
-    size_t ring_bytes = (size_t)96 << 20;
+    size_t ring_bytes = (size_t)128 << 20;
     ring_bytes *= (size_t)n_dev;
-    if (ring_bytes < ((size_t)128 << 20)) ring_bytes = (size_t)128 << 20;
-    if (ring_bytes > ((size_t)512 << 20)) ring_bytes = (size_t)512 << 20;
+    if (ring_bytes < ((size_t)256 << 20)) ring_bytes = (size_t)256 << 20;
+    if (ring_bytes > ((size_t)768 << 20)) ring_bytes = (size_t)768 << 20;
     int n_ring = (int)(ring_bytes / block);
     if (n_ring < 6) n_ring = 6;
     int n_threads = prod.threads < 1 ? 1 : prod.threads;
@@ -868,6 +886,7 @@ int run_bgzf_gpu(vfb_ctx **ctxs, int n_dev, ChunkProducer &prod, size_t text_tar
     }
     for (auto &q : gp.queues) for (Segment *g : q) { for (uint64_t b : g->blocks) ring.unref(b); delete g; }
     ring.stop();
+    const double ring_read_ms = ring.t_read_ms, ring_wait_ms = ring.t_wait_ms;
     if (rc) { set_error(keep); return rc; }
     GpuPhase::Link &last = gp.link(gp.n_segments);
     prod.carry = last.carry;
@@ -875,6 +894,11 @@ int run_bgzf_gpu(vfb_ctx **ctxs, int n_dev, ChunkProducer &prod, size_t text_tar
     if (trace) {
         fprintf(stderr, "[vfb ingest] gpu phase %.1f ms; indexer %.1f ms (waited %.1f for blocks, %.1f for queue room)\n",
                 now_ms() - phase_t0, gp.ix_total, gp.ix_wait_block, gp.ix_wait_queue);
+        fprintf(stderr, "[vfb ingest]   readers (summed over %d threads): %.1f ms in pread, %.1f ms waiting for a free block of %d\n",
+                n_threads, ring_read_ms, ring_wait_ms, n_ring);
+        if (gp.n_segments)
+            fprintf(stderr, "[vfb ingest]   per segment: %.2f ms queued, %.2f ms from begin to the start of finish, %.2f ms in finish\n",
+                    gp.sum_queue_ms / gp.n_segments, gp.sum_begin_to_fin_ms / gp.n_segments, gp.sum_fin_ms / gp.n_segments);
         for (int d = 0; d < n_dev; ++d)
             fprintf(stderr, "[vfb ingest]   device %d: waited %.1f ms for segments, %.1f ms for the chain; begin %.1f ms, finish %.1f ms\n",
                     ctxs[d]->device, gp.w_wait_seg[(size_t)d], gp.w_wait_chain[(size_t)d], gp.w_begin[(size_t)d], gp.w_finish[(size_t)d]);

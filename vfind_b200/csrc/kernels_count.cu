@@ -631,6 +631,7 @@ k4_publish(const __grid_constant__ InsertArgs a)
     t.row_hash[row] = h;
     t.row_off[row] = off;
     t.row_len[row] = klen;
+    t.row_slot[row] = slot;
     unsigned long long *ent = t.slots + (uint64_t)slot * VFB_SLOT_WORDS;
     ent[2] = off;
     ent[3] = klen;
@@ -667,6 +668,7 @@ k4_rehash(const DevTable o, const DevTable n)
             slot = (slot + 1) & mask;
         }
         unsigned long long *ne = n.slots + slot * VFB_SLOT_WORDS;
+        n.row_slot[row] = (uint32_t)slot;
         ne[1] = oe[1];
         ne[2] = oe[2];
         ne[3] = oe[3];
@@ -684,21 +686,19 @@ int launch_rehash(const DevTable &old_t, const DevTable &new_t, cudaStream_t st)
 }
 
 __global__ void __launch_bounds__(256)
-k4_export_counts(const DevTable t, unsigned long long *row_count)
+k4_export_counts(const DevTable t, uint64_t rows, unsigned long long *row_count)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < t.capacity; s += stride) {
-        const ulonglong2 e = *reinterpret_cast<const ulonglong2 *>(t.slots + s * VFB_SLOT_WORDS);
-        if (e.x) row_count[(uint32_t)e.x - 1] = e.y;
-    }
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += stride)
+        row_count[r] = t.slots[(uint64_t)t.row_slot[r] * VFB_SLOT_WORDS + 1];
 }
 
 int launch_export_counts(const DevTable &t, uint64_t rows, unsigned long long *row_count, cudaStream_t st)
 {
     if (rows == 0) return VFB_OK;
-    uint64_t blocks = (t.capacity + 255) / 256;
+    uint64_t blocks = (rows + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    k4_export_counts<<<(uint32_t)blocks, 256, 0, st>>>(t, row_count);
+    k4_export_counts<<<(uint32_t)blocks, 256, 0, st>>>(t, rows, row_count);
     ++g_launches;
     VFB_CUDA(cudaGetLastError());
     return VFB_OK;
@@ -889,18 +889,21 @@ __device__ __forceinline__ void part_group(uint32_t p, bool valid, uint32_t padd
 
 // Rows take part in a merge when their count is not zero and, if `self` names a part (self < n_parts), when
 // they are owned by another part: a rank keeps the rows it owns where they are.
-__device__ __forceinline__ bool part_of(const DevTable &t, uint64_t r, const unsigned long long *row_count,
-                                        uint32_t n_parts, uint32_t self, uint64_t *h_out, uint32_t *p_out)
+__device__ __forceinline__ bool part_of(const DevTable &t, uint64_t r, uint32_t n_parts, uint32_t self, uint64_t *h_out,
+                                        uint32_t *p_out, unsigned long long **cnt_out)
 {
     const uint64_t h = t.row_hash[r];
     const uint32_t p = vfb_hash_owner(h, n_parts);
     *h_out = h;
     *p_out = p;
-    return row_count[r] != 0ull && p != self;
+    if (p == self) return false;
+    unsigned long long *cnt = t.slots + (uint64_t)t.row_slot[r] * VFB_SLOT_WORDS + 1;
+    *cnt_out = cnt;
+    return *cnt != 0ull;
 }
 
 __global__ void __launch_bounds__(256)
-k5_partition_count(const DevTable t, uint64_t rows, const unsigned long long *__restrict__ row_count, uint32_t n_parts,
+k5_partition_count(const DevTable t, uint64_t rows, uint32_t n_parts,
                    uint32_t self, unsigned long long *part_rows, unsigned long long *part_keybytes)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -909,7 +912,8 @@ k5_partition_count(const DevTable t, uint64_t rows, const unsigned long long *__
         const uint64_t r = r0 + lane;
         uint64_t h = 0;
         uint32_t p = 0;
-        const bool valid = r < rows && part_of(t, r, row_count, n_parts, self, &h, &p);
+        unsigned long long *cnt = nullptr;
+        const bool valid = r < rows && part_of(t, r, n_parts, self, &h, &p, &cnt);
         const uint32_t padded = valid ? (t.row_len[r] + 15u) & ~15u : 0u;
         unsigned peers;
         uint32_t rank, brank, gbytes;
@@ -921,14 +925,14 @@ k5_partition_count(const DevTable t, uint64_t rows, const unsigned long long *__
     }
 }
 
-int launch_partition_count(const DevTable &t, uint64_t rows, const unsigned long long *row_count, uint32_t n_parts,
+int launch_partition_count(const DevTable &t, uint64_t rows, uint32_t n_parts,
                            uint32_t self, unsigned long long *part_rows, unsigned long long *part_keybytes,
                            cudaStream_t st)
 {
     if (rows == 0) return VFB_OK;
     uint64_t blocks = (rows + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    k5_partition_count<<<(uint32_t)blocks, 256, 0, st>>>(t, rows, row_count, n_parts, self, part_rows, part_keybytes);
+    k5_partition_count<<<(uint32_t)blocks, 256, 0, st>>>(t, rows, n_parts, self, part_rows, part_keybytes);
     ++g_launches;
     VFB_CUDA(cudaGetLastError());
     return VFB_OK;
@@ -936,14 +940,14 @@ int launch_partition_count(const DevTable &t, uint64_t rows, const unsigned long
 
 // Chunk headers are written by the kernel too (block 0), from the part sizes the count pass left on the device.
 __global__ void __launch_bounds__(256)
-k5_partition_fill(const DevTable t, uint64_t rows, uint32_t n_parts, uint32_t self,
-                  const unsigned long long *row_count, uint8_t *buf, const uint64_t *chunk_off,
+k5_partition_fill(const DevTable t, uint64_t rows, uint32_t n_parts, uint32_t self, bool release,
+                  uint8_t *buf, const uint64_t *chunk_off,
                   const uint64_t *part_rows, const uint64_t *part_keybytes,
                   unsigned long long *cursors)
 {
     if (blockIdx.x == 0)
         for (uint32_t p = threadIdx.x; p < n_parts; p += blockDim.x)
-            if (p != self) {
+            if (p != self && part_rows[p]) {
                 ChunkHeader *hd = reinterpret_cast<ChunkHeader *>(buf + chunk_off[p]);
                 hd->magic = VFB_CHUNK_MAGIC; hd->rows = part_rows[p]; hd->key_bytes = part_keybytes[p]; hd->reserved = 0;
             }
@@ -953,7 +957,8 @@ k5_partition_fill(const DevTable t, uint64_t rows, uint32_t n_parts, uint32_t se
         const uint64_t r = r0 + lane;
         uint64_t h = 0;
         uint32_t p = 0;
-        const bool valid = r < rows && part_of(t, r, row_count, n_parts, self, &h, &p);
+        unsigned long long *cnt = nullptr;
+        const bool valid = r < rows && part_of(t, r, n_parts, self, &h, &p, &cnt);
         const uint32_t len = valid ? t.row_len[r] : 0u;
         const uint32_t padded = (len + 15u) & ~15u;
         unsigned peers;
@@ -977,7 +982,8 @@ k5_partition_fill(const DevTable t, uint64_t rows, uint32_t n_parts, uint32_t se
         uint32_t *c_klen = reinterpret_cast<uint32_t *>(c + sizeof(ChunkHeader) + vfb_align16(n * 8) * 3);
         uint8_t *c_keys = c + sizeof(ChunkHeader) + vfb_align16(n * 8) * 3 + vfb_align16(n * 4);
         c_hash[idx] = h;
-        c_count[idx] = row_count[r];
+        c_count[idx] = *cnt;
+        if (release) *cnt = 0ull;            // the count travels with the chunk
         c_koff[idx] = koff;
         c_klen[idx] = len;
         const uint4 *src = reinterpret_cast<const uint4 *>(t.arena + t.row_off[r]);
@@ -986,41 +992,16 @@ k5_partition_fill(const DevTable t, uint64_t rows, uint32_t n_parts, uint32_t se
     }
 }
 
-int launch_partition_fill(const DevTable &t, uint64_t rows, uint32_t n_parts, uint32_t self,
-                          const unsigned long long *row_count, uint8_t *buf,
-                          const uint64_t *d_chunk_off, const uint64_t *d_part_rows,
+int launch_partition_fill(const DevTable &t, uint64_t rows, uint32_t n_parts, uint32_t self, bool release,
+                          uint8_t *buf, const uint64_t *d_chunk_off, const uint64_t *d_part_rows,
                           const uint64_t *d_part_keybytes, unsigned long long *cursors,
                           cudaStream_t st)
 {
     uint64_t blocks = (rows + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    k5_partition_fill<<<(uint32_t)blocks, 256, 0, st>>>(t, rows, n_parts, self, row_count, buf, d_chunk_off,
+    k5_partition_fill<<<(uint32_t)blocks, 256, 0, st>>>(t, rows, n_parts, self, release, buf, d_chunk_off,
                                                         d_part_rows, d_part_keybytes, cursors);
-    ++g_launches;
-    VFB_CUDA(cudaGetLastError());
-    return VFB_OK;
-}
-
-// After the chunks have been filled: the rows that went to another part keep their slot (a later read with the
-// same key finds it again) but give up their count, so that neither the export nor a later merge sees them.
-__global__ void __launch_bounds__(256)
-k5_release_foreign(const DevTable t, uint32_t n_parts, uint32_t self)
-{
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < t.capacity; s += stride) {
-        unsigned long long *e = t.slots + s * VFB_SLOT_WORDS;
-        const unsigned long long w = e[0];
-        if (!w || !e[1]) continue;
-        if (vfb_hash_owner(t.row_hash[(uint32_t)w - 1], n_parts) != self) e[1] = 0ull;
-    }
-}
-
-int launch_release_foreign(const DevTable &t, uint32_t n_parts, uint32_t self, cudaStream_t st)
-{
-    uint64_t blocks = (t.capacity + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    k5_release_foreign<<<(uint32_t)blocks, 256, 0, st>>>(t, n_parts, self);
     ++g_launches;
     VFB_CUDA(cudaGetLastError());
     return VFB_OK;

@@ -173,10 +173,7 @@ int vfb_merge_nccl(vfb_ctx *c, void *comm, uint32_t rank, uint32_t n_ranks)
     if ((rc = c->m_send.ensure(s_total ? s_total : 16))) return rc;
     if ((rc = c->m_recv.ensure(r_total ? r_total : 16))) return rc;
     const uint64_t before = g_launches;
-    if (s_total) {
-        if ((rc = vfb_internal_partition_fill(c, n, rank, c->m_send.as<uint8_t>(), s_off.data()))) return rc;
-        if ((rc = launch_release_foreign(c->tab, n, rank, c->st_compute))) return rc;
-    }
+    if (s_total && (rc = vfb_internal_partition_fill(c, n, rank, true, c->m_send.as<uint8_t>(), s_off.data()))) return rc;
     VFB_NCCL(a, a->GroupStart());
     for (uint32_t k = 1; k < n; ++k) {
         const uint32_t to = (rank + k) % n, from = (rank + n - k) % n;

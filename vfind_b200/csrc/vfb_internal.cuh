@@ -169,6 +169,7 @@ struct DevTable {
     uint64_t *row_hash;
     uint64_t *row_off;           // into arena
     uint32_t *row_len;
+    uint32_t *row_slot;          // the slot that holds the row's count: export and merge walk rows, not the slot array
     uint64_t row_capacity;
     uint8_t *arena;              // keys, each padded to 16 bytes
     uint64_t arena_capacity;
@@ -214,16 +215,15 @@ __host__ __device__ __forceinline__ uint64_t chunk_bytes_for(uint64_t rows, uint
     return sizeof(ChunkHeader) + vfb_align16(rows * 8) * 3 + vfb_align16(rows * 4) + vfb_align16(key_bytes);
 }
 // `self` < n_parts: rows owned by that part stay where they are (keep-own merge); self >= n_parts: every row
-// with a non-zero count is exported.
-int launch_partition_count(const DevTable &t, uint64_t rows, const unsigned long long *row_count, uint32_t n_parts,
+// with a non-zero count is exported.  `release`: the rows written to a chunk give up their count (they keep their
+// slot, so a later read with the same key finds the row again).
+int launch_partition_count(const DevTable &t, uint64_t rows, uint32_t n_parts,
                            uint32_t self, unsigned long long *part_rows, unsigned long long *part_keybytes,
                            cudaStream_t st);
-int launch_partition_fill(const DevTable &t, uint64_t rows, uint32_t n_parts, uint32_t self,
-                          const unsigned long long *row_count, uint8_t *buf,
-                          const uint64_t *d_chunk_off, const uint64_t *d_part_rows,
+int launch_partition_fill(const DevTable &t, uint64_t rows, uint32_t n_parts, uint32_t self, bool release,
+                          uint8_t *buf, const uint64_t *d_chunk_off, const uint64_t *d_part_rows,
                           const uint64_t *d_part_keybytes, unsigned long long *cursors,
                           cudaStream_t st);
-int launch_release_foreign(const DevTable &t, uint32_t n_parts, uint32_t self, cudaStream_t st);
 
 // ---------------------------------------------------------------- FASTQ parse (ingest)
 // d_text holds n_lines complete lines (n_records = n_lines / 4 records, text starts at a record
