@@ -339,6 +339,7 @@ def main():
     comm = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        idle_group = dist.new_group(backend="gloo")     # the ranks that sit out the ingest leg wait on sockets, not on a spinning kernel
         # the table merge runs inside the library over its own NCCL communicator; torch.distributed only carries
         # the 128-byte id (and the timing reductions of this script)
         ids = [api.nccl_unique_id() if rank == 0 else None]
@@ -568,8 +569,8 @@ def main():
 
     if rank != 0:
         if world > 1:
-            dist.barrier()              # rank 0's ingest leg
             api.nccl_comm_destroy(comm)
+            dist.barrier(group=idle_group)              # rank 0's ingest leg
             dist.destroy_process_group()
         return
 
@@ -757,8 +758,8 @@ def main():
     }
     emit(line)
     if world > 1:
-        dist.barrier()
         api.nccl_comm_destroy(comm)
+        dist.barrier(group=idle_group)
         dist.destroy_process_group()
 
 

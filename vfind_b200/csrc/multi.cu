@@ -151,7 +151,15 @@ int vfb_merge_nccl(vfb_ctx *c, void *comm, uint32_t rank, uint32_t n_ranks)
     int rc = nccl_need(&a);
     if (rc) return rc;
     const uint32_t n = n_ranks;
+    const bool tr = trace_on();          // VFB_TRACE: synchronise between the phases and print their times
+    auto stamp = [&](const char *what) {
+        if (!tr) return;
+        cudaStreamSynchronize(c->st_compute);
+        trace("merge_nccl rank %u: %s", rank, what);
+    };
+    stamp("start (lanes joined)");
     if ((rc = vfb_internal_partition_count(c, n, rank, nullptr))) return rc;
+    stamp("partition count");
     // every rank's [rows per part | key bytes per part]
     if ((rc = c->m_cursors.ensure((size_t)n * n * 16 + (size_t)n * 16))) return rc;     // gathered sizes live behind the cursors
     unsigned long long *d_all = c->m_cursors.as<unsigned long long>() + 2 * n;
@@ -160,6 +168,7 @@ int vfb_merge_nccl(vfb_ctx *c, void *comm, uint32_t rank, uint32_t n_ranks)
     VFB_CUDA(cudaMemcpyAsync(all.data(), d_all, all.size() * 8, cudaMemcpyDeviceToHost, c->st_compute));
     VFB_CUDA(cudaStreamSynchronize(c->st_compute));
     c->stats.d2h_bytes += all.size() * 8;
+    stamp("sizes gathered");
     auto rows_of = [&](uint32_t src, uint32_t dst) { return all[(size_t)src * 2 * n + dst]; };
     auto keys_of = [&](uint32_t src, uint32_t dst) { return all[(size_t)src * 2 * n + n + dst]; };
     std::vector<uint64_t> s_bytes(n, 0), s_off(n, 0), r_bytes(n, 0), r_off(n, 0);
@@ -174,6 +183,7 @@ int vfb_merge_nccl(vfb_ctx *c, void *comm, uint32_t rank, uint32_t n_ranks)
     if ((rc = c->m_recv.ensure(r_total ? r_total : 16))) return rc;
     const uint64_t before = g_launches;
     if (s_total && (rc = vfb_internal_partition_fill(c, n, rank, true, c->m_send.as<uint8_t>(), s_off.data()))) return rc;
+    stamp("chunks filled");
     VFB_NCCL(a, a->GroupStart());
     for (uint32_t k = 1; k < n; ++k) {
         const uint32_t to = (rank + k) % n, from = (rank + n - k) % n;
@@ -182,8 +192,11 @@ int vfb_merge_nccl(vfb_ctx *c, void *comm, uint32_t rank, uint32_t n_ranks)
     }
     VFB_NCCL(a, a->GroupEnd());
     bump_launches_for(c, before);
+    stamp("chunks exchanged");
     for (uint32_t p = 0; p < n; ++p)
         if (r_bytes[p] && (rc = vfb_internal_absorb_known(c, c->m_recv.as<uint8_t>() + r_off[p], rows_of(p, rank), keys_of(p, rank)))) return rc;
+    stamp("absorbed");
+    if (tr) trace("merge_nccl rank %u: sent %.1f MB, received %.1f MB", rank, s_total / 1e6, r_total / 1e6);
     return VFB_OK;
 }
 
