@@ -203,7 +203,10 @@ def run_reference(args):
         return
     import oracle
     oracle.build()
-    conf = CONFIGS[args.config]
+    conf = dict(CONFIGS[args.config])
+    if args.thr > 0:
+        conf["thr"] = args.thr
+        conf["workload"] += " [thresholds overridden: %g]" % args.thr
     cfg = oracle.synth_cfg(**conf["synth"])
     adapters = oracle.synth_adapters(cfg)
     threads = os.cpu_count() or 1
@@ -302,6 +305,7 @@ def main():
     ap.add_argument("--config", default="C3", choices=sorted(CONFIGS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --reads per GPU; strong: --reads in total, split over the ranks")
+    ap.add_argument("--thr", type=float, default=0.0, help="override the config's accept thresholds (both adapters)")
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU per step (strong: in total); 0 = the config's")
     ap.add_argument("--chunk-reads", type=int, default=12_500_000)
     ap.add_argument("--e2e-reads", type=int, default=-1, help="reads per e2e step (-1 = same as --reads)")
@@ -347,7 +351,10 @@ def main():
         comm = api.nccl_comm_init(ids[0], world, rank, local)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node = --gpus"
 
-    conf = CONFIGS[args.config]
+    conf = dict(CONFIGS[args.config])
+    if args.thr > 0:
+        conf["thr"] = args.thr
+        conf["workload"] += " [thresholds overridden: %g]" % args.thr
     cfg = api.synth_cfg(**conf["synth"])
     thr = conf["thr"]
     adapters = api.synth_adapters(cfg)

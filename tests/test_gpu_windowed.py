@@ -76,6 +76,27 @@ def test_windowed_adapter_lengths(A):
     check_windowed(seqs, (pre, suf), expect_windowed=False, accept_prefix_alignment=0.6, accept_suffix_alignment=0.7)
 
 
+@pytest.mark.parametrize("A", [33, 34, 36, 39, 40, 41, 47, 48, 50, 56, 59, 63, 64])
+def test_windowed_long_adapters(A):
+    """Adapters of 33..64 bases: the filter runs Myers' recurrence on one 64-bit word per vector, the window kernel has
+    up to 64 register-resident rows (BASELINE config 5's 40-nt adapters; src/lib.rs:155-160)."""
+    rng = random.Random(4000 + A)
+    pre = bytes(rng.choice(b"ACGT") for _ in range(A))
+    suf = bytes(rng.choice(b"ACGT") for _ in range(A))
+    seqs = make_reads(rng, pre, suf, 1500, lead=(0, 60))
+    for _ in range(300):        # heavier damage, several sites, overhangs
+        a = mutate(rng, pre, max_edits=8)
+        b = mutate(rng, suf, max_edits=8)
+        body = bytes(rng.choice(b"ACGT") for _ in range(rng.randrange(0, 80)))
+        seqs.append((a + body + b)[rng.randrange(0, 10):])
+        seqs.append(a + body + a + body + b)
+    seqs += [b"A", pre[: A - 1], pre, suf, pre + suf, pre + b"ACG" + suf, pre[1:], suf[:-1]]
+    st = check_windowed(seqs, (pre, suf), expect_windowed=True, accept_prefix_alignment=0.8, accept_suffix_alignment=0.75)
+    assert st["dp_windows"] > 0
+    # at 0.6 the budget admits too many edits for the filter to be selective: the full-matrix kernel runs, same answers
+    check_windowed(seqs[:800], (pre, suf), expect_windowed=False, accept_prefix_alignment=0.6, accept_suffix_alignment=0.6)
+
+
 def test_windowed_applies_at_defaults():
     rng = random.Random(3)
     seqs = make_reads(rng, PREFIX, SUFFIX, 2000, lead=(0, 100))

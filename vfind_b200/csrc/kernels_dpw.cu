@@ -28,8 +28,9 @@
 //       cell with score >= T when the alignment is accepted; all such cells are exact, all other
 //       cells are <= their true value < T.  If nothing reaches T the read is rejected, as in the
 //       reference (its score is then not needed: only the accept decision reaches the table).
-// The filter needs positive edit costs and a selective K; otherwise, for adapters longer than 32,
-// and in diagnostics mode (exact scores of rejected alignments) the full kernel runs instead.
+// The filter needs positive edit costs and a selective K (3K <= A); otherwise, for adapters longer than 64,
+// and in diagnostics mode (exact scores of rejected alignments) the full kernel runs instead.  Adapters of up to 32
+// bases use one 32-bit word per Myers vector, 33..64 bases one 64-bit word (two ALU instructions per logic op).
 #include <climits>
 
 #include "vfb_internal.cuh"
@@ -42,7 +43,7 @@ namespace vfb {
 int dpw_max_edits(const DpScoring &s, uint32_t A, int min_accept)
 {
     // returns K >= 0, or -1 when the filter does not apply
-    if (A < 4 || A > 32) return -1;
+    if (A < 4 || A > 64) return -1;
     if (s.match <= 0 || s.mismatch >= s.match || s.open <= 0 || s.extend <= 0) return -1;
     const long long B = (long long)A * s.match - min_accept;
     if (B < 0) return 0;                       // not even a perfect alignment reaches the bound
@@ -99,17 +100,19 @@ __device__ __forceinline__ void win_emit(const DpwArgs &a, uint32_t r, uint32_t 
 }
 
 // One column of Myers' bit-vector recurrence.  The adapter occupies the HIGH A bits of the word
-// (row A = bit 31, so the score delta is the top bit of Ph / Mh); the 32-A low bits are rows
+// (row A = the top bit, so the score delta is the top bit of Ph / Mh); the low bits are rows
 // that match every byte and start at D = 0, which leaves the adapter rows' values unchanged
 // (a free text start already gives them D[0][j] = 0 underneath).
-__device__ __forceinline__ void myers_col(uint32_t Eq, uint32_t &Pv, uint32_t &Mv, int &score)
+template <typename W>
+__device__ __forceinline__ void myers_col(W Eq, W &Pv, W &Mv, int &score)
 {
-    const uint32_t Xv = Eq | Mv;
-    const uint32_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
-    uint32_t Ph = Mv | ~(Xh | Pv);
-    uint32_t Mh = Pv & Xh;
-    score += (int)(Ph >> 31);
-    score += ((int)Mh >> 31);
+    constexpr int TOP = (int)sizeof(W) * 8 - 1;
+    const W Xv = Eq | Mv;
+    const W Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+    W Ph = Mv | ~(Xh | Pv);
+    W Mh = Pv & Xh;
+    score += (int)(Ph >> TOP);
+    score -= (int)(Mh >> TOP);
     Ph <<= 1;
     Mh <<= 1;
     Pv = Mh | ~(Xv | Ph);
@@ -121,22 +124,28 @@ __device__ __forceinline__ void myers_col(uint32_t Eq, uint32_t &Pv, uint32_t &M
 // well: extra text on the left can only lower ed(j), so the flagged set stays a superset.  Each
 // chunk first runs 16 unrolled columns tracking only the minimum of ed; the (few) chunks whose
 // minimum reaches K are replayed from the saved state with the per-column window bookkeeping.
-// Byte -> Eq goes through a 64-entry table keyed by byte & 0x3F (entries OR-ed over the four
-// bytes that share a key: again a superset, and exact for every letter).
-__global__ void __launch_bounds__(DPW_THREADS, 8)
+// Byte -> Eq goes through a small table keyed by the byte's low bits (6 bits for 32-bit words, 5 bits for
+// 64-bit words — the key times the entry size must fit a byte lane; entries OR-ed over the bytes that
+// share a key: again a superset, and exact for every letter).
+template <typename W>
+__global__ void __launch_bounds__(DPW_THREADS, sizeof(W) == 4 ? 8 : 5)
 k2_filter(const __grid_constant__ DpwArgs a)
 {
-    __shared__ uint32_t lutEq[64];
+    constexpr int BITS = (int)sizeof(W) * 8;
+    constexpr int KEYBITS = sizeof(W) == 4 ? 6 : 5;
+    constexpr int ESH = sizeof(W) == 4 ? 2 : 3;               // log2(entry size)
+    constexpr uint32_t KMASK = ((1u << KEYBITS) - 1u) * 0x01010101u;
+    __shared__ W lutEq[1 << KEYBITS];
     const DpJob &job = a.job;
     const int A = (int)job.adapter_len;
-    const int sh = 32 - A;
-    if (threadIdx.x < 64) {
-        uint32_t m = sh ? (1u << sh) - 1u : 0u;
-        for (int b = threadIdx.x; b < 256; b += 64) {
+    const int sh = BITS - A;
+    if (threadIdx.x < (1 << KEYBITS)) {
+        W m = sh ? (((W)1 << sh) - (W)1) : (W)0;
+        for (int b = threadIdx.x; b < 256; b += (1 << KEYBITS)) {
             const int c = dp_code((uint8_t)b);
             if (c < 4)
                 for (int i = 0; i < A; ++i)
-                    if (job.adapter_code[i] == c) m |= 1u << (i + sh);
+                    if (job.adapter_code[i] == c) m |= (W)1 << (i + sh);
         }
         lutEq[threadIdx.x] = m;
     }
@@ -166,7 +175,7 @@ k2_filter(const __grid_constant__ DpwArgs a)
         const uint4 *base16 = reinterpret_cast<const uint4 *>(addr & ~(uintptr_t)15);
         const int lead = (int)(addr & 15u);
         const int n_chunks = (lead + L + 15) >> 4;
-        uint32_t Pv = 0xFFFFFFFFu << sh, Mv = 0;
+        W Pv = ~(W)0 << sh, Mv = 0;
         int score = A;
         int first = 0, last = 0;          // current group of flagged columns (0 = none)
         bool overflow = false;
@@ -176,16 +185,16 @@ k2_filter(const __grid_constant__ DpwArgs a)
             nx = nx2;
             if (c + 2 < n_chunks) nx2 = __ldg(base16 + c + 2);
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            const uint32_t Pv0 = Pv, Mv0 = Mv;
+            const W Pv0 = Pv, Mv0 = Mv;
             const int score0 = score;
             int mn = INT_MAX;
 #pragma unroll
             for (int wi = 0; wi < 4; ++wi) {
-                const uint32_t w4 = (w[wi] & 0x3F3F3F3Fu) << 2;
+                const uint32_t w4 = (w[wi] & KMASK) << ESH;
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
                     const uint32_t key = __byte_perm(w4, 0, 0x4440 + b);
-                    myers_col(*reinterpret_cast<const uint32_t *>(lutb + key), Pv, Mv, score);
+                    myers_col<W>(*reinterpret_cast<const W *>(lutb + key), Pv, Mv, score);
                     mn = min(mn, score);
                 }
             }
@@ -195,11 +204,11 @@ k2_filter(const __grid_constant__ DpwArgs a)
                 uint32_t flags = 0;
 #pragma unroll
                 for (int wi = 0; wi < 4; ++wi) {
-                    const uint32_t w4 = (w[wi] & 0x3F3F3F3Fu) << 2;
+                    const uint32_t w4 = (w[wi] & KMASK) << ESH;
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
                         const uint32_t key = __byte_perm(w4, 0, 0x4440 + b);
-                        myers_col(*reinterpret_cast<const uint32_t *>(lutb + key), Pv, Mv, score);
+                        myers_col<W>(*reinterpret_cast<const W *>(lutb + key), Pv, Mv, score);
                         if (score <= K) flags |= 1u << (wi * 4 + b);
                     }
                 }
@@ -236,7 +245,7 @@ k2_filter(const __grid_constant__ DpwArgs a)
 
 // ------------------------------------------------------------------------------------ window DP
 // Same cell as k2_dp_packed (kernels_dp.cu): 3 IMAD + 2 VIADDMNMX + 1 VIMNMX3 + 1 LOP3.
-template <int AMAX> struct DpwOcc { static constexpr int value = AMAX <= 20 ? 6 : (AMAX <= 28 ? 4 : 3); };
+template <int AMAX> struct DpwOcc { static constexpr int value = AMAX <= 20 ? 6 : (AMAX <= 28 ? 4 : (AMAX <= 40 ? 3 : 2)); };
 
 template <int AMAX, bool EXACT>
 __global__ void __launch_bounds__(DPW_THREADS, DpwOcc<AMAX>::value)
@@ -430,7 +439,8 @@ int launch_dp_windowed(const DpJob &job, const DpLayout &lay, int K, uint32_t lc
         filter_bps = e ? atoi(e) : 48;
         if (filter_bps < 1) filter_bps = 48;
     }
-    k2_filter<<<sm_count * filter_bps, DPW_THREADS, 0, st>>>(a);
+    if (job.adapter_len <= 32) k2_filter<uint32_t><<<sm_count * filter_bps, DPW_THREADS, 0, st>>>(a);
+    else k2_filter<unsigned long long><<<sm_count * filter_bps, DPW_THREADS, 0, st>>>(a);
     ++g_launches;
     if (ev_filter_done) VFB_CUDA(cudaEventRecord(ev_filter_done, st));
     int rc;
@@ -443,6 +453,14 @@ int launch_dp_windowed(const DpJob &job, const DpLayout &lay, int K, uint32_t lc
     case 24: rc = launch_window<24>(a, sm_count, st); break;
     case 28: rc = launch_window<28>(a, sm_count, st); break;
     case 32: rc = launch_window<32>(a, sm_count, st); break;
+    case 36: rc = launch_window<36>(a, sm_count, st); break;
+    case 40: rc = launch_window<40>(a, sm_count, st); break;
+    case 44: rc = launch_window<44>(a, sm_count, st); break;
+    case 48: rc = launch_window<48>(a, sm_count, st); break;
+    case 52: rc = launch_window<52>(a, sm_count, st); break;
+    case 56: rc = launch_window<56>(a, sm_count, st); break;
+    case 60: rc = launch_window<60>(a, sm_count, st); break;
+    case 64: rc = launch_window<64>(a, sm_count, st); break;
     default: set_error("adapter too long for the windowed DP"); return VFB_ERR_ARG;
     }
     if (rc) return rc;
