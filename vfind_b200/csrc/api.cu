@@ -585,7 +585,11 @@ int vfb_create(const vfb_params *p, vfb_ctx **out)
     for (auto &s : c->slots) ev_ok = ev_ok && new_event(&s.copied) && new_event(&s.computed[0]) && new_event(&s.computed[1]);
     for (auto &g : c->seg) ev_ok = ev_ok && new_event(&g.inflated) && new_event(&g.parsed) && new_event(&g.computed[0]) && new_event(&g.computed[1]);
     for (auto &ln : c->lanes)
-        ev_ok = ev_ok && new_event(&ln.done) && (e = cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking)) == cudaSuccess;
+        ev_ok = ev_ok && new_event(&ln.done) && new_event(&ln.ev_scanned) && new_event(&ln.ev_aligned) &&
+                (e = cudaStreamCreateWithPriority(&ln.st, cudaStreamNonBlocking, prio_hi)) == cudaSuccess &&
+                (e = cudaStreamCreateWithPriority(&ln.st_dp, cudaStreamNonBlocking, prio_lo)) == cudaSuccess;
+    c->split_dp = true;
+    if (const char *se = getenv("VFB_SPLIT_DP")) c->split_dp = atoi(se) != 0;
     if (!ev_ok) return fail(cuda_fail(e, "cudaEventCreate / cudaStreamCreate", __FILE__, __LINE__));
     // two lanes unless the per-read diagnostics of "the last batch" are wanted (or VFB_LANES=1 says so)
     c->n_lanes = VFB_LANES;
@@ -646,7 +650,7 @@ int vfb_destroy(vfb_ctx *c)
     if (c->st_copy) cudaStreamSynchronize(c->st_copy);
     if (c->st_ingest) cudaStreamSynchronize(c->st_ingest);
     if (c->st_parse) cudaStreamSynchronize(c->st_parse);
-    for (auto &ln : c->lanes) if (ln.st) cudaStreamSynchronize(ln.st);
+    for (auto &ln : c->lanes) { if (ln.st) cudaStreamSynchronize(ln.st); if (ln.st_dp) cudaStreamSynchronize(ln.st_dp); }
     for (auto &s : c->slots) {
         s.d_text.release(); s.d_spans.release(); s.h_text.release(); s.h_spans.release();
         if (s.copied) cudaEventDestroy(s.copied);
@@ -663,7 +667,10 @@ int vfb_destroy(vfb_ctx *c)
                         &ln.d_koff, &ln.d_klen, &ln.d_khash, &ln.d_owner, &ln.d_wins, &ln.d_bestkey, &ln.d_cbval, &ln.d_fb2};
         for (auto *b : lb) b->release();
         if (ln.done) cudaEventDestroy(ln.done);
+        if (ln.ev_scanned) cudaEventDestroy(ln.ev_scanned);
+        if (ln.ev_aligned) cudaEventDestroy(ln.ev_aligned);
         if (ln.st) cudaStreamDestroy(ln.st);
+        if (ln.st_dp) cudaStreamDestroy(ln.st_dp);
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_k4) cudaEventDestroy(c->ev_k4);
@@ -896,14 +903,26 @@ static int process_batch(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_sp
     }
     // DP.  The prefix pass runs first: reads it rejects need no suffix alignment (no region
     // either way, src/lib.rs:288), reads it accepts join the suffix worklist if they need one.
+    // split mode: the (ALU-bound) alignment kernels of the batch run on the lane's lower-priority stream, so that the
+    // other lane's memory-bound kernels get SM resources as soon as alignment blocks retire
+    const bool split = c->split_dp && c->n_lanes > 1 && !prof;
+    cudaStream_t sd = split ? ln.st_dp : st;
+    if (split) {
+        VFB_CUDA(cudaEventRecord(ln.ev_scanned, st));
+        VFB_CUDA(cudaStreamWaitEvent(sd, ln.ev_scanned, 0));
+    }
     if (prof) VFB_CUDA(cudaEventRecord(pev[2], st));
-    if (c->align_pre) if ((rc = run_dp(c, ln, st, d_text, d_spans, true, n, prof ? pev : nullptr))) return rc;
+    if (c->align_pre) if ((rc = run_dp(c, ln, sd, d_text, d_spans, true, n, prof ? pev : nullptr))) return rc;
     if (prof) VFB_CUDA(cudaEventRecord(pev[3], st));
     if (prof) VFB_CUDA(cudaEventRecord(pev[4], st));
-    if (c->align_suf) if ((rc = run_dp(c, ln, st, d_text, d_spans, false, n, prof ? pev : nullptr))) return rc;
+    if (c->align_suf) if ((rc = run_dp(c, ln, sd, d_text, d_spans, false, n, prof ? pev : nullptr))) return rc;
     if (prof) VFB_CUDA(cudaEventRecord(pev[5], st));
-    k_accumulate<<<1, 1, 0, st>>>(ln.d_t64.as<unsigned long long>(), ln.d_c32.as<uint32_t>(), ln.win_cap);
+    k_accumulate<<<1, 1, 0, sd>>>(ln.d_t64.as<unsigned long long>(), ln.d_c32.as<uint32_t>(), ln.win_cap);
     ++g_launches;
+    if (split) {
+        VFB_CUDA(cudaEventRecord(ln.ev_aligned, sd));
+        VFB_CUDA(cudaStreamWaitEvent(st, ln.ev_aligned, 0));
+    }
 
     KeyJob kj;
     kj.text = d_text; kj.spans = d_spans;

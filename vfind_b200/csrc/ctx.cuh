@@ -81,7 +81,9 @@ struct PinBuf {
 // neighbours; only the table insert (K4) is serialised between the lanes.
 #define VFB_LANES 2
 struct Lane {
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr;          // scan, keys, count (and everything else of the batch)
+    cudaStream_t st_dp = nullptr;       // split mode: the alignment kernels, at a lower priority than `st`
+    cudaEvent_t ev_scanned = nullptr, ev_aligned = nullptr;
     cudaEvent_t done = nullptr;         // the lane's last batch has finished
     bool pending = false;               // `done` has not been joined into the compute stream yet
     DevBuf d_start, d_end, d_list_a, d_list_b, d_fb_a, d_fb_b, d_c32, d_t64;
@@ -146,6 +148,7 @@ struct vfb_ctx {
     // per-batch scratch, one set per lane
     vfb::Lane lanes[VFB_LANES];
     int n_lanes = VFB_LANES;                    // 1: every batch on the compute stream itself (diagnostics, VFB_LANES=1)
+    bool split_dp = true;                       // a lane's alignment kernels on a lower-priority stream (VFB_SPLIT_DP=0: off)
     uint64_t lane_seq = 0;
     cudaEvent_t ev_fork = nullptr, ev_k4 = nullptr;   // compute stream -> lane; the previous batch's insert is done
     bool k4_pending = false;
