@@ -104,7 +104,8 @@ struct Slot {
 #define VFB_SEG_SLOTS 3
 struct SegSlot {
     DevBuf text, z, members, spans;
-    cudaEvent_t inflated = nullptr, parsed = nullptr;                         // recorded on st_ingest / st_parse
+    cudaEvent_t copied = nullptr, inflated = nullptr, parsed = nullptr;       // recorded on st_copy / st_ingest / st_parse
+    bool used = false;                                                        // `inflated` has been recorded at least once
     cudaEvent_t computed[VFB_LANES] = {nullptr, nullptr};                     // recorded on the lanes
     unsigned busy = 0;                                  // lanes whose `computed` event is pending
     uint64_t text_bytes = 0, z_bytes = 0;

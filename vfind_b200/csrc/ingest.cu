@@ -799,6 +799,7 @@ void device_worker(vfb_ctx *ctx, int dev_index, GpuPhase &gp)
     // an abort may leave segments behind whose release callback is still queued: wait for the stream, then free
     if (!pending.empty()) {
         cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->st_copy);
         cudaStreamSynchronize(ctx->st_ingest);
         for (Segment *g : pending) delete g;
     }
