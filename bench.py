@@ -608,7 +608,8 @@ def main():
     dp_achieved = kernel_gcups * ALU_OPS_PER_CELL     # G lane-ops/s on the ALU pipe
     scan_bytes = st_reads * (L + 12)                  # N*(L+12)
     scan_gbs = scan_bytes / (st["ms_scan"] * 1e-3) / 1e9 if st["ms_scan"] > 0 else 0.0
-    key_bytes = st["counted"] * (cfg.region_len + cfg.region_len // 3 + 8)
+    # every step starts from a cleared table (counters included): `counted` / `unique` / `fused_hits` are one step's
+    key_bytes = st["counted"] * args.steps * (cfg.region_len + cfg.region_len // 3 + 8)
     roofline = {"bound": "int32", "kernel": dp_kernel, "achieved": dp_achieved, "peak": alu_gops,
                 "unit": "Gop/s", "frac": dp_achieved / alu_gops if alu_gops else None,
                 "traffic": traffic.get(dp_kernel), "traffic_unit": "DRAM bytes per launch", "traffic_how": traffic_how,
@@ -631,7 +632,7 @@ def main():
     stages = {k: st[k] / args.steps for k in ("ms_scan", "ms_worklist", "ms_dp", "ms_dp_filter", "ms_dp_window",
                                               "ms_translate", "ms_count", "ms_total")}
     stages["translate_gbs"] = key_bytes / (st["ms_translate"] * 1e-3) / 1e9 if st["ms_translate"] > 0 else 0.0
-    count_bytes = st["counted"] * (cfg.region_len // 3 + 24) + st["unique"] * args.steps * (cfg.region_len // 3 + 8)
+    count_bytes = (st["counted"] * (cfg.region_len // 3 + 24) + st["unique"] * (cfg.region_len // 3 + 8)) * args.steps
     stages["count_gbs"] = count_bytes / (st["ms_count"] * 1e-3) / 1e9 if st["ms_count"] > 0 else 0.0
 
     import oracle
@@ -760,7 +761,9 @@ def main():
                "cells_computed_per_step": st["dp_cells_computed"] // args.steps,
                "windows_per_step": st["dp_windows"] // args.steps,
                "alignments_per_step": (st["dp_prefix"] + st["dp_suffix"]) // args.steps},
-        "merge_ms_per_step": merge_ms, "table": {"unique": st["unique"], "counted_per_step": st["counted"] // args.steps, "merge_check": merge_check},
+        "merge_ms_per_step": merge_ms, "table": {"unique": st["unique"], "counted_per_step": st["counted"],
+                                                        "counted_by_the_key_kernel_per_step": st.get("fused_hits", 0),
+                                                        "fused_key_count": bool(st.get("fused_batches", 0)), "merge_check": merge_check},
         "cpu_baseline": cpu, "ingest": ingest,
     }
     emit(line)

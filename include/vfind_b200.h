@@ -143,6 +143,8 @@ typedef struct vfb_stats {
     uint64_t dp_cells_computed; /* cells the DP kernels actually evaluated (== dp_cells for the full DP) */
     uint64_t dp_windows;        /* windows the filter produced (windowed DP)            */
     double ms_dp_filter, ms_dp_window;   /* parts of ms_dp: k2_filter and k2_dp_window (profiling only) */
+    uint64_t fused_batches;     /* batches whose key kernel probed the count table itself (k34_keys_count)   */
+    uint64_t fused_hits;        /* counted reads whose key never left the key kernel (row already in the table) */
 } vfb_stats;
 
 typedef struct vfb_ctx vfb_ctx;
@@ -323,6 +325,11 @@ int vfb_measure_int_peak(int device, double *alu_gops, double *dual_gops);
  * the first member that failed (bad deflate data, CRC-32 or ISIZE mismatch) or 0xFFFFFFFF. */
 int vfb_debug_gpu_inflate(const uint8_t *z, uint64_t z_bytes, const uint32_t *members, uint32_t n_members,
                           uint8_t *out, uint64_t out_bytes, int device, uint32_t *first_bad, double *kernel_ms);
+
+/* Test hook for the arithmetic fast path of the key kernel's translate (src/lib.rs:16-44): runs the HOST build of
+ * the code the kernel uses (csrc/translate_fast.h) on twelve bases; aa receives four amino acids, *canonical is 1
+ * when all twelve bytes are A/C/G/T/U of either case (only then does the kernel take this path). No GPU needed. */
+int vfb_debug_translate12(const uint8_t *bases12, uint8_t *aa4, int *canonical);
 
 /* Pinned host memory for callers without their own allocator. */
 int vfb_host_alloc(void **p, uint64_t bytes);

@@ -664,3 +664,48 @@ def test_arrow_c_data_export_is_zero_copy_and_outlives_the_context():
     with api.Context((PREFIX, SUFFIX)) as ctx:
         empty = ctx.finish_arrow()
     assert empty.num_rows == 0 and empty.schema.names == ["sequence", "count"]
+
+
+@pytest.mark.parametrize("skip", [False, True])
+def test_fused_key_count_kernel_matches_separate_kernels(monkeypatch, skip):
+    """k34_keys_count (the key kernel probes the table and counts reads whose key already has a row; only the rest
+    go through k4_insert / k4_publish) against K3 + K4 over every read (VFB_FUSED_COUNT=0) and the oracle:
+    many small batches, so that later batches find most of their keys in the table; regions with lower case, U, N,
+    '-' and non-ASCII bytes (the arithmetic translate must hand those groups to the per-byte tables)."""
+    rng = random.Random(41)
+    seqs = make_reads(rng, PREFIX, SUFFIX, 24000, lib=700, alphabet=b"ACGTACGTACGTACGTacgtUuN-")
+    seqs += make_reads(rng, PREFIX, SUFFIX, 2000, lib=50, alphabet=b"ACGT\xc3\xa9\xff")
+    rng.shuffle(seqs)
+    kw = dict(want_diag=False, skip_translation=skip, batch_reads=1500)
+    want = oracle_run(seqs, (PREFIX, SUFFIX), skip_translation=skip)[0]
+    fused, _, sf = gpu_run(seqs, (PREFIX, SUFFIX), **kw)
+    assert fused == want
+    assert sf["fused_batches"] == (len(seqs) + 1499) // 1500 and 0 < sf["fused_hits"] < sf["counted"]
+    assert sf["counted"] == sum(want.values()) and sf["unique"] == len(want)
+    monkeypatch.setenv("VFB_FUSED_COUNT", "0")
+    plain, _, sp = gpu_run(seqs, (PREFIX, SUFFIX), **kw)
+    assert plain == want and sp["fused_batches"] == 0 and sp["fused_hits"] == 0
+    monkeypatch.delenv("VFB_FUSED_COUNT")
+    # forced hash collisions: long probe chains leave the fused kernel and are settled by the insert kernels
+    for bits in (1, 5):
+        got, _, st = gpu_run(seqs, (PREFIX, SUFFIX), debug_hash_bits=bits, **kw)
+        assert got == want and st["counted"] == sum(want.values())
+
+
+def test_fused_key_count_second_pass_is_all_hits():
+    """The same reads twice through one context: every key of the second pass already has a row, so the fused
+    kernel counts all of them itself and the counts double."""
+    rng = random.Random(42)
+    seqs = make_reads(rng, PREFIX, SUFFIX, 9000, lib=400)
+    text, off, ln = oracle.pack_reads(seqs)
+    want = oracle_run(seqs, (PREFIX, SUFFIX))[0]
+    with api.Context((PREFIX, SUFFIX), batch_reads=3000) as ctx:
+        ctx.submit_host(text, spans_of(off, ln))
+        ctx.sync()
+        first = ctx.stats()
+        ctx.submit_host(text, spans_of(off, ln))
+        got = ctx.finish_dict()
+        st = ctx.stats()
+    assert got == {k: 2 * v for k, v in want.items()}
+    assert st["unique"] == first["unique"] == len(want)
+    assert st["fused_hits"] - first["fused_hits"] == sum(want.values())

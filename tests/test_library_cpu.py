@@ -153,3 +153,52 @@ def test_oracle_side_generator_matches_the_library(lib, tmp_path):
     for i in (0, 1, 1999):
         rec = raw[i * (2 * L + 17):(i + 1) * (2 * L + 17)].split(b"\n")
         assert rec[0] == b"@r%010d" % (7 + i) and rec[1] == text[i * L:(i + 1) * L].tobytes() and rec[2] == b"+" and rec[3] == b"F" * L
+
+
+def test_translate_fast_path_arithmetic(lib):
+    """The key kernel's arithmetic translate (csrc/translate_fast.h, host build of the same code): twelve bases ->
+    four amino acids whenever all twelve are canonical; anything else must be flagged (the kernel then takes the
+    per-byte tables).  Against the oracle's translate (src/lib.rs:16-44, tables :52-95)."""
+    import ctypes as C
+    import itertools
+    import random
+
+    import oracle
+
+    fn = lib.vfb_debug_translate12
+    fn.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_int)]
+    fn.restype = C.c_int
+    canonical = b"ACGTUacgtu"
+
+    def run(b12):
+        out = C.create_string_buffer(4)
+        ok = C.c_int(-1)
+        assert fn(bytes(b12), out, C.byref(ok)) == 0
+        return out.raw, ok.value
+
+    # every canonical triplet in each of the four codon slots, the other slots filled with a varying background
+    rng = random.Random(5)
+    for trip in itertools.product(canonical, repeat=3):
+        for slot in range(4):
+            b = bytearray(rng.choice(canonical) for _ in range(12))
+            b[3 * slot:3 * slot + 3] = bytes(trip)
+            aa, ok = run(b)
+            assert ok == 1, bytes(b)
+            assert aa == oracle.translate(bytes(b)), bytes(b)
+    # every byte value in every position: canonical iff the byte is one of the ten letters
+    base = bytearray(b"ACGTUacgtuAC")
+    for pos in range(12):
+        for v in range(256):
+            b = bytearray(base)
+            b[pos] = v
+            aa, ok = run(b)
+            assert ok == (1 if v in canonical else 0), (pos, v)
+            if ok:
+                assert aa == oracle.translate(bytes(b))
+    # random byte strings
+    for _ in range(20000):
+        b = bytes(rng.choice(b"ACGTUacgtuNn-@BDHKXxY\x00\xff\x41\x61") for _ in range(12))
+        aa, ok = run(b)
+        assert ok == (1 if all(c in canonical for c in b) else 0), b
+        if ok:
+            assert aa == oracle.translate(b), b

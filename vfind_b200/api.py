@@ -77,7 +77,8 @@ class Stats(C.Structure):
                 ("ms_translate", C.c_double), ("ms_count", C.c_double), ("ms_total", C.c_double),
                 ("dp_kernel_launches", C.c_uint64), ("dp_kernel_kind", C.c_int32),
                 ("reserved", C.c_int32), ("dp_cells_computed", C.c_uint64), ("dp_windows", C.c_uint64),
-                ("ms_dp_filter", C.c_double), ("ms_dp_window", C.c_double)]
+                ("ms_dp_filter", C.c_double), ("ms_dp_window", C.c_double),
+                ("fused_batches", C.c_uint64), ("fused_hits", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

@@ -590,6 +590,8 @@ int vfb_create(const vfb_params *p, vfb_ctx **out)
                 (e = cudaStreamCreateWithPriority(&ln.st_dp, cudaStreamNonBlocking, prio_lo)) == cudaSuccess;
     c->split_dp = true;
     if (const char *se = getenv("VFB_SPLIT_DP")) c->split_dp = atoi(se) != 0;
+    c->fused_count = true;
+    if (const char *se = getenv("VFB_FUSED_COUNT")) c->fused_count = atoi(se) != 0;
     if (!ev_ok) return fail(cuda_fail(e, "cudaEventCreate / cudaStreamCreate", __FILE__, __LINE__));
     // two lanes unless the per-read diagnostics of "the last batch" are wanted (or VFB_LANES=1 says so)
     c->n_lanes = VFB_LANES;
@@ -933,14 +935,24 @@ static int process_batch(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_sp
     kj.key_cursor = ln.d_t64.as<unsigned long long>() + T_KEYBYTES;
     kj.klen = ln.d_klen.as<uint32_t>(); kj.khash = ln.d_khash.as<uint64_t>();
     kj.hash_bits = c->prm.debug_hash_bits;
-    if ((rc = launch_keys(kj, st))) return rc;
-    if (prof) VFB_CUDA(cudaEventRecord(pev[6], st));
-
+    kj.flank_bytes = (uint32_t)(c->prefix.size() + c->suffix.size());
+    // the table work of a batch claims slots by batch-relative index, and the fused key kernel reads slots without
+    // fences: one batch at a time from here on
+    bool k4_waited = false;
     InsertJob ij;
     ij.keys = kj.keys; ij.klen = kj.klen; ij.khash = kj.khash; ij.kcount = nullptr; ij.koff = kj.koff;
     ij.key_stride = 0; ij.n_keys = n; ij.owner_slot = ln.d_owner.as<uint32_t>();
-    // the table insert of a batch claims slots by batch-relative read index: one batch at a time
-    if (c->n_lanes > 1 && c->k4_pending) VFB_CUDA(cudaStreamWaitEvent(st, c->ev_k4, 0));
+    int frc = -1;
+    if (c->fused_count) {
+        if (c->n_lanes > 1 && c->k4_pending) { VFB_CUDA(cudaStreamWaitEvent(st, c->ev_k4, 0)); k4_waited = true; }
+        frc = launch_keys_count(kj, c->tab, ln.d_c32.as<uint32_t>() + C_NMISS, st);
+        if (frc > 0) return frc;
+        if (frc == VFB_OK) { ij.n_keys_dev = ln.d_c32.as<uint32_t>() + C_NMISS; ++c->stats.fused_batches; }
+    }
+    if (frc != VFB_OK && (rc = launch_keys(kj, st))) return rc;
+    if (prof) VFB_CUDA(cudaEventRecord(pev[6], st));
+
+    if (c->n_lanes > 1 && c->k4_pending && !k4_waited) VFB_CUDA(cudaStreamWaitEvent(st, c->ev_k4, 0));
     if ((rc = launch_insert(c->tab, ij, st))) return rc;
     if ((rc = snaps_push(c, n, key_bytes_ub, st))) return rc;
     if (c->n_lanes > 1) {
@@ -1401,7 +1413,7 @@ int vfb_get_stats(vfb_ctx *c, vfb_stats *out)
     if (!c || !out) { set_error("null argument"); return VFB_ERR_ARG; }
     int rc = vfb_sync(c);
     if (rc) return rc;
-    unsigned long long t64[T_COUNT64] = {0}, ctr[3];
+    unsigned long long t64[T_COUNT64] = {0}, ctr[4];
     for (auto &ln : c->lanes) {
         unsigned long long one[T_COUNT64];
         VFB_CUDA(cudaMemcpy(one, ln.d_t64.p, sizeof one, cudaMemcpyDeviceToHost));
@@ -1415,6 +1427,7 @@ int vfb_get_stats(vfb_ctx *c, vfb_stats *out)
     c->stats.dp_windows = t64[T_WINDOWS];
     c->stats.unique = ctr[0];
     c->stats.counted = ctr[2];
+    c->stats.fused_hits = ctr[3];
     *out = c->stats;
     return VFB_OK;
 }

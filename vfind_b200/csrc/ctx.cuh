@@ -117,7 +117,8 @@ enum { C_NPRE = 0, C_NSUF, C_FBPRE, C_FBSUF, C_FB2PRE, C_FB2SUF, C_NWINPRE, C_NW
        // work cursors of the filter / window kernels (dynamic distribution), each in a 128-byte line of its own: the
        // counters above take millions of atomics per launch, a cursor in their line would queue behind them
        C_WORKPRE = 32, C_WORKPRE2 = 64, C_WORKSUF = 96, C_WORKSUF2 = 128,
-       C_COUNT32 = 160 };
+       C_NMISS = 160,        // fused key + count kernel: keys left for the insert kernels
+       C_COUNT32 = 192 };
 // 64-bit device counters
 enum { T_CELLS = 0, T_DPPRE, T_DPSUF, T_KEYBYTES, T_CELLSCOMP, T_WINDOWS, T_COUNT64 };
 
@@ -150,6 +151,7 @@ struct vfb_ctx {
     vfb::Lane lanes[VFB_LANES];
     int n_lanes = VFB_LANES;                    // 1: every batch on the compute stream itself (diagnostics, VFB_LANES=1)
     bool split_dp = true;                       // a lane's alignment kernels on a lower-priority stream (VFB_SPLIT_DP=0: off)
+    bool fused_count = true;                    // the key kernel probes the table itself (VFB_FUSED_COUNT=0: K3 then K4 over every read)
     uint64_t lane_seq = 0;
     cudaEvent_t ev_fork = nullptr, ev_k4 = nullptr;   // compute stream -> lane; the previous batch's insert is done
     bool k4_pending = false;

@@ -151,8 +151,14 @@ struct KeyJob {
     uint32_t *klen;           // 0 = no key
     uint64_t *khash;
     int hash_bits;            // 0 = 64
+    uint32_t flank_bytes;     // prefix + suffix adapter length: a region is at most a read minus this (sizes key blocks)
 };
 int launch_keys(const KeyJob &job, cudaStream_t st);
+struct DevTable;
+// Fused keys + count (k34_keys_count): reads whose key already has a row in `tab` are counted by the key kernel;
+// the others are left in job.koff / klen / khash as a compact list of *n_miss entries for launch_insert
+// (InsertJob::n_keys_dev).  -1: the tile kernel does not apply to this batch (run launch_keys + launch_insert).
+int launch_keys_count(const KeyJob &job, const DevTable &tab, uint32_t *n_miss, cudaStream_t st);
 
 // Open-addressing table in device memory.  A slot is ONE 32-byte sector of four words:
 //   [0] (tag << 32 | ref)   tag = high 32 hash bits, ref = row id + 1 (bit31 clear) or, only inside the
@@ -185,6 +191,7 @@ struct InsertJob {
     const uint64_t *koff;               // nullable: per-key byte offset into keys; else i * key_stride
     uint32_t key_stride;
     uint32_t n_keys;
+    const uint32_t *n_keys_dev = nullptr;   // nullable: device word holding the list's true length (<= n_keys)
     uint32_t *owner_slot;               // scratch, n_keys: slot claimed by this key or VFB_NONE
 };
 int launch_insert(const DevTable &t, const InsertJob &job, cudaStream_t st);
