@@ -537,33 +537,57 @@ __device__ __forceinline__ uint32_t k34_group(const Key34Tables &T, uint32_t x0,
     return k34_group_slow(&T.k3, x0, x1, x2);
 }
 
-// The common case: region in the shared-memory tile, key block in shared memory, at most KEY_MULTS key words.
+// The common case: region in the shared-memory tile, key block in shared memory, at most 32 key words.  The loop
+// has no branch (four groups are in flight per lane): a group that holds anything but canonical bases only sets its
+// bit, and those groups are redone through the per-byte tables afterwards, with the hash corrected by the difference.
 // The last word (1..4 amino acids, masked) is peeled off the loop.
+__device__ __forceinline__ uint32_t k34_group_fast(const Key34Tables &T, uint32_t x0, uint32_t x1, uint32_t x2, bool &ok)
+{
+    uint32_t i0, i1, i2, i3;
+    ok = tf_codons12(x0, x1, x2, i0, i1, i2, i3);           // the indices stay below 4096 whatever the bytes are
+    return (uint32_t)T.codon[i0] | ((uint32_t)T.codon[i1] << 8) | ((uint32_t)T.codon[i2] << 16) | ((uint32_t)T.codon[i3] << 24);
+}
+
 __device__ __forceinline__ uint64_t k34_lane_hot(const Key34Tables &T, const uint32_t *w, uint32_t sh, uint32_t kl, uint32_t *out)
 {
     const uint32_t nw = (kl + 3) >> 2, npad = ((kl + 15u) & ~15u) >> 2;
     uint64_t acc = 0;
+    uint32_t bad = 0;                                      // bit wi: group wi must be redone
     uint32_t t0 = w[0];
-    ++w;
+    const uint32_t *p = w + 1;
     uint32_t wi = 0;
 #pragma unroll 4
     for (; wi + 1 < nw; ++wi) {
-        const uint32_t t1 = w[0], t2 = w[1], t3 = w[2];
-        w += 3;
-        const uint32_t word = k34_group(T, __funnelshift_r(t0, t1, sh), __funnelshift_r(t1, t2, sh), __funnelshift_r(t2, t3, sh));
+        const uint32_t t1 = p[0], t2 = p[1], t3 = p[2];
+        p += 3;
+        bool ok;
+        const uint32_t word = k34_group_fast(T, __funnelshift_r(t0, t1, sh), __funnelshift_r(t1, t2, sh), __funnelshift_r(t2, t3, sh), ok);
         t0 = t3;
+        bad |= (ok ? 0u : 1u) << wi;
         acc += (uint64_t)(word ^ VFB_HASH_K) * T.k3.mult[wi];
         out[wi] = word;
     }
+    const uint32_t left = kl - 4 * wi;                     // 1..4 key bytes in the last word
+    const uint32_t last_mask = left < 4 ? (1u << (8 * left)) - 1u : 0xFFFFFFFFu;
     {
-        const uint32_t t1 = w[0], t2 = w[1], t3 = w[2];
-        uint32_t word = k34_group(T, __funnelshift_r(t0, t1, sh), __funnelshift_r(t1, t2, sh), __funnelshift_r(t2, t3, sh));
-        const uint32_t left = kl - 4 * wi;                 // 1..4 key bytes in the last word
-        if (left < 4) word &= (1u << (8 * left)) - 1u;
+        const uint32_t t1 = p[0], t2 = p[1], t3 = p[2];
+        bool ok;
+        const uint32_t word = k34_group_fast(T, __funnelshift_r(t0, t1, sh), __funnelshift_r(t1, t2, sh), __funnelshift_r(t2, t3, sh), ok) & last_mask;
+        bad |= (ok ? 0u : 1u) << wi;
         acc += (uint64_t)(word ^ VFB_HASH_K) * T.k3.mult[wi];
         out[wi] = word;
     }
     for (wi = nw; wi < npad; ++wi) out[wi] = 0u;
+    while (bad) {
+        const uint32_t g = (uint32_t)__ffs((int)bad) - 1u;
+        bad &= bad - 1u;
+        const uint32_t *q = w + 3 * g;
+        uint32_t word = k34_group_slow(&T.k3, __funnelshift_r(q[0], q[1], sh), __funnelshift_r(q[1], q[2], sh), __funnelshift_r(q[2], q[3], sh));
+        if (g + 1 == nw) word &= last_mask;
+        const uint32_t was = out[g];
+        acc += ((uint64_t)(word ^ VFB_HASH_K) - (uint64_t)(was ^ VFB_HASH_K)) * T.k3.mult[g];
+        out[g] = word;
+    }
     return acc;
 }
 
@@ -851,7 +875,7 @@ k34_keys_count(const __grid_constant__ KeyJob job, const __grid_constant__ DevTa
                 uint32_t high = 0;
                 if (cur.staged) {
                     const uint32_t toff = cur.lead + (cur.roff - cur.lo);
-                    if (TRANSLATE && out_staged && klen <= 4 * KEY_MULTS)
+                    if (TRANSLATE && out_staged && klen <= 128u)
                         acc = k34_lane_hot(T, tile32 + (toff >> 2), (toff & 3u) * 8u, klen, blk + (local >> 2));
                     else if (TRANSLATE) acc = k34_lane_translate<true>(T, tile32 + (toff >> 2), nullptr, (toff & 3u) * 8u, klen, out);
                     else acc = k3_lane<true, false>(T.k3, tile32 + (toff >> 2), nullptr, (toff & 3u) * 8u, klen, out, high);
@@ -940,8 +964,12 @@ k34_keys_count(const __grid_constant__ KeyJob job, const __grid_constant__ DevTa
                     const uint32_t t = __shfl_up_sync(0xffffffffu, mi, o);
                     if (lane >= o) mi += t;
                 }
-                if (lane == 0) rsv_m0 = atomicAdd(n_miss, (uint32_t)__popc(rsv_mask));
-                if (lane == 31) rsv_base = atomicAdd(job.key_cursor, (unsigned long long)mi);
+                // (predicated atomics written straight into the loop-carried registers: a compiler-made copy of the
+                // result would wait for it here)
+                asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, %2, 0;\n@p atom.global.add.u32 %0, [%1], %3;\n}"
+                             : "+r"(rsv_m0) : "l"(n_miss), "r"(lane), "r"((uint32_t)__popc(rsv_mask)) : "memory");
+                asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, %2, 31;\n@p atom.global.add.u64 %0, [%1], %3;\n}"
+                             : "+l"(rsv_base) : "l"(job.key_cursor), "r"(lane), "l"((unsigned long long)mi) : "memory");
                 rsv_rank = (uint32_t)__popc(rsv_mask & ((1u << lane) - 1u));
                 rsv_off = mi - padded1;
             }
