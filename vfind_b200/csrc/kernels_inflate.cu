@@ -279,7 +279,8 @@ struct InfWarp {
     uint16_t lcount[16], dcount[16];  // canonical code: symbols per length
     uint16_t lsym[INF_MAXL], dsym[32];
     uint8_t lens[32 + INF_MAXL + 32];   // code lengths being read (staged 32 bytes up while the code-length code is in use)
-    uint32_t ring[128];               // 4 lines of 32 compressed words
+    uint32_t ring[128 + 4];           // 4 lines of 32 compressed words; ring[128] mirrors ring[0] (the symbol loop reads
+                                      // word pairs without wrapping the second index)
 };
 
 struct InfShared {
@@ -326,9 +327,13 @@ struct WBits {
 __device__ __forceinline__ void wb_refill(WBits &b, InfWarp *W, int lane)
 {
     if (b.cnt > 32) return;
-    while (b.next_line <= (b.rw >> 5) + 3) {
+    // (two lines ahead of the word that enters next: the ring's four lines then still hold the line before it, which
+    // the symbol loop — it works from a bit position, not from this buffer — may have to read again)
+    while (b.next_line <= (b.rw >> 5) + 2) {
         const uint32_t w = b.next_line * 32u + (uint32_t)lane;
-        W->ring[w & 127u] = w < b.nwords ? __ldg(b.words + w) : 0u;
+        const uint32_t v = w < b.nwords ? __ldg(b.words + w) : 0u;
+        W->ring[w & 127u] = v;
+        if ((w & 127u) == 0u) W->ring[128] = v;
         ++b.next_line;
         __syncwarp();
     }
@@ -583,60 +588,93 @@ __device__ int inflate_member_warp(const InfShared *S, InfWarp *W, const uint8_t
             }
             const int brc = infw_build(T, W, nl, nd, lane, type == 1);
             if (brc) return brc;
-            for (;;) {
-                wb_refill(b, W, lane);
-                uint32_t e = W->ltab[(uint32_t)b.buf & ((1u << INFW_LBITS) - 1u)];
-                if (e == 0) {
-                    int cl = 0;
-                    const int sym = canon_decode((uint32_t)b.buf, W->lcount, W->lsym, INF_MAXBITS, &cl);
-                    if (sym < 0) return -13;
-                    e = lit_entry(T, sym, cl);
-                }
-                const int nb = (int)(e & 15u);
-                b.buf >>= nb; b.cnt -= nb;
-                const uint32_t kind = (e >> 4) & 3u;
-                if (kind == 0) {
-                    const uint32_t cnt = 1u + ((e >> 6) & 3u);       // one to three literals per look-up
-                    if (n_out + cnt > isize) return -14;
-                    if ((uint32_t)lane < cnt) out[n_out + lane] = (uint8_t)(e >> (8 + 8 * lane));
-                    n_out += cnt;
-                } else if (kind == 2) {
-                    break;
-                } else if (kind == 3) {
-                    return -15;
-                } else {
-                    const int xb = (int)(e >> 24);
-                    const uint32_t len = ((e >> 8) & 0xFFFFu) + ((uint32_t)b.buf & ((1u << xb) - 1u));
-                    b.buf >>= xb; b.cnt -= xb;
-                    wb_refill(b, W, lane);
-                    uint32_t d = W->dtab[(uint32_t)b.buf & ((1u << INFW_DBITS) - 1u)];
-                    if (d == 0) {
-                        int cl = 0;
-                        const int ds = canon_decode((uint32_t)b.buf, W->dcount, W->dsym, INF_MAXBITS, &cl);
-                        if (ds < 0) return -16;
-                        d = dist_entry(T, ds, cl);
+            // ---- the symbol loop.  The bit buffer of the header code gives way to a bit POSITION `bp` (relative to
+            // b.words): a symbol starts by fetching the 32 bits at bp — two ring words and a funnel shift, no buffer
+            // to shift and count down — and a literal/length code with its extra bits (<= 20 bits) or a distance
+            // code with its extra bits (<= 28 bits) is taken out of that one window.  `thr` is the position from which
+            // the ring needs its next line (lines up to two ahead of the reader are kept loaded, the line behind it stays).
+            {
+                uint32_t bp = b.rw * 32u - (uint32_t)b.cnt;
+                uint32_t thr = (b.next_line - 2u) << 10;
+                const uint32_t *ring = W->ring;
+                const uint32_t lane_sh = 8u + 8u * (uint32_t)(lane < 2 ? lane : 2);
+                uint8_t *out_lane = out + lane;
+                // One way out of the loop (`status`: 1 = end of block, anything else an error code): early returns from
+                // inside it cost several reconvergence instructions per symbol.
+                int status = 0;
+                do {
+                    while (bp >= thr) {                            // (rarely taken: once per 128 bytes of input)
+                        const uint32_t w = b.next_line * 32u + (uint32_t)lane;
+                        const uint32_t v = w < b.nwords ? __ldg(b.words + w) : 0u;
+                        W->ring[w & 127u] = v;
+                        if ((w & 127u) == 0u) W->ring[128] = v;
+                        ++b.next_line;
+                        thr += 1024u;
+                        __syncwarp();
                     }
-                    const int db = (int)(d & 15u), dx = (int)((d >> 4) & 15u);
-                    if (dx == 15) return -16;
-                    b.buf >>= db; b.cnt -= db;
-                    const uint32_t dist = (d >> 8) + ((uint32_t)b.buf & ((1u << dx) - 1u));
-                    b.buf >>= dx; b.cnt -= dx;
-                    if (dist > n_out) return -17;
-                    if (n_out + len > isize) return -18;
-                    __syncwarp();                                 // earlier stores of all lanes are visible
-                    const uint8_t *from = out + n_out - dist;
-                    if (dist >= len) {
-                        // (most matches in read text are a few bases long: one predicated load / store)
-                        if (len <= 32) {
-                            if ((uint32_t)lane < len) out[n_out + lane] = __ldcg(from + lane);
+                    const uint32_t i0 = (bp >> 5) & 127u;
+                    const uint32_t win = __funnelshift_r(ring[i0], ring[i0 + 1], bp);
+                    uint32_t e = W->ltab[win & ((1u << INFW_LBITS) - 1u)];
+                    if (e == 0) {
+                        int cl = 0;
+                        const int sym = canon_decode(win, W->lcount, W->lsym, INF_MAXBITS, &cl);
+                        e = sym < 0 ? (1u | (3u << 4)) : lit_entry(T, sym, cl);      // no such code: an invalid entry
+                    }
+                    const uint32_t nb = e & 15u, kind = e & 0x30u;
+                    bp += nb;
+                    if (kind == 0) {
+                        // one to three literals per look-up: bytes in bits 8.., (count - 1) in bits 6-7
+                        const uint32_t c1 = (e >> 6) & 3u;
+                        if (n_out + c1 < isize) {
+                            if ((uint32_t)lane <= c1) out_lane[n_out] = (uint8_t)(e >> lane_sh);
+                            n_out += c1 + 1u;
                         } else {
-                            for (uint32_t i = lane; i < len; i += 32) out[n_out + i] = __ldcg(from + i);
+                            status = -14;
+                        }
+                    } else if (kind == 0x10u) {
+                        const uint32_t xb = e >> 24;
+                        const uint32_t len = ((e >> 8) & 0xFFFFu) + ((win >> nb) & ~(0xFFFFFFFFu << xb));
+                        bp += xb;
+                        const uint32_t j0 = (bp >> 5) & 127u;
+                        const uint32_t win2 = __funnelshift_r(ring[j0], ring[j0 + 1], bp);
+                        uint32_t d = W->dtab[win2 & ((1u << INFW_DBITS) - 1u)];
+                        if (d == 0) {
+                            int cl = 0;
+                            const int ds = canon_decode(win2, W->dcount, W->dsym, INF_MAXBITS, &cl);
+                            d = ds < 0 ? (1u | (15u << 4)) : dist_entry(T, ds, cl);  // no such code: an invalid entry
+                        }
+                        const uint32_t db = d & 15u, dx = (d >> 4) & 15u;
+                        // (dx = 15 marks an invalid distance symbol: its 15 "extra bits" only yield a distance that is checked
+                        // like any other and then rejected by the flag)
+                        const uint32_t dist = (d >> 8) + ((win2 >> db) & ~(0xFFFFFFFFu << dx));
+                        bp += db + dx;
+                        if (dx != 15u && dist <= n_out && n_out + len <= isize) {
+                            __syncwarp();                             // earlier stores of all lanes are visible
+                            const uint8_t *from = out_lane + (n_out - dist);
+                            if (dist >= len) {
+                                // (most matches in read text are a few bases long: one predicated load / store)
+                                if (len <= 32) {
+                                    if ((uint32_t)lane < len) out_lane[n_out] = __ldcg(from);
+                                } else {
+                                    for (uint32_t i = 0; i + lane < len; i += 32) out_lane[n_out + i] = __ldcg(from + i);
+                                }
+                            } else {
+                                for (uint32_t i = lane; i < len; i += 32) out[n_out + i] = __ldcg(out + (n_out - dist) + i % dist);
+                            }
+                            n_out += len;
+                        } else {
+                            status = dx == 15u ? -16 : (dist > n_out ? -17 : -18);
                         }
                     } else {
-                        for (uint32_t i = lane; i < len; i += 32) out[n_out + i] = __ldcg(from + i % dist);
+                        status = kind == 0x20u ? 1 : (nb == 1u && e == (1u | (3u << 4)) ? -13 : -15);
                     }
-                    n_out += len;
-                }
+                } while (status == 0);
+                if (status != 1) return status;
+                // back to the bit buffer for the next block header / the trailer check
+                b.rw = bp >> 5;
+                b.buf = (uint64_t)(W->ring[b.rw & 127u] >> (bp & 31u));
+                b.cnt = 32 - (int)(bp & 31u);
+                ++b.rw;
             }
         } else {
             return -20;
