@@ -943,7 +943,9 @@ static int process_batch(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_sp
     ij.keys = kj.keys; ij.klen = kj.klen; ij.khash = kj.khash; ij.kcount = nullptr; ij.koff = kj.koff;
     ij.key_stride = 0; ij.n_keys = n; ij.owner_slot = ln.d_owner.as<uint32_t>();
     int frc = -1;
-    if (c->fused_count) {
+    // (a table that is known to be empty — the first batch after a clear — has nothing to find: the probe would
+    // only cost)
+    if (c->fused_count && c->ub_rows > 0) {
         if (c->n_lanes > 1 && c->k4_pending) { VFB_CUDA(cudaStreamWaitEvent(st, c->ev_k4, 0)); k4_waited = true; }
         frc = launch_keys_count(kj, c->tab, ln.d_c32.as<uint32_t>() + C_NMISS, st);
         if (frc > 0) return frc;
