@@ -36,6 +36,7 @@
 #include <vector>
 
 #include "ctx.cuh"
+#include "gunzip_gpu.h"
 #include "pgunzip.h"
 
 using namespace vfb;
@@ -189,7 +190,9 @@ int peek_bgzf(FILE *f, size_t *member_size)
 struct ChunkProducer {
     FILE *f = nullptr;
     ParallelGunzip pgz;         // plain gzip streams on `threads` > 1 host threads
-    int pgz_state = 0;          // 0 = not decided, 1 = in use, -1 = zlib stream
+    GpuGunzip ggz;              // ... or on the device (gpu_device >= 0): block-start search, marker decode, resolve
+    int gpu_device = -1;
+    int pgz_state = 0;          // 0 = not decided, 1 = host threads, 2 = device, -1 = zlib stream
     uint64_t file_size = 0;
     std::atomic<uint64_t> consumed{0};   // compressed bytes read so far (progress only)
     Inflater serial;
@@ -301,9 +304,32 @@ struct ChunkProducer {
                 if (bgzf && !at_end) break;                   // as full as whole members allow
             } else {
                 if (!plain && pgz_state == 0) {
-                    const char *e = getenv("VFB_PGUNZIP");
-                    pgz_state = threads > 1 && !(e && e[0] == '0') ? 1 : -1;
-                    if (pgz_state == 1) pgz.init(f, threads);
+                    // a plain gzip stream: on the device when there is one (VFB_GPU_GUNZIP=0: never; files under
+                    // 4 MB are not worth the set-up), else in parallel on the host threads, else one zlib stream
+                    const char *g = getenv("VFB_GPU_GUNZIP");
+                    const bool want_gpu = gpu_device >= 0 && !(g && g[0] == '0') && (file_size >= ((uint64_t)4 << 20) || (g && g[0] == '2'));
+                    std::string ge;
+                    if (want_gpu && ggz.init(f, gpu_device, &ge)) pgz_state = 2;
+                    else {
+                        const char *e = getenv("VFB_PGUNZIP");
+                        pgz_state = threads > 1 && !(e && e[0] == '0') ? 1 : -1;
+                        if (pgz_state == 1) pgz.init(f, threads);
+                    }
+                }
+                if (!plain && pgz_state == 2) {
+                    const size_t want = cap - used;
+                    size_t nl = 0;
+                    const long long got = ggz.read_counting(buf + used, want, &nl, &err);
+                    if (got < 0) return VFB_ERR_FORMAT;
+                    lines += nl;
+                    used += (size_t)got;
+                    if ((size_t)got < want) {
+                        // the member has ended (trailer checked): further members go through the zlib stream
+                        long off = 0;
+                        if (ggz.handover(&off) && (uint64_t)off < file_size) { fseek(f, off, SEEK_SET); pgz_state = -1; }
+                        else at_end = true;
+                    }
+                    continue;
                 }
                 if (!plain && pgz_state == 1) {
                     // already decoded in the background: take all the chunk has room for, copied and counted in parallel
@@ -927,6 +953,13 @@ extern "C" int vfb_debug_inflate_file(const char *path, uint32_t n_threads, uint
     ChunkProducer prod;
     std::string e;
     if (!prod.open(path, (int)n_threads, &e)) { set_error(e); return VFB_ERR_IO; }
+    {
+        // the device decoder for plain gzip takes part when asked for (VFB_GPU_GUNZIP=1 / 2) and a device is there
+        const char *g = getenv("VFB_GPU_GUNZIP");
+        int nd = 0;
+        if (g && g[0] != '0' && cudaGetDeviceCount(&nd) == cudaSuccess && nd > 0) prod.gpu_device = 0;
+        else cudaGetLastError();
+    }
     const size_t cap = pick_chunk(prod.f);
     std::vector<uint8_t> buf(cap + 64);
     uint64_t total = 0, lines = 0, chunks = 0;
@@ -970,6 +1003,7 @@ int vfb_internal_run_file(vfb_ctx **ctxs, uint32_t n_ctx, const char *path, uint
     {
         std::string e;
         if (!prod.open(path, vfb_internal_ingest_threads(ctx), &e, (flags & VFB_INPUT_ALLOW_TEXT) != 0)) { set_error(e); return VFB_ERR_IO; }
+        prod.gpu_device = ctx->device;
     }
     size_t cap = pick_chunk(prod.f);
     const bool trace = getenv("VFB_INGEST_TRACE") != nullptr;

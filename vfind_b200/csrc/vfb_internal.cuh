@@ -255,6 +255,27 @@ struct vfb_member {
 int launch_inflate(const uint8_t *d_z, const vfb_member *d_members, uint32_t n_members, uint8_t *d_out,
                    uint32_t *d_first_bad, cudaStream_t st);
 
+// ---------------------------------------------------------------- single-stream gzip on the device (kernels_inflate.cu)
+// Bit positions are relative to the word-aligned compressed segment d_z32 (at most 2^32 bits = 512 MiB).
+#define VFB_GZ_WIN 32768u
+#define VFB_GZ_PIECE 65536u        // newline counts come per piece of this many text bytes
+#define VFB_GZ_CRC_PIECE 16384u    // CRC-32 values come per piece of this many text bytes
+struct vfb_gz_chain_out {          // = GzChainOut
+    uint32_t n_live, end_kind, end_bit, reserved;
+    unsigned long long total_text;
+};
+#define VFB_GZ_RES_BYTES 16        // sizeof(GzChunkRes)
+int launch_gz_search(const uint32_t *d_z32, uint32_t n_words, uint32_t lo_bit, uint32_t hi_bit, uint32_t *d_cand, uint32_t *d_n_cand,
+                     uint32_t cand_cap, uint32_t *d_list, uint32_t list_cap, cudaStream_t st);
+int launch_gz_decode(const uint32_t *d_z32, uint32_t n_words, const uint32_t *d_starts, uint32_t n_chunks, uint32_t n_decode,
+                     uint16_t *d_out16, uint32_t cap, uint32_t max_span_bits, void *d_res, cudaStream_t st);
+int launch_gz_chain(const void *d_res, const uint32_t *d_starts, uint32_t n_chunks, const uint16_t *d_out16, uint32_t cap,
+                    uint32_t limit_bit, const uint8_t *d_first_window, uint32_t *d_live, unsigned long long *d_text_off,
+                    uint8_t *d_win_store, uint8_t *d_out_window, void *d_out, cudaStream_t st);
+int launch_gz_resolve(const uint32_t *d_live, const unsigned long long *d_text_off, uint32_t n_live, unsigned long long total_text,
+                      const uint16_t *d_out16, uint32_t cap, const uint8_t *d_win_store, uint8_t *d_text, uint32_t *d_piece_nl,
+                      uint32_t *d_piece_crc, int first_window_known, uint32_t *d_flag_unknown, cudaStream_t st);
+
 // ---------------------------------------------------------------- misc
 int launch_synth(const vfb_synth_cfg &cfg, uint64_t first, uint64_t n, uint8_t *d_text,
                  vfb_span *d_spans, cudaStream_t st);
