@@ -340,7 +340,7 @@ int vfb_host_free(void *p);
  * default 1024). */
 int vfb_pinned_pool_trim(void);
 /* Device buffers are cached the same way (cudaMalloc / cudaFree cost milliseconds apiece; VFB_DEVICE_POOL_MB caps
- * the cache per device, default 8192). */
+ * the cache per device, default 24576). */
 int vfb_device_pool_trim(void);
 
 #ifdef __cplusplus

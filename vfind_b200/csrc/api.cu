@@ -162,7 +162,7 @@ static size_t device_pool_limit()
     static size_t limit = 0;
     if (!limit) {
         const char *e = getenv("VFB_DEVICE_POOL_MB");
-        limit = ((size_t)(e ? strtoull(e, nullptr, 10) : 8192ull) << 20) + 1;
+        limit = ((size_t)(e ? strtoull(e, nullptr, 10) : 24576ull) << 20) + 1;
     }
     return limit;
 }

@@ -892,12 +892,16 @@ k_gz_search2(const uint32_t *__restrict__ z32, uint32_t n_words, const uint32_t 
     }
 }
 
-struct GzChunkRes {
+struct __align__(16) GzChunkRes {
     uint32_t n_sym;      // symbols decoded (without the window prefix)
     uint32_t land;       // chunk on whose start the decode ended, GZ_NONE if none
     uint32_t end_bit;    // bit position where the decode stopped
     uint32_t flags;      // 1 = the stream's final block ended here, 2 = the decode failed / ran out of room
+    uint32_t start_bit;  // where the chunk starts (0xFFFFFFFF in the records of landing spots that are not decoded)
+    uint32_t pad[3];
 };
+
+static_assert(sizeof(GzChunkRes) == VFB_GZ_RES_BYTES, "GzChunkRes layout");
 
 struct GzDecodeArgs {
     const uint32_t *z32;         // compressed segment, word aligned
@@ -1140,7 +1144,7 @@ k_gz_decode(const __grid_constant__ GzDecodeArgs a)
     const uint32_t warps_total = gridDim.x * INFW_WARPS;
     for (uint32_t i = blockIdx.x * INFW_WARPS + warp; i < a.n_decode; i += warps_total) {
         GzChunkRes r;
-        r.n_sym = 0; r.land = GZ_NONE; r.end_bit = 0; r.flags = 0;
+        r.n_sym = 0; r.land = GZ_NONE; r.end_bit = 0; r.flags = 0; r.start_bit = a.starts[i]; r.pad[0] = r.pad[1] = r.pad[2] = 0;
         const int rc = gz_chunk_warp(&S, &S.w[warp], a, i, lane, &r);
         if (rc != 0) { r.flags = 2u | ((uint32_t)(-rc) << 8); r.land = GZ_NONE; }      // (the reason travels along for traces)
         if (lane == 0) a.res[i] = r;
@@ -1166,7 +1170,7 @@ struct GzChainOut {
 __device__ __forceinline__ GzChunkRes gz_res_or_none(const GzChunkRes *res, uint32_t c, uint32_t n_chunks)
 {
     GzChunkRes r;
-    r.n_sym = 0; r.land = GZ_NONE; r.end_bit = 0; r.flags = 2u;
+    r.n_sym = 0; r.land = GZ_NONE; r.end_bit = 0; r.flags = 2u; r.start_bit = 0xFFFFFFFFu; r.pad[0] = r.pad[1] = r.pad[2] = 0;
     if (c < n_chunks) r = res[c];
     return r;
 }
@@ -1199,14 +1203,15 @@ k_gz_chain(const GzChunkRes *res, const uint32_t *starts, uint32_t n_chunks, con
     if (have_v) gz_tail_load(out16 + GZ_WIN, r.n_sym, v);
     for (;;) {
         if (c >= n_chunks) { kind = 2; end_bit = 0; break; }      // (cannot happen: a landing is a chunk index)
-        const uint32_t sb = starts[c];
-        if (c != 0 && sb >= limit_bit) { kind = 0; end_bit = sb; break; }
+        // (a landing spot beyond the limit is not decoded: its record says 0xFFFFFFFF and its start comes from the list)
+        if (c != 0 && r.start_bit >= limit_bit) { kind = 0; end_bit = starts[c]; break; }
+        const uint32_t sb = r.start_bit;
         if (r.flags & 2u) { kind = 2; end_bit = sb; why = r.flags >> 8; break; }
         // ---- ask for what the next two steps need
         const bool next_valid = !(r.flags & 1u) && r.land < n_chunks;
         const uint32_t c2 = r.land;
         GzChunkRes r3 = gz_res_or_none(res, (next_valid && !(r2.flags & 3u)) ? r2.land : GZ_NONE, n_chunks);
-        const bool have_v2 = next_valid && !(r2.flags & 2u) && r2.n_sym >= GZ_WIN && starts[c2] < limit_bit;
+        const bool have_v2 = next_valid && !(r2.flags & 2u) && r2.n_sym >= GZ_WIN && r2.start_bit < limit_bit;
         if (have_v2) gz_tail_load(out16 + (size_t)c2 * region + GZ_WIN, r2.n_sym, v2);
         // ---- this chunk
         if (threadIdx.x == 0) { live[k] = c; text_off[k] = off; }
@@ -1218,9 +1223,12 @@ k_gz_chain(const GzChunkRes *res, const uint32_t *starts, uint32_t n_chunks, con
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const uint32_t s0 = v[j] & 0xFFFFu, s1 = v[j] >> 16;
-                const uint8_t b0 = s0 < 256u ? (uint8_t)s0 : cur[(s0 - 256u) & (GZ_WIN - 1u)];
-                const uint8_t b1 = s1 < 256u ? (uint8_t)s1 : cur[(s1 - 256u) & (GZ_WIN - 1u)];
-                *reinterpret_cast<uint16_t *>(nxt + 2u * threadIdx.x + 2048u * j) = (uint16_t)(b0 | ((uint16_t)b1 << 8));
+                uint32_t b0 = s0, b1 = s1;
+                if (v[j] & 0xFF00FF00u) {                         // (two literals need no look-up)
+                    if (s0 >= 256u) b0 = cur[(s0 - 256u) & (GZ_WIN - 1u)];
+                    if (s1 >= 256u) b1 = cur[(s1 - 256u) & (GZ_WIN - 1u)];
+                }
+                *reinterpret_cast<uint16_t *>(nxt + 2u * threadIdx.x + 2048u * j) = (uint16_t)(b0 | (b1 << 8));
             }
         } else {
             // a chunk shorter than the window: the last GZ_WIN bytes of (window ++ chunk)

@@ -264,7 +264,7 @@ struct vfb_gz_chain_out {          // = GzChainOut
     uint32_t n_live, end_kind, end_bit, reserved;
     unsigned long long total_text;
 };
-#define VFB_GZ_RES_BYTES 16        // sizeof(GzChunkRes)
+#define VFB_GZ_RES_BYTES 32        // sizeof(GzChunkRes)
 int launch_gz_search(const uint32_t *d_z32, uint32_t n_words, uint32_t lo_bit, uint32_t hi_bit, uint32_t *d_cand, uint32_t *d_n_cand,
                      uint32_t cand_cap, uint32_t *d_list, uint32_t list_cap, cudaStream_t st);
 int launch_gz_decode(const uint32_t *d_z32, uint32_t n_words, const uint32_t *d_starts, uint32_t n_chunks, uint32_t n_decode,
