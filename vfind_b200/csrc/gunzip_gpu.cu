@@ -53,7 +53,7 @@ struct GpuGunzip::Impl {
     // parameters
     size_t seg_bytes = (size_t)224 << 20;    // compressed bytes per segment (a chunk is one warp: thousands are wanted at once)
     size_t ovl_bytes = (size_t)2 << 20;      // looked at beyond the segment for a landing spot
-    uint32_t min_gap_bits = 12u * 1024u * 8u;
+    uint32_t min_gap_bits = 32u * 1024u * 8u;   // chunk starts at least this far apart: the chain is serial over the chunks
     uint32_t cap_syms = 768u * 1024u;        // symbols per chunk region (a chunk may have to run over a block start the search missed)
     // buffers
     PinBuf h_z, h_small;

@@ -721,7 +721,8 @@ __device__ int inflate_member_warp(const InfShared *S, InfWarp *W, const uint8_t
 // Occupancy: a member is one long serial chain (a launch of 2048 members takes 4.9 ms, one of 4096 members 5.5 ms), so
 // throughput is members in flight per SM: the tables are sized (9-bit literal/length look-up, 20 KB per block) and the
 // registers capped (40) for 11 blocks = 44 members per SM; at 6500 members per launch 55.6 GB/s of text (32 per SM: 48.3).
-__global__ void __launch_bounds__(INFW_WARPS * 32, 11)
+template <int MINB>
+__global__ void __launch_bounds__(INFW_WARPS * 32, MINB)
 k_inflate_warp(const __grid_constant__ InflateArgs a)
 {
     __shared__ InfShared S;
@@ -1177,10 +1178,18 @@ __device__ __forceinline__ GzChunkRes gz_res_or_none(const GzChunkRes *res, uint
 
 __device__ __forceinline__ void gz_tail_load(const uint16_t *sym, uint32_t n, uint32_t v[16])
 {
-    // the last GZ_WIN symbols of a chunk of n >= GZ_WIN symbols
+    // the last GZ_WIN symbols of a chunk of n >= GZ_WIN symbols, two per register; 32-bit loads (the pair straddles two
+    // words when the tail starts at an odd symbol)
     const uint16_t *p = sym + (n - GZ_WIN) + 2u * threadIdx.x;
+    if (((n - GZ_WIN) & 1u) == 0u) {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(p);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = (uint32_t)p[2048 * j] | ((uint32_t)p[2048 * j + 1] << 16);
+        for (int j = 0; j < 16; ++j) v[j] = q[1024 * j];
+    } else {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(p - 1);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __funnelshift_r(q[1024 * j], q[1024 * j + 1], 16);
+    }
 }
 
 __global__ void __launch_bounds__(1024)
@@ -1414,17 +1423,23 @@ int launch_inflate(const uint8_t *d_z, const vfb_member *d_members, uint32_t n_m
     static int v1 = -1;
     if (v1 < 0) v1 = getenv("VFB_INFLATE_V1") ? 1 : 0;
     if (!v1) {
-        static int bps = 0, sms = 0;
+        // blocks per SM the kernel is compiled for: 11 (40 registers) by default; VFB_INFLATE_BPS=9 / 10 for comparison
+        static int bps = 0, sms = 0, minb = 11;
         if (!bps) {
             int dev = 0;
             VFB_CUDA(cudaGetDevice(&dev));
             VFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-            VFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_inflate_warp, INFW_WARPS * 32, 0));
+            if (const char *e = getenv("VFB_INFLATE_BPS")) { const int v = atoi(e); if (v == 9 || v == 10) minb = v; }
+            if (minb == 9) VFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_inflate_warp<9>, INFW_WARPS * 32, 0));
+            else if (minb == 10) VFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_inflate_warp<10>, INFW_WARPS * 32, 0));
+            else VFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_inflate_warp<11>, INFW_WARPS * 32, 0));
             if (bps < 1) bps = 1;
         }
         uint32_t blocks = (n_members + INFW_WARPS - 1) / INFW_WARPS;
         if (blocks > (uint32_t)(sms * bps)) blocks = (uint32_t)(sms * bps);
-        k_inflate_warp<<<blocks, INFW_WARPS * 32, 0, st>>>(a);
+        if (minb == 9) k_inflate_warp<9><<<blocks, INFW_WARPS * 32, 0, st>>>(a);
+        else if (minb == 10) k_inflate_warp<10><<<blocks, INFW_WARPS * 32, 0, st>>>(a);
+        else k_inflate_warp<11><<<blocks, INFW_WARPS * 32, 0, st>>>(a);
         ++g_launches;
         VFB_CUDA(cudaGetLastError());
         return VFB_OK;
