@@ -56,9 +56,28 @@ struct GpuGunzip::Impl {
     uint32_t min_gap_bits = 32u * 1024u * 8u;   // chunk starts at least this far apart: the chain is serial over the chunks
     uint32_t cap_syms = 768u * 1024u;        // symbols per chunk region (a chunk may have to run over a block start the search missed)
     // buffers
-    PinBuf h_z, h_small;
-    DevBuf d_z, d_cand, d_list, d_starts, d_res, d_out16, d_live, d_text_off, d_win_store, d_win_in, d_win_out, d_chain, d_nl,
+    PinBuf h_small;
+    DevBuf d_starts, d_res, d_out16, d_live, d_text_off, d_win_store, d_win_in, d_win_out, d_chain, d_nl,
         d_crc, d_flags;
+    // The front half of a segment — read the compressed bytes, copy them in, search the candidates — does not depend on
+    // where exactly the stream enters the segment (a candidate inside the first `ovl_bytes`), so the NEXT segment's front runs
+    // on a thread and a stream of its own while this segment is decoded, chained and resolved.
+    struct Front {
+        PinBuf h_z, h_cand;
+        DevBuf d_z, d_cand, d_list;
+        cudaStream_t st = nullptr;
+        std::thread th;
+        bool started = false, ok = false;
+        std::string err;
+        uint64_t base_byte = 0;              // file offset of the buffer's first byte
+        size_t want = 0;
+        bool last_segment = false;
+        uint32_t n_words = 0, n_cand = 0;
+        double t_read = 0, t_search = 0;
+    };
+    Front fronts[2];
+    int front_cur = 0;
+
     // Segments are produced by a thread of their own, two ahead of the reader at most: a slot is a segment's text on the
     // device with its newline counts.
     struct Slot {
@@ -99,10 +118,15 @@ struct GpuGunzip::Impl {
         cudaSetDevice(device);
         if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
         if (st_out) { cudaStreamSynchronize(st_out); cudaStreamDestroy(st_out); }
-        DevBuf *db[] = {&d_z, &d_cand, &d_list, &d_starts, &d_res, &d_out16, &d_live, &d_text_off, &d_win_store, &d_win_in, &d_win_out,
+        for (auto &fr : fronts) {
+            if (fr.th.joinable()) fr.th.join();
+            if (fr.st) { cudaStreamSynchronize(fr.st); cudaStreamDestroy(fr.st); }
+            fr.d_z.release(); fr.d_cand.release(); fr.d_list.release();
+            fr.h_z.release(); fr.h_cand.release();
+        }
+        DevBuf *db[] = {&d_starts, &d_res, &d_out16, &d_live, &d_text_off, &d_win_store, &d_win_in, &d_win_out,
                         &d_chain, &d_nl, &d_crc, &d_flags, &slots[0].d_text, &slots[1].d_text};
         for (auto *b : db) b->release();
-        h_z.release();
         h_small.release();
     }
 
@@ -131,6 +155,70 @@ struct GpuGunzip::Impl {
         return true;
     }
 
+    // Read [base, base + seg + ovl), copy it in, search every bit offset: on a thread of its own.
+    void front_start(Front &fr, uint64_t base)
+    {
+        if (fr.th.joinable()) fr.th.join();
+        fr.started = true;
+        fr.ok = false;
+        fr.err.clear();
+        fr.base_byte = base;
+        const uint64_t avail = file_size - base;
+        fr.want = (size_t)std::min<uint64_t>(avail, seg_bytes + ovl_bytes);
+        fr.last_segment = avail <= seg_bytes + ovl_bytes;
+        fr.th = std::thread([this, &fr]() {
+            CudaCheck ck{&fr.err};
+            const auto t0 = std::chrono::steady_clock::now();
+            auto ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+            if (!ck.ok(cudaSetDevice(device), "set device")) return;
+            if (!fr.st && !ck.ok(cudaStreamCreateWithFlags(&fr.st, cudaStreamNonBlocking), "stream")) return;
+            const size_t want = fr.want;
+            if (fr.h_z.ensure(want + 64)) { fr.err = "cannot allocate pinned memory"; return; }
+            {
+                // the page cache hands a few GB/s to one thread: read in parallel
+                const int parts = want >= ((size_t)32 << 20) ? 8 : 1;
+                const size_t part = ((want / parts) + 4095) & ~(size_t)4095;
+                std::vector<int> bad((size_t)parts, 0);
+                auto rd = [&](int i) {
+                    const size_t lo = (size_t)i * part, hi = std::min(want, lo + part);
+                    size_t got = lo;
+                    while (got < hi) {
+                        const ssize_t r = pread(fd, (uint8_t *)fr.h_z.p + got, hi - got, (off_t)(fr.base_byte + got));
+                        if (r <= 0) { bad[(size_t)i] = 1; return; }
+                        got += (size_t)r;
+                    }
+                };
+                std::vector<std::thread> pool;
+                for (int i = 1; i < parts; ++i) pool.emplace_back(rd, i);
+                rd(0);
+                for (auto &t : pool) t.join();
+                for (int b : bad) if (b) { fr.err = "truncated gzip stream"; return; }
+            }
+            fr.t_read = ms();
+            fr.n_words = (uint32_t)((want + 3) / 4);
+            memset((uint8_t *)fr.h_z.p + want, 0, 8);
+            if (fr.d_z.ensure((size_t)fr.n_words * 4 + 64)) { fr.err = vfb_last_error(); return; }
+            if (!ck.ok(cudaMemcpyAsync(fr.d_z.p, fr.h_z.p, (size_t)fr.n_words * 4, cudaMemcpyHostToDevice, fr.st), "copy in")) return;
+            const uint32_t total_bits = (uint32_t)(want * 8);
+            const uint32_t cand_cap = (uint32_t)(want / 256) + 1024;
+            if (fr.d_cand.ensure((size_t)(cand_cap + 4) * 4)) { fr.err = vfb_last_error(); return; }
+            uint32_t *d_ncand = fr.d_cand.as<uint32_t>() + cand_cap;
+            if (!ck.ok(cudaMemsetAsync(d_ncand, 0, 4, fr.st), "memset")) return;
+            const uint32_t list_cap = (uint32_t)(want / 16) + 4096;       // about one offset in 500 passes the first test
+            if (fr.d_list.ensure((size_t)(list_cap + 4) * 4)) { fr.err = vfb_last_error(); return; }
+            if (launch_gz_search(fr.d_z.as<uint32_t>(), fr.n_words, 0, total_bits, fr.d_cand.as<uint32_t>(), d_ncand, cand_cap,
+                                 fr.d_list.as<uint32_t>(), list_cap, fr.st)) { fr.err = vfb_last_error(); return; }
+            if (fr.h_cand.ensure((size_t)(cand_cap + 4) * 4)) { fr.err = "cannot allocate pinned memory"; return; }
+            uint32_t *h_cand = (uint32_t *)fr.h_cand.p;
+            if (!ck.ok(cudaMemcpyAsync(h_cand, fr.d_cand.p, (size_t)(cand_cap + 4) * 4, cudaMemcpyDeviceToHost, fr.st), "copy candidates")) return;
+            if (!ck.ok(cudaStreamSynchronize(fr.st), "search")) return;
+            fr.n_cand = std::min(h_cand[cand_cap], cand_cap);   // (more than one per 256 bytes: keep what fits; they only bound chunk sizes)
+            std::sort(h_cand, h_cand + fr.n_cand);
+            fr.t_search = ms();
+            fr.ok = true;
+        });
+    }
+
     // ---- one segment on the device.  Returns false with *err set on a CUDA / IO error; otherwise the segment's text is
     // in d_text (seg_text bytes, possibly 0) and the state has moved on (mode may have changed).
     bool run_segment(Slot &slot, std::string *err)
@@ -141,60 +229,39 @@ struct GpuGunzip::Impl {
         const auto t0 = std::chrono::steady_clock::now();
         auto ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
         double t_read = 0, t_search = 0, t_decode = 0, t_resolve = 0;
-        const uint64_t avail = file_size - byte_pos;
-        const size_t want = (size_t)std::min<uint64_t>(avail, seg_bytes + ovl_bytes);
-        const bool last_segment = avail <= seg_bytes + ovl_bytes;
-        if (h_z.ensure(want + 64)) { *err = "cannot allocate pinned memory"; return false; }
-        {
-            // the page cache hands a few GB/s to one thread: read in parallel
-            const int parts = want >= ((size_t)32 << 20) ? 8 : 1;
-            const size_t part = ((want / parts) + 4095) & ~(size_t)4095;
-            std::vector<int> bad((size_t)parts, 0);
-            auto rd = [&](int i) {
-                const size_t lo = (size_t)i * part, hi = std::min(want, lo + part);
-                size_t got = lo;
-                while (got < hi) {
-                    const ssize_t r = pread(fd, (uint8_t *)h_z.p + got, hi - got, (off_t)(byte_pos + got));
-                    if (r <= 0) { bad[(size_t)i] = 1; return; }
-                    got += (size_t)r;
-                }
-            };
-            std::vector<std::thread> pool;
-            for (int i = 1; i < parts; ++i) pool.emplace_back(rd, i);
-            rd(0);
-            for (auto &t : pool) t.join();
-            for (int b : bad) if (b) { *err = "truncated gzip stream"; return false; }
+        // ---- the front: prefetched (the buffer then starts seg_bytes behind the previous one's, the stream enters it a
+        // little later), or done now (the first segment, and after zlib has handed the stream back)
+        Front *fr = &fronts[front_cur];
+        if (fr->started && !(fr->base_byte <= byte_pos && byte_pos - fr->base_byte < ovl_bytes)) {
+            if (fr->th.joinable()) fr->th.join();
+            fr->started = false;                              // not where the stream is: drop it
         }
-        t_read = ms();
-        const uint32_t n_words = (uint32_t)((want + 3) / 4);
-        memset((uint8_t *)h_z.p + want, 0, 8);
-        if (d_z.ensure((size_t)n_words * 4 + 64)) { *err = vfb_last_error(); return false; }
-        if (!ck.ok(cudaMemcpyAsync(d_z.p, h_z.p, (size_t)n_words * 4, cudaMemcpyHostToDevice, st), "copy in")) return false;
-        const uint32_t total_bits = (uint32_t)(want * 8);
+        if (!fr->started) front_start(*fr, byte_pos);
+        if (fr->th.joinable()) fr->th.join();
+        fr->started = false;
+        if (!fr->ok) { *err = fr->err; return false; }
+        const uint64_t base = fr->base_byte;
+        const size_t want = fr->want;
+        const bool last_segment = fr->last_segment;
+        const uint32_t n_words = fr->n_words;
+        DevBuf &d_z = fr->d_z;
+        const uint32_t start_bit = (uint32_t)((byte_pos - base) * 8u) + bit_in_byte;
+        t_read = fr->t_read;
+        t_search = fr->t_search;
         const uint32_t limit_bit = last_segment ? 0xFFFFFFFFu : (uint32_t)(seg_bytes * 8);
-        // ---- candidate block starts
-        const uint32_t cand_cap = (uint32_t)(want / 256) + 1024;
-        if (d_cand.ensure((size_t)(cand_cap + 4) * 4)) { *err = vfb_last_error(); return false; }
-        uint32_t *d_ncand = d_cand.as<uint32_t>() + cand_cap;
-        if (!ck.ok(cudaMemsetAsync(d_ncand, 0, 4, st), "memset")) return false;
-        const uint32_t list_cap = (uint32_t)(want / 16) + 4096;       // about one offset in 500 passes the first test
-        if (d_list.ensure((size_t)(list_cap + 4) * 4)) { *err = vfb_last_error(); return false; }
-        if (launch_gz_search(d_z.as<uint32_t>(), n_words, bit_in_byte + 1, total_bits, d_cand.as<uint32_t>(), d_ncand, cand_cap,
-                             d_list.as<uint32_t>(), list_cap, st)) {
-            *err = vfb_last_error(); return false;
+        // the next segment's front starts right away
+        if (!last_segment) {
+            front_cur ^= 1;
+            front_start(fronts[front_cur], base + seg_bytes);
         }
-        if (h_small.ensure((size_t)(cand_cap + 4) * 4 + VFB_GZ_WIN + 256)) { *err = "cannot allocate pinned memory"; return false; }
-        uint32_t *h_cand = (uint32_t *)h_small.p;
-        if (!ck.ok(cudaMemcpyAsync(h_cand, d_cand.p, (size_t)(cand_cap + 4) * 4, cudaMemcpyDeviceToHost, st), "copy candidates")) return false;
-        if (!ck.ok(cudaStreamSynchronize(st), "search")) return false;
-        t_search = ms();
-        uint32_t n_cand = h_cand[cand_cap];
-        if (n_cand > cand_cap) n_cand = cand_cap;            // (more than one per 256 bytes: keep what fits; they only bound chunk sizes)
-        std::sort(h_cand, h_cand + n_cand);
+        const uint32_t cand_cap = (uint32_t)(want / 256) + 1024;
+        if (h_small.ensure(VFB_GZ_WIN + 256)) { *err = "cannot allocate pinned memory"; return false; }
+        const uint32_t *h_cand = (const uint32_t *)fr->h_cand.p;
+        const uint32_t n_cand = fr->n_cand;
         std::vector<uint32_t> starts;
-        starts.push_back(bit_in_byte);
+        starts.push_back(start_bit);
         for (uint32_t i = 0; i < n_cand; ++i)
-            if (h_cand[i] >= starts.back() + min_gap_bits) starts.push_back(h_cand[i]);
+            if (h_cand[i] > start_bit && h_cand[i] >= starts.back() + min_gap_bits) starts.push_back(h_cand[i]);
         const uint32_t n_chunks = (uint32_t)starts.size();
         // ---- decode
         if (d_starts.ensure((size_t)n_chunks * 4) || d_res.ensure((size_t)n_chunks * VFB_GZ_RES_BYTES)) { *err = vfb_last_error(); return false; }
@@ -202,7 +269,8 @@ struct GpuGunzip::Impl {
         if (d_live.ensure((size_t)(n_chunks + 1) * 4) || d_text_off.ensure((size_t)(n_chunks + 2) * 8) ||
             d_win_store.ensure((size_t)n_chunks * VFB_GZ_WIN) || d_win_in.ensure(VFB_GZ_WIN) || d_win_out.ensure(VFB_GZ_WIN) ||
             d_chain.ensure(64) || d_flags.ensure(16)) { *err = vfb_last_error(); return false; }
-        uint8_t *h_win = (uint8_t *)h_small.p + (size_t)(cand_cap + 4) * 4;
+        (void)cand_cap;
+        uint8_t *h_win = (uint8_t *)h_small.p;
         memcpy(h_win, window.data(), VFB_GZ_WIN);
         if (!ck.ok(cudaMemcpyAsync(d_win_in.p, h_win, VFB_GZ_WIN, cudaMemcpyHostToDevice, st), "copy window")) return false;
         if (!ck.ok(cudaMemcpyAsync(d_starts.p, starts.data(), (size_t)n_chunks * 4, cudaMemcpyHostToDevice, st), "copy starts")) return false;
@@ -217,7 +285,7 @@ struct GpuGunzip::Impl {
         // (the starts handed to the kernel include the landing spots; only the first n_decode are decoded)
         cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
         if (trace) { for (auto &e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], st); }
-        if (launch_gz_decode_n(n_decode, n_chunks, n_words, max_span)) { *err = vfb_last_error(); return false; }
+        if (launch_gz_decode_n(d_z, n_decode, n_chunks, n_words, max_span)) { *err = vfb_last_error(); return false; }
         if (trace) cudaEventRecord(ev[1], st);
         if (launch_gz_chain(d_res.p, d_starts.as<uint32_t>(), n_chunks, d_out16.as<uint16_t>(), cap_syms, limit_bit,
                             d_win_in.as<uint8_t>(), d_live.as<uint32_t>(), d_text_off.as<unsigned long long>(),
@@ -269,13 +337,12 @@ struct GpuGunzip::Impl {
         slot.text = total;
         t_resolve = ms();
         if (trace)
-            fprintf(stderr, "[vfb gunzip]   read %.1f ms, copy + search %.1f, decode + chain %.1f, resolve + crc %.1f\n", t_read,
-                    t_search - t_read, t_decode - t_search, t_resolve - t_decode);
+            fprintf(stderr, "[vfb gunzip]   front (ahead of time when prefetched): read %.1f ms, copy + search %.1f; decode + chain %.1f, resolve + crc %.1f\n",
+                    t_read, t_search - t_read, t_decode, t_resolve - t_decode);
         if (trace)
             fprintf(stderr, "[vfb gunzip] segment %llu: %zu compressed bytes, %u candidates, %u chunks, %u visited, %llu text bytes, end %u at bit %u (code %u)\n",
                     (unsigned long long)n_segments, want, n_cand, n_decode, co.n_live, (unsigned long long)total, co.end_kind, co.end_bit, co.reserved);
         // ---- where the stream goes on
-        const uint64_t base = byte_pos;
         byte_pos = base + (co.end_bit >> 3);
         bit_in_byte = co.end_bit & 7u;
         if (co.end_kind == 1) {
@@ -290,7 +357,7 @@ struct GpuGunzip::Impl {
         return true;
     }
 
-    int launch_gz_decode_n(uint32_t n_decode, uint32_t n_chunks, uint32_t n_words, uint32_t max_span)
+    int launch_gz_decode_n(const DevBuf &d_z, uint32_t n_decode, uint32_t n_chunks, uint32_t n_words, uint32_t max_span)
     {
         // the kernel looks landings up in all n_chunks starts and decodes the first n_decode chunks
         return launch_gz_decode(d_z.as<uint32_t>(), n_words, d_starts.as<uint32_t>(), n_chunks, n_decode, d_out16.as<uint16_t>(), cap_syms,
