@@ -645,6 +645,14 @@ def _find_variants(paths, adapters, match_score, mismatch_score, gap_open_penalt
         with open(p, "rb"):
             pass
     devs = _pick_devices(device, devices, paths)
+    if not table_capacity_hint:
+        # a count table that starts near its final size never has to grow in the middle of the run (a rehash stalls the
+        # pipeline): about one distinct variant per 512 compressed bytes per device covers the BASELINE shapes; the table
+        # still grows by itself when that is not enough.  Small inputs keep the library's default (2 M rows).
+        total = sum(os.path.getsize(p) for p in paths)
+        guess = total // (512 * len(devs))
+        if guess > (2 << 20):
+            table_capacity_hint = int(min(guess, 48 << 20))
     if len(devs) == 1:
         ctx = Context(adapters, match_score, mismatch_score, gap_open_penalty, gap_extend_penalty,
                       accept_prefix_alignment, accept_suffix_alignment, n_threads, queue_len,

@@ -437,7 +437,20 @@ static int table_reserve(vfb_ctx *c, uint64_t new_keys, uint64_t new_bytes)
     c->base_arena = c->ub_arena = ctr[1];
     want_rows = c->ub_rows + new_keys;
     want_arena = c->ub_arena + new_bytes;
-    if (fits()) return VFB_OK;
+    // The bounds of the batches still in flight (each counts ALL its reads as new rows) are what failed, so room for
+    // this batch alone would only bring the next batch back here, with another wait for the counters: unless there is
+    // room for a pipeline's worth of batches like this one, grow now — once, geometrically.
+    {
+        const uint64_t ahead = (uint64_t)vfb_ctx::N_SNAP + 1;
+        const uint64_t rows_ahead = c->ub_rows + ahead * new_keys, arena_ahead = c->ub_arena + ahead * new_bytes;
+        const bool roomy = rows_ahead * 2 <= c->tab.capacity && rows_ahead <= c->tab.row_capacity && arena_ahead <= c->tab.arena_capacity;
+        if (fits() && (roomy || rows_ahead >= 0x7FFFFFF0ull)) return VFB_OK;
+        if (fits()) {
+            trace("table_reserve: growing ahead of need (rows %llu, %llu per batch)", (unsigned long long)c->ub_rows, (unsigned long long)new_keys);
+            want_rows = rows_ahead;
+            want_arena = arena_ahead;
+        }
+    }
     if (want_rows >= 0x7FFFFFF0ull) {
         set_error("more than 2^31 distinct variants are not supported");
         return VFB_ERR_ARG;
@@ -1146,9 +1159,10 @@ __global__ void k_parse_err_fold(uint32_t *err32, unsigned long long base, unsig
     *err32 = 0xFFFFFFFFu;
 }
 
-int vfb_internal_submit_fastq(vfb_ctx *c, const uint8_t *pinned_text, uint64_t n_bytes, uint64_t n_lines,
-                              uint64_t record_base, cudaEvent_t copied)
+static int submit_fastq_impl(vfb_ctx *c, const uint8_t *pinned_text, uint64_t host_len, const uint8_t *dev_text, uint64_t dev_len,
+                            int dev_device, uint64_t n_lines, uint64_t record_base, cudaEvent_t copied)
 {
+    const uint64_t n_bytes = host_len + dev_len;
     if (n_bytes > 0xFFFFFFF0ull || n_lines > 0xFFFFFFF0ull) { set_error("ingest chunk too large"); return VFB_ERR_ARG; }
     VFB_CUDA(cudaSetDevice(c->device));
     const uint64_t before = g_launches;
@@ -1160,16 +1174,28 @@ int vfb_internal_submit_fastq(vfb_ctx *c, const uint8_t *pinned_text, uint64_t n
         c->p_err_init = true;
     }
     Slot &s = c->slots[c->batch_seq & 1];
+    const bool tr = trace_on() && dev_len;
+    const auto tt0 = std::chrono::steady_clock::now();
+    auto tms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tt0).count(); };
     if ((rc = slot_wait(s))) return rc;
+    const double t_wait = tms();
     if ((rc = s.d_text.ensure(n_bytes + 32))) return rc;
     if ((rc = s.d_spans.ensure((size_t)(n_rec ? n_rec : 1) * sizeof(vfb_span)))) return rc;
     if ((rc = c->p_tiles.ensure(parse_tile_words((uint32_t)n_bytes) * 8 + 8))) return rc;
     if ((rc = c->p_line_end.ensure((n_lines ? n_lines : 1) * 4))) return rc;
-    VFB_CUDA(cudaMemcpyAsync(s.d_text.p, pinned_text, n_bytes, cudaMemcpyHostToDevice, c->st_copy));
+    if (host_len) VFB_CUDA(cudaMemcpyAsync(s.d_text.p, pinned_text, host_len, cudaMemcpyHostToDevice, c->st_copy));
     if (copied) VFB_CUDA(cudaEventRecord(copied, c->st_copy));
+    if (dev_len) {
+        // text that is already in device memory (plain gzip decoded on the device): device to device, or peer to peer
+        uint8_t *dst = s.d_text.as<uint8_t>() + host_len;
+        if (dev_device == c->device) VFB_CUDA(cudaMemcpyAsync(dst, dev_text, dev_len, cudaMemcpyDeviceToDevice, c->st_copy));
+        else VFB_CUDA(cudaMemcpyPeerAsync(dst, c->device, dev_text, dev_device, dev_len, c->st_copy));
+    }
     VFB_CUDA(cudaEventRecord(s.copied, c->st_copy));
     VFB_CUDA(cudaStreamWaitEvent(c->st_compute, s.copied, 0));
-    c->stats.h2d_bytes += n_bytes;
+    c->stats.h2d_bytes += host_len;
+    if (dev_len) VFB_CUDA(cudaEventSynchronize(s.copied));      // the caller lets go of dev_text when this returns
+    const double t_copy = tms();
     unsigned used = 0;
     if (n_rec) {
         if ((rc = launch_parse(s.d_text.as<uint8_t>(), (uint32_t)n_bytes, (uint32_t)n_lines, n_rec,
@@ -1188,9 +1214,22 @@ int vfb_internal_submit_fastq(vfb_ctx *c, const uint8_t *pinned_text, uint64_t n
         }
     }
     if ((rc = mark_computed(c, s.computed, &s.busy, used))) return rc;
+    if (tr) trace("submit_fastq_dev: slot wait %.2f ms, allocations + copies %.2f, parse + batches queued %.2f", t_wait, t_copy - t_wait, tms() - t_copy);
     ++c->batch_seq;
     bump_launches(c, before);
     return VFB_OK;
+}
+
+int vfb_internal_submit_fastq(vfb_ctx *c, const uint8_t *pinned_text, uint64_t n_bytes, uint64_t n_lines,
+                              uint64_t record_base, cudaEvent_t copied)
+{
+    return submit_fastq_impl(c, pinned_text, n_bytes, nullptr, 0, -1, n_lines, record_base, copied);
+}
+
+int vfb_internal_submit_fastq_dev(vfb_ctx *c, const uint8_t *host_text, uint64_t host_len, const uint8_t *dev_text, uint64_t dev_len,
+                                  int dev_device, uint64_t n_lines, uint64_t record_base, cudaEvent_t copied)
+{
+    return submit_fastq_impl(c, host_text, host_len, dev_text, dev_len, dev_device, n_lines, record_base, copied);
 }
 
 // ---- block-gzip segments, in two phases so that several segments (on one device or on several) overlap:

@@ -84,6 +84,7 @@ struct GpuGunzip::Impl {
         DevBuf d_text;
         uint64_t text = 0;
         std::vector<uint32_t> nl;            // newlines per VFB_GZ_PIECE
+        uint32_t outstanding = 0;            // ranges handed out with peek / commit_device and not released yet
     };
     static constexpr int N_SLOTS = 2;
     Slot slots[N_SLOTS];
@@ -105,6 +106,8 @@ struct GpuGunzip::Impl {
     uint64_t n_segments = 0, n_chunks_total = 0, n_live_total = 0, host_bytes = 0, host_takeovers = 0;
     uint64_t host_since = 0;                 // text bytes zlib has produced since it last took over
     bool trace = false;
+    std::chrono::steady_clock::time_point t_init = std::chrono::steady_clock::now();
+    double since_init() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_init).count(); }
 
     ~Impl()
     {
@@ -494,7 +497,7 @@ bool GpuGunzip::init(FILE *f, int device, std::string *err)
 // The producer: segment after segment while the device decoder is in charge.
 static void gz_producer(GpuGunzip::Impl *m);
 
-long long GpuGunzip::read_counting(uint8_t *out, size_t cap, size_t *newlines, std::string *err)
+long long GpuGunzip::read_counting(uint8_t *out, size_t cap, size_t *newlines, std::string *err, bool stop_at_segment)
 {
     Impl &m = *impl_;
     size_t produced = 0;
@@ -535,10 +538,13 @@ long long GpuGunzip::read_counting(uint8_t *out, size_t cap, size_t *newlines, s
                 produced += n;
             }
             if (m.cur_served >= slot->text) {
-                std::lock_guard<std::mutex> lk(m.mu);
+                std::unique_lock<std::mutex> lk(m.mu);
+                m.cv.wait(lk, [&] { return slot->outstanding == 0; });      // ranges still being copied out of the slot
+                if (m.trace) fprintf(stderr, "[vfb gunzip] reader: segment %llu handed out at %.1f ms\n", (unsigned long long)m.consumed_seq, m.since_init());
                 ++m.consumed_seq;
                 m.cur_served = 0;
                 m.cv.notify_all();
+                if (stop_at_segment) return (long long)produced;      // (the next segment starts piece-aligned: peek_device again)
             }
             continue;
         }
@@ -579,7 +585,9 @@ static void gz_producer(GpuGunzip::Impl *mp)
             slot = &m.slots[m.produced_seq % GpuGunzip::Impl::N_SLOTS];
         }
         std::string e;
+        const double t_begin = m.since_init();
         const bool ok = m.run_segment(*slot, &e);
+        if (m.trace) fprintf(stderr, "[vfb gunzip] producer: segment ran %.1f .. %.1f ms\n", t_begin, m.since_init());
         std::lock_guard<std::mutex> lk(m.mu);
         if (!ok) { m.mode = GpuGunzip::Impl::FAILED; m.producer_err = e; break; }
         if (slot->text) ++m.produced_seq;
@@ -589,6 +597,72 @@ static void gz_producer(GpuGunzip::Impl *mp)
     std::lock_guard<std::mutex> lk(m.mu);
     m.producer_done = true;
     m.cv.notify_all();
+}
+
+bool GpuGunzip::peek_device(size_t max_len, size_t keep_tail, DeviceRange *out)
+{
+    Impl &m = *impl_;
+    if (!m.producer.joinable() && !m.producer_done) m.producer = std::thread(gz_producer, impl_);
+    Impl::Slot *slot = nullptr;
+    {
+        std::unique_lock<std::mutex> lk(m.mu);
+        m.cv.wait(lk, [&] { return m.consumed_seq < m.produced_seq || m.producer_done; });
+        if (m.consumed_seq < m.produced_seq) slot = &m.slots[m.consumed_seq % Impl::N_SLOTS];
+    }
+    if (!slot) return false;
+    if (m.cur_served % VFB_GZ_PIECE) return false;                   // (only after a read_counting inside the segment)
+    const uint64_t left = slot->text - m.cur_served;
+    if (left <= keep_tail + VFB_GZ_PIECE) return false;
+    uint64_t n = std::min<uint64_t>(max_len, left - keep_tail);
+    n -= n % VFB_GZ_PIECE;
+    if (n == 0) return false;
+    size_t nl = 0;
+    for (uint64_t p = m.cur_served / VFB_GZ_PIECE; p < (m.cur_served + n) / VFB_GZ_PIECE; ++p) nl += slot->nl[(size_t)p];
+    out->d_ptr = slot->d_text.as<uint8_t>() + m.cur_served;
+    out->len = (size_t)n;
+    out->newlines = nl;
+    out->device = m.device;
+    out->seq = m.consumed_seq;
+    return true;
+}
+
+bool GpuGunzip::range_tail(const DeviceRange &r, uint8_t *out_host, size_t n, std::string *err)
+{
+    Impl &m = *impl_;
+    if (n > r.len) n = r.len;
+    if (cudaSetDevice(m.device) != cudaSuccess ||
+        cudaMemcpyAsync(out_host, r.d_ptr + (r.len - n), n, cudaMemcpyDeviceToHost, m.st_out) != cudaSuccess ||
+        cudaStreamSynchronize(m.st_out) != cudaSuccess) {
+        cudaGetLastError();
+        *err = "CUDA error in the gzip decoder (copy out)";
+        return false;
+    }
+    return true;
+}
+
+void GpuGunzip::commit_device(const DeviceRange &r)
+{
+    Impl &m = *impl_;
+    std::lock_guard<std::mutex> lk(m.mu);
+    Impl::Slot &slot = m.slots[r.seq % Impl::N_SLOTS];
+    m.cur_served += r.len;
+    ++slot.outstanding;
+}
+
+void GpuGunzip::release_device(const DeviceRange &r)
+{
+    Impl &m = *impl_;
+    std::lock_guard<std::mutex> lk(m.mu);
+    Impl::Slot &slot = m.slots[r.seq % Impl::N_SLOTS];
+    if (slot.outstanding) --slot.outstanding;
+    m.cv.notify_all();
+}
+
+bool GpuGunzip::member_ended() const
+{
+    if (!impl_) return true;
+    std::lock_guard<std::mutex> lk(impl_->mu);
+    return impl_->mode == Impl::TRAILER_DONE && impl_->producer_done && impl_->consumed_seq >= impl_->produced_seq;
 }
 
 bool GpuGunzip::handover(long *file_off) const

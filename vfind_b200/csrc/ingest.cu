@@ -200,6 +200,7 @@ struct ChunkProducer {
     bool plain = false;         // uncompressed FASTQ text (vfb_run_file_ex with VFB_INPUT_ALLOW_TEXT only)
     int threads = 1;
     std::vector<uint8_t> carry;
+    std::vector<uint8_t> dev_tail;
     std::vector<uint8_t> zbuf;  // compressed members of the current chunk
     bool at_end = false;
     std::string err;
@@ -292,12 +293,47 @@ struct ChunkProducer {
     // Produce the next chunk into buf (capacity cap, plus 64 spare bytes).  On success sets
     // cut (bytes to submit) and keep_lines (complete lines in [0,cut)); *last when the input is
     // exhausted.  Returns VFB_OK or an error code with `err` set.
-    int next(uint8_t *buf, size_t cap, size_t *cut_out, size_t *lines_out, bool *last)
+    // dev_out (optional): the chunk may be [carry in buf | text that stays on the device] — see Chunk::dev.
+    int next(uint8_t *buf, size_t cap, size_t *cut_out, size_t *lines_out, bool *last, GpuGunzip::DeviceRange *dev_out = nullptr,
+             size_t *dev_len_out = nullptr)
     {
         if (carry.size() >= cap) { err = "a FASTQ record is larger than the ingest chunk"; return VFB_ERR_FORMAT; }
         size_t used = carry.size();
         if (used) memcpy(buf, carry.data(), used);
         size_t lines = count_nl(buf, used);
+        if (dev_out) { *dev_out = GpuGunzip::DeviceRange(); *dev_len_out = 0; }
+        if (dev_out && pgz_state == 2 && !at_end && cap - used > ((size_t)8 << 20)) {
+            // decoded on the device: hand the text on without a round trip through host memory.  Only the range's tail
+            // comes over, to find the last record boundary; what follows it is the next chunk's carry.
+            const size_t tail_cap = (size_t)256 << 10;
+            GpuGunzip::DeviceRange r;
+            if (ggz.peek_device(cap - used, tail_cap, &r)) {
+                const size_t total = lines + r.newlines, rem = total % 4, keep = total - rem;
+                const size_t tn = std::min(r.len, tail_cap);
+                dev_tail.resize(tn);
+                if (!ggz.range_tail(r, dev_tail.data(), tn, &err)) return VFB_ERR_CUDA;
+                // just behind newline number `keep`: walk back over the last rem + 1 newlines
+                size_t end = tn;
+                bool found = keep != 0;
+                for (size_t sft = 0; sft <= rem && found; ++sft) {
+                    const void *q = end ? memrchr(dev_tail.data(), '\n', end) : nullptr;
+                    if (!q) found = false;
+                    else end = (size_t)((const uint8_t *)q - dev_tail.data());
+                }
+                if (found) {
+                    const size_t cut_in_tail = end + 1;
+                    ggz.commit_device(r);
+                    *dev_out = r;
+                    *dev_len_out = r.len - (tn - cut_in_tail);
+                    carry.assign(dev_tail.data() + cut_in_tail, dev_tail.data() + tn);
+                    *cut_out = used;
+                    *lines_out = keep;
+                    *last = false;
+                    return VFB_OK;
+                }
+                // (a record longer than the tail: this stretch goes through host memory)
+            }
+        }
         while (used < cap && !at_end) {
             if (bgzf) {
                 if (!fill_bgzf(buf, cap, used, lines)) return VFB_ERR_FORMAT;
@@ -319,10 +355,13 @@ struct ChunkProducer {
                 if (!plain && pgz_state == 2) {
                     const size_t want = cap - used;
                     size_t nl = 0;
-                    const long long got = ggz.read_counting(buf + used, want, &nl, &err);
+                    // (with the hand-off on the device, host memory only takes what is left of the current segment — its
+                    // tail — so that the next segment can be handed on from its first, piece-aligned byte)
+                    const long long got = ggz.read_counting(buf + used, want, &nl, &err, dev_out != nullptr);
                     if (got < 0) return VFB_ERR_FORMAT;
                     lines += nl;
                     used += (size_t)got;
+                    if ((size_t)got < want && dev_out && !ggz.member_ended()) break;      // a segment's tail: cut the chunk here
                     if ((size_t)got < want) {
                         // the member has ended (trailer checked): further members go through the zlib stream
                         long off = 0;
@@ -398,6 +437,9 @@ struct Chunk {
     size_t cut = 0;        // bytes to submit (ends at a record boundary)
     size_t lines = 0;      // complete lines in [0, cut)
     cudaEvent_t copied = nullptr;
+    // text that never left the device follows buf[0..cut) (plain gzip decoded on the device): lines counts both parts
+    GpuGunzip::DeviceRange dev;
+    size_t dev_len = 0;    // bytes of dev.d_ptr to submit (its rest is the next chunk's carry)
 };
 
 struct Pipe {
@@ -1026,6 +1068,7 @@ int vfb_internal_run_file(vfb_ctx **ctxs, uint32_t n_ctx, const char *path, uint
 
     constexpr int NCH = 3;
     Chunk ch[NCH];
+    const bool dev_handoff = !(getenv("VFB_GUNZIP_HANDOFF") && getenv("VFB_GUNZIP_HANDOFF")[0] == '0');
     std::vector<cudaEvent_t> ch_events((size_t)NCH * n_ctx, nullptr);     // [chunk][context]: an event belongs to a device
     int ch_ctx[NCH] = {0, 0, 0};
     Pipe pp;
@@ -1061,7 +1104,7 @@ int vfb_internal_run_file(vfb_ctx **ctxs, uint32_t n_ctx, const char *path, uint
             }
             bool last = false;
             const auto t0 = std::chrono::steady_clock::now();
-            const int prc = prod.next(ch[k].buf, cap, &ch[k].cut, &ch[k].lines, &last);
+            const int prc = prod.next(ch[k].buf, cap, &ch[k].cut, &ch[k].lines, &last, dev_handoff ? &ch[k].dev : nullptr, &ch[k].dev_len);
             if (trace) fprintf(stderr, "[vfb ingest] chunk %zu bytes %zu lines inflated in %.1f ms\n", ch[k].cut, ch[k].lines,
                                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
             std::lock_guard<std::mutex> lk(pp.mu);
@@ -1094,6 +1137,11 @@ int vfb_internal_run_file(vfb_ctx **ctxs, uint32_t n_ctx, const char *path, uint
         c.copied = ch_events[(size_t)k * n_ctx + d];
         if (c.lines) {
             const auto t0 = std::chrono::steady_clock::now();
+            if (c.dev_len) {
+                rc = vfb_internal_submit_fastq_dev(ctxs[d], c.buf, c.cut, c.dev.d_ptr, c.dev_len, c.dev.device, c.lines, n_total, c.copied);
+                prod.ggz.release_device(c.dev);       // (the copy out of the range has completed)
+                c.dev_len = 0;
+            } else
             rc = vfb_internal_submit_fastq(ctxs[d], c.buf, c.cut, c.lines, n_total, c.copied);
             if (trace) fprintf(stderr, "[vfb ingest] submit at %.1f ms took %.1f ms\n", ms_since(t_start), ms_since(t0));
             n_total += c.lines / 4;

@@ -291,6 +291,11 @@ extern thread_local uint64_t g_launches;   // kernels launched by this thread's 
 // hot loop.  `copied` is recorded on the copy stream once the host buffer may be reused.
 int vfb_internal_submit_fastq(vfb_ctx *ctx, const uint8_t *pinned_text, uint64_t n_bytes, uint64_t n_lines,
                               uint64_t record_base, cudaEvent_t copied);
+// The same for a chunk whose text is [host_text (pinned, host_len bytes) | dev_text (dev_len bytes in the memory of device
+// dev_device)]: the device part is copied device to device (or peer to peer); synchronous for that copy, so the caller may
+// let go of dev_text when the call returns.
+int vfb_internal_submit_fastq_dev(vfb_ctx *ctx, const uint8_t *host_text, uint64_t host_len, const uint8_t *dev_text, uint64_t dev_len,
+                                  int dev_device, uint64_t n_lines, uint64_t record_base, cudaEvent_t copied);
 // One segment of block-gzip members, in two phases (api.cu).  begin: the compressed members (pieces of PINNED host
 // memory, back to back on the device; members[].z_off counts from the first piece) are copied and inflated on the
 // ingest stream — asynchronous; `release(arg)` runs on a driver thread once the pieces have been copied (it must
