@@ -444,7 +444,10 @@ static int table_reserve(vfb_ctx *c, uint64_t new_keys, uint64_t new_bytes)
         const uint64_t ahead = (uint64_t)vfb_ctx::N_SNAP + 1;
         const uint64_t rows_ahead = c->ub_rows + ahead * new_keys, arena_ahead = c->ub_arena + ahead * new_bytes;
         const bool roomy = rows_ahead * 2 <= c->tab.capacity && rows_ahead <= c->tab.row_capacity && arena_ahead <= c->tab.arena_capacity;
-        if (fits() && (roomy || rows_ahead >= 0x7FFFFFF0ull)) return VFB_OK;
+        // (only where that is a modest step: batches of millions of reads each are worth a wait for the counters, not a
+        // table sized for seventeen of them)
+        const bool modest = rows_ahead <= 4 * c->tab.row_capacity && arena_ahead <= 4 * c->tab.arena_capacity;
+        if (fits() && (roomy || !modest || rows_ahead >= 0x7FFFFFF0ull)) return VFB_OK;
         if (fits()) {
             trace("table_reserve: growing ahead of need (rows %llu, %llu per batch)", (unsigned long long)c->ub_rows, (unsigned long long)new_keys);
             want_rows = rows_ahead;
