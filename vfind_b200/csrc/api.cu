@@ -437,23 +437,7 @@ static int table_reserve(vfb_ctx *c, uint64_t new_keys, uint64_t new_bytes)
     c->base_arena = c->ub_arena = ctr[1];
     want_rows = c->ub_rows + new_keys;
     want_arena = c->ub_arena + new_bytes;
-    // The bounds of the batches still in flight (each counts ALL its reads as new rows) are what failed, so room for
-    // this batch alone would only bring the next batch back here, with another wait for the counters: unless there is
-    // room for a pipeline's worth of batches like this one, grow now — once, geometrically.
-    {
-        const uint64_t ahead = (uint64_t)vfb_ctx::N_SNAP + 1;
-        const uint64_t rows_ahead = c->ub_rows + ahead * new_keys, arena_ahead = c->ub_arena + ahead * new_bytes;
-        const bool roomy = rows_ahead * 2 <= c->tab.capacity && rows_ahead <= c->tab.row_capacity && arena_ahead <= c->tab.arena_capacity;
-        // (only where that is a modest step: batches of millions of reads each are worth a wait for the counters, not a
-        // table sized for seventeen of them)
-        const bool modest = rows_ahead <= 4 * c->tab.row_capacity && arena_ahead <= 4 * c->tab.arena_capacity;
-        if (fits() && (roomy || !modest || rows_ahead >= 0x7FFFFFF0ull)) return VFB_OK;
-        if (fits()) {
-            trace("table_reserve: growing ahead of need (rows %llu, %llu per batch)", (unsigned long long)c->ub_rows, (unsigned long long)new_keys);
-            want_rows = rows_ahead;
-            want_arena = arena_ahead;
-        }
-    }
+    if (fits()) return VFB_OK;
     if (want_rows >= 0x7FFFFFF0ull) {
         set_error("more than 2^31 distinct variants are not supported");
         return VFB_ERR_ARG;
