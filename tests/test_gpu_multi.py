@@ -96,6 +96,14 @@ def test_multi_file_variants(tmp_path, raw_block):
                 try:
                     for d in ([0], devs):
                         assert _rows(find_variants(str(p), ad, n_threads=4, devices=d, show_progress=False)) == want, (name, chunk, d)
+                        if "gzip" in name:
+                            # the plain gzip part decoded on the device (forced: these files are small), its text handed on
+                            # device to device — to the other context's device by a peer copy
+                            os.environ["VFB_GPU_GUNZIP"] = "2"
+                            try:
+                                assert _rows(find_variants(str(p), ad, n_threads=4, devices=d, show_progress=False)) == want, (name, chunk, d, "device gunzip")
+                            finally:
+                                os.environ.pop("VFB_GPU_GUNZIP", None)
                 finally:
                     os.environ.pop("VFB_INGEST_CHUNK", None)
     finally:
