@@ -412,8 +412,9 @@ static void snaps_reset(vfb_ctx *c)           // the table was cleared (after a 
 }
 
 // Make room for `new_keys` more keys of `new_bytes` padded key bytes (upper bounds).  The caller queues the inserts
-// and then calls snaps_push with the same numbers.
-static int table_reserve(vfb_ctx *c, uint64_t new_keys, uint64_t new_bytes)
+// and then calls snaps_push with the same numbers.  `stream_of_batches`: the caller is one of a run of batches like this
+// one (a submit), not a one-off (a merge's absorb).
+static int table_reserve(vfb_ctx *c, uint64_t new_keys, uint64_t new_bytes, bool stream_of_batches)
 {
     snaps_poll(c, false);
     uint64_t want_rows = c->ub_rows + new_keys, want_arena = c->ub_arena + new_bytes;
@@ -437,7 +438,25 @@ static int table_reserve(vfb_ctx *c, uint64_t new_keys, uint64_t new_bytes)
     c->base_arena = c->ub_arena = ctr[1];
     want_rows = c->ub_rows + new_keys;
     want_arena = c->ub_arena + new_bytes;
-    if (fits()) return VFB_OK;
+    if (!stream_of_batches) {
+        if (fits()) return VFB_OK;
+    } else {
+        // The bounds of the batches still in flight (each counts ALL its reads as new rows) are what failed, so room for
+        // this batch alone would only bring the next batch back here, with another wait for the counters (which halves
+        // the pace of a plain-gzip file's chunks): unless there is room for a pipeline's worth of batches like this one,
+        // grow now — once, geometrically.  Only where that is a modest step: batches of millions of reads each are
+        // worth a wait for the counters, not a table sized for seventeen of them; and never for a merge's absorb.
+        const uint64_t ahead = (uint64_t)vfb_ctx::N_SNAP + 1;
+        const uint64_t rows_ahead = c->ub_rows + ahead * new_keys, arena_ahead = c->ub_arena + ahead * new_bytes;
+        const bool roomy = rows_ahead * 2 <= c->tab.capacity && rows_ahead <= c->tab.row_capacity && arena_ahead <= c->tab.arena_capacity;
+        const bool modest = rows_ahead <= 4 * c->tab.row_capacity && arena_ahead <= 4 * c->tab.arena_capacity;
+        if (fits() && (roomy || !modest || rows_ahead >= 0x7FFFFFF0ull)) return VFB_OK;
+        if (fits()) {
+            trace("table_reserve: growing ahead of need (rows %llu, %llu per batch)", (unsigned long long)c->ub_rows, (unsigned long long)new_keys);
+            want_rows = rows_ahead;
+            want_arena = arena_ahead;
+        }
+    }
     if (want_rows >= 0x7FFFFFF0ull) {
         set_error("more than 2^31 distinct variants are not supported");
         return VFB_ERR_ARG;
@@ -874,7 +893,7 @@ static int process_batch(vfb_ctx *c, const uint8_t *d_text, const vfb_span *d_sp
                         &c->d_diag_score_suf, &c->d_diag_len_suf};
         for (auto *b : db) if ((rc = b->ensure((size_t)n * 4))) return rc;
     }
-    if ((rc = table_reserve(c, n, key_bytes_ub))) return rc;
+    if ((rc = table_reserve(c, n, key_bytes_ub, true))) return rc;
     cudaEvent_t *pev = nullptr;
     if (prof && (rc = prof_events(c, &pev))) return rc;
     if (c->n_lanes > 1) {
@@ -1773,7 +1792,7 @@ int vfb_internal_absorb_known(vfb_ctx *c, const uint8_t *d_chunk, uint64_t rows,
     const uint64_t before = g_launches;
     int rc;
     if ((rc = lanes_join(c))) return rc;
-    if ((rc = table_reserve(c, rows, key_bytes))) return rc;
+    if ((rc = table_reserve(c, rows, key_bytes, false))) return rc;
     if ((rc = c->lanes[0].d_owner.ensure(rows * 4))) return rc;
     const uint64_t n = rows;
     const uint8_t *base = d_chunk + sizeof(ChunkHeader);
