@@ -102,7 +102,8 @@ def write_fastq(cfg, first: int, n: int, path: str, bgzf: bool = True, level: in
 
 def build(force: bool = False) -> str:
     """Compile the oracle with oracle/Makefile (gcc).  Building the checker is not using it."""
-    srcs = [os.path.join(_HERE, "vfind_oracle.c"), os.path.join(_HERE, "synth_host.c"), os.path.join(_HERE, "vfind_oracle.h"),
+    srcs = [os.path.join(_HERE, "vfind_oracle.c"), os.path.join(_HERE, "sg_stats_simd.c"), os.path.join(_HERE, "synth_host.c"),
+            os.path.join(_HERE, "vfind_oracle.h"),
             os.path.join(os.path.dirname(_HERE), "vfind_b200", "csrc", "synth.h")]
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "libvfind_oracle.so"])
@@ -141,9 +142,13 @@ def lib():
         L.vfo_table_key_bytes.restype = C.c_uint64
         L.vfo_table_key_bytes.argtypes = [C.c_void_p]
         L.vfo_table_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.vfo_table_export_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.vfo_process_reads.argtypes = [C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_uint64, C.c_int, C.c_void_p, C.c_void_p,
                                         C.POINTER(C.c_uint64)]
+        L.vfo_process_reads_ex.argtypes = L.vfo_process_reads.argtypes + [C.c_uint]
+        L.vfo_sg_stats_x16.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.c_int,
+                                       C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(DpRules)] + [C.POINTER(C.c_int)] * 4
         L.vfo_find_variants_file.argtypes = [C.c_char_p, C.POINTER(Params), C.c_int, C.c_void_p,
                                              C.POINTER(C.c_uint64), C.c_char_p, C.c_size_t]
         _lib = L
@@ -178,6 +183,25 @@ def sg_stats(adapter: bytes, read: bytes, match=3, mismatch=-2, gap_open=5, gap_
     return tuple(o.value for o in out)
 
 
+def simd_available() -> bool:
+    return bool(lib().vfo_simd_available())
+
+
+def sg_stats_x16(adapter: bytes, reads, match=3, mismatch=-2, gap_open=5, gap_extend=2, rules: DpRules | None = None):
+    """The sixteen-lane kernel of the CPU baseline on up to 16 reads: a list of (score, length, end_i, end_j), or None
+    when it declines (no AVX2, values outside its 16-bit lanes) and the caller has to use sg_stats."""
+    r = rules or DpRules()
+    n = len(reads)
+    arr = (C.c_char_p * n)(*reads)
+    lens = (C.c_int * n)(*[len(x) for x in reads])
+    out = [(C.c_int * n)() for _ in range(4)]
+    rc = lib().vfo_sg_stats_x16(adapter, len(adapter), arr, lens, n, match, mismatch, gap_open, gap_extend, C.byref(r),
+                                *out)
+    if rc != 0:
+        return None
+    return [tuple(o[k] for o in out) for k in range(n)]
+
+
 def translate(seq: bytes):
     buf = C.create_string_buffer(len(seq) // 3 + 1)
     k = lib().vfo_translate(seq, len(seq), buf)
@@ -209,22 +233,27 @@ def make_params(adapters, match_score=3, mismatch_score=-2, gap_open_penalty=5,
     return p
 
 
-def _export(t) -> dict:
+def _export(t, as_dict=True):
     L = lib()
     rows = int(L.vfo_table_rows(t))
     kb = int(L.vfo_table_key_bytes(t))
     offs = np.zeros(rows + 1, dtype=np.uint64)
     data = np.zeros(max(kb, 1), dtype=np.uint8)
     counts = np.zeros(max(rows, 1), dtype=np.uint64)
-    L.vfo_table_export(t, offs.ctypes.data, data.ctypes.data, counts.ctypes.data)
+    L.vfo_table_export_ex(t, offs.ctypes.data, data.ctypes.data, counts.ctypes.data, 1 if as_dict else 0)
+    if not as_dict:
+        return offs, data[:kb], counts[:rows]          # the columns in table order, as the reference's `unzip` leaves them (src/lib.rs:312)
     raw = data.tobytes()
     return {raw[int(offs[i]):int(offs[i + 1])]: int(counts[i]) for i in range(rows)}
 
 
-def process_reads(params: Params, text, off, length, n_threads=1, want_diag=False):
+def process_reads(params: Params, text, off, length, n_threads=1, want_diag=False, simd=False, as_dict=True):
     """Run the worker+reducer closures over packed reads.
 
     text: bytes / uint8 array; off, length: uint32 arrays.  Returns (table dict, diag|None, cells).
+    simd: gather the alignments of a block of reads and run them sixteen at a time (the CPU baseline's fast leg;
+    identical outputs — the parity tests use the scalar default).  as_dict=False: the table as (offsets, data, counts)
+    columns in table order instead of a Python dict (what a timed baseline run wants).
     """
     L = lib()
     text = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else \
@@ -236,13 +265,13 @@ def process_reads(params: Params, text, off, length, n_threads=1, want_diag=Fals
     cells = C.c_uint64(0)
     t = L.vfo_table_new()
     try:
-        rc = L.vfo_process_reads(C.byref(params), text.ctypes.data if len(text) else None,
-                                 off.ctypes.data if n else None,
-                                 length.ctypes.data if n else None, n, n_threads, t,
-                                 diag.ctypes.data if want_diag and n else None, C.byref(cells))
+        rc = L.vfo_process_reads_ex(C.byref(params), text.ctypes.data if len(text) else None,
+                                    off.ctypes.data if n else None,
+                                    length.ctypes.data if n else None, n, n_threads, t,
+                                    diag.ctypes.data if want_diag and n else None, C.byref(cells), 1 if simd else 0)
         if rc == -1:
             raise ValueError("Accept alignment threshold must be between 0 and 1.")
-        return _export(t), diag, int(cells.value)
+        return _export(t, as_dict), diag, int(cells.value)
     finally:
         L.vfo_table_free(t)
 

@@ -393,11 +393,16 @@ static int cmp_ent(const void *a, const void *b)
 
 void vfo_table_export(const vfo_table *t, uint64_t *offsets, uint8_t *data, uint64_t *counts)
 {
+    vfo_table_export_ex(t, offsets, data, counts, 1);
+}
+
+void vfo_table_export_ex(const vfo_table *t, uint64_t *offsets, uint8_t *data, uint64_t *counts, int sorted)
+{
     sort_ent *e = (sort_ent *)malloc(sizeof(sort_ent) * (t->rows ? t->rows : 1));
     uint64_t k = 0;
     for (uint64_t i = 0; i < t->cap; ++i)
         if (t->slots[i].used) { e[k].arena = t->arena; e[k].s = &t->slots[i]; k++; }
-    qsort(e, k, sizeof(sort_ent), cmp_ent);
+    if (sorted) qsort(e, k, sizeof(sort_ent), cmp_ent);
     uint64_t o = 0;
     for (uint64_t i = 0; i < k; ++i) {
         offsets[i] = o;
@@ -421,6 +426,7 @@ typedef struct {
     vfo_table *table;
     vfo_read_diag *diag;
     uint64_t cells;
+    int simd;
 } work_t;
 
 /* worker closure src/lib.rs:275-291 followed by the reducer closure :292-306 for one read.
@@ -458,6 +464,111 @@ static void do_read(work_t *w, uint64_t r, uint8_t *scratch)
     }
 }
 
+/* The same closures with the alignments of a block of reads gathered and run sixteen at a time (sg_stats_simd.c).
+ * Per read nothing changes: exact search, alignment on a miss, accept test, region, reducer — only the ORDER in which
+ * the alignments of a block are evaluated does, and they are independent. */
+#define SIMD_BLOCK 1024
+static void run_alignments(work_t *w, const uint32_t *list, int n_list, int is_prefix, vfo_read_diag *bd, uint64_t b0)
+{
+    const vfo_params *p = w->p;
+    const uint8_t *ad = is_prefix ? p->prefix : p->suffix;
+    const int A = (int)(is_prefix ? p->prefix_len : p->suffix_len);
+    for (int g = 0; g < n_list; g += 16) {
+        const int m = n_list - g < 16 ? n_list - g : 16;
+        const uint8_t *rd[16];
+        int ln[16], sc[16], al[16];
+        for (int k = 0; k < m; ++k) {
+            const uint64_t r = b0 + list[g + k];
+            rd[k] = w->text + w->off[r];
+            ln[k] = (int)w->len[r];
+        }
+        if (vfo_sg_stats_x16(ad, A, rd, ln, m, p->match_score, p->mismatch_score, p->gap_open_penalty,
+                             p->gap_extend_penalty, &p->rules, sc, al, NULL, NULL) != 0) {
+            for (int k = 0; k < m; ++k)       /* out of the 16-bit lanes' range: one at a time */
+                if (vfo_sg_stats(ad, A, rd[k], ln[k], p->match_score, p->mismatch_score, p->gap_open_penalty,
+                                 p->gap_extend_penalty, &p->rules, &sc[k], &al[k], NULL, NULL) != 0) {
+                    sc[k] = INT32_MIN; al[k] = -1;
+                }
+        }
+        for (int k = 0; k < m; ++k) {
+            vfo_read_diag *d = &bd[list[g + k]];
+            if (is_prefix) { d->score_prefix = sc[k]; d->len_prefix = al[k]; }
+            else           { d->score_suffix = sc[k]; d->len_suffix = al[k]; }
+        }
+    }
+}
+
+/* the tail of vfo_find_adapter_match (src/lib.rs:149-165) from its parts */
+static int64_t boundary_of(int64_t pos, size_t m, size_t n, int is_prefix, int32_t score, int32_t length, double min_score)
+{
+    if (pos != VFO_NONE) return is_prefix ? pos + (int64_t)m : pos;    /* :151-152 */
+    if (score == INT32_MIN) return VFO_NONE;                           /* no alignment ran */
+    if ((double)score > min_score) {                                   /* :157 */
+        if (is_prefix) return (int64_t)length;                         /* :159 */
+        if ((size_t)length > n) return VFO_NONE;                       /* :160 underflow (Q8) -> no region */
+        return (int64_t)n - (int64_t)length;
+    }
+    return VFO_NONE;
+}
+
+/* the C library's vectorised search (the reference's memchr::memmem is a SIMD search too); same answer as vfo_memmem */
+static inline int64_t fast_memmem(const uint8_t *hay, size_t n, const uint8_t *needle, size_t m)
+{
+    if (m == 0) return 0;
+    if (m > n) return VFO_NONE;
+    const uint8_t *q = (const uint8_t *)memmem(hay, n, needle, m);
+    return q ? (int64_t)(q - hay) : VFO_NONE;
+}
+
+static void worker_blocks_simd(work_t *w, uint8_t *scratch)
+{
+    const vfo_params *p = w->p;
+    vfo_read_diag bd[SIMD_BLOCK];
+    uint32_t lp[SIMD_BLOCK], ls[SIMD_BLOCK];
+    for (uint64_t b0 = w->lo; b0 < w->hi; b0 += SIMD_BLOCK) {
+        const int nb = (int)(w->hi - b0 < SIMD_BLOCK ? w->hi - b0 : SIMD_BLOCK);
+        int np = 0, ns = 0;
+        for (int k = 0; k < nb; ++k) {
+            const uint8_t *seq = w->text + w->off[b0 + k];
+            const size_t n = w->len[b0 + k];
+            vfo_read_diag *d = &bd[k];
+            d->exact_prefix = (int32_t)fast_memmem(seq, n, p->prefix, p->prefix_len);  /* :148 */
+            d->exact_suffix = (int32_t)fast_memmem(seq, n, p->suffix, p->suffix_len);
+            d->score_prefix = d->score_suffix = INT32_MIN;
+            d->len_prefix = d->len_suffix = -1;
+            /* `aligner?` :155; an empty read or adapter never reaches the matrices (vfo_sg_stats refuses it) */
+            if (d->exact_prefix == VFO_NONE && w->prefix_align && n > 0 && p->prefix_len > 0) lp[np++] = (uint32_t)k;
+            if (d->exact_suffix == VFO_NONE && w->suffix_align && n > 0 && p->suffix_len > 0) ls[ns++] = (uint32_t)k;
+        }
+        run_alignments(w, lp, np, 1, bd, b0);
+        run_alignments(w, ls, ns, 0, bd, b0);
+        for (int k = 0; k < nb; ++k) {
+            const uint64_t r = b0 + k;
+            const uint8_t *seq = w->text + w->off[r];
+            const size_t n = w->len[r];
+            vfo_read_diag *d = &bd[k];
+            const int64_t start = boundary_of(d->exact_prefix, p->prefix_len, n, 1, d->score_prefix, d->len_prefix, w->min_prefix);
+            const int64_t end = boundary_of(d->exact_suffix, p->suffix_len, n, 0, d->score_suffix, d->len_suffix, w->min_suffix);
+            if (d->score_prefix != INT32_MIN) w->cells += (uint64_t)p->prefix_len * n;
+            if (d->score_suffix != INT32_MIN) w->cells += (uint64_t)p->suffix_len * n;
+            d->start = (int32_t)start;
+            d->end = (int32_t)end;
+            if (w->diag) w->diag[r] = *d;
+            if (start != VFO_NONE && end != VFO_NONE && start < end) {                 /* :288 */
+                if ((size_t)end > n) continue;
+                const uint8_t *var = seq + start;
+                const size_t vn = (size_t)(end - start);
+                if (p->skip_translation) {
+                    if (vfo_is_utf8(var, vn)) vfo_table_add(w->table, var, vn, 1);      /* :294-297 */
+                } else {
+                    const int64_t kk = vfo_translate(var, vn, scratch);                /* :300 */
+                    if (kk >= 0) vfo_table_add(w->table, scratch, (size_t)kk, 1);      /* :301 */
+                }
+            }
+        }
+    }
+}
+
 static void *worker_main(void *arg)
 {
     work_t *w = (work_t *)arg;
@@ -465,7 +576,8 @@ static void *worker_main(void *arg)
     for (uint64_t r = w->lo; r < w->hi; ++r)
         if (w->len[r] > maxlen) maxlen = w->len[r];
     uint8_t *scratch = (uint8_t *)malloc((size_t)maxlen / 3 + 8);
-    for (uint64_t r = w->lo; r < w->hi; ++r) do_read(w, r, scratch);
+    if (w->simd) worker_blocks_simd(w, scratch);
+    else for (uint64_t r = w->lo; r < w->hi; ++r) do_read(w, r, scratch);
     free(scratch);
     return NULL;
 }
@@ -486,6 +598,13 @@ int vfo_process_reads(const vfo_params *p, const uint8_t *text,
                       const uint32_t *off, const uint32_t *len, uint64_t n,
                       int n_threads, vfo_table *table, vfo_read_diag *diag, uint64_t *dp_cells)
 {
+    return vfo_process_reads_ex(p, text, off, len, n, n_threads, table, diag, dp_cells, 0);
+}
+
+int vfo_process_reads_ex(const vfo_params *p, const uint8_t *text,
+                         const uint32_t *off, const uint32_t *len, uint64_t n,
+                         int n_threads, vfo_table *table, vfo_read_diag *diag, uint64_t *dp_cells, unsigned flags)
+{
     int pa, sa;
     double minp, mins;
     if (setup_thresholds(p, &pa, &sa, &minp, &mins) != 0) return -1;
@@ -500,6 +619,7 @@ int vfo_process_reads(const vfo_params *p, const uint8_t *text,
         w[t].prefix_align = pa; w[t].suffix_align = sa;
         w[t].min_prefix = minp; w[t].min_suffix = mins;
         w[t].diag = diag;
+        w[t].simd = (flags & VFO_FLAG_SIMD) && vfo_simd_available();
         w[t].table = (t == 0) ? table : vfo_table_new();
     }
     if (n_threads == 1) {

@@ -326,3 +326,89 @@ def test_process_reads_threads_and_skip_translation():
     assert t == {}
     t, _, _ = oracle.process_reads(oracle.make_params((PREFIX, SUFFIX)), text, off, ln)
     assert t == {b"XV": 1}
+
+
+# ---- the CPU baseline's fast leg (oracle/sg_stats_simd.c): sixteen alignments per AVX2 vector, checked against the
+# scalar statement of the same recurrence, which stays the parity checker
+
+def _mutated(rng, ad, alpha):
+    m = bytearray(ad)
+    for _ in range(rng.randint(0, 4)):
+        op, pos = rng.random(), rng.randrange(len(m)) if m else 0
+        if op < 0.4 and m:
+            m[pos] = rng.choice(alpha)
+        elif op < 0.7 and m:
+            del m[pos]
+        else:
+            m.insert(pos, rng.choice(alpha))
+    return bytes(m)
+
+
+@pytest.mark.skipif(not oracle.simd_available(), reason="no AVX2 on this host")
+def test_simd_kernel_equals_scalar_under_every_rule():
+    rng = random.Random(20261019)
+    scorings = [(3, -2, 5, 2), (1, -1, 1, 1), (2, -3, 4, 1), (5, -4, 10, 1), (1, -1, 0, 0), (3, -2, 5, 5), (2, 2, 1, 1)]
+    compared = 0
+    for it in range(700):
+        A = rng.choice([1, 2, 5, 12, 20, 20, 33, 40, 64])
+        alpha = rng.choice([b"ACGT", b"ACGTN", b"AC", b"ACGTacgtNx"])
+        ad = bytes(rng.choice(alpha) for _ in range(A))
+        reads = []
+        for _ in range(rng.randint(1, 16)):                 # ragged lengths inside one vector
+            L = rng.choice([1, 2, 3, A, A + 1, 30, 60, 150]) + rng.randint(0, 3)
+            r = bytearray(rng.choice(alpha) for _ in range(L))
+            if rng.random() < 0.7 and L > A:
+                m = _mutated(rng, ad, alpha)
+                p = rng.randint(0, max(0, L - len(m)))
+                r[p:p + len(m)] = m
+            reads.append(bytes(r))
+        sc = rng.choice(scorings)
+        rules = oracle.DpRules(rng.randint(0, 1), rng.randint(0, 1), it % 4, rng.randint(0, 1))
+        got = oracle.sg_stats_x16(ad, reads, *sc, rules=rules)
+        assert got is not None
+        for k, r in enumerate(reads):
+            assert got[k] == oracle.sg_stats(ad, r, *sc, rules=rules), (ad, r, sc, it % 4)
+            compared += 1
+    assert compared > 5000
+
+
+@pytest.mark.skipif(not oracle.simd_available(), reason="no AVX2 on this host")
+def test_simd_kernel_declines_what_16_bit_lanes_cannot_hold():
+    ad, reads = b"ACGTACGTAC", [b"ACGTTCGTACGG"]
+    assert oracle.sg_stats_x16(ad, reads) is not None
+    assert oracle.sg_stats_x16(ad, reads, match=4000) is None               # 10 rows x 4000 > 16 bit
+    assert oracle.sg_stats_x16(ad, reads, gap_open=20000) is None
+    assert oracle.sg_stats_x16(ad, reads, gap_extend=-1) is None
+    assert oracle.sg_stats_x16(ad, [b"A" * 31000]) is None                  # lengths beyond the lanes
+    assert oracle.sg_stats_x16(ad, [b""]) is None                           # vfo_sg_stats refuses it too
+
+
+@pytest.mark.parametrize("skip_translation", [False, True])
+def test_process_reads_simd_leg_is_identical(skip_translation):
+    rng = random.Random(77 + skip_translation)
+    reads = []
+    for i in range(5000):
+        lead = bytes(rng.choice(b"ACGT") for _ in range(rng.randint(0, 12)))
+        region = bytes(rng.choice(b"ACGTacgtN") for _ in range(3 * rng.randint(0, 20) + (rng.random() < 0.1)))
+        pre = PREFIX if rng.random() < 0.5 else _mutated(rng, PREFIX, b"ACGT")
+        suf = SUFFIX if rng.random() < 0.5 else _mutated(rng, SUFFIX, b"ACGT")
+        tail = bytes(rng.choice(b"ACGT") for _ in range(rng.randint(0, 12)))
+        r = lead + pre + region + suf + tail
+        if i % 97 == 0:
+            r = b""                                          # empty reads never reach the matrices
+        elif i % 101 == 0:
+            r = r[:rng.randint(1, 10)]                       # shorter than the adapters
+        reads.append(r)
+    text, off, ln = oracle.pack_reads(reads)
+    for kw in (dict(), dict(match_score=4000, mismatch_score=-3000), dict(rules=oracle.DpRules(1, 1, 3, 0)),
+               dict(accept_prefix_alignment=1.0), dict(accept_prefix_alignment=0.5, accept_suffix_alignment=0.5)):
+        p = oracle.make_params((PREFIX, SUFFIX), skip_translation=skip_translation, **kw)
+        want, wdiag, wcells = oracle.process_reads(p, text, off, ln, n_threads=1, want_diag=True)
+        for threads in (1, 3):
+            got, gdiag, gcells = oracle.process_reads(p, text, off, ln, n_threads=threads, want_diag=True, simd=True)
+            assert got == want and gcells == wcells, kw
+            for f in wdiag.dtype.names:
+                assert (gdiag[f] == wdiag[f]).all(), (f, kw)
+        offs, data, counts = oracle.process_reads(p, text, off, ln, n_threads=2, simd=True, as_dict=False)[0]
+        raw = data.tobytes()
+        assert {raw[int(offs[i]):int(offs[i + 1])]: int(counts[i]) for i in range(len(counts))} == want
