@@ -337,7 +337,7 @@ int vfb_host_free(void *p);
 
 /* Pinned staging buffers (ingest segments, result columns) are cached process-wide between calls,
  * because page-locking costs more than a small run; this frees the cache (VFB_PINNED_POOL_MB caps it,
- * default 1024). */
+ * default 4096). */
 int vfb_pinned_pool_trim(void);
 /* Device buffers are cached the same way (cudaMalloc / cudaFree cost milliseconds apiece; VFB_DEVICE_POOL_MB caps
  * the cache per device, default 24576). */

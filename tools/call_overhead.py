@@ -21,6 +21,8 @@ for rep in range(6):
     t0 = time.perf_counter()
     out = find_variants(toy, ads, show_progress=False)
     print("toy call %d: %.2f ms  rows %d" % (rep, 1e3 * (time.perf_counter() - t0), out.num_rows), flush=True)
+if "--toy-only" in sys.argv:
+    sys.exit(0)
 cfg = oracle.synth_cfg()
 small = "/tmp/small.fq.gz"
 oracle.write_fastq(cfg, 0, 4_000_000, small, bgzf=True)

@@ -63,7 +63,9 @@ void trace(const char *fmt, ...)
 
 // Process-wide cache of pinned host buffers: page-locking costs about 1 ms per MB, more than a
 // whole small run.  Buffers released by a context / an ingest are kept (up to VFB_PINNED_POOL_MB,
-// default 1024) and handed to the next one; vfb_pinned_pool_trim() frees them.
+// default 4096: a call on a plain gzip file holds 0.9 GB of staging — three 128 MB text chunks, two 254 MB compressed
+// segments — plus its result columns, and the previous call's result is usually still alive; with a 1 GB cap every call
+// page-locked 0.1-0.5 GB anew, 0.08-0.5 s on a 0.3 s call) and handed to the next one; vfb_pinned_pool_trim() frees them.
 struct PinnedPool {
     std::mutex mu;
     std::vector<std::pair<void *, size_t>> idle;
@@ -109,7 +111,7 @@ void pinned_release(void *p, size_t cap)
     static size_t limit = 0;
     if (!limit) {
         const char *e = getenv("VFB_PINNED_POOL_MB");
-        limit = ((size_t)(e ? strtoull(e, nullptr, 10) : 1024ull) << 20) + 1;
+        limit = ((size_t)(e ? strtoull(e, nullptr, 10) : 4096ull) << 20) + 1;
     }
     PinnedPool &pp = pinned_pool();
     std::vector<void *> evict;
@@ -444,12 +446,16 @@ static int table_reserve(vfb_ctx *c, uint64_t new_keys, uint64_t new_bytes, bool
         // The bounds of the batches still in flight (each counts ALL its reads as new rows) are what failed, so room for
         // this batch alone would only bring the next batch back here, with another wait for the counters (which halves
         // the pace of a plain-gzip file's chunks): unless there is room for a pipeline's worth of batches like this one,
-        // grow now — once, geometrically.  Only where that is a modest step: batches of millions of reads each are
-        // worth a wait for the counters, not a table sized for seventeen of them; and never for a merge's absorb.
+        // grow now — once, geometrically.  Only where that is a modest step (at most four times what there is, or a few
+        // GB in absolute terms: a file's chunks of 128 MB of text must always qualify, or the call's pace depends on
+        // how many batches happened to be in flight): batches of millions of reads each are worth a wait for the
+        // counters, not a table sized for seventeen of them; and never for a merge's absorb.
         const uint64_t ahead = (uint64_t)vfb_ctx::N_SNAP + 1;
         const uint64_t rows_ahead = c->ub_rows + ahead * new_keys, arena_ahead = c->ub_arena + ahead * new_bytes;
         const bool roomy = rows_ahead * 2 <= c->tab.capacity && rows_ahead <= c->tab.row_capacity && arena_ahead <= c->tab.arena_capacity;
-        const bool modest = rows_ahead <= 4 * c->tab.row_capacity && arena_ahead <= 4 * c->tab.arena_capacity;
+        const uint64_t rows_step = std::max<uint64_t>(4 * c->tab.row_capacity, 32ull << 20);
+        const uint64_t arena_step = std::max<uint64_t>(4 * c->tab.arena_capacity, 4ull << 30);
+        const bool modest = rows_ahead <= rows_step && arena_ahead <= arena_step;
         if (fits() && (roomy || !modest || rows_ahead >= 0x7FFFFFF0ull)) return VFB_OK;
         if (fits()) {
             trace("table_reserve: growing ahead of need (rows %llu, %llu per batch)", (unsigned long long)c->ub_rows, (unsigned long long)new_keys);

@@ -12,7 +12,7 @@ namespace vfb {
 // Process-wide caches of device and pinned host buffers (api.cu): cudaMalloc / cudaFree cost 2-8 ms apiece in
 // a process that holds a lot of device memory, page-locking about 1 ms per MB — more than a whole small run.
 // Buffers released by a context are kept (VFB_DEVICE_POOL_MB per device, default 24576; VFB_PINNED_POOL_MB,
-// default 1024) and handed to the next one; vfb_device_pool_trim() / vfb_pinned_pool_trim() free them.
+// default 4096) and handed to the next one; vfb_device_pool_trim() / vfb_pinned_pool_trim() free them.
 void *device_acquire(int device, size_t want, size_t *cap_out);
 void device_release(int device, void *p, size_t cap);
 void device_pool_trim();
