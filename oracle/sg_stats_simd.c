@@ -82,6 +82,13 @@ static int scratch_fit(int A, int Lmax)
     return 0;
 }
 
+/* the calling thread's scratch (a worker calls this before it ends) */
+void vfo_simd_thread_release(void)
+{
+    free(tls.codes); free(tls.state); free(tls.col);
+    memset(&tls, 0, sizeof tls);
+}
+
 /* The matrices.  TIE_OPEN / HPRI / ROW_GE are compile-time constants in the four instantiations below. */
 __attribute__((target("avx2"), always_inline)) static inline void
 fill16(const uint8_t *acode, int A, int Lmax, const int16_t *lens16, int match, int mismatch, int open, int extend,
@@ -169,6 +176,10 @@ FILL_VARIANT(fill_100, 1, 0, 0) FILL_VARIANT(fill_101, 1, 0, 1) FILL_VARIANT(fil
 static inline int iabs(int v) { return v < 0 ? -v : v; }
 
 #endif /* VFO_HAVE_X86 */
+
+#if !VFO_HAVE_X86
+void vfo_simd_thread_release(void) {}
+#endif
 
 /* Up to 16 reads against one adapter.  Returns 0 when every output has been written, 1 when the caller has to use
  * vfo_sg_stats (no AVX2, values that do not fit 16-bit lanes, empty inputs).  The outputs equal vfo_sg_stats's. */

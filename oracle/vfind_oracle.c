@@ -576,7 +576,7 @@ static void *worker_main(void *arg)
     for (uint64_t r = w->lo; r < w->hi; ++r)
         if (w->len[r] > maxlen) maxlen = w->len[r];
     uint8_t *scratch = (uint8_t *)malloc((size_t)maxlen / 3 + 8);
-    if (w->simd) worker_blocks_simd(w, scratch);
+    if (w->simd) { worker_blocks_simd(w, scratch); vfo_simd_thread_release(); }
     else for (uint64_t r = w->lo; r < w->hi; ++r) do_read(w, r, scratch);
     free(scratch);
     return NULL;
