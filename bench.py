@@ -215,6 +215,30 @@ def cpu_baseline_of(oracle, adapters, thr, text, off, ln, threads, seconds, what
                        "sample": "first %d reads, %d pass(es), %.1f s" % (sn // sp, sp, sdt)}}
 
 
+def oracle_file_leg(oracle, cfg, adapters, thr, tmp, n_reads, threads):
+    """The CPU port on a gzipped FASTQ FILE, whole call (the ingest legs' baseline): a block-gzip file of the first n_reads
+    reads of the stream, inflated by ONE zlib stream (the reference's MultiGzDecoder runs on one reader thread), framed,
+    then the closures on every host thread with the AVX2 leg.  The port runs the three phases one after the other; the
+    reference overlaps its reader thread with its workers, so `value_if_overlapped` (reads / the longer of the two) is
+    the number to hold the GPU path against."""
+    path = os.path.join(tmp, "oracle_leg.fq.gz")
+    tb, zb = oracle.write_fastq(cfg, 0, n_reads, path, bgzf=True, level=1)
+    try:
+        t0 = time.perf_counter()
+        rows, n, ph = oracle.find_variants_file_timed(path, adapters, n_threads=threads, simd=True,
+                                                      accept_prefix_alignment=thr, accept_suffix_alignment=thr)
+        dt = time.perf_counter() - t0
+    finally:
+        os.remove(path)
+    reader = ph[0] + ph[1]
+    return {"value": n / dt, "unit": "reads/s", "value_if_overlapped": n / max(reader, ph[2], 1e-9), "cores": threads, "kind": "port",
+            "input": "block-gzip FASTQ, first %d reads of the stream, %.0f MB text, %.0f MB compressed" % (n, tb / 1e6, zb / 1e6),
+            "seconds": dt, "seconds_inflate_one_zlib_stream": ph[0], "seconds_fastq_framing": ph[1],
+            "seconds_closures_all_threads_avx2": ph[2], "table_rows": rows,
+            "note": "the reference's reader (flate2 MultiGzDecoder + seq_io) is one thread too: from a .gz file it is bound by that "
+                    "thread whatever the aligner costs"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (the oracle port — the Rust/parasail reference cannot be built in
     this image), all host threads, a bounded sample of the workload per step.  Inputs come from the oracle side's own
@@ -738,6 +762,13 @@ def main():
                 else:
                     ingest[name] = leg
                 os.remove(path)
+            if world == 1 and not args.no_cpu:
+                try:
+                    full_affinity()
+                    ingest["cpu_baseline"] = oracle_file_leg(oracle, cfg, adapters, thr, tmp, min(args.ingest_reads, 2_000_000),
+                                                             os.cpu_count() or 1)
+                except Exception as e:
+                    ingest["cpu_baseline"] = {"error": repr(e)}
             if world == 1:
                 # the same call on ONE plain gzip stream (what `gzip` / pigz / fastp write): decoded on the device
                 # (block-start search, marker decode, resolve: kernels_inflate.cu k_gz_*), and for comparison by the

@@ -151,6 +151,8 @@ def lib():
                                        C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(DpRules)] + [C.POINTER(C.c_int)] * 4
         L.vfo_find_variants_file.argtypes = [C.c_char_p, C.POINTER(Params), C.c_int, C.c_void_p,
                                              C.POINTER(C.c_uint64), C.c_char_p, C.c_size_t]
+        L.vfo_find_variants_file_ex.argtypes = [C.c_char_p, C.POINTER(Params), C.c_int, C.c_void_p,
+                                                C.POINTER(C.c_uint64), C.c_char_p, C.c_size_t, C.c_uint, C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -304,5 +306,24 @@ def find_variants_file(path: str, adapters, n_threads=1, **kw) -> dict:
         if rc != 0:
             raise RuntimeError(err.value.decode())
         return _export(t)
+    finally:
+        L.vfo_table_free(t)
+
+
+def find_variants_file_timed(path: str, adapters, n_threads=1, simd=True, **kw):
+    """The oracle end to end over a gzipped FASTQ file as a CPU baseline: (rows, reads, [inflate s, framing s, closures s]).
+    The table is not turned into a Python dict."""
+    L = lib()
+    p = make_params(adapters, **kw)
+    t = L.vfo_table_new()
+    err = C.create_string_buffer(256)
+    n = C.c_uint64(0)
+    ph = (C.c_double * 3)()
+    try:
+        rc = L.vfo_find_variants_file_ex(os.fsencode(path), C.byref(p), n_threads, t, C.byref(n), err, 256,
+                                         1 if simd else 0, ph)
+        if rc != 0:
+            raise RuntimeError(err.value.decode() or "oracle failed (%d)" % rc)
+        return int(L.vfo_table_rows(t)), int(n.value), [float(x) for x in ph]
     finally:
         L.vfo_table_free(t)

@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <zlib.h>
 
 /* ------------------------------------------------------------------ rules */
@@ -763,7 +764,24 @@ static int parse_fastq(const uint8_t *t, uint64_t n, uint32_t **off_o, uint32_t 
 int vfo_find_variants_file(const char *path, const vfo_params *p, int n_threads,
                            vfo_table *table, uint64_t *n_reads, char *err, size_t errlen)
 {
+    return vfo_find_variants_file_ex(path, p, n_threads, table, n_reads, err, errlen, 0, NULL);
+}
+
+static double now_s(void)
+{
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
+
+int vfo_find_variants_file_ex(const char *path, const vfo_params *p, int n_threads,
+                              vfo_table *table, uint64_t *n_reads, char *err, size_t errlen,
+                              unsigned flags, double *phase_seconds)
+{
     char dummy[8];
+    double ph_dummy[3];
+    if (!phase_seconds) phase_seconds = ph_dummy;
+    phase_seconds[0] = phase_seconds[1] = phase_seconds[2] = 0.;
     if (!err) { err = dummy; errlen = sizeof dummy; }
     err[0] = 0;
     /* the reference opens the file first (:233) and validates thresholds after (:239) */
@@ -778,16 +796,22 @@ int vfo_find_variants_file(const char *path, const vfo_params *p, int n_threads,
     }
     int st = 0;
     uint64_t tlen = 0;
+    double t0 = now_s();
     uint8_t *text = inflate_all(path, &tlen, &st);
+    phase_seconds[0] = now_s() - t0;
     if (!text) {
         snprintf(err, errlen, st == -2 ? "cannot open %s" : "malformed gzip: %s", path);
         return st;
     }
     uint32_t *off = NULL, *len = NULL;
     uint64_t n = 0;
+    t0 = now_s();
     st = parse_fastq(text, tlen, &off, &len, &n, err, errlen);
+    phase_seconds[1] = now_s() - t0;
     if (st != 0) { free(text); return st; }
-    st = vfo_process_reads(p, text, off, len, n, n_threads, table, NULL, NULL);
+    t0 = now_s();
+    st = vfo_process_reads_ex(p, text, off, len, n, n_threads, table, NULL, NULL, flags);
+    phase_seconds[2] = now_s() - t0;
     if (n_reads) *n_reads = n;
     free(off); free(len); free(text);
     return st;

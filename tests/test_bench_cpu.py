@@ -43,3 +43,22 @@ def test_reference_arm_other_configs_and_ranks():
     assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, "--gpus", "2").strip() == ""
     d = json.loads(_run({"RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"}, "--gpus", "2"))
     assert d["n_gpus"] == 2 and d["impl"] == "reference"
+
+
+def test_oracle_file_leg(tmp_path):
+    """The ingest legs' CPU baseline: the port on a gzipped FASTQ file, phases timed, same table as the plain file call."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    import oracle
+    cfg = oracle.synth_cfg(seed=5, read_len=150, adapter_len=20, region_len=99, n_variants=500)
+    ad = oracle.synth_adapters(cfg)
+    leg = bench.oracle_file_leg(oracle, cfg, ad, 0.75, str(tmp_path), 30000, 2)
+    assert leg["value"] > 0 and leg["value_if_overlapped"] >= leg["value"] and leg["cores"] == 2 and leg["kind"] == "port"
+    assert abs(leg["seconds_inflate_one_zlib_stream"] + leg["seconds_fastq_framing"] + leg["seconds_closures_all_threads_avx2"]
+               - leg["seconds"]) < 0.25 * leg["seconds"] + 0.05
+    assert os.listdir(tmp_path) == []
+    path = str(tmp_path / "same.fq.gz")
+    oracle.write_fastq(cfg, 0, 30000, path, bgzf=True, level=1)
+    assert leg["table_rows"] == len(oracle.find_variants_file(path, ad, n_threads=2))
