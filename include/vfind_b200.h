@@ -331,6 +331,13 @@ int vfb_debug_gpu_inflate(const uint8_t *z, uint64_t z_bytes, const uint32_t *me
  * when all twelve bytes are A/C/G/T/U of either case (only then does the kernel take this path). No GPU needed. */
 int vfb_debug_translate12(const uint8_t *bases12, uint8_t *aa4, int *canonical);
 
+/* Test hook for the windowed alignment path (what vfb_create decides for one adapter; no GPU needed): *accept_bound
+ * receives the integer T with score >= T <=> score as f64 > accept_alignment * match_score * adapter_len
+ * (src/lib.rs:157, :260-261), *max_edits the K of csrc/kernels_dpw.cu — the most edits an alignment with score >= T can
+ * hold — or -1 when the edit-distance filter does not apply (non-positive edit costs, adapter > 64, 3K > adapter_len). */
+int vfb_debug_window_plan(int32_t match_score, int32_t mismatch_score, int32_t gap_open_penalty, int32_t gap_extend_penalty,
+                          uint32_t adapter_len, double accept_alignment, int32_t *accept_bound, int32_t *max_edits);
+
 /* Pinned host memory for callers without their own allocator. */
 int vfb_host_alloc(void **p, uint64_t bytes);
 int vfb_host_free(void *p);

@@ -1940,6 +1940,17 @@ int vfb_measure_int_peak(int device, double *alu_gops, double *dual_gops)
     return measure_int_peak(device, alu_gops, dual_gops);
 }
 
+int vfb_debug_window_plan(int32_t match_score, int32_t mismatch_score, int32_t gap_open_penalty, int32_t gap_extend_penalty,
+                          uint32_t adapter_len, double accept_alignment, int32_t *accept_bound_out, int32_t *max_edits_out)
+{
+    if (!accept_bound_out || !max_edits_out || adapter_len == 0) { set_error("bad argument"); return VFB_ERR_ARG; }
+    const int t = accept_bound(accept_alignment, match_score, adapter_len);
+    const DpScoring sc{match_score, mismatch_score, gap_open_penalty, gap_extend_penalty};
+    *accept_bound_out = t;
+    *max_edits_out = dpw_max_edits(sc, adapter_len, t);
+    return VFB_OK;
+}
+
 int vfb_host_alloc(void **p, uint64_t bytes)
 {
     if (!p) { set_error("null argument"); return VFB_ERR_ARG; }
