@@ -162,3 +162,58 @@ def test_malformed_streams_fail_like_zlib(lib, tmp_path):
         for threads, segment in ((1, None), (4, None), (4, 50000), (8, 20000)):
             with pytest.raises(RuntimeError):
                 inflate(lib, p, threads, len(text), segment)
+
+
+def _piecewise_member(data, rng):
+    """ONE gzip member whose deflate stream is a chain of independently compressed pieces (the way pigz writes): every piece
+    has its own level / strategy and ends byte aligned with a sync or full flush, the last one with the final block."""
+    import struct
+    out = [b"\x1f\x8b\x08\x00\0\0\0\0\0\xff"]
+    pos = 0
+    while True:
+        n = rng.choice([1, 7, 300, 5000, 70000, 200000])
+        n = min(n + rng.randrange(n), len(data) - pos)
+        last = pos + n >= len(data)
+        co = zlib.compressobj(rng.randrange(0, 10), zlib.DEFLATED, -15, rng.choice([1, 8, 9]),
+                              rng.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED]))
+        out.append(co.compress(data[pos:pos + n]))
+        out.append(co.flush(zlib.Z_FINISH) if last else co.flush(rng.choice([zlib.Z_SYNC_FLUSH, zlib.Z_FULL_FLUSH])))
+        pos += n
+        if last:
+            break
+    out.append(struct.pack("<II", zlib.crc32(data) & 0xffffffff, len(data) & 0xffffffff))
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_layouts_against_zlib(lib, tmp_path, seed):
+    """Seeded fuzz: random content (reads, incompressible stretches, long runs, repeats at window distance), random piece
+    sizes / levels / strategies / flush kinds / member boundaries, random thread counts and segment sizes."""
+    rng = random.Random(1000 + seed)
+    if seed % 3 == 0:
+        text = fastq(rng.randrange(1, 9000), rng)
+    else:
+        block = bytes(rng.randrange(256) for _ in range(33000))
+        parts = []
+        for _ in range(rng.randrange(5, 60)):
+            k = rng.randrange(5)
+            if k == 0:
+                parts.append(bytes(rng.randrange(256) for _ in range(rng.randrange(1, 50000))))
+            elif k == 1:
+                parts.append(block[rng.randrange(0, 2000):rng.randrange(2000, 33000)])
+            elif k == 2:
+                parts.append(bytes([rng.randrange(256)]) * rng.randrange(1, 90000))
+            elif k == 3:
+                parts.append(bytes(rng.choice(b"ACGT") for _ in range(rng.randrange(1, 40000))))
+            else:
+                parts.append(fastq(rng.randrange(1, 300), rng))
+        text = b"@h\n" + b"".join(parts).replace(b"\n", b" ").replace(b"\r", b" ") + b"\n+\nq\n"      # one giant record
+    cuts = sorted(rng.sample(range(1, len(text)), min(rng.choice([0, 0, 1, 3]), len(text) - 1))) if len(text) > 1 else []
+    blob = b"".join(_piecewise_member(text[a:b], rng) for a, b in zip([0] + cuts, cuts + [len(text)]))
+    assert gzip.decompress(blob) == text
+    p = tmp_path / "f.gz"
+    p.write_bytes(blob)
+    want = normalised(text) if seed % 3 == 0 else text
+    for _ in range(4):
+        threads, segment = rng.randrange(2, 9), rng.choice([None, 20000, 65536, 150000, 400000])
+        assert inflate(lib, p, threads, len(text), segment) == want, (seed, threads, segment)
