@@ -150,3 +150,37 @@ def test_corrupt_inputs(lib, tmp_path):
         run(lib, p, 1)
     with pytest.raises(RuntimeError, match="cannot open"):
         run(lib, tmp_path / "missing.gz", 1)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_member_mixes_and_chunk_sizes(lib, tmp_path, seed):
+    """Seeded fuzz of the front half: runs of block-gzip members of random sizes (some empty), plain gzip members in
+    between, records that straddle every kind of boundary, CR LF or LF, trailing blank lines, random chunk sizes and
+    thread counts.  The submitted text is the file's text, cut into chunks of whole records."""
+    rng = random.Random(400 + seed)
+    text = fastq_text(rng.randrange(1, 2500), rng, crlf=(seed % 4 == 1))
+    blob, pos, max_blk = [], 0, 1
+    while pos < len(text):
+        n = min(len(text) - pos, rng.choice([1, 100, 3000, 40000, 65000, 200000]))
+        piece = text[pos:pos + n]
+        pos += n
+        if rng.random() < 0.6:
+            blk = rng.choice([1 if n <= 1000 else 2000, 500 if n <= 40000 else 5000, 20000, 65000])
+            max_blk = max(max_blk, min(blk, len(piece)))
+            blob.append(bgzf(piece, block=blk, eof=rng.random() < 0.3))          # an end-of-file member mid-file is legal
+        else:
+            blob.append(gzip.compress(piece, rng.randrange(0, 10)))
+    tail = rng.choice([b"", b"\n", b"\n\n", b"\r\n\r\n"])
+    if tail:
+        blob.append(rng.choice([gzip.compress, lambda d: bgzf(d, eof=True)])(tail))
+    blob = b"".join(blob)
+    assert gzip.decompress(blob) == text + tail
+    p = tmp_path / "z.fq.gz"
+    p.write_bytes(blob)
+    want = normalised(text)
+    for _ in range(4):
+        # (a chunk has to hold one member's text plus a carried record: the knob is for tests, the default is 128 MB)
+        threads, chunk = rng.choice([1, 2, 5, 8]), rng.choice([c for c in (None, 3000, 20000, 70000, 1 << 20) if c is None or c >= max_blk + 2000])
+        got, lines, chunks = run(lib, p, threads, chunk)
+        assert got == want, (seed, threads, chunk)
+        assert lines == want.count(b"\n") and lines % 4 == 0
